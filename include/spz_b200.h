@@ -1,0 +1,189 @@
+/*
+ * spz_b200 -- C-ABI of the B200-native .spz per-gaussian codec.
+ *
+ * This is the drop-in boundary for the reference's hot path (citations: lanxinger/spz, src/cc/):
+ *
+ *     spz::packGaussians(const GaussianCloud&, const PackOptions&)        load-spz.cc:257-331
+ *     spz::unpackGaussians(const PackedGaussians&, const UnpackOptions&)  load-spz.cc:467-531
+ *
+ * Plain C: pointers, sizes, integer status codes; no C++ or torch types.  Everything the codec
+ * does runs in hand-written sm_100a kernels; there is NO CPU implementation behind these entry
+ * points -- without a usable CUDA device every call fails with SPZB200_ERR_NO_DEVICE.
+ *
+ * The C++ drop-in API of the reference (namespace spz, include/spz/load-spz.h) and the Python
+ * mirror (spz_b200/) are thin layers over exactly these functions.  INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Plane layouts are the reference's own:
+ *   float side  (GaussianCloud, splat-types.h:90-115): positions[3n] scales[3n] rotations[4n]
+ *               (x,y,z,w) alphas[n] colors[3n] sh[3*shDim*n] (coefficient-major, colour channel
+ *               innermost), shDim = 0/3/8/15 for shDegree 0..3 (load-spz.cc:58-72).
+ *   packed side (PackedGaussians, load-spz.h:42-59): positions[9n] (24-bit LE fixed point; 6n
+ *               float16 for version 1) scales[3n] rotations[4n] (version 3 smallest-three) or
+ *               [3n] (versions 1,2) alphas[n] colors[3n] sh[3*shDim*n].
+ */
+#ifndef SPZ_B200_H_
+#define SPZ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPZB200_VERSION 100 /* 0.1.0 */
+
+/* Status codes.  0 = success; negative = failure, message via spzb200_last_error(). */
+enum {
+  SPZB200_OK = 0,
+  SPZB200_ERR_INVALID = -1,    /* bad sizes / degree / version / null pointer: the cases the
+                                  reference's checkSizes (load-spz.cc:106-127) rejects */
+  SPZB200_ERR_NO_DEVICE = -2,  /* no CUDA device, or not an sm_100 part */
+  SPZB200_ERR_CUDA = -3,       /* a CUDA call failed */
+  SPZB200_ERR_NOMEM = -4       /* device or pinned-host allocation failed */
+};
+
+/* CoordinateSystem (splat-types.h:24-34); passed as int32. */
+enum {
+  SPZB200_COORD_UNSPECIFIED = 0,
+  SPZB200_COORD_LDB = 1, SPZB200_COORD_RDB = 2, SPZB200_COORD_LUB = 3, SPZB200_COORD_RUB = 4,
+  SPZB200_COORD_LDF = 5, SPZB200_COORD_RDF = 6, SPZB200_COORD_LUF = 7, SPZB200_COORD_RUF = 8
+};
+
+/* Float planes of n gaussians: a borrowed view of GaussianCloud (splat-types.h:90-115).  The
+ * pointers are device pointers for the *_device entry points and host pointers for *_host. */
+typedef struct {
+  int64_t num_points;
+  int32_t sh_degree; /* 0..3 */
+  int32_t reserved;
+  float *positions;
+  float *scales;
+  float *rotations;
+  float *alphas;
+  float *colors;
+  float *sh; /* may be NULL when sh_degree == 0 */
+} SpzB200Cloud;
+
+/* Byte planes of n gaussians: a borrowed view of PackedGaussians (load-spz.h:42-59). */
+typedef struct {
+  int64_t num_points;
+  int32_t sh_degree;       /* 0..3 */
+  int32_t fractional_bits; /* header byte; the encoder always writes 12 (load-spz.cc:270) */
+  int32_t version;         /* container version 1..3 (load-spz.cc:571-572); encoder writes 3 */
+  int32_t reserved;
+  uint8_t *positions;
+  uint8_t *scales;
+  uint8_t *rotations;
+  uint8_t *alphas;
+  uint8_t *colors;
+  uint8_t *sh; /* may be NULL when sh_degree == 0 */
+} SpzB200Packed;
+
+/* Per-phase timings of a *_host call, milliseconds, measured with CUDA events on the call's own
+ * streams (kernel_ms = sum over chunks) plus the host wall clock of the whole call. */
+typedef struct {
+  double h2d_ms;
+  double kernel_ms;
+  double d2h_ms;
+  double wall_ms;
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int32_t kernel_launches;
+  int32_t chunks;
+} SpzB200Timings;
+
+/* One context per (thread, device): immutable codec tables resident on the device, two worker
+ * streams and the staging buffers of the host-pointer pipeline.  A context is not thread-safe;
+ * create one per host thread.  Creation fails (no CPU fallback) without an sm_100 device. */
+typedef struct SpzB200Context SpzB200Context;
+
+int spzb200_create(int32_t device, SpzB200Context **out);
+void spzb200_destroy(SpzB200Context *ctx);
+
+/* ---- device-resident codec: what the benchmark's `value` times ------------------------------
+ *
+ * Replaces packGaussians (load-spz.cc:257-331).  `from` is PackOptions::from (load-spz.h:61-63);
+ * the flips of coordinateConverter(from, RUB) (splat-types.h:55-81) are folded into the kernel.
+ * in/out hold DEVICE pointers; out->fractional_bits and out->version are set to 12 and 3.
+ * Asynchronous on `stream` (a cudaStream_t, NULL = the legacy default stream); nothing is
+ * retained after the call returns except work queued on the stream.  num_points is 64-bit: the
+ * reference's int32 size arithmetic (load-spz.cc:110-115) does not limit this implementation. */
+int spzb200_encode_device(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from,
+                          SpzB200Packed *out, void *stream);
+
+/* Replaces unpackGaussians (load-spz.cc:467-531) including its trailing
+ * convertCoordinates(RUB, to) (load-spz.cc:529, splat-types.h:134-164), fused into the kernel.
+ * `to` is UnpackOptions::to.  in->version selects the stream flavour: 3 = smallest-three
+ * rotations, 2 = first-three rotations, 1 = float16 positions + first-three. */
+int spzb200_decode_device(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to,
+                          SpzB200Cloud *out, void *stream);
+
+/* ---- host-pointer codec: what the C++ / Python drop-in API calls ----------------------------
+ *
+ * Same contracts with HOST pointers (pinned or pageable; pinned copies overlap).  The cloud is
+ * cut into contiguous point ranges; each range is copied in, transformed and copied out on
+ * alternating streams so H2D, kernel and D2H overlap.  Synchronous: returns when `out` is
+ * complete.  timings may be NULL. */
+int spzb200_encode_host(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from,
+                        SpzB200Packed *out, SpzB200Timings *timings);
+int spzb200_decode_host(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to,
+                        SpzB200Cloud *out, SpzB200Timings *timings);
+
+/* Multi-GPU form: shards [0, n) by contiguous point range (spzb200_shard_range) over the given
+ * devices, one host thread and one context per device; every device writes its slice of each
+ * output plane at its precomputed offset.  No collective, no peer traffic.  timings (may be
+ * NULL) receives the slowest device's figures. */
+int spzb200_encode_host_multi(const int32_t *devices, int32_t num_devices, const SpzB200Cloud *in,
+                              int32_t from, SpzB200Packed *out, SpzB200Timings *timings);
+int spzb200_decode_host_multi(const int32_t *devices, int32_t num_devices,
+                              const SpzB200Packed *in, int32_t to, SpzB200Cloud *out,
+                              SpzB200Timings *timings);
+
+/* Page-locked host buffers for the *_host entry points (cudaHostAlloc, portable across devices).
+ * Pageable memory works too but its copies neither overlap nor reach PCIe bandwidth. */
+int spzb200_alloc_pinned(size_t bytes, void **out);
+void spzb200_free_pinned(void *ptr);
+
+/* ---- host-side helpers (no GPU needed) ------------------------------------------------------ */
+
+/* Point range [*begin, *end) of shard `index` out of `num_shards` over n gaussians of the given
+ * SH degree.  Boundaries are multiples of the kernel tile, so every shard but the last runs
+ * entirely on the vector path and every plane slice stays 16-byte aligned. */
+int spzb200_shard_range(int64_t n, int32_t sh_degree, int32_t num_shards, int32_t index,
+                        int64_t *begin, int64_t *end);
+
+/* Gaussians per kernel tile for an SH degree (the sharding granule). */
+int32_t spzb200_tile_gaussians(int32_t sh_degree);
+
+/* Sign sets of coordinateConverter(from, to) (splat-types.h:55-81): bit i of *flip_p negates
+ * position axis i, of *flip_q quaternion component i (x,y,z), of *flip_sh SH coefficient i. */
+void spzb200_flip_bits(int32_t from, int32_t to, uint32_t *flip_p, uint32_t *flip_q,
+                       uint32_t *flip_sh);
+
+/* The two host-built tables of a context (for inspection and tests): the 255 ascending alpha
+ * thresholds (out[255] = +Inf) and the 256-entry inverse-sigmoid table. */
+int spzb200_get_tables(const SpzB200Context *ctx, float alpha_thresholds[256],
+                       float alpha_lut[256]);
+/* The same construction without a context or a GPU (what spzb200_create runs on the host). */
+int spzb200_build_tables(float alpha_thresholds[256], float alpha_lut[256]);
+
+/* Context facts: 148 on a B200, which byte packer the encoder uses (1 = cvt.pack/I2IP, 0 = ALU),
+ * kernels launched through this context so far. */
+int spzb200_info(const SpzB200Context *ctx, int32_t *sm_count, int32_t *pack_mode,
+                 int64_t *kernel_launches);
+
+/* Test hooks: force the scalar kernels (1) / restore (0); choose the byte packer. */
+void spzb200_set_force_generic(SpzB200Context *ctx, int32_t on);
+void spzb200_set_pack_mode(SpzB200Context *ctx, int32_t mode);
+/* Point ranges of at most this many gaussians per pipeline stage of the *_host calls. */
+void spzb200_set_chunk_points(SpzB200Context *ctx, int64_t points);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *spzb200_last_error(void);
+int32_t spzb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPZ_B200_H_ */

@@ -1,0 +1,696 @@
+// C-ABI of the codec (include/spz_b200.h): contexts, the two host-built tables, the
+// device-pointer entry points, the chunked host-pointer pipeline and its multi-GPU form.
+//
+// There is no CPU implementation of the codec in this library.  The only per-value arithmetic
+// done on the host is the one-time construction of two small tables per context, both of which
+// depend on the host's libm exactly as the reference does (load-spz.cc:85,87):
+//   * the 255 thresholds of the alpha quantizer  a -> toUint8(sigmoid(a) * 255)   (uses expf)
+//   * the 256 values of the alpha dequantizer    b -> invSigmoid(b / 255.0f)      (uses logf)
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/spz_b200.h"
+#include "codec_kernels.cuh"
+#include "codec_math.cuh"
+
+namespace {
+
+thread_local std::string tlsError;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  tlsError = buf;
+  return code;
+}
+
+int cudaFail(cudaError_t e, const char *what) {
+  return fail(e == cudaErrorMemoryAllocation ? SPZB200_ERR_NOMEM : SPZB200_ERR_CUDA, "%s: %s",
+              what, cudaGetErrorString(e));
+}
+
+#define CU(call)                                   \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) return cudaFail(e_, #call); \
+  } while (0)
+
+int shDimOf(int degree) { return degree == 0 ? 0 : degree == 1 ? 3 : degree == 2 ? 8 : 15; }
+
+// ---- the two libm-dependent tables ------------------------------------------------------------
+
+// The reference expression, load-spz.cc:301 with :85 and :74, for a non-NaN argument.  This file
+// is compiled with -ffp-contract=off so the product s * 255 is rounded on its own.
+uint32_t alphaByteOnHost(float a) {
+  const float s = 1 / (1 + std::exp(-a));
+  float r = std::round(s * 255.0f);
+  r = r < 0.0f ? 0.0f : (255.0f < r ? 255.0f : r);
+  return (uint32_t)r;
+}
+
+// order-preserving map float <-> uint32 (negative floats reversed below positives)
+uint32_t keyOf(float f) {
+  uint32_t b;
+  std::memcpy(&b, &f, 4);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+float floatOf(uint32_t k) {
+  const uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  float f;
+  std::memcpy(&f, &b, 4);
+  return f;
+}
+
+// thr[L-1] = the smallest float whose alpha byte is >= L, L = 1..255; thr[255] = +Inf.
+// Exact because the byte is monotone in a (checked below on a 2^16-point grid plus both
+// neighbours of every threshold; exhaustively in tests/test_tables.py).
+bool buildAlphaThresholds(float thr[256], std::string *why) {
+  const uint32_t kLo = keyOf(-std::numeric_limits<float>::infinity());
+  const uint32_t kHi = keyOf(std::numeric_limits<float>::infinity());
+  for (uint32_t level = 1; level <= 255; level++) {
+    uint32_t lo = kLo, hi = kHi;  // f(hi) = 255 >= level always; find the first key with f >= level
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (alphaByteOnHost(floatOf(mid)) >= level) hi = mid; else lo = mid + 1;
+    }
+    thr[level - 1] = floatOf(lo);
+  }
+  thr[255] = std::numeric_limits<float>::infinity();
+  auto viaTable = [&](float a) {
+    uint32_t c = 0;
+    for (int i = 0; i < 255; i++) c += a >= thr[i];
+    return c;
+  };
+  for (uint32_t level = 1; level <= 255; level++) {
+    const uint32_t k = keyOf(thr[level - 1]);
+    const float here = thr[level - 1], below = floatOf(k - 1);
+    if (viaTable(here) != alphaByteOnHost(here) || (k > kLo && viaTable(below) != alphaByteOnHost(below))) {
+      *why = "alpha quantizer is not a monotone step function with this libm";
+      return false;
+    }
+  }
+  for (uint32_t i = 0; i < 65536; i++) {
+    const float a = floatOf(kLo + (uint32_t)(((uint64_t)(kHi - kLo) * i) >> 16));
+    if (viaTable(a) != alphaByteOnHost(a)) {
+      *why = "alpha threshold table disagrees with the direct expression";
+      return false;
+    }
+  }
+  return true;
+}
+
+void buildAlphaLut(float lut[256]) {
+  for (int i = 0; i < 256; i++) {
+    const float x = (float)i / 255.0f;        // load-spz.cc:518
+    lut[i] = std::log(x / (1.0f - x));        // load-spz.cc:87
+  }
+}
+
+struct Stage {
+  cudaStream_t stream = nullptr;
+  uint8_t *dFloats = nullptr;  // float planes of one chunk
+  uint8_t *dBytes = nullptr;   // byte planes of one chunk
+  size_t floatsCap = 0, bytesCap = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct SpzB200Context {
+  int device = 0;
+  int smCount = 0;
+  int packMode = spzb200::kPackAlu;
+  bool cvtPackOk = false;  // the init-time probe of cvt.pack.sat.u8.s32 agreed with the ALU packer
+  bool forceGeneric = false;
+  long long chunkPoints = 1 << 21;
+  long long kernelLaunches = 0;
+  float hThr[256];
+  float hLut[256];
+  float *dThr = nullptr;
+  float *dLut = nullptr;
+  Stage stage[2];
+};
+
+namespace {
+
+int validDegree(int d) { return d >= 0 && d <= 3; }
+
+int checkCloud(const SpzB200Cloud *c, const char *who) {
+  if (!c) return fail(SPZB200_ERR_INVALID, "%s: null cloud view", who);
+  if (c->num_points < 0) return fail(SPZB200_ERR_INVALID, "%s: num_points < 0", who);
+  if (!validDegree(c->sh_degree)) return fail(SPZB200_ERR_INVALID, "%s: sh_degree %d not in 0..3", who, c->sh_degree);
+  if (c->num_points > 0) {
+    if (!c->positions || !c->scales || !c->rotations || !c->alphas || !c->colors)
+      return fail(SPZB200_ERR_INVALID, "%s: null plane pointer", who);
+    if (c->sh_degree > 0 && !c->sh) return fail(SPZB200_ERR_INVALID, "%s: null sh plane", who);
+  }
+  return SPZB200_OK;
+}
+
+int checkPacked(const SpzB200Packed *p, const char *who, bool needVersion) {
+  if (!p) return fail(SPZB200_ERR_INVALID, "%s: null packed view", who);
+  if (p->num_points < 0) return fail(SPZB200_ERR_INVALID, "%s: num_points < 0", who);
+  if (!validDegree(p->sh_degree)) return fail(SPZB200_ERR_INVALID, "%s: sh_degree %d not in 0..3", who, p->sh_degree);
+  if (needVersion && (p->version < 1 || p->version > 3))
+    return fail(SPZB200_ERR_INVALID, "%s: version %d not in 1..3", who, p->version);
+  if (p->num_points > 0) {
+    if (!p->positions || !p->scales || !p->rotations || !p->alphas || !p->colors)
+      return fail(SPZB200_ERR_INVALID, "%s: null plane pointer", who);
+    if (p->sh_degree > 0 && !p->sh) return fail(SPZB200_ERR_INVALID, "%s: null sh plane", who);
+  }
+  return SPZB200_OK;
+}
+
+// (float)(1.0 / (1 << fractionalBits)), load-spz.cc:495.  The shift count is taken modulo 32, which
+// is what the reference's x86 build does for header bytes >= 32.
+float positionScaleFor(int fractionalBits) {
+  const int32_t one = (int32_t)(1u << (fractionalBits & 31));
+  return (float)(1.0 / one);
+}
+
+spzb200::EncodeArgs makeEncodeArgs(const SpzB200Context *ctx, const SpzB200Cloud &in,
+                                   const SpzB200Packed &out, int32_t from) {
+  spzb200::EncodeArgs a;
+  a.positions = in.positions; a.scales = in.scales; a.rotations = in.rotations;
+  a.alphas = in.alphas; a.colors = in.colors; a.sh = in.sh;
+  a.oPositions = out.positions; a.oScales = out.scales; a.oRotations = out.rotations;
+  a.oAlphas = out.alphas; a.oColors = out.colors; a.oSh = out.sh;
+  a.n = in.num_points;
+  a.shDim = shDimOf(in.sh_degree);
+  const spzb200::m::FlipBits f = spzb200::m::make_flip_bits(from, SPZB200_COORD_RUB);
+  a.flipP = f.p; a.flipQ = f.q; a.flipSh = f.sh;
+  a.alphaThresholds = ctx->dThr;
+  return a;
+}
+
+spzb200::DecodeArgs makeDecodeArgs(const SpzB200Context *ctx, const SpzB200Packed &in,
+                                   const SpzB200Cloud &out, int32_t to) {
+  spzb200::DecodeArgs a;
+  a.positions = in.positions; a.scales = in.scales; a.rotations = in.rotations;
+  a.alphas = in.alphas; a.colors = in.colors; a.sh = in.sh;
+  a.oPositions = out.positions; a.oScales = out.scales; a.oRotations = out.rotations;
+  a.oAlphas = out.alphas; a.oColors = out.colors; a.oSh = out.sh;
+  a.n = in.num_points;
+  a.shDim = shDimOf(in.sh_degree);
+  a.version = in.version;
+  a.positionScale = positionScaleFor(in.fractional_bits);
+  const spzb200::m::FlipBits f = spzb200::m::make_flip_bits(SPZB200_COORD_RUB, to);
+  a.flipP = f.p; a.flipQ = f.q; a.flipSh = f.sh;
+  a.alphaLut = ctx->dLut;
+  return a;
+}
+
+spzb200::LaunchPlan planOf(const SpzB200Context *ctx) {
+  spzb200::LaunchPlan p;
+  p.smCount = ctx->smCount;
+  p.packMode = ctx->packMode;
+  p.forceGeneric = ctx->forceGeneric;
+  return p;
+}
+
+// bytes per gaussian of each plane, in the struct order positions, scales, rotations, alphas,
+// colors, sh
+void floatPlaneBytes(int shDim, size_t b[6]) {
+  b[0] = 12; b[1] = 12; b[2] = 16; b[3] = 4; b[4] = 12; b[5] = (size_t)12 * shDim;
+}
+void bytePlaneBytes(int shDim, int version, size_t b[6]) {
+  b[0] = version == 1 ? 6 : 9; b[1] = 3; b[2] = version >= 3 ? 4 : 3; b[3] = 1; b[4] = 3;
+  b[5] = (size_t)3 * shDim;
+}
+
+int ensureStage(Stage &s, size_t floatsBytes, size_t bytesBytes) {
+  if (s.floatsCap < floatsBytes) {
+    if (s.dFloats) cudaFree(s.dFloats);
+    s.dFloats = nullptr; s.floatsCap = 0;
+    CU(cudaMalloc(&s.dFloats, floatsBytes));
+    s.floatsCap = floatsBytes;
+  }
+  if (s.bytesCap < bytesBytes) {
+    if (s.dBytes) cudaFree(s.dBytes);
+    s.dBytes = nullptr; s.bytesCap = 0;
+    CU(cudaMalloc(&s.dBytes, bytesBytes));
+    s.bytesCap = bytesBytes;
+  }
+  return SPZB200_OK;
+}
+
+// carve six 256-byte-aligned sub-buffers for `points` gaussians
+size_t carve(uint8_t *base, const size_t per[6], long long points, uint8_t *out[6]) {
+  size_t off = 0;
+  for (int i = 0; i < 6; i++) {
+    out[i] = base ? base + off : nullptr;
+    off += alignUp(per[i] * (size_t)points, 256);
+  }
+  return off;
+}
+
+double nowMs() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct ChunkRec { int stage; };
+
+// The chunked H2D || kernel || D2H pipeline shared by encode_host and decode_host.
+// isEncode: float planes in, byte planes out; otherwise the reverse.
+int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &cloud,
+                    const SpzB200Packed &packed, int32_t coord, SpzB200Timings *timings) {
+  const double w0 = nowMs();
+  CU(cudaSetDevice(ctx->device));
+  const long long n = cloud.num_points;
+  const int shDim = shDimOf(cloud.sh_degree);
+  const int version = isEncode ? 3 : packed.version;
+  size_t fper[6], bper[6];
+  floatPlaneBytes(shDim, fper);
+  bytePlaneBytes(shDim, version, bper);
+  const long long tg = spzb200::tileGaussians(shDim);
+  long long chunk = std::max<long long>(tg, ctx->chunkPoints / tg * tg);
+  if (chunk > n) chunk = std::max<long long>(n, 1);
+  const long long numChunks = n == 0 ? 0 : (n + chunk - 1) / chunk;
+
+  SpzB200Timings tm;
+  std::memset(&tm, 0, sizeof tm);
+  if (numChunks > 0) {
+    uint8_t *unused[6];
+    const size_t fBytes = carve(nullptr, fper, chunk, unused);
+    const size_t bBytes = carve(nullptr, bper, chunk, unused);
+    const int stages = numChunks > 1 ? 2 : 1;
+    for (int s = 0; s < stages; s++) {
+      int rc = ensureStage(ctx->stage[s], fBytes, bBytes);
+      if (rc != SPZB200_OK) return rc;
+    }
+  }
+
+  float *const cloudPlanes[6] = {cloud.positions, cloud.scales, cloud.rotations, cloud.alphas, cloud.colors, cloud.sh};
+  uint8_t *const packedPlanes[6] = {packed.positions, packed.scales, packed.rotations, packed.alphas, packed.colors, packed.sh};
+  const spzb200::LaunchPlan plan = planOf(ctx);
+
+  for (long long c = 0; c < numChunks; c++) {
+    Stage &st = ctx->stage[c & 1];
+    const long long a = c * chunk, b = std::min(n, a + chunk), pts = b - a;
+    if (c >= 2) {
+      // the stage's previous chunk (c-2) has fully drained once its last event completed; collect
+      // its timings before the events are re-recorded
+      CU(cudaEventSynchronize(st.ev[3]));
+      float ms;
+      CU(cudaEventElapsedTime(&ms, st.ev[0], st.ev[1])); tm.h2d_ms += ms;
+      CU(cudaEventElapsedTime(&ms, st.ev[1], st.ev[2])); tm.kernel_ms += ms;
+      CU(cudaEventElapsedTime(&ms, st.ev[2], st.ev[3])); tm.d2h_ms += ms;
+    }
+    uint8_t *df[6], *db[6];
+    carve(st.dFloats, fper, chunk, df);
+    carve(st.dBytes, bper, chunk, db);
+    CU(cudaEventRecord(st.ev[0], st.stream));
+    for (int i = 0; i < 6; i++) {
+      if (isEncode) {
+        const size_t bytes = fper[i] * (size_t)pts;
+        if (bytes) CU(cudaMemcpyAsync(df[i], reinterpret_cast<const uint8_t *>(cloudPlanes[i]) + fper[i] * (size_t)a, bytes, cudaMemcpyHostToDevice, st.stream));
+        tm.h2d_bytes += (int64_t)bytes;
+      } else {
+        const size_t bytes = bper[i] * (size_t)pts;
+        if (bytes) CU(cudaMemcpyAsync(db[i], packedPlanes[i] + bper[i] * (size_t)a, bytes, cudaMemcpyHostToDevice, st.stream));
+        tm.h2d_bytes += (int64_t)bytes;
+      }
+    }
+    CU(cudaEventRecord(st.ev[1], st.stream));
+    SpzB200Cloud dc = cloud;
+    SpzB200Packed dp = packed;
+    dc.num_points = dp.num_points = pts;
+    dc.positions = (float *)df[0]; dc.scales = (float *)df[1]; dc.rotations = (float *)df[2];
+    dc.alphas = (float *)df[3]; dc.colors = (float *)df[4]; dc.sh = (float *)df[5];
+    dp.positions = db[0]; dp.scales = db[1]; dp.rotations = db[2]; dp.alphas = db[3];
+    dp.colors = db[4]; dp.sh = db[5];
+    dp.version = version;
+    int launches = 0;
+    if (isEncode) {
+      CU(spzb200::launchEncode(makeEncodeArgs(ctx, dc, dp, coord), plan, st.stream, &launches));
+    } else {
+      CU(spzb200::launchDecode(makeDecodeArgs(ctx, dp, dc, coord), plan, st.stream, &launches));
+    }
+    ctx->kernelLaunches += launches;
+    tm.kernel_launches += launches;
+    CU(cudaEventRecord(st.ev[2], st.stream));
+    for (int i = 0; i < 6; i++) {
+      if (isEncode) {
+        const size_t bytes = bper[i] * (size_t)pts;
+        if (bytes) CU(cudaMemcpyAsync(packedPlanes[i] + bper[i] * (size_t)a, db[i], bytes, cudaMemcpyDeviceToHost, st.stream));
+        tm.d2h_bytes += (int64_t)bytes;
+      } else {
+        const size_t bytes = fper[i] * (size_t)pts;
+        if (bytes) CU(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(cloudPlanes[i]) + fper[i] * (size_t)a, df[i], bytes, cudaMemcpyDeviceToHost, st.stream));
+        tm.d2h_bytes += (int64_t)bytes;
+      }
+    }
+    CU(cudaEventRecord(st.ev[3], st.stream));
+  }
+  // drain: the last (up to two) chunks still hold unread events
+  for (long long c = std::max<long long>(0, numChunks - 2); c < numChunks; c++) {
+    Stage &st = ctx->stage[c & 1];
+    CU(cudaEventSynchronize(st.ev[3]));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, st.ev[0], st.ev[1])); tm.h2d_ms += ms;
+    CU(cudaEventElapsedTime(&ms, st.ev[1], st.ev[2])); tm.kernel_ms += ms;
+    CU(cudaEventElapsedTime(&ms, st.ev[2], st.ev[3])); tm.d2h_ms += ms;
+  }
+  tm.chunks = (int32_t)numChunks;
+  tm.wall_ms = nowMs() - w0;
+  if (timings) *timings = tm;
+  return SPZB200_OK;
+}
+
+template <class Fn>
+int runSharded(const int32_t *devices, int32_t numDevices, int64_t n, int32_t shDegree, Fn &&perShard,
+               SpzB200Timings *timings) {
+  if (!devices || numDevices <= 0) return fail(SPZB200_ERR_INVALID, "multi: no devices given");
+  std::vector<int> rc(numDevices, SPZB200_OK);
+  std::vector<std::string> msg(numDevices);
+  std::vector<SpzB200Timings> tms(numDevices);
+  std::vector<std::thread> threads;
+  const double w0 = nowMs();
+  for (int32_t i = 0; i < numDevices; i++) {
+    threads.emplace_back([&, i]() {
+      std::memset(&tms[i], 0, sizeof(SpzB200Timings));
+      int64_t a = 0, b = 0;
+      rc[i] = spzb200_shard_range(n, shDegree, numDevices, i, &a, &b);
+      if (rc[i] == SPZB200_OK && b > a) {
+        SpzB200Context *ctx = nullptr;
+        rc[i] = spzb200_create(devices[i], &ctx);
+        if (rc[i] == SPZB200_OK) {
+          rc[i] = perShard(ctx, a, b, &tms[i]);
+          spzb200_destroy(ctx);
+        }
+      }
+      if (rc[i] != SPZB200_OK) msg[i] = spzb200_last_error();
+    });
+  }
+  for (auto &t : threads) t.join();
+  for (int32_t i = 0; i < numDevices; i++)
+    if (rc[i] != SPZB200_OK) return fail(rc[i], "device %d: %s", devices[i], msg[i].c_str());
+  if (timings) {
+    SpzB200Timings out;
+    std::memset(&out, 0, sizeof out);
+    for (auto &t : tms) {
+      out.h2d_ms = std::max(out.h2d_ms, t.h2d_ms);
+      out.kernel_ms = std::max(out.kernel_ms, t.kernel_ms);
+      out.d2h_ms = std::max(out.d2h_ms, t.d2h_ms);
+      out.h2d_bytes += t.h2d_bytes;
+      out.d2h_bytes += t.d2h_bytes;
+      out.kernel_launches += t.kernel_launches;
+      out.chunks += t.chunks;
+    }
+    out.wall_ms = nowMs() - w0;
+    *timings = out;
+  }
+  return SPZB200_OK;
+}
+
+SpzB200Cloud sliceCloud(const SpzB200Cloud &c, int64_t a, int64_t b) {
+  const int d = shDimOf(c.sh_degree);
+  SpzB200Cloud s = c;
+  s.num_points = b - a;
+  s.positions = c.positions + 3 * a; s.scales = c.scales + 3 * a; s.rotations = c.rotations + 4 * a;
+  s.alphas = c.alphas + a; s.colors = c.colors + 3 * a; s.sh = c.sh ? c.sh + (int64_t)3 * d * a : nullptr;
+  return s;
+}
+
+SpzB200Packed slicePacked(const SpzB200Packed &p, int64_t a, int64_t b) {
+  const int d = shDimOf(p.sh_degree);
+  SpzB200Packed s = p;
+  s.num_points = b - a;
+  s.positions = p.positions + (p.version == 1 ? 6 : 9) * a; s.scales = p.scales + 3 * a;
+  s.rotations = p.rotations + (p.version >= 3 ? 4 : 3) * a; s.alphas = p.alphas + a;
+  s.colors = p.colors + 3 * a; s.sh = p.sh ? p.sh + (int64_t)3 * d * a : nullptr;
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *spzb200_last_error(void) { return tlsError.c_str(); }
+int32_t spzb200_version(void) { return SPZB200_VERSION; }
+
+int spzb200_create(int32_t device, SpzB200Context **out) {
+  if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_create: null out");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(SPZB200_ERR_NO_DEVICE, "spzb200_create: no CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    return fail(SPZB200_ERR_NO_DEVICE, "spzb200_create: device %d out of range (0..%d)", device, count - 1);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SPZB200_ERR_NO_DEVICE, "spzb200_create: device %d is sm_%d%d; kernels are built for sm_100a only",
+                device, prop.major, prop.minor);
+  CU(cudaSetDevice(device));
+  SpzB200Context *ctx = new SpzB200Context;
+  ctx->device = device;
+  ctx->smCount = prop.multiProcessorCount;
+  std::string why;
+  if (!buildAlphaThresholds(ctx->hThr, &why)) {
+    delete ctx;
+    return fail(SPZB200_ERR_INVALID, "spzb200_create: %s", why.c_str());
+  }
+  buildAlphaLut(ctx->hLut);
+  auto bail = [&](cudaError_t err, const char *what) {
+    spzb200_destroy(ctx);
+    return cudaFail(err, what);
+  };
+  if ((e = cudaMalloc(&ctx->dThr, 256 * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc tables");
+  if ((e = cudaMalloc(&ctx->dLut, 256 * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc tables");
+  if ((e = cudaMemcpy(ctx->dThr, ctx->hThr, sizeof ctx->hThr, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "table upload");
+  if ((e = cudaMemcpy(ctx->dLut, ctx->hLut, sizeof ctx->hLut, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "table upload");
+  for (int s = 0; s < 2; s++) {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stage[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (int k = 0; k < 4; k++)
+      if ((e = cudaEventCreate(&ctx->stage[s].ev[k])) != cudaSuccess) return bail(e, "cudaEventCreate");
+  }
+  int ok = 0;
+  if ((e = spzb200::probePackCvt(ctx->stage[0].stream, &ok)) != cudaSuccess) return bail(e, "pack probe");
+  ctx->cvtPackOk = ok != 0;
+  ctx->packMode = ok ? spzb200::kPackCvt : spzb200::kPackAlu;
+  if (const char *env = std::getenv("SPZB200_PACK")) {
+    if (!std::strcmp(env, "alu")) ctx->packMode = spzb200::kPackAlu;
+  }
+  *out = ctx;
+  return SPZB200_OK;
+}
+
+void spzb200_destroy(SpzB200Context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int s = 0; s < 2; s++) {
+    Stage &st = ctx->stage[s];
+    if (st.stream) cudaStreamSynchronize(st.stream);
+    for (int k = 0; k < 4; k++) if (st.ev[k]) cudaEventDestroy(st.ev[k]);
+    if (st.dFloats) cudaFree(st.dFloats);
+    if (st.dBytes) cudaFree(st.dBytes);
+    if (st.stream) cudaStreamDestroy(st.stream);
+  }
+  if (ctx->dThr) cudaFree(ctx->dThr);
+  if (ctx->dLut) cudaFree(ctx->dLut);
+  delete ctx;
+}
+
+int spzb200_encode_device(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from,
+                          SpzB200Packed *out, void *stream) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_encode_device: null context");
+  int rc = checkCloud(in, "spzb200_encode_device");
+  if (rc) return rc;
+  if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_encode_device: null out");
+  out->num_points = in->num_points;
+  out->sh_degree = in->sh_degree;
+  out->fractional_bits = 12;  // load-spz.cc:270
+  out->version = 3;           // load-spz.cc:133,272
+  rc = checkPacked(out, "spzb200_encode_device", true);
+  if (rc) return rc;
+  if (from < 0 || from > 8) return fail(SPZB200_ERR_INVALID, "spzb200_encode_device: coordinate system %d", from);
+  CU(cudaSetDevice(ctx->device));
+  int launches = 0;
+  CU(spzb200::launchEncode(makeEncodeArgs(ctx, *in, *out, from), planOf(ctx), (cudaStream_t)stream, &launches));
+  ctx->kernelLaunches += launches;
+  return SPZB200_OK;
+}
+
+int spzb200_decode_device(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to,
+                          SpzB200Cloud *out, void *stream) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_decode_device: null context");
+  int rc = checkPacked(in, "spzb200_decode_device", true);
+  if (rc) return rc;
+  if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_decode_device: null out");
+  out->num_points = in->num_points;
+  out->sh_degree = in->sh_degree;
+  rc = checkCloud(out, "spzb200_decode_device");
+  if (rc) return rc;
+  if (to < 0 || to > 8) return fail(SPZB200_ERR_INVALID, "spzb200_decode_device: coordinate system %d", to);
+  CU(cudaSetDevice(ctx->device));
+  int launches = 0;
+  CU(spzb200::launchDecode(makeDecodeArgs(ctx, *in, *out, to), planOf(ctx), (cudaStream_t)stream, &launches));
+  ctx->kernelLaunches += launches;
+  return SPZB200_OK;
+}
+
+int spzb200_encode_host(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from,
+                        SpzB200Packed *out, SpzB200Timings *timings) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_encode_host: null context");
+  int rc = checkCloud(in, "spzb200_encode_host");
+  if (rc) return rc;
+  if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_encode_host: null out");
+  out->num_points = in->num_points;
+  out->sh_degree = in->sh_degree;
+  out->fractional_bits = 12;
+  out->version = 3;
+  rc = checkPacked(out, "spzb200_encode_host", true);
+  if (rc) return rc;
+  if (from < 0 || from > 8) return fail(SPZB200_ERR_INVALID, "spzb200_encode_host: coordinate system %d", from);
+  return runHostPipeline(ctx, true, *in, *out, from, timings);
+}
+
+int spzb200_decode_host(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to,
+                        SpzB200Cloud *out, SpzB200Timings *timings) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_decode_host: null context");
+  int rc = checkPacked(in, "spzb200_decode_host", true);
+  if (rc) return rc;
+  if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_decode_host: null out");
+  out->num_points = in->num_points;
+  out->sh_degree = in->sh_degree;
+  rc = checkCloud(out, "spzb200_decode_host");
+  if (rc) return rc;
+  if (to < 0 || to > 8) return fail(SPZB200_ERR_INVALID, "spzb200_decode_host: coordinate system %d", to);
+  return runHostPipeline(ctx, false, *out, *in, to, timings);
+}
+
+int spzb200_encode_host_multi(const int32_t *devices, int32_t num_devices, const SpzB200Cloud *in,
+                              int32_t from, SpzB200Packed *out, SpzB200Timings *timings) {
+  int rc = checkCloud(in, "spzb200_encode_host_multi");
+  if (rc) return rc;
+  if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_encode_host_multi: null out");
+  out->num_points = in->num_points;
+  out->sh_degree = in->sh_degree;
+  out->fractional_bits = 12;
+  out->version = 3;
+  rc = checkPacked(out, "spzb200_encode_host_multi", true);
+  if (rc) return rc;
+  const SpzB200Cloud cin = *in;
+  const SpzB200Packed cout = *out;
+  return runSharded(devices, num_devices, in->num_points, in->sh_degree,
+                    [&](SpzB200Context *ctx, int64_t a, int64_t b, SpzB200Timings *tm) {
+                      SpzB200Cloud ci = sliceCloud(cin, a, b);
+                      SpzB200Packed po = slicePacked(cout, a, b);
+                      return spzb200_encode_host(ctx, &ci, from, &po, tm);
+                    }, timings);
+}
+
+int spzb200_decode_host_multi(const int32_t *devices, int32_t num_devices,
+                              const SpzB200Packed *in, int32_t to, SpzB200Cloud *out,
+                              SpzB200Timings *timings) {
+  int rc = checkPacked(in, "spzb200_decode_host_multi", true);
+  if (rc) return rc;
+  if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_decode_host_multi: null out");
+  out->num_points = in->num_points;
+  out->sh_degree = in->sh_degree;
+  rc = checkCloud(out, "spzb200_decode_host_multi");
+  if (rc) return rc;
+  const SpzB200Packed cin = *in;
+  const SpzB200Cloud cout = *out;
+  return runSharded(devices, num_devices, in->num_points, in->sh_degree,
+                    [&](SpzB200Context *ctx, int64_t a, int64_t b, SpzB200Timings *tm) {
+                      SpzB200Packed pi = slicePacked(cin, a, b);
+                      SpzB200Cloud co = sliceCloud(cout, a, b);
+                      return spzb200_decode_host(ctx, &pi, to, &co, tm);
+                    }, timings);
+}
+
+int spzb200_alloc_pinned(size_t bytes, void **out) {
+  if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_alloc_pinned: null out");
+  *out = nullptr;
+  if (bytes == 0) return SPZB200_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(SPZB200_ERR_NO_DEVICE, "spzb200_alloc_pinned: no CUDA device");
+  e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    *out = nullptr;
+    cudaGetLastError();
+    return fail(SPZB200_ERR_NOMEM, "spzb200_alloc_pinned: %zu bytes: %s", bytes, cudaGetErrorString(e));
+  }
+  return SPZB200_OK;
+}
+
+void spzb200_free_pinned(void *ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+int32_t spzb200_tile_gaussians(int32_t sh_degree) {
+  return validDegree(sh_degree) ? spzb200::tileGaussians(shDimOf(sh_degree)) : 0;
+}
+
+int spzb200_shard_range(int64_t n, int32_t sh_degree, int32_t num_shards, int32_t index,
+                        int64_t *begin, int64_t *end) {
+  if (n < 0 || !validDegree(sh_degree) || num_shards <= 0 || index < 0 || index >= num_shards || !begin || !end)
+    return fail(SPZB200_ERR_INVALID, "spzb200_shard_range: bad arguments");
+  const int64_t g = spzb200::tileGaussians(shDimOf(sh_degree));
+  const int64_t tiles = n / g;
+  // whole tiles are dealt out as evenly as possible; the sub-tile remainder rides on the last shard
+  const int64_t a = tiles * index / num_shards * g;
+  const int64_t b = index == num_shards - 1 ? n : tiles * (index + 1) / num_shards * g;
+  *begin = a;
+  *end = b;
+  return SPZB200_OK;
+}
+
+void spzb200_flip_bits(int32_t from, int32_t to, uint32_t *flip_p, uint32_t *flip_q, uint32_t *flip_sh) {
+  const spzb200::m::FlipBits f = spzb200::m::make_flip_bits(from, to);
+  if (flip_p) *flip_p = f.p;
+  if (flip_q) *flip_q = f.q;
+  if (flip_sh) *flip_sh = f.sh;
+}
+
+int spzb200_build_tables(float alpha_thresholds[256], float alpha_lut[256]) {
+  std::string why;
+  if (alpha_thresholds && !buildAlphaThresholds(alpha_thresholds, &why))
+    return fail(SPZB200_ERR_INVALID, "spzb200_build_tables: %s", why.c_str());
+  if (alpha_lut) buildAlphaLut(alpha_lut);
+  return SPZB200_OK;
+}
+
+int spzb200_get_tables(const SpzB200Context *ctx, float alpha_thresholds[256], float alpha_lut[256]) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_get_tables: null context");
+  if (alpha_thresholds) std::memcpy(alpha_thresholds, ctx->hThr, sizeof ctx->hThr);
+  if (alpha_lut) std::memcpy(alpha_lut, ctx->hLut, sizeof ctx->hLut);
+  return SPZB200_OK;
+}
+
+int spzb200_info(const SpzB200Context *ctx, int32_t *sm_count, int32_t *pack_mode, int64_t *kernel_launches) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_info: null context");
+  if (sm_count) *sm_count = ctx->smCount;
+  if (pack_mode) *pack_mode = ctx->packMode;
+  if (kernel_launches) *kernel_launches = ctx->kernelLaunches;
+  return SPZB200_OK;
+}
+
+void spzb200_set_force_generic(SpzB200Context *ctx, int32_t on) { if (ctx) ctx->forceGeneric = on != 0; }
+void spzb200_set_pack_mode(SpzB200Context *ctx, int32_t mode) {
+  if (ctx) ctx->packMode = (mode && ctx->cvtPackOk) ? spzb200::kPackCvt : spzb200::kPackAlu;
+}
+void spzb200_set_chunk_points(SpzB200Context *ctx, int64_t points) { if (ctx && points > 0) ctx->chunkPoints = points; }
+
+}  // extern "C"

@@ -1,0 +1,563 @@
+// sm_100a kernels of the .spz per-gaussian codec: packGaussians (load-spz.cc:257-331) and
+// unpackGaussians (load-spz.cc:467-531, with convertCoordinates splat-types.h:134-164 fused in).
+//
+// Layout insight that shapes the kernels: every plane of GaussianCloud / PackedGaussians is a
+// flat array in which four consecutive floats correspond to a whole number of packed 32-bit
+// words (4 floats <-> 4 bytes for scales / colours / alphas / SH, 4 floats <-> 12 bytes for
+// 24-bit positions, 1 quaternion <-> 4 bytes).  So the codec is an ELEMENTWISE stream transform
+// on 16-byte granules: consecutive lanes touch consecutive float4s (512 B per warp instruction)
+// and consecutive packed words (128 B per warp instruction).  No transposition through shared
+// memory is needed; the only position-dependent parameters are the coordinate-flip sign and the
+// SH bucket size, which depend on (element index mod 3*shDim) resp. (element index mod 3).
+//
+// Tiling: a CTA has 320 threads of which S (315, or 318 for SH degree 2) are active; a tile is
+// 4*S gaussians.  S is a multiple of 3 and 4*S a multiple of 3*shDim, so a thread's phase inside
+// the 45-float SH row (and the xyz triple) is the same for every float4 it ever touches: the
+// flip signs and bucket constants are 12 loop-invariant registers.  CTAs are persistent
+// (gridDim = SMs x resident CTAs) and stride over tiles.  The remainder (< one tile) and any
+// call with under-aligned pointers goes to a scalar one-thread-per-gaussian kernel.
+//
+// HBM traffic is exactly the algorithmic 301 B per gaussian at SH degree 3 (236 B floats + 65 B
+// packed); nothing is read twice.
+#include "codec_kernels.cuh"
+
+#include "codec_math.cuh"
+
+namespace spzb200 {
+namespace {
+
+constexpr int kThreads = 320;
+constexpr int kCtasPerSm = 3;
+
+template <int D>
+struct Geo {
+  static constexpr int S = (D == 8) ? 318 : 315;  // active threads per CTA
+  static constexpr int TG = 4 * S;                // gaussians per tile
+  static_assert(S % 3 == 0, "xyz phase must be loop invariant");
+  static_assert(D == 0 || (4 * S) % (3 * D) == 0, "SH row phase must be loop invariant");
+  static_assert(S <= kThreads, "");
+};
+
+// ---- memory helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldStream(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ uint32_t ldStream(const uint32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ void stStream(uint32_t *p, uint32_t v) { __stcs(p, v); }
+__device__ __forceinline__ void stStream(float4 *p, float4 v) { __stcs(p, v); }
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// Saturate four int32 to [0,255] and pack them little-endian (v0 lowest byte).
+template <int MODE>
+__device__ __forceinline__ uint32_t packSat4(int32_t v0, int32_t v1, int32_t v2, int32_t v3) {
+  if (MODE == kPackCvt) {
+    // cvt.pack.sat.u8.s32.b32 d, a, b, c:  d = sat(a) << 8 | sat(b) | c << 16   (I2IP in SASS)
+    uint32_t hi, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v1), "r"(v0), "r"(hi));
+    return r;
+  }
+  return (uint32_t)m::clamp_u8(v0) | ((uint32_t)m::clamp_u8(v1) << 8) |
+         ((uint32_t)m::clamp_u8(v2) << 16) | ((uint32_t)m::clamp_u8(v3) << 24);
+}
+
+// byte k of w as the float 2^23 + byte (exact), built with one PRMT
+template <int K>
+__device__ __forceinline__ float byteAsMagicFloat(uint32_t w) {
+  return __uint_as_float(prmt(w, 0x4b000000u, 0x7650u + K));
+}
+
+__device__ __forceinline__ float signedConst(float magnitude, uint32_t negate) {
+  return __uint_as_float(__float_as_uint(magnitude) | (negate << 31));
+}
+
+// =================================================================================================
+// encode, vector path
+// =================================================================================================
+template <int D, int MODE>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+encodeTilesKernel(const EncodeArgs a, const long long numTiles) {
+  constexpr int S = Geo<D>::S;
+  __shared__ float sThr[256];
+  for (int i = threadIdx.x; i < 256; i += kThreads) sThr[i] = a.alphaThresholds[i];
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= S) return;  // spare lanes; no barrier follows
+
+  // loop-invariant per-thread constants
+  float posScale[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) posScale[e] = signedConst(4096.0f, (a.flipP >> ((t + e) % 3)) & 1u);
+  float shMul[4];
+  uint32_t shAdd[4], shMask[4];
+  if (D > 0) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int pos = (4 * t + e) % (3 * D);
+      shMul[e] = signedConst(128.0f, (a.flipSh >> (pos / 3)) & 1u);
+      const uint32_t bucket = pos < 9 ? 8u : 16u;  // load-spz.cc:312-326
+      shAdd[e] = 128u + bucket / 2u;
+      shMask[e] = ~(bucket - 1u);
+    }
+  }
+
+  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+    // ---- positions: float4 -> three words (4 x 24 bit) -------------------------------------
+    {
+      const float4 *in = reinterpret_cast<const float4 *>(a.positions) + tile * (3 * S) + t;
+      uint32_t *out = reinterpret_cast<uint32_t *>(a.oPositions) + (tile * (3 * S) + t) * 3;
+      float4 v[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) v[i] = ldStream(in + i * S);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const uint32_t n0 = m::quant_position24(v[i].x, posScale[0]);
+        const uint32_t n1 = m::quant_position24(v[i].y, posScale[1]);
+        const uint32_t n2 = m::quant_position24(v[i].z, posScale[2]);
+        const uint32_t n3 = m::quant_position24(v[i].w, posScale[3]);
+        uint32_t *o = out + i * (3 * S);
+        o[0] = prmt(n0, n1, 0x4210u);
+        o[1] = prmt(n1, n2, 0x5421u);
+        o[2] = prmt(n2, n3, 0x6542u);
+      }
+    }
+    // ---- scales and colours: float4 -> word ------------------------------------------------
+    {
+      const float4 *inS = reinterpret_cast<const float4 *>(a.scales) + tile * (3 * S) + t;
+      const float4 *inC = reinterpret_cast<const float4 *>(a.colors) + tile * (3 * S) + t;
+      uint32_t *outS = reinterpret_cast<uint32_t *>(a.oScales) + tile * (3 * S) + t;
+      uint32_t *outC = reinterpret_cast<uint32_t *>(a.oColors) + tile * (3 * S) + t;
+      float4 vs[3], vc[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) { vs[i] = ldStream(inS + i * S); vc[i] = ldStream(inC + i * S); }
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        stStream(outS + i * S, packSat4<MODE>(m::quant_scale_raw(vs[i].x), m::quant_scale_raw(vs[i].y),
+                                              m::quant_scale_raw(vs[i].z), m::quant_scale_raw(vs[i].w)));
+        stStream(outC + i * S, packSat4<MODE>(m::quant_color_raw(vc[i].x), m::quant_color_raw(vc[i].y),
+                                              m::quant_color_raw(vc[i].z), m::quant_color_raw(vc[i].w)));
+      }
+    }
+    // ---- alphas (float4 -> word) and rotations (quaternion -> word) -------------------------
+    {
+      const float4 va = ldStream(reinterpret_cast<const float4 *>(a.alphas) + tile * S + t);
+      const float4 *inR = reinterpret_cast<const float4 *>(a.rotations) + tile * (4 * S) + t;
+      uint32_t *outR = reinterpret_cast<uint32_t *>(a.oRotations) + tile * (4 * S) + t;
+      float4 vr[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) vr[i] = ldStream(inR + i * S);
+      const uint32_t a0 = m::quant_alpha(va.x, sThr), a1 = m::quant_alpha(va.y, sThr);
+      const uint32_t a2 = m::quant_alpha(va.z, sThr), a3 = m::quant_alpha(va.w, sThr);
+      stStream(reinterpret_cast<uint32_t *>(a.oAlphas) + tile * S + t,
+               a0 | (a1 << 8) | (a2 << 16) | (a3 << 24));
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        stStream(outR + i * S,
+                 m::quant_rotation_smallest3(vr[i].x, vr[i].y, vr[i].z, vr[i].w, a.flipQ));
+    }
+    // ---- spherical harmonics: float4 -> word, 3*D float4 per thread per tile ----------------
+    if (D > 0) {
+      constexpr int U = (D == 15) ? 5 : (D == 8) ? 4 : 3;
+      static_assert((3 * D) % U == 0, "");
+      const float4 *in = reinterpret_cast<const float4 *>(a.sh) + tile * (3LL * D * S) + t;
+      uint32_t *out = reinterpret_cast<uint32_t *>(a.oSh) + tile * (3LL * D * S) + t;
+#pragma unroll 1
+      for (int it = 0; it < 3 * D; it += U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = ldStream(in + (it + u) * S);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          stStream(out + (it + u) * S,
+                   packSat4<MODE>(m::quant_sh_raw(v[u].x, shMul[0], shAdd[0], shMask[0]),
+                                  m::quant_sh_raw(v[u].y, shMul[1], shAdd[1], shMask[1]),
+                                  m::quant_sh_raw(v[u].z, shMul[2], shAdd[2], shMask[2]),
+                                  m::quant_sh_raw(v[u].w, shMul[3], shAdd[3], shMask[3])));
+        }
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// encode, scalar path: remainders, tiny clouds, under-aligned pointers.  One thread per gaussian.
+// =================================================================================================
+__global__ void __launch_bounds__(128)
+encodeGenericKernel(const EncodeArgs a, const long long first) {
+  const long long g = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.n) return;
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    const uint32_t n = m::quant_position24(a.positions[g * 3 + ax],
+                                           signedConst(4096.0f, (a.flipP >> ax) & 1u));
+    uint8_t *o = a.oPositions + (g * 3 + ax) * 3;
+    o[0] = (uint8_t)n; o[1] = (uint8_t)(n >> 8); o[2] = (uint8_t)(n >> 16);
+    a.oScales[g * 3 + ax] = (uint8_t)m::quant_scale(a.scales[g * 3 + ax]);
+    a.oColors[g * 3 + ax] = (uint8_t)m::quant_color(a.colors[g * 3 + ax]);
+  }
+  a.oAlphas[g] = (uint8_t)m::quant_alpha(a.alphas[g], a.alphaThresholds);
+  const float *r = a.rotations + g * 4;
+  const uint32_t comp = m::quant_rotation_smallest3(r[0], r[1], r[2], r[3], a.flipQ);
+  uint8_t *ro = a.oRotations + g * 4;
+  ro[0] = (uint8_t)comp; ro[1] = (uint8_t)(comp >> 8); ro[2] = (uint8_t)(comp >> 16); ro[3] = (uint8_t)(comp >> 24);
+  const int per = a.shDim * 3;
+  const float *s = a.sh + g * per;
+  uint8_t *so = a.oSh + g * per;
+  for (int j = 0; j < per; j++) {
+    const uint32_t bucket = j < 9 ? 8u : 16u;
+    so[j] = (uint8_t)m::quant_sh(s[j], signedConst(128.0f, (a.flipSh >> (j / 3)) & 1u),
+                                 128u + bucket / 2u, ~(bucket - 1u));
+  }
+}
+
+// =================================================================================================
+// decode, vector path.  VER: 1 = half positions + first-three quaternion, 2 = 24-bit positions +
+// first-three, 3 = 24-bit + smallest-three (load-spz.cc:571-572).
+// =================================================================================================
+template <int D, int VER>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
+  constexpr int S = Geo<D>::S;
+  __shared__ float sAlpha[256];
+  __shared__ float sColor[256];
+  __shared__ float sMag[512];
+  for (int i = threadIdx.x; i < 256; i += kThreads) {
+    sAlpha[i] = a.alphaLut[i];
+    sColor[i] = m::dequant_color((uint32_t)i);
+  }
+  if (VER == 3)
+    for (int i = threadIdx.x; i < 512; i += kThreads) sMag[i] = m::dequant_s3_magnitude((uint32_t)i);
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= S) return;
+
+  float posScale[4];
+  uint32_t posFlip[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    posFlip[e] = ((a.flipP >> ((t + e) % 3)) & 1u) << 31;
+    posScale[e] = __uint_as_float(__float_as_uint(a.positionScale) ^ posFlip[e]);
+  }
+  float shMul[4];
+  if (D > 0) {
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+      shMul[e] = signedConst(0.0078125f, (a.flipSh >> (((4 * t + e) % (3 * D)) / 3)) & 1u);
+  }
+
+  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+    // ---- positions ------------------------------------------------------------------------
+    {
+      float4 *out = reinterpret_cast<float4 *>(a.oPositions) + tile * (3 * S) + t;
+      if (VER == 1) {
+        const uint2 *in = reinterpret_cast<const uint2 *>(a.positions) + tile * (3 * S) + t;
+        uint2 w[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) w[i] = __ldcs(in + i * S);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          float4 o;
+          o.x = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x & 0xffffu)) ^ posFlip[0]);
+          o.y = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x >> 16)) ^ posFlip[1]);
+          o.z = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y & 0xffffu)) ^ posFlip[2]);
+          o.w = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y >> 16)) ^ posFlip[3]);
+          stStream(out + i * S, o);
+        }
+      } else {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(a.positions) + (tile * (3 * S) + t) * 3;
+        uint32_t w[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) w[i][k] = __ldg(in + i * (3 * S) + k);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          // PRMT with the sign-replicate bit (selector nibble 8|idx) sign-extends 24 -> 32 bits
+          const int32_t f0 = (int32_t)prmt(w[i][0], w[i][0], 0xA210u);
+          const int32_t f1 = (int32_t)prmt(w[i][0], w[i][1], 0xD543u);
+          const int32_t f2 = (int32_t)prmt(w[i][1], w[i][2], 0xC432u);
+          const int32_t f3 = (int32_t)prmt(w[i][2], w[i][2], 0xB321u);
+          float4 o;
+          o.x = m::mul(m::i2f(f0), posScale[0]);
+          o.y = m::mul(m::i2f(f1), posScale[1]);
+          o.z = m::mul(m::i2f(f2), posScale[2]);
+          o.w = m::mul(m::i2f(f3), posScale[3]);
+          stStream(out + i * S, o);
+        }
+      }
+    }
+    // ---- scales (exact FMA on the magic float) and colours (table) ---------------------------
+    {
+      const uint32_t *inS = reinterpret_cast<const uint32_t *>(a.scales) + tile * (3 * S) + t;
+      const uint32_t *inC = reinterpret_cast<const uint32_t *>(a.colors) + tile * (3 * S) + t;
+      float4 *outS = reinterpret_cast<float4 *>(a.oScales) + tile * (3 * S) + t;
+      float4 *outC = reinterpret_cast<float4 *>(a.oColors) + tile * (3 * S) + t;
+      uint32_t ws[3], wc[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) { ws[i] = ldStream(inS + i * S); wc[i] = ldStream(inC + i * S); }
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        // (2^23 + s) / 16 - (2^19 + 10) = s/16 - 10: both steps exact, so the fused form equals
+        // the reference's s / 16.0f - 10.0f (load-spz.cc:506) bit for bit, +0 at s = 160.
+        float4 o;
+        o.x = __fmaf_rn(byteAsMagicFloat<0>(ws[i]), 0.0625f, -524298.0f);
+        o.y = __fmaf_rn(byteAsMagicFloat<1>(ws[i]), 0.0625f, -524298.0f);
+        o.z = __fmaf_rn(byteAsMagicFloat<2>(ws[i]), 0.0625f, -524298.0f);
+        o.w = __fmaf_rn(byteAsMagicFloat<3>(ws[i]), 0.0625f, -524298.0f);
+        stStream(outS + i * S, o);
+        float4 c;
+        c.x = sColor[wc[i] & 0xffu];
+        c.y = sColor[(wc[i] >> 8) & 0xffu];
+        c.z = sColor[(wc[i] >> 16) & 0xffu];
+        c.w = sColor[wc[i] >> 24];
+        stStream(outC + i * S, c);
+      }
+    }
+    // ---- alphas (table) ---------------------------------------------------------------------
+    {
+      const uint32_t w = ldStream(reinterpret_cast<const uint32_t *>(a.alphas) + tile * S + t);
+      float4 o;
+      o.x = sAlpha[w & 0xffu];
+      o.y = sAlpha[(w >> 8) & 0xffu];
+      o.z = sAlpha[(w >> 16) & 0xffu];
+      o.w = sAlpha[w >> 24];
+      stStream(reinterpret_cast<float4 *>(a.oAlphas) + tile * S + t, o);
+    }
+    // ---- rotations ----------------------------------------------------------------------------
+    if (VER == 3) {
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + tile * (4 * S) + t;
+      float4 *out = reinterpret_cast<float4 *>(a.oRotations) + tile * (4 * S) + t;
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) w[i] = ldStream(in + i * S);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float r[4];
+        m::dequant_rotation_smallest3(w[i], sMag, a.flipQ, r);
+        stStream(out + i * S, make_float4(r[0], r[1], r[2], r[3]));
+      }
+    } else {
+      // 3 bytes per quaternion: a thread takes 4 quaternions = 3 words -> 4 float4
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + (tile * S + t) * 3;
+      float4 *out = reinterpret_cast<float4 *>(a.oRotations) + (tile * S + t) * 4;
+      const uint32_t w0 = __ldg(in), w1 = __ldg(in + 1), w2 = __ldg(in + 2);
+      const uint32_t b[12] = {w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu, w0 >> 24,
+                              w1 & 0xffu, (w1 >> 8) & 0xffu, (w1 >> 16) & 0xffu, w1 >> 24,
+                              w2 & 0xffu, (w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float r[4];
+        m::dequant_rotation_first3(b[3 * i], b[3 * i + 1], b[3 * i + 2], a.flipQ, r);
+        out[i] = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    // ---- spherical harmonics: word -> float4 -------------------------------------------------
+    if (D > 0) {
+      constexpr int U = (D == 15) ? 5 : (D == 8) ? 4 : 3;
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.sh) + tile * (3LL * D * S) + t;
+      float4 *out = reinterpret_cast<float4 *>(a.oSh) + tile * (3LL * D * S) + t;
+#pragma unroll 1
+      for (int it = 0; it < 3 * D; it += U) {
+        uint32_t w[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) w[u] = ldStream(in + (it + u) * S);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          // (2^23 + x) - (2^23 + 128) = x - 128 exactly (+0 at x = 128), then * +-1/128: the
+          // reference's ((float)x - 128.0f) / 128.0f followed by the flip (load-spz.cc:83).
+          float4 o;
+          o.x = m::mul(m::add(byteAsMagicFloat<0>(w[u]), -8388736.0f), shMul[0]);
+          o.y = m::mul(m::add(byteAsMagicFloat<1>(w[u]), -8388736.0f), shMul[1]);
+          o.z = m::mul(m::add(byteAsMagicFloat<2>(w[u]), -8388736.0f), shMul[2]);
+          o.w = m::mul(m::add(byteAsMagicFloat<3>(w[u]), -8388736.0f), shMul[3]);
+          stStream(out + (it + u) * S, o);
+        }
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// decode, scalar path
+// =================================================================================================
+__global__ void __launch_bounds__(128)
+decodeGenericKernel(const DecodeArgs a, const long long first) {
+  const long long g = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.n) return;
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    const uint32_t flip = ((a.flipP >> ax) & 1u) << 31;
+    float p;
+    if (a.version == 1) {
+      const uint8_t *h = a.positions + (g * 3 + ax) * 2;
+      p = __uint_as_float(__float_as_uint(m::half_bits_to_float((uint32_t)h[0] | ((uint32_t)h[1] << 8))) ^ flip);
+    } else {
+      const uint8_t *b = a.positions + (g * 3 + ax) * 3;
+      const uint32_t lo24 = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16);
+      p = m::dequant_position24(lo24, __uint_as_float(__float_as_uint(a.positionScale) ^ flip));
+    }
+    a.oPositions[g * 3 + ax] = p;
+    a.oScales[g * 3 + ax] = m::dequant_scale(a.scales[g * 3 + ax]);
+    a.oColors[g * 3 + ax] = m::dequant_color(a.colors[g * 3 + ax]);
+  }
+  a.oAlphas[g] = a.alphaLut[a.alphas[g]];
+  float r[4];
+  if (a.version >= 3) {
+    const uint8_t *b = a.rotations + g * 4;
+    uint32_t comp = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+    // no table here: compute the three magnitudes directly (same expression as the table fill)
+    const uint32_t big = comp >> 30;
+    float sum = 0.0f;
+    for (int i = 3; i >= 0; --i) {
+      if ((uint32_t)i == big) continue;
+      const float v = __uint_as_float(__float_as_uint(m::dequant_s3_magnitude(comp & 511u)) | ((comp & 512u) << 22));
+      comp >>= 10;
+      r[i] = v;
+      sum = m::add(sum, m::mul(v, v));
+    }
+    r[big] = m::sqrt_rn(m::sub(1.0f, sum));
+    for (int i = 0; i < 3; i++) r[i] = __uint_as_float(__float_as_uint(r[i]) ^ (((a.flipQ >> i) & 1u) << 31));
+  } else {
+    const uint8_t *b = a.rotations + g * 3;
+    m::dequant_rotation_first3(b[0], b[1], b[2], a.flipQ, r);
+  }
+  for (int i = 0; i < 4; i++) a.oRotations[g * 4 + i] = r[i];
+  const int per = a.shDim * 3;
+  const uint8_t *s = a.sh + g * per;
+  float *so = a.oSh + g * per;
+  for (int j = 0; j < per; j++)
+    so[j] = m::dequant_sh(s[j], signedConst(0.0078125f, (a.flipSh >> (j / 3)) & 1u));
+}
+
+__global__ void probePackKernel(int *ok) {
+  const int32_t v[3][4] = {{-5, 300, 17, 255}, {0, 1, 2, 3}, {1000, -1000, 128, 64}};
+  int good = 1;
+  for (int i = 0; i < 3; i++) {
+    const uint32_t x = packSat4<kPackAlu>(v[i][0], v[i][1], v[i][2], v[i][3]);
+    const uint32_t y = packSat4<kPackCvt>(v[i][0], v[i][1], v[i][2], v[i][3]);
+    if (x != y) good = 0;
+  }
+  *ok = good;
+}
+
+bool aligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+template <int D, int MODE>
+cudaError_t launchEncodeTiles(const EncodeArgs &a, long long tiles, int grid, cudaStream_t s) {
+  encodeTilesKernel<D, MODE><<<grid, kThreads, 0, s>>>(a, tiles);
+  return cudaGetLastError();
+}
+
+template <int D>
+cudaError_t launchDecodeTiles(const DecodeArgs &a, long long tiles, int grid, cudaStream_t s) {
+  switch (a.version) {
+    case 1: decodeTilesKernel<D, 1><<<grid, kThreads, 0, s>>>(a, tiles); break;
+    case 2: decodeTilesKernel<D, 2><<<grid, kThreads, 0, s>>>(a, tiles); break;
+    default: decodeTilesKernel<D, 3><<<grid, kThreads, 0, s>>>(a, tiles); break;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int tileGaussians(int shDim) { return shDim == 8 ? Geo<8>::TG : Geo<15>::TG; }
+
+cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream,
+                         int *launches) {
+  int count = 0;
+  if (launches) *launches = 0;
+  if (a.n <= 0) return cudaSuccess;
+  const bool vec = !plan.forceGeneric && aligned(a.positions, 16) && aligned(a.scales, 16) &&
+                   aligned(a.rotations, 16) && aligned(a.alphas, 16) && aligned(a.colors, 16) &&
+                   (a.shDim == 0 || aligned(a.sh, 16)) && aligned(a.oPositions, 4) &&
+                   aligned(a.oScales, 4) && aligned(a.oRotations, 4) && aligned(a.oAlphas, 4) &&
+                   aligned(a.oColors, 4) && (a.shDim == 0 || aligned(a.oSh, 4));
+  const long long tg = tileGaussians(a.shDim);
+  const long long tiles = vec ? a.n / tg : 0;
+  if (tiles > 0) {
+    const long long cap = (long long)plan.smCount * kCtasPerSm;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    cudaError_t e;
+    const bool cvt = plan.packMode == kPackCvt;
+    switch (a.shDim) {
+      case 0: e = cvt ? launchEncodeTiles<0, kPackCvt>(a, tiles, grid, stream) : launchEncodeTiles<0, kPackAlu>(a, tiles, grid, stream); break;
+      case 3: e = cvt ? launchEncodeTiles<3, kPackCvt>(a, tiles, grid, stream) : launchEncodeTiles<3, kPackAlu>(a, tiles, grid, stream); break;
+      case 8: e = cvt ? launchEncodeTiles<8, kPackCvt>(a, tiles, grid, stream) : launchEncodeTiles<8, kPackAlu>(a, tiles, grid, stream); break;
+      case 15: e = cvt ? launchEncodeTiles<15, kPackCvt>(a, tiles, grid, stream) : launchEncodeTiles<15, kPackAlu>(a, tiles, grid, stream); break;
+      default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    count++;
+  }
+  const long long first = tiles * tg;
+  if (first < a.n) {
+    const long long rest = a.n - first;
+    const long long blocks = (rest + 127) / 128;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    encodeGenericKernel<<<(unsigned)blocks, 128, 0, stream>>>(a, first);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    count++;
+  }
+  if (launches) *launches = count;
+  return cudaSuccess;
+}
+
+cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream,
+                         int *launches) {
+  int count = 0;
+  if (launches) *launches = 0;
+  if (a.n <= 0) return cudaSuccess;
+  const bool vec = !plan.forceGeneric && aligned(a.positions, a.version == 1 ? 8 : 4) &&
+                   aligned(a.scales, 4) && aligned(a.rotations, 4) && aligned(a.alphas, 4) &&
+                   aligned(a.colors, 4) && (a.shDim == 0 || aligned(a.sh, 4)) &&
+                   aligned(a.oPositions, 16) && aligned(a.oScales, 16) &&
+                   aligned(a.oRotations, 16) && aligned(a.oAlphas, 16) && aligned(a.oColors, 16) &&
+                   (a.shDim == 0 || aligned(a.oSh, 16));
+  const long long tg = tileGaussians(a.shDim);
+  const long long tiles = vec ? a.n / tg : 0;
+  if (tiles > 0) {
+    const long long cap = (long long)plan.smCount * kCtasPerSm;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    cudaError_t e;
+    switch (a.shDim) {
+      case 0: e = launchDecodeTiles<0>(a, tiles, grid, stream); break;
+      case 3: e = launchDecodeTiles<3>(a, tiles, grid, stream); break;
+      case 8: e = launchDecodeTiles<8>(a, tiles, grid, stream); break;
+      case 15: e = launchDecodeTiles<15>(a, tiles, grid, stream); break;
+      default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    count++;
+  }
+  const long long first = tiles * tg;
+  if (first < a.n) {
+    const long long rest = a.n - first;
+    const long long blocks = (rest + 127) / 128;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    decodeGenericKernel<<<(unsigned)blocks, 128, 0, stream>>>(a, first);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    count++;
+  }
+  if (launches) *launches = count;
+  return cudaSuccess;
+}
+
+cudaError_t probePackCvt(cudaStream_t stream, int *ok) {
+  int *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(int));
+  if (e != cudaSuccess) return e;
+  probePackKernel<<<1, 1, 0, stream>>>(d);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ok, d, sizeof(int), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d);
+  return e;
+}
+
+}  // namespace spzb200

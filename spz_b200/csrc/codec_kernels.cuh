@@ -1,0 +1,52 @@
+// Launch interface of the codec kernels (internal to the library; the public boundary is the
+// C-ABI in include/spz_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spzb200 {
+
+// GaussianCloud planes (splat-types.h:90-115) -> PackedGaussians planes (load-spz.h:42-59),
+// both device-resident.  n gaussians, shDim in {0,3,8,15}.
+struct EncodeArgs {
+  const float *positions, *scales, *rotations, *alphas, *colors, *sh;
+  uint8_t *oPositions, *oScales, *oRotations, *oAlphas, *oColors, *oSh;
+  long long n;
+  int shDim;
+  uint32_t flipP, flipQ, flipSh;  // sign-bit sets of coordinateConverter(from, RUB)
+  const float *alphaThresholds;   // device, 256 floats (255 thresholds + +Inf pad)
+};
+
+struct DecodeArgs {
+  const uint8_t *positions, *scales, *rotations, *alphas, *colors, *sh;
+  float *oPositions, *oScales, *oRotations, *oAlphas, *oColors, *oSh;
+  long long n;
+  int shDim;
+  int version;                    // 1: half positions + first-three; 2: 24-bit + first-three; 3
+  float positionScale;            // (float)(1.0 / (1 << fractionalBits)), load-spz.cc:495
+  uint32_t flipP, flipQ, flipSh;  // sign-bit sets of coordinateConverter(RUB, to)
+  const float *alphaLut;          // device, 256 floats: invSigmoid(a / 255.0f)
+};
+
+enum PackMode { kPackAlu = 0, kPackCvt = 1 };
+
+struct LaunchPlan {
+  int smCount;
+  int packMode;        // encode only: how four bytes are saturated and packed into a word
+  bool forceGeneric;   // test hook: route everything through the scalar kernels
+};
+
+// Number of kernels launched is returned through *launches (0, 1 or 2).
+cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream,
+                         int *launches);
+cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream,
+                         int *launches);
+
+// Gaussians per tile of the vector kernels for a given shDim (the sharding granule).
+int tileGaussians(int shDim);
+
+// Runs both byte packers on probe values; *ok = 1 when cvt.pack.sat.u8.s32.b32 orders and
+// saturates bytes the way the kernels assume (decided once per context).
+cudaError_t probePackCvt(cudaStream_t stream, int *ok);
+
+}  // namespace spzb200

@@ -1,0 +1,62 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference (oracle/_ref).  Present in the build container and, as a shipped
+    artefact, on the GPU box; tests that need it skip elsewhere."""
+    from oracle import Ref
+    if not Ref.available():
+        pytest.skip("oracle/_ref/libspz_ref.so not built and /root/reference absent")
+    return Ref()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def emul():
+    """Host build of the device math header (tests/host_emul/quant_host.cc)."""
+    import ctypes
+    here = os.path.join(ROOT, "tests", "host_emul")
+    out_dir = os.path.join(here, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libquant_host.so")
+    src = os.path.join(here, "quant_host.cc")
+    hdr = os.path.join(ROOT, "spz_b200", "csrc", "codec_math.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-frounding-math",
+                        "-Wno-unknown-pragmas", "-shared", "-fPIC", src, "-o", so], check=True)
+    return ctypes.CDLL(so)
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from spz_b200.codec import Context
+    ctx = Context(0)
+    yield ctx
+    ctx.close()

@@ -1,0 +1,61 @@
+"""Shared helpers for the test-suite."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import Cloud, Packed, SH_DIM, bits
+
+PLANES = "positions scales rotations alphas colors sh".split()
+
+SPECIALS = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 1e30, -1e30, 3e9, -3e9, 2147483520.0,
+                     2147483392.0, 1e-40, 524288.0, -524288.0, 2047.99, -2048.0, 0.49999997,
+                     0.5, -0.5, 1.5 / 128, 2.5 / 128, -2.5 / 128], np.float32)
+
+
+def golden_cloud(G, key, n, deg) -> Cloud:
+    return Cloud(n, deg, *[G[f"{key}_{p}"].view(np.float32) for p in PLANES])
+
+
+def golden_packed(G, key, n, deg, fb=12, ver=3) -> Packed:
+    return Packed(n, deg, fb, ver, *[G[f"{key}_{p}"] for p in PLANES])
+
+
+def random_cloud(rng, n, deg, special=False) -> Cloud:
+    d = SH_DIM[deg] * 3
+
+    def f(k, lo, hi):
+        a = rng.uniform(lo, hi, k).astype(np.float32)
+        if special and k:
+            idx = rng.integers(0, k, max(1, k // 12))
+            a[idx] = rng.choice(SPECIALS, idx.size)
+        return a
+
+    return Cloud(n, deg, f(3 * n, -10, 10), f(3 * n, -12, 8), f(4 * n, -1, 1), f(n, -8, 8),
+                 f(3 * n, -4, 4), f(d * n, -1.2, 1.2))
+
+
+def random_stream(rng, n, deg, ver, fb=12) -> Packed:
+    d = SH_DIM[deg] * 3
+    r = lambda k: rng.integers(0, 256, k).astype(np.uint8)  # noqa: E731
+    return Packed(n, deg, fb, ver, r(n * (6 if ver == 1 else 9)), r(n * 3), r(n * (4 if ver == 3 else 3)),
+                  r(n), r(n * 3), r(n * d))
+
+
+def assert_packed_equal(a, b, what=""):
+    for name, x, y in zip(PLANES, a.planes(), b.planes()):
+        x, y = np.asarray(x), np.asarray(y)
+        assert x.shape == y.shape, f"{what} {name}: shape {x.shape} vs {y.shape}"
+        if not np.array_equal(x, y):
+            i = np.flatnonzero(x != y)
+            raise AssertionError(f"{what} plane {name}: {i.size} byte mismatches, first at {i[:5]}: {x[i[:5]]} vs {y[i[:5]]}")
+
+
+def assert_cloud_bits_equal(a, b, what=""):
+    for name, x, y in zip(PLANES, a.planes(), b.planes()):
+        bx = bits(np.asarray(x)) if np.asarray(x).dtype == np.float32 else np.asarray(x)
+        by = bits(np.asarray(y)) if np.asarray(y).dtype == np.float32 else np.asarray(y)
+        assert bx.shape == by.shape, f"{what} {name}: shape {bx.shape} vs {by.shape}"
+        if not np.array_equal(bx, by):
+            i = np.flatnonzero(bx != by)
+            raise AssertionError(f"{what} plane {name}: {i.size} float-bit mismatches, first at {i[:5]}: "
+                                 f"{[hex(v) for v in bx[i[:5]]]} vs {[hex(v) for v in by[i[:5]]]}")
