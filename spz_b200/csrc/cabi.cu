@@ -137,6 +137,8 @@ struct SpzB200Context {
   int packMode = spzb200::kPackAlu;
   bool cvtPackOk = false;  // the init-time probe of cvt.pack.sat.u8.s32 agreed with the ALU packer
   bool forceGeneric = false;
+  int ctasPerSm = 0;
+  bool flatGrid = false;
   long long chunkPoints = 1 << 21;
   long long kernelLaunches = 0;
   float hThr[256];
@@ -220,6 +222,8 @@ spzb200::LaunchPlan planOf(const SpzB200Context *ctx) {
   p.smCount = ctx->smCount;
   p.packMode = ctx->packMode;
   p.forceGeneric = ctx->forceGeneric;
+  p.ctasPerSm = ctx->ctasPerSm;
+  p.flatGrid = ctx->flatGrid;
   return p;
 }
 
@@ -486,9 +490,12 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   if ((e = spzb200::probePackCvt(ctx->stage[0].stream, &ok)) != cudaSuccess) return bail(e, "pack probe");
   ctx->cvtPackOk = ok != 0;
   ctx->packMode = ok ? spzb200::kPackCvt : spzb200::kPackAlu;
+  // development knobs (profiles/ records which settings the shipped defaults came from)
   if (const char *env = std::getenv("SPZB200_PACK")) {
     if (!std::strcmp(env, "alu")) ctx->packMode = spzb200::kPackAlu;
   }
+  if (const char *env = std::getenv("SPZB200_CTAS_PER_SM")) ctx->ctasPerSm = std::atoi(env);
+  if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = !std::strcmp(env, "flat");
   *out = ctx;
   return SPZB200_OK;
 }

@@ -6,16 +6,25 @@
 // words (4 floats <-> 4 bytes for scales / colours / alphas / SH, 4 floats <-> 12 bytes for
 // 24-bit positions, 1 quaternion <-> 4 bytes).  So the codec is an ELEMENTWISE stream transform
 // on 16-byte granules: consecutive lanes touch consecutive float4s (512 B per warp instruction)
-// and consecutive packed words (128 B per warp instruction).  No transposition through shared
-// memory is needed; the only position-dependent parameters are the coordinate-flip sign and the
-// SH bucket size, which depend on (element index mod 3*shDim) resp. (element index mod 3).
+// and consecutive packed words (128 B per warp instruction).  No transposition of planes is
+// needed; the only position-dependent parameters are the coordinate-flip sign and the SH bucket
+// size, which depend on (element index mod 3*shDim) resp. (element index mod 3).
 //
-// Tiling: a CTA has 320 threads of which S (315, or 318 for SH degree 2) are active; a tile is
-// 4*S gaussians.  S is a multiple of 3 and 4*S a multiple of 3*shDim, so a thread's phase inside
-// the 45-float SH row (and the xyz triple) is the same for every float4 it ever touches: the
-// flip signs and bucket constants are 12 loop-invariant registers.  CTAs are persistent
-// (gridDim = SMs x resident CTAs) and stride over tiles.  The remainder (< one tile) and any
-// call with under-aligned pointers goes to a scalar one-thread-per-gaussian kernel.
+// Tiling: a CTA has 320 threads (10 full warps); a "row" is 320 consecutive float4s (5120 B) of
+// a float plane and the 320 (or 960) packed words that belong to them, so every warp-level access
+// is 128-byte aligned and covers whole 32-byte sectors -- the first version of this kernel used
+// rows of 315 and paid 11% (encode) / 24% (decode) extra DRAM reads for the misalignment (L2
+// fills of partially written sectors, re-fetched straddled sectors; profiles/r1_*).  A tile is
+// 4*320*M gaussians (M = 5 for SH degree 1, else 1) = 3*shDim*M rows of the SH plane.  The phase
+// of a thread's four elements inside the 3*shDim-float SH record advances by a constant
+// (4*320 mod 3*shDim) per row and therefore repeats with a short cycle (9 rows for degree 3 and
+// 1, 3 rows for degree 2): rows c, c+CYC, c+2*CYC, ... share their flip signs and bucket sizes, so
+// they are loaded together (5 or 8 float4 in flight per thread) under one set of constants.
+// The 24-bit position words (3 per float4) are exchanged through a per-warp shared-memory
+// stage so that their global loads and stores are contiguous 128-byte lines as well.
+// CTAs are persistent (gridDim = SMs x resident CTAs) and stride over tiles.  The remainder
+// (< one tile) and any call with under-aligned pointers goes to a scalar one-thread-per-gaussian
+// kernel.
 //
 // HBM traffic is exactly the algorithmic 301 B per gaussian at SH degree 3 (236 B floats + 65 B
 // packed); nothing is read twice.
@@ -27,20 +36,28 @@ namespace spzb200 {
 namespace {
 
 constexpr int kThreads = 320;
+constexpr int kWarps = kThreads / 32;
 constexpr int kCtasPerSm = 3;
+
+constexpr int gcdc(int a, int b) { return b == 0 ? a : gcdc(b, a % b); }
 
 template <int D>
 struct Geo {
-  static constexpr int S = (D == 8) ? 318 : 315;  // active threads per CTA
-  static constexpr int TG = 4 * S;                // gaussians per tile
-  static_assert(S % 3 == 0, "xyz phase must be loop invariant");
-  static_assert(D == 0 || (4 * S) % (3 * D) == 0, "SH row phase must be loop invariant");
-  static_assert(S <= kThreads, "");
+  static constexpr int M = (D == 3) ? 5 : 1;          // sub-tiles (4*320 gaussians each) per tile
+  static constexpr int TG = 4 * kThreads * M;         // gaussians per tile
+  static constexpr int MOD = 3 * D;                   // floats per SH record
+  static constexpr int STEP = D ? (4 * kThreads) % (D ? MOD : 1) : 0;  // phase advance per row
+  static constexpr int CYC = D ? MOD / gcdc(STEP, MOD) : 1;            // rows until the phase repeats
+  static constexpr int ROWS = 3 * D * M;              // SH rows per tile
+  static constexpr int U = D ? ROWS / CYC : 1;        // rows sharing one set of constants
+  static_assert(D == 0 || ROWS % CYC == 0, "tile must hold whole phase cycles");
+  static_assert(D == 0 || (CYC * STEP) % MOD == 0, "");
 };
 
 // ---- memory helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldStream(const float4 *p) { return __ldcs(p); }
 __device__ __forceinline__ uint32_t ldStream(const uint32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ uint2 ldStream(const uint2 *p) { return __ldcs(p); }
 __device__ __forceinline__ void stStream(uint32_t *p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ void stStream(float4 *p, float4 v) { __stcs(p, v); }
 
@@ -74,109 +91,144 @@ __device__ __forceinline__ float signedConst(float magnitude, uint32_t negate) {
   return __uint_as_float(__float_as_uint(magnitude) | (negate << 31));
 }
 
+// Phase bookkeeping of the SH plane: pos[e] = index of the thread's element e inside its
+// 3*D-float SH record for the current row class; advance() moves to the next class.
+template <int D>
+struct ShPhase {
+  int pos[4];
+  __device__ __forceinline__ void init(int t) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) pos[e] = (4 * t + e) % Geo<D>::MOD;
+  }
+  __device__ __forceinline__ void advance() {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      pos[e] += Geo<D>::STEP;
+      if (pos[e] >= Geo<D>::MOD) pos[e] -= Geo<D>::MOD;
+    }
+  }
+  __device__ __forceinline__ uint32_t flip(int e, uint32_t flipSh) const {
+    return (flipSh >> ((uint32_t)pos[e] / 3u)) & 1u;
+  }
+};
+
 // =================================================================================================
 // encode, vector path
 // =================================================================================================
 template <int D, int MODE>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 encodeTilesKernel(const EncodeArgs a, const long long numTiles) {
-  constexpr int S = Geo<D>::S;
+  constexpr int S = kThreads;
+  constexpr int M = Geo<D>::M;
   __shared__ float sThr[256];
+  __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
   for (int i = threadIdx.x; i < 256; i += kThreads) sThr[i] = a.alphaThresholds[i];
   __syncthreads();
   const int t = threadIdx.x;
-  if (t >= S) return;  // spare lanes; no barrier follows
+  const int lane = t & 31, warp = t >> 5;
+  uint32_t *stage = sStage[warp];
 
-  // loop-invariant per-thread constants
-  float posScale[4];
+  // +-4096 for the xyz phase (t + k) mod 3; element e of row i has phase (t + e + 2i) mod 3
+  // because a row is 4*320 = 1280 = 2 (mod 3) floats long
+  float posScale3[3];
 #pragma unroll
-  for (int e = 0; e < 4; e++) posScale[e] = signedConst(4096.0f, (a.flipP >> ((t + e) % 3)) & 1u);
-  float shMul[4];
-  uint32_t shAdd[4], shMask[4];
-  if (D > 0) {
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int pos = (4 * t + e) % (3 * D);
-      shMul[e] = signedConst(128.0f, (a.flipSh >> (pos / 3)) & 1u);
-      const uint32_t bucket = pos < 9 ? 8u : 16u;  // load-spz.cc:312-326
-      shAdd[e] = 128u + bucket / 2u;
-      shMask[e] = ~(bucket - 1u);
-    }
-  }
+  for (int k = 0; k < 3; k++) posScale3[k] = signedConst(4096.0f, (a.flipP >> ((t + k) % 3)) & 1u);
 
   for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-    // ---- positions: float4 -> three words (4 x 24 bit) -------------------------------------
-    {
-      const float4 *in = reinterpret_cast<const float4 *>(a.positions) + tile * (3 * S) + t;
-      uint32_t *out = reinterpret_cast<uint32_t *>(a.oPositions) + (tile * (3 * S) + t) * 3;
-      float4 v[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) v[i] = ldStream(in + i * S);
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const uint32_t n0 = m::quant_position24(v[i].x, posScale[0]);
-        const uint32_t n1 = m::quant_position24(v[i].y, posScale[1]);
-        const uint32_t n2 = m::quant_position24(v[i].z, posScale[2]);
-        const uint32_t n3 = m::quant_position24(v[i].w, posScale[3]);
-        uint32_t *o = out + i * (3 * S);
-        o[0] = prmt(n0, n1, 0x4210u);
-        o[1] = prmt(n1, n2, 0x5421u);
-        o[2] = prmt(n2, n3, 0x6542u);
-      }
-    }
-    // ---- scales and colours: float4 -> word ------------------------------------------------
-    {
-      const float4 *inS = reinterpret_cast<const float4 *>(a.scales) + tile * (3 * S) + t;
-      const float4 *inC = reinterpret_cast<const float4 *>(a.colors) + tile * (3 * S) + t;
-      uint32_t *outS = reinterpret_cast<uint32_t *>(a.oScales) + tile * (3 * S) + t;
-      uint32_t *outC = reinterpret_cast<uint32_t *>(a.oColors) + tile * (3 * S) + t;
-      float4 vs[3], vc[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) { vs[i] = ldStream(inS + i * S); vc[i] = ldStream(inC + i * S); }
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        stStream(outS + i * S, packSat4<MODE>(m::quant_scale_raw(vs[i].x), m::quant_scale_raw(vs[i].y),
-                                              m::quant_scale_raw(vs[i].z), m::quant_scale_raw(vs[i].w)));
-        stStream(outC + i * S, packSat4<MODE>(m::quant_color_raw(vc[i].x), m::quant_color_raw(vc[i].y),
-                                              m::quant_color_raw(vc[i].z), m::quant_color_raw(vc[i].w)));
-      }
-    }
-    // ---- alphas (float4 -> word) and rotations (quaternion -> word) -------------------------
-    {
-      const float4 va = ldStream(reinterpret_cast<const float4 *>(a.alphas) + tile * S + t);
-      const float4 *inR = reinterpret_cast<const float4 *>(a.rotations) + tile * (4 * S) + t;
-      uint32_t *outR = reinterpret_cast<uint32_t *>(a.oRotations) + tile * (4 * S) + t;
-      float4 vr[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) vr[i] = ldStream(inR + i * S);
-      const uint32_t a0 = m::quant_alpha(va.x, sThr), a1 = m::quant_alpha(va.y, sThr);
-      const uint32_t a2 = m::quant_alpha(va.z, sThr), a3 = m::quant_alpha(va.w, sThr);
-      stStream(reinterpret_cast<uint32_t *>(a.oAlphas) + tile * S + t,
-               a0 | (a1 << 8) | (a2 << 16) | (a3 << 24));
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        stStream(outR + i * S,
-                 m::quant_rotation_smallest3(vr[i].x, vr[i].y, vr[i].z, vr[i].w, a.flipQ));
-    }
-    // ---- spherical harmonics: float4 -> word, 3*D float4 per thread per tile ----------------
-    if (D > 0) {
-      constexpr int U = (D == 15) ? 5 : (D == 8) ? 4 : 3;
-      static_assert((3 * D) % U == 0, "");
-      const float4 *in = reinterpret_cast<const float4 *>(a.sh) + tile * (3LL * D * S) + t;
-      uint32_t *out = reinterpret_cast<uint32_t *>(a.oSh) + tile * (3LL * D * S) + t;
 #pragma unroll 1
-      for (int it = 0; it < 3 * D; it += U) {
+    for (int mm = 0; mm < M; mm++) {
+      const long long q = tile * M + mm;  // sub-tile: gaussians [q*1280, (q+1)*1280)
+      // ---- positions: float4 -> three words (4 x 24 bit), staged so the stores are contiguous --
+      {
+        const float4 *in = reinterpret_cast<const float4 *>(a.positions) + q * (3 * S) + t;
+        uint32_t *out = reinterpret_cast<uint32_t *>(a.oPositions) + q * (9 * S) + warp * 96 + lane;
+        float4 v[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) v[i] = ldStream(in + i * S);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const uint32_t n0 = m::quant_position24(v[i].x, posScale3[(0 + 2 * i) % 3]);
+          const uint32_t n1 = m::quant_position24(v[i].y, posScale3[(1 + 2 * i) % 3]);
+          const uint32_t n2 = m::quant_position24(v[i].z, posScale3[(2 + 2 * i) % 3]);
+          const uint32_t n3 = m::quant_position24(v[i].w, posScale3[(3 + 2 * i) % 3]);
+          uint32_t *sp = stage + i * 96 + 3 * lane;  // stride 3 words: conflict free
+          sp[0] = prmt(n0, n1, 0x4210u);
+          sp[1] = prmt(n1, n2, 0x5421u);
+          sp[2] = prmt(n2, n3, 0x6542u);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) stStream(out + i * (3 * S) + k * 32, stage[i * 96 + k * 32 + lane]);
+        }
+        __syncwarp();
+      }
+      // ---- scales and colours: float4 -> word ------------------------------------------------
+      {
+        const float4 *inS = reinterpret_cast<const float4 *>(a.scales) + q * (3 * S) + t;
+        const float4 *inC = reinterpret_cast<const float4 *>(a.colors) + q * (3 * S) + t;
+        uint32_t *outS = reinterpret_cast<uint32_t *>(a.oScales) + q * (3 * S) + t;
+        uint32_t *outC = reinterpret_cast<uint32_t *>(a.oColors) + q * (3 * S) + t;
+        float4 vs[3], vc[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { vs[i] = ldStream(inS + i * S); vc[i] = ldStream(inC + i * S); }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          stStream(outS + i * S, packSat4<MODE>(m::quant_scale_raw(vs[i].x), m::quant_scale_raw(vs[i].y),
+                                                m::quant_scale_raw(vs[i].z), m::quant_scale_raw(vs[i].w)));
+          stStream(outC + i * S, packSat4<MODE>(m::quant_color_raw(vc[i].x), m::quant_color_raw(vc[i].y),
+                                                m::quant_color_raw(vc[i].z), m::quant_color_raw(vc[i].w)));
+        }
+      }
+      // ---- alphas (float4 -> word) and rotations (quaternion -> word) -------------------------
+      {
+        const float4 va = ldStream(reinterpret_cast<const float4 *>(a.alphas) + q * S + t);
+        const float4 *inR = reinterpret_cast<const float4 *>(a.rotations) + q * (4 * S) + t;
+        uint32_t *outR = reinterpret_cast<uint32_t *>(a.oRotations) + q * (4 * S) + t;
+        float4 vr[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) vr[i] = ldStream(inR + i * S);
+        const uint32_t a0 = m::quant_alpha(va.x, sThr), a1 = m::quant_alpha(va.y, sThr);
+        const uint32_t a2 = m::quant_alpha(va.z, sThr), a3 = m::quant_alpha(va.w, sThr);
+        stStream(reinterpret_cast<uint32_t *>(a.oAlphas) + q * S + t,
+                 a0 | (a1 << 8) | (a2 << 16) | (a3 << 24));
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          stStream(outR + i * S,
+                   m::quant_rotation_smallest3(vr[i].x, vr[i].y, vr[i].z, vr[i].w, a.flipQ));
+      }
+    }
+    // ---- spherical harmonics: float4 -> word; rows c, c+CYC, ... share their constants ---------
+    if (D > 0) {
+      constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS;
+      const float4 *in = reinterpret_cast<const float4 *>(a.sh) + tile * ((long long)ROWS * S) + t;
+      uint32_t *out = reinterpret_cast<uint32_t *>(a.oSh) + tile * ((long long)ROWS * S) + t;
+      ShPhase<D> ph;
+      ph.init(t);
+#pragma unroll 1
+      for (int c = 0; c < CYC; c++) {
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = ldStream(in + (it + u) * S);
+        for (int u = 0; u < U; u++) v[u] = ldStream(in + (c + u * CYC) * S);
+        float shMul[4];
+        uint32_t shAdd[4], shMask[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          shMul[e] = signedConst(128.0f, ph.flip(e, a.flipSh));
+          const bool fine = ph.pos[e] < 9;  // 5-bit band: first 9 values, load-spz.cc:312-326
+          shAdd[e] = fine ? 132u : 136u;    // 128 + bucket/2
+          shMask[e] = fine ? ~7u : ~15u;    // ~(bucket-1)
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          stStream(out + (it + u) * S,
+          stStream(out + (c + u * CYC) * S,
                    packSat4<MODE>(m::quant_sh_raw(v[u].x, shMul[0], shAdd[0], shMask[0]),
                                   m::quant_sh_raw(v[u].y, shMul[1], shAdd[1], shMask[1]),
                                   m::quant_sh_raw(v[u].z, shMul[2], shAdd[2], shMask[2]),
                                   m::quant_sh_raw(v[u].w, shMul[3], shAdd[3], shMask[3])));
         }
+        ph.advance();
       }
     }
   }
@@ -220,10 +272,12 @@ encodeGenericKernel(const EncodeArgs a, const long long first) {
 template <int D, int VER>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
-  constexpr int S = Geo<D>::S;
+  constexpr int S = kThreads;
+  constexpr int M = Geo<D>::M;
   __shared__ float sAlpha[256];
   __shared__ float sColor[256];
-  __shared__ float sMag[512];
+  __shared__ float sMag[VER == 3 ? 512 : 1];
+  __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
   for (int i = threadIdx.x; i < 256; i += kThreads) {
     sAlpha[i] = a.alphaLut[i];
     sColor[i] = m::dequant_color((uint32_t)i);
@@ -232,139 +286,159 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
     for (int i = threadIdx.x; i < 512; i += kThreads) sMag[i] = m::dequant_s3_magnitude((uint32_t)i);
   __syncthreads();
   const int t = threadIdx.x;
-  if (t >= S) return;
+  const int lane = t & 31, warp = t >> 5;
+  uint32_t *stage = sStage[warp];
 
-  float posScale[4];
-  uint32_t posFlip[4];
+  // sign bit / signed scale for the xyz phase (t + k) mod 3 (see the encoder)
+  uint32_t posFlip3[3];
+  float posScale3[3];
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
-    posFlip[e] = ((a.flipP >> ((t + e) % 3)) & 1u) << 31;
-    posScale[e] = __uint_as_float(__float_as_uint(a.positionScale) ^ posFlip[e]);
-  }
-  float shMul[4];
-  if (D > 0) {
-#pragma unroll
-    for (int e = 0; e < 4; e++)
-      shMul[e] = signedConst(0.0078125f, (a.flipSh >> (((4 * t + e) % (3 * D)) / 3)) & 1u);
+  for (int k = 0; k < 3; k++) {
+    posFlip3[k] = ((a.flipP >> ((t + k) % 3)) & 1u) << 31;
+    posScale3[k] = __uint_as_float(__float_as_uint(a.positionScale) ^ posFlip3[k]);
   }
 
   for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-    // ---- positions ------------------------------------------------------------------------
-    {
-      float4 *out = reinterpret_cast<float4 *>(a.oPositions) + tile * (3 * S) + t;
-      if (VER == 1) {
-        const uint2 *in = reinterpret_cast<const uint2 *>(a.positions) + tile * (3 * S) + t;
-        uint2 w[3];
+#pragma unroll 1
+    for (int mm = 0; mm < M; mm++) {
+      const long long q = tile * M + mm;
+      // ---- positions ------------------------------------------------------------------------
+      {
+        float4 *out = reinterpret_cast<float4 *>(a.oPositions) + q * (3 * S) + t;
+        if (VER == 1) {
+          const uint2 *in = reinterpret_cast<const uint2 *>(a.positions) + q * (3 * S) + t;
+          uint2 w[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) w[i] = __ldcs(in + i * S);
+          for (int i = 0; i < 3; i++) w[i] = ldStream(in + i * S);
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            float4 o;
+            o.x = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x & 0xffffu)) ^ posFlip3[(0 + 2 * i) % 3]);
+            o.y = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x >> 16)) ^ posFlip3[(1 + 2 * i) % 3]);
+            o.z = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y & 0xffffu)) ^ posFlip3[(2 + 2 * i) % 3]);
+            o.w = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y >> 16)) ^ posFlip3[(3 + 2 * i) % 3]);
+            stStream(out + i * S, o);
+          }
+        } else {
+          // contiguous 128-byte loads of the 96 words a warp needs per row, re-dealt through the
+          // per-warp stage so each lane gets the three words of its four 24-bit values
+          const uint32_t *in = reinterpret_cast<const uint32_t *>(a.positions) + q * (9 * S) + warp * 96 + lane;
+          uint32_t g[3][3];
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) g[i][k] = ldStream(in + i * (3 * S) + k * 32);
+          }
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) stage[i * 96 + k * 32 + lane] = g[i][k];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            const uint32_t *sp = stage + i * 96 + 3 * lane;
+            const uint32_t w0 = sp[0], w1 = sp[1], w2 = sp[2];
+            // PRMT with the sign-replicate bit (selector nibble 8|idx) sign-extends 24 -> 32 bits
+            const int32_t f0 = (int32_t)prmt(w0, w0, 0xA210u);
+            const int32_t f1 = (int32_t)prmt(w0, w1, 0xD543u);
+            const int32_t f2 = (int32_t)prmt(w1, w2, 0xC432u);
+            const int32_t f3 = (int32_t)prmt(w2, w2, 0xB321u);
+            float4 o;
+            o.x = m::mul(m::i2f(f0), posScale3[(0 + 2 * i) % 3]);
+            o.y = m::mul(m::i2f(f1), posScale3[(1 + 2 * i) % 3]);
+            o.z = m::mul(m::i2f(f2), posScale3[(2 + 2 * i) % 3]);
+            o.w = m::mul(m::i2f(f3), posScale3[(3 + 2 * i) % 3]);
+            stStream(out + i * S, o);
+          }
+          __syncwarp();
+        }
+      }
+      // ---- scales (exact FMA on the magic float) and colours (table) ---------------------------
+      {
+        const uint32_t *inS = reinterpret_cast<const uint32_t *>(a.scales) + q * (3 * S) + t;
+        const uint32_t *inC = reinterpret_cast<const uint32_t *>(a.colors) + q * (3 * S) + t;
+        float4 *outS = reinterpret_cast<float4 *>(a.oScales) + q * (3 * S) + t;
+        float4 *outC = reinterpret_cast<float4 *>(a.oColors) + q * (3 * S) + t;
+        uint32_t ws[3], wc[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { ws[i] = ldStream(inS + i * S); wc[i] = ldStream(inC + i * S); }
 #pragma unroll
         for (int i = 0; i < 3; i++) {
+          // (2^23 + s) / 16 - (2^19 + 10) = s/16 - 10: both steps exact, so the fused form equals
+          // the reference's s / 16.0f - 10.0f (load-spz.cc:506) bit for bit, +0 at s = 160.
           float4 o;
-          o.x = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x & 0xffffu)) ^ posFlip[0]);
-          o.y = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x >> 16)) ^ posFlip[1]);
-          o.z = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y & 0xffffu)) ^ posFlip[2]);
-          o.w = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y >> 16)) ^ posFlip[3]);
-          stStream(out + i * S, o);
+          o.x = __fmaf_rn(byteAsMagicFloat<0>(ws[i]), 0.0625f, -524298.0f);
+          o.y = __fmaf_rn(byteAsMagicFloat<1>(ws[i]), 0.0625f, -524298.0f);
+          o.z = __fmaf_rn(byteAsMagicFloat<2>(ws[i]), 0.0625f, -524298.0f);
+          o.w = __fmaf_rn(byteAsMagicFloat<3>(ws[i]), 0.0625f, -524298.0f);
+          stStream(outS + i * S, o);
+          float4 c;
+          c.x = sColor[wc[i] & 0xffu];
+          c.y = sColor[(wc[i] >> 8) & 0xffu];
+          c.z = sColor[(wc[i] >> 16) & 0xffu];
+          c.w = sColor[wc[i] >> 24];
+          stStream(outC + i * S, c);
+        }
+      }
+      // ---- alphas (table) ---------------------------------------------------------------------
+      {
+        const uint32_t w = ldStream(reinterpret_cast<const uint32_t *>(a.alphas) + q * S + t);
+        float4 o;
+        o.x = sAlpha[w & 0xffu];
+        o.y = sAlpha[(w >> 8) & 0xffu];
+        o.z = sAlpha[(w >> 16) & 0xffu];
+        o.w = sAlpha[w >> 24];
+        stStream(reinterpret_cast<float4 *>(a.oAlphas) + q * S + t, o);
+      }
+      // ---- rotations ----------------------------------------------------------------------------
+      if (VER == 3) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (4 * S) + t;
+        float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + t;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = ldStream(in + i * S);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          float r[4];
+          m::dequant_rotation_smallest3(w[i], sMag, a.flipQ, r);
+          stStream(out + i * S, make_float4(r[0], r[1], r[2], r[3]));
         }
       } else {
-        const uint32_t *in = reinterpret_cast<const uint32_t *>(a.positions) + (tile * (3 * S) + t) * 3;
-        uint32_t w[3][3];
+        // 3 bytes per quaternion.  A warp owns 128 consecutive quaternions = 96 words, loaded as
+        // three contiguous lines into the stage; lane L then decodes quaternions L, L+32, L+64,
+        // L+96 so that each of its four float4 stores is a contiguous 512-byte warp store.
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (3 * S) + warp * 96 + lane;
+        float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + warp * 128 + lane;
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
+        for (int k = 0; k < 3; k++) stage[k * 32 + lane] = ldStream(in + k * 32);
+        __syncwarp();
+        const uint8_t *sb = reinterpret_cast<const uint8_t *>(stage);
 #pragma unroll
-          for (int k = 0; k < 3; k++) w[i][k] = __ldg(in + i * (3 * S) + k);
+        for (int i = 0; i < 4; i++) {
+          const int qi = 3 * (lane + 32 * i);
+          float r[4];
+          m::dequant_rotation_first3(sb[qi], sb[qi + 1], sb[qi + 2], a.flipQ, r);
+          stStream(out + 32 * i, make_float4(r[0], r[1], r[2], r[3]));
         }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          // PRMT with the sign-replicate bit (selector nibble 8|idx) sign-extends 24 -> 32 bits
-          const int32_t f0 = (int32_t)prmt(w[i][0], w[i][0], 0xA210u);
-          const int32_t f1 = (int32_t)prmt(w[i][0], w[i][1], 0xD543u);
-          const int32_t f2 = (int32_t)prmt(w[i][1], w[i][2], 0xC432u);
-          const int32_t f3 = (int32_t)prmt(w[i][2], w[i][2], 0xB321u);
-          float4 o;
-          o.x = m::mul(m::i2f(f0), posScale[0]);
-          o.y = m::mul(m::i2f(f1), posScale[1]);
-          o.z = m::mul(m::i2f(f2), posScale[2]);
-          o.w = m::mul(m::i2f(f3), posScale[3]);
-          stStream(out + i * S, o);
-        }
-      }
-    }
-    // ---- scales (exact FMA on the magic float) and colours (table) ---------------------------
-    {
-      const uint32_t *inS = reinterpret_cast<const uint32_t *>(a.scales) + tile * (3 * S) + t;
-      const uint32_t *inC = reinterpret_cast<const uint32_t *>(a.colors) + tile * (3 * S) + t;
-      float4 *outS = reinterpret_cast<float4 *>(a.oScales) + tile * (3 * S) + t;
-      float4 *outC = reinterpret_cast<float4 *>(a.oColors) + tile * (3 * S) + t;
-      uint32_t ws[3], wc[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) { ws[i] = ldStream(inS + i * S); wc[i] = ldStream(inC + i * S); }
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        // (2^23 + s) / 16 - (2^19 + 10) = s/16 - 10: both steps exact, so the fused form equals
-        // the reference's s / 16.0f - 10.0f (load-spz.cc:506) bit for bit, +0 at s = 160.
-        float4 o;
-        o.x = __fmaf_rn(byteAsMagicFloat<0>(ws[i]), 0.0625f, -524298.0f);
-        o.y = __fmaf_rn(byteAsMagicFloat<1>(ws[i]), 0.0625f, -524298.0f);
-        o.z = __fmaf_rn(byteAsMagicFloat<2>(ws[i]), 0.0625f, -524298.0f);
-        o.w = __fmaf_rn(byteAsMagicFloat<3>(ws[i]), 0.0625f, -524298.0f);
-        stStream(outS + i * S, o);
-        float4 c;
-        c.x = sColor[wc[i] & 0xffu];
-        c.y = sColor[(wc[i] >> 8) & 0xffu];
-        c.z = sColor[(wc[i] >> 16) & 0xffu];
-        c.w = sColor[wc[i] >> 24];
-        stStream(outC + i * S, c);
-      }
-    }
-    // ---- alphas (table) ---------------------------------------------------------------------
-    {
-      const uint32_t w = ldStream(reinterpret_cast<const uint32_t *>(a.alphas) + tile * S + t);
-      float4 o;
-      o.x = sAlpha[w & 0xffu];
-      o.y = sAlpha[(w >> 8) & 0xffu];
-      o.z = sAlpha[(w >> 16) & 0xffu];
-      o.w = sAlpha[w >> 24];
-      stStream(reinterpret_cast<float4 *>(a.oAlphas) + tile * S + t, o);
-    }
-    // ---- rotations ----------------------------------------------------------------------------
-    if (VER == 3) {
-      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + tile * (4 * S) + t;
-      float4 *out = reinterpret_cast<float4 *>(a.oRotations) + tile * (4 * S) + t;
-      uint32_t w[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) w[i] = ldStream(in + i * S);
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        float r[4];
-        m::dequant_rotation_smallest3(w[i], sMag, a.flipQ, r);
-        stStream(out + i * S, make_float4(r[0], r[1], r[2], r[3]));
-      }
-    } else {
-      // 3 bytes per quaternion: a thread takes 4 quaternions = 3 words -> 4 float4
-      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + (tile * S + t) * 3;
-      float4 *out = reinterpret_cast<float4 *>(a.oRotations) + (tile * S + t) * 4;
-      const uint32_t w0 = __ldg(in), w1 = __ldg(in + 1), w2 = __ldg(in + 2);
-      const uint32_t b[12] = {w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu, w0 >> 24,
-                              w1 & 0xffu, (w1 >> 8) & 0xffu, (w1 >> 16) & 0xffu, w1 >> 24,
-                              w2 & 0xffu, (w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24};
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        float r[4];
-        m::dequant_rotation_first3(b[3 * i], b[3 * i + 1], b[3 * i + 2], a.flipQ, r);
-        out[i] = make_float4(r[0], r[1], r[2], r[3]);
+        __syncwarp();
       }
     }
     // ---- spherical harmonics: word -> float4 -------------------------------------------------
     if (D > 0) {
-      constexpr int U = (D == 15) ? 5 : (D == 8) ? 4 : 3;
-      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.sh) + tile * (3LL * D * S) + t;
-      float4 *out = reinterpret_cast<float4 *>(a.oSh) + tile * (3LL * D * S) + t;
+      constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS;
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.sh) + tile * ((long long)ROWS * S) + t;
+      float4 *out = reinterpret_cast<float4 *>(a.oSh) + tile * ((long long)ROWS * S) + t;
+      ShPhase<D> ph;
+      ph.init(t);
 #pragma unroll 1
-      for (int it = 0; it < 3 * D; it += U) {
+      for (int c = 0; c < CYC; c++) {
         uint32_t w[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) w[u] = ldStream(in + (it + u) * S);
+        for (int u = 0; u < U; u++) w[u] = ldStream(in + (c + u * CYC) * S);
+        float shMul[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) shMul[e] = signedConst(0.0078125f, ph.flip(e, a.flipSh));
 #pragma unroll
         for (int u = 0; u < U; u++) {
           // (2^23 + x) - (2^23 + 128) = x - 128 exactly (+0 at x = 128), then * +-1/128: the
@@ -374,8 +448,9 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
           o.y = m::mul(m::add(byteAsMagicFloat<1>(w[u]), -8388736.0f), shMul[1]);
           o.z = m::mul(m::add(byteAsMagicFloat<2>(w[u]), -8388736.0f), shMul[2]);
           o.w = m::mul(m::add(byteAsMagicFloat<3>(w[u]), -8388736.0f), shMul[3]);
-          stStream(out + (it + u) * S, o);
+          stStream(out + (c + u * CYC) * S, o);
         }
+        ph.advance();
       }
     }
   }
@@ -464,7 +539,7 @@ cudaError_t launchDecodeTiles(const DecodeArgs &a, long long tiles, int grid, cu
 
 }  // namespace
 
-int tileGaussians(int shDim) { return shDim == 8 ? Geo<8>::TG : Geo<15>::TG; }
+int tileGaussians(int shDim) { return shDim == 3 ? Geo<3>::TG : Geo<15>::TG; }
 
 cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream,
                          int *launches) {
@@ -479,7 +554,8 @@ cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream
   const long long tg = tileGaussians(a.shDim);
   const long long tiles = vec ? a.n / tg : 0;
   if (tiles > 0) {
-    const long long cap = (long long)plan.smCount * kCtasPerSm;
+    const int per = plan.ctasPerSm >= 1 && plan.ctasPerSm <= kCtasPerSm ? plan.ctasPerSm : kCtasPerSm;
+    const long long cap = plan.flatGrid ? 0x7fffffffLL : (long long)plan.smCount * per;
     const int grid = (int)(tiles < cap ? tiles : cap);
     cudaError_t e;
     const bool cvt = plan.packMode == kPackCvt;
@@ -521,7 +597,8 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
   const long long tg = tileGaussians(a.shDim);
   const long long tiles = vec ? a.n / tg : 0;
   if (tiles > 0) {
-    const long long cap = (long long)plan.smCount * kCtasPerSm;
+    const int per = plan.ctasPerSm >= 1 && plan.ctasPerSm <= kCtasPerSm ? plan.ctasPerSm : kCtasPerSm;
+    const long long cap = plan.flatGrid ? 0x7fffffffLL : (long long)plan.smCount * per;
     const int grid = (int)(tiles < cap ? tiles : cap);
     cudaError_t e;
     switch (a.shDim) {

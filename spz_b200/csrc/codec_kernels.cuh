@@ -34,6 +34,8 @@ struct LaunchPlan {
   int smCount;
   int packMode;        // encode only: how four bytes are saturated and packed into a word
   bool forceGeneric;   // test hook: route everything through the scalar kernels
+  int ctasPerSm;       // persistent grid = smCount * ctasPerSm (1..3); 0 = default (3)
+  bool flatGrid;       // experiment knob: one CTA per tile instead of persistent CTAs
 };
 
 // Number of kernels launched is returned through *launches (0, 1 or 2).
