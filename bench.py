@@ -166,8 +166,21 @@ def cpu_reference_run(points_total, deg, frm, to, steps, warmup, threads, sample
         out["pack_mgs"] = n_step / pk / 1e6
         out["unpack_mgs"] = n_step / up / 1e6
         out["value"] = n_step / (pk + up) / 1e6
+        out["ms_per_step"] = (pk + up) * 1e3
         out["sample"] += "; value = time inside packGaussians+unpackGaussians only"
     return out
+
+
+def traffic_for(kernel, gaussians, override):
+    """DRAM bytes per launch of `kernel`: the ncu --set full capture recorded in profiles/traffic.json
+    (taken at a different launch size), scaled per gaussian to this launch."""
+    if override is not None:
+        return override
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        return t["dram_bytes"] / t["gaussians"] * gaussians
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def host_memory_available():
@@ -383,7 +396,8 @@ def run_b200_arm(args):
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom[1], "peak": peak, "unit": "GB/s",
                          "frac": dom[1] / peak, "frac_of_nominal_8TBs": dom[1] / 8000.0, "peak_source": peak_src,
                          "algorithmic_bytes_per_gaussian": alg_bytes, "gaussians_per_launch": n,
-                         "avg_launch_ms": dom[2], "traffic": args.traffic_bytes,
+                         "avg_launch_ms": dom[2], "traffic": traffic_for(dom[0], n, args.traffic_bytes),
+                         "traffic_source": "profiles/traffic.json (ncu --set full dram bytes per gaussian x gaussians per launch)",
                          "encode": {"achieved": enc_gbs, "frac": enc_gbs / peak, "avg_launch_ms": enc_ms},
                          "decode": {"achieved": dec_gbs, "frac": dec_gbs / peak, "avg_launch_ms": dec_ms}},
             "gpu_launches": launches, "clocks": clocks,

@@ -78,7 +78,12 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path) or (not _build.up_to_date() and os.environ.get("SPZB200_NO_REBUILD") is None):
+    variant = os.environ.get("SPZB200_LIB")  # a tuning variant built by scripts/ (development only)
+    if variant:
+        if not os.path.exists(variant):
+            raise NativeLibraryError(f"SPZB200_LIB={variant} does not exist")
+        path = variant
+    elif not os.path.exists(path) or (not _build.up_to_date() and os.environ.get("SPZB200_NO_REBUILD") is None):
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001

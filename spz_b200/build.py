@@ -58,15 +58,19 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """Default: the shipped library.  `extra_flags` + `out` build a tuning variant next to it
+    (loaded with SPZB200_LIB=<path>); used only by scripts/ experiments."""
+    if out is None and not force and up_to_date():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
+    lib_path = out or LIB
+    tag = "" if out is None else "." + os.path.basename(out)
     objs = []
     procs = []
     for src in _sources():
-        obj = os.path.join(OUT_DIR, os.path.basename(src) + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(HERE, "..", "include"), "-c", src, "-o", obj]
+        obj = os.path.join(OUT_DIR, os.path.basename(src) + tag + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(HERE, "..", "include"), "-c", src, "-o", obj]
         if src.endswith(".cc"):
             cmd.insert(1, "-x")
             cmd.insert(2, "cu")
@@ -80,11 +84,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out)
-    link = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lz", "-cudart", "static"]
+    link = [_nvcc(), "-shared", "-o", lib_path] + objs + ["-lz", "-cudart", "static"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -138,7 +138,7 @@ struct SpzB200Context {
   bool cvtPackOk = false;  // the init-time probe of cvt.pack.sat.u8.s32 agreed with the ALU packer
   bool forceGeneric = false;
   int ctasPerSm = 0;
-  bool flatGrid = false;
+  bool flatGrid = true;  // one CTA per tile: the block scheduler keeps the tile frontier compact
   long long chunkPoints = 1 << 21;
   long long kernelLaunches = 0;
   float hThr[256];
@@ -213,7 +213,7 @@ spzb200::DecodeArgs makeDecodeArgs(const SpzB200Context *ctx, const SpzB200Packe
   a.positionScale = positionScaleFor(in.fractional_bits);
   const spzb200::m::FlipBits f = spzb200::m::make_flip_bits(SPZB200_COORD_RUB, to);
   a.flipP = f.p; a.flipQ = f.q; a.flipSh = f.sh;
-  a.alphaLut = ctx->dLut;
+  a.tables = ctx->dLut;
   return a;
 }
 
@@ -478,7 +478,7 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
     return cudaFail(err, what);
   };
   if ((e = cudaMalloc(&ctx->dThr, 256 * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc tables");
-  if ((e = cudaMalloc(&ctx->dLut, 256 * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc tables");
+  if ((e = cudaMalloc(&ctx->dLut, spzb200::kDecodeTableFloats * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc tables");
   if ((e = cudaMemcpy(ctx->dThr, ctx->hThr, sizeof ctx->hThr, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "table upload");
   if ((e = cudaMemcpy(ctx->dLut, ctx->hLut, sizeof ctx->hLut, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "table upload");
   for (int s = 0; s < 2; s++) {
@@ -486,6 +486,7 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
     for (int k = 0; k < 4; k++)
       if ((e = cudaEventCreate(&ctx->stage[s].ev[k])) != cudaSuccess) return bail(e, "cudaEventCreate");
   }
+  if ((e = spzb200::buildDecodeTables(ctx->dLut, ctx->stage[0].stream)) != cudaSuccess) return bail(e, "decode tables");
   int ok = 0;
   if ((e = spzb200::probePackCvt(ctx->stage[0].stream, &ok)) != cudaSuccess) return bail(e, "pack probe");
   ctx->cvtPackOk = ok != 0;
@@ -495,7 +496,7 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
     if (!std::strcmp(env, "alu")) ctx->packMode = spzb200::kPackAlu;
   }
   if (const char *env = std::getenv("SPZB200_CTAS_PER_SM")) ctx->ctasPerSm = std::atoi(env);
-  if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = !std::strcmp(env, "flat");
+  if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = std::strcmp(env, "persistent") != 0;
   *out = ctx;
   return SPZB200_OK;
 }

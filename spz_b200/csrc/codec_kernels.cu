@@ -37,7 +37,10 @@ namespace {
 
 constexpr int kThreads = 320;
 constexpr int kWarps = kThreads / 32;
-constexpr int kCtasPerSm = 3;
+#ifndef SPZ_CTAS_PER_SM
+#define SPZ_CTAS_PER_SM 4
+#endif
+constexpr int kCtasPerSm = SPZ_CTAS_PER_SM;  // resident CTAs per SM the register budget is set for
 
 constexpr int gcdc(int a, int b) { return b == 0 ? a : gcdc(b, a % b); }
 
@@ -274,16 +277,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
   constexpr int S = kThreads;
   constexpr int M = Geo<D>::M;
-  __shared__ float sAlpha[256];
-  __shared__ float sColor[256];
-  __shared__ float sMag[VER == 3 ? 512 : 1];
+  __shared__ float sTab[VER == 3 ? kDecodeTableFloats : 512];
   __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
-  for (int i = threadIdx.x; i < 256; i += kThreads) {
-    sAlpha[i] = a.alphaLut[i];
-    sColor[i] = m::dequant_color((uint32_t)i);
-  }
-  if (VER == 3)
-    for (int i = threadIdx.x; i < 512; i += kThreads) sMag[i] = m::dequant_s3_magnitude((uint32_t)i);
+  for (int i = threadIdx.x; i < (VER == 3 ? kDecodeTableFloats : 512); i += kThreads) sTab[i] = __ldg(a.tables + i);
+  const float *sAlpha = sTab, *sColor = sTab + 256, *sMag = sTab + 512;
   __syncthreads();
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
@@ -479,7 +476,7 @@ decodeGenericKernel(const DecodeArgs a, const long long first) {
     a.oScales[g * 3 + ax] = m::dequant_scale(a.scales[g * 3 + ax]);
     a.oColors[g * 3 + ax] = m::dequant_color(a.colors[g * 3 + ax]);
   }
-  a.oAlphas[g] = a.alphaLut[a.alphas[g]];
+  a.oAlphas[g] = a.tables[a.alphas[g]];
   float r[4];
   if (a.version >= 3) {
     const uint8_t *b = a.rotations + g * 4;
@@ -506,6 +503,12 @@ decodeGenericKernel(const DecodeArgs a, const long long first) {
   float *so = a.oSh + g * per;
   for (int j = 0; j < per; j++)
     so[j] = m::dequant_sh(s[j], signedConst(0.0078125f, (a.flipSh >> (j / 3)) & 1u));
+}
+
+__global__ void buildDecodeTablesKernel(float *tables) {
+  const int i = threadIdx.x;  // 512 threads
+  if (i < 256) tables[256 + i] = m::dequant_color((uint32_t)i);
+  tables[512 + i] = m::dequant_s3_magnitude((uint32_t)i);
 }
 
 __global__ void probePackKernel(int *ok) {
@@ -623,6 +626,11 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
   }
   if (launches) *launches = count;
   return cudaSuccess;
+}
+
+cudaError_t buildDecodeTables(float *tables, cudaStream_t stream) {
+  buildDecodeTablesKernel<<<1, 512, 0, stream>>>(tables);
+  return cudaGetLastError();
 }
 
 cudaError_t probePackCvt(cudaStream_t stream, int *ok) {

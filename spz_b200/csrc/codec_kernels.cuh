@@ -25,8 +25,12 @@ struct DecodeArgs {
   int version;                    // 1: half positions + first-three; 2: 24-bit + first-three; 3
   float positionScale;            // (float)(1.0 / (1 << fractionalBits)), load-spz.cc:495
   uint32_t flipP, flipQ, flipSh;  // sign-bit sets of coordinateConverter(RUB, to)
-  const float *alphaLut;          // device, 256 floats: invSigmoid(a / 255.0f)
+  const float *tables;            // device, kDecodeTableFloats floats: [0,256) alpha LUT
+                                  // invSigmoid(a / 255.0f) (host-built, libm logf), [256,512)
+                                  // colour LUT, [512,1024) smallest-three magnitudes (device-built)
 };
+
+constexpr int kDecodeTableFloats = 1024;
 
 enum PackMode { kPackAlu = 0, kPackCvt = 1 };
 
@@ -46,6 +50,10 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
 
 // Gaussians per tile of the vector kernels for a given shDim (the sharding granule).
 int tileGaussians(int shDim);
+
+// Fills tables[256, 1024) on the device (colour LUT load-spz.cc:522, smallest-three magnitude LUT
+// load-spz.cc:367); tables[0, 256) is uploaded by the caller.
+cudaError_t buildDecodeTables(float *tables, cudaStream_t stream);
 
 // Runs both byte packers on probe values; *ok = 1 when cvt.pack.sat.u8.s32.b32 orders and
 // saturates bytes the way the kernels assume (decided once per context).
