@@ -51,6 +51,18 @@ enum {
   SPZB200_COORD_LDF = 5, SPZB200_COORD_RDF = 6, SPZB200_COORD_LUF = 7, SPZB200_COORD_RUF = 8
 };
 
+/* Stream flavours a decoder accepts in SpzB200Packed.version.  1..3 are the container versions
+ * (load-spz.cc:571-572): 1 = float16 positions + first-three rotations, 2 = 24-bit positions +
+ * first-three, 3 = 24-bit + smallest-three.  4 has no file form: it is the in-memory combination
+ * "float16 positions with usesQuaternionSmallestThree = true" that unpackGaussians accepts for a
+ * hand-built PackedGaussians (load-spz.cc:465,509) -- notably the default-constructed empty one. */
+enum {
+  SPZB200_STREAM_V1 = 1,
+  SPZB200_STREAM_V2 = 2,
+  SPZB200_STREAM_V3 = 3,
+  SPZB200_STREAM_HALF_POSITIONS_SMALLEST_THREE = 4
+};
+
 /* Float planes of n gaussians: a borrowed view of GaussianCloud (splat-types.h:90-115).  The
  * pointers are device pointers for the *_device entry points and host pointers for *_host. */
 typedef struct {
@@ -70,7 +82,8 @@ typedef struct {
   int64_t num_points;
   int32_t sh_degree;       /* 0..3 */
   int32_t fractional_bits; /* header byte; the encoder always writes 12 (load-spz.cc:270) */
-  int32_t version;         /* container version 1..3 (load-spz.cc:571-572); encoder writes 3 */
+  int32_t version;         /* container version 1..3 (load-spz.cc:571-572), or
+                              SPZB200_STREAM_HALF_POSITIONS_SMALLEST_THREE; the encoder writes 3 */
   int32_t reserved;
   uint8_t *positions;
   uint8_t *scales;
@@ -115,7 +128,8 @@ int spzb200_encode_device(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t f
 /* Replaces unpackGaussians (load-spz.cc:467-531) including its trailing
  * convertCoordinates(RUB, to) (load-spz.cc:529, splat-types.h:134-164), fused into the kernel.
  * `to` is UnpackOptions::to.  in->version selects the stream flavour: 3 = smallest-three
- * rotations, 2 = first-three rotations, 1 = float16 positions + first-three. */
+ * rotations, 2 = first-three rotations, 1 = float16 positions + first-three, 4 = float16 +
+ * smallest-three. */
 int spzb200_decode_device(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to,
                           SpzB200Cloud *out, void *stream);
 

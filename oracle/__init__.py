@@ -97,7 +97,7 @@ class Packed:
 
     def slice(self, a: int, b: int) -> "Packed":
         d = SH_DIM[self.sh_degree] * 3
-        pb = 6 if self.version == 1 else 9
+        pb = 6 if self.version in (1, 4) else 9
         rb = 4 if self.version >= 3 else 3
         return Packed(b - a, self.sh_degree, self.fractional_bits, self.version,
                       self.positions[pb * a:pb * b], self.scales[3 * a:3 * b],
@@ -108,7 +108,7 @@ class Packed:
 def _empty_packed(n: int, deg: int, version: int = 3, fb: int = 12) -> Packed:
     d = SH_DIM[deg] * 3
     return Packed(n, deg, fb, version,
-                  np.zeros(n * (6 if version == 1 else 9), np.uint8), np.zeros(n * 3, np.uint8),
+                  np.zeros(n * (6 if version in (1, 4) else 9), np.uint8), np.zeros(n * 3, np.uint8),
                   np.zeros(n * (4 if version >= 3 else 3), np.uint8), np.zeros(n, np.uint8),
                   np.zeros(n * 3, np.uint8), np.zeros(n * d, np.uint8))
 

@@ -85,7 +85,8 @@ int ref_pack(int32_t n, int32_t shDegree, int32_t from, const float *positions,
 }
 
 // version: 1 (float16 positions, first-three quaternion), 2 (24-bit, first-three), 3 (24-bit,
-// smallest-three) -- the mapping deserializePackedGaussians applies (load-spz.cc:571-572).
+// smallest-three) -- the mapping deserializePackedGaussians applies (load-spz.cc:571-572); 4 =
+// float16 positions with usesQuaternionSmallestThree = true (a hand-built struct, no file form).
 int ref_unpack(int32_t n, int32_t shDegree, int32_t fractionalBits, int32_t version, int32_t to,
                const uint8_t *positions, const uint8_t *scales, const uint8_t *rotations,
                const uint8_t *alphas, const uint8_t *colors, const uint8_t *sh, float *oPositions,
@@ -99,7 +100,7 @@ int ref_unpack(int32_t n, int32_t shDegree, int32_t fractionalBits, int32_t vers
   p.fractionalBits = fractionalBits;
   p.antialiased = false;
   p.usesQuaternionSmallestThree = version >= 3;
-  p.positions.assign(positions, positions + N * 3 * (version == 1 ? 2 : 3));
+  p.positions.assign(positions, positions + N * 3 * ((version == 1 || version == 4) ? 2 : 3));
   p.scales.assign(scales, scales + N * 3);
   p.rotations.assign(rotations, rotations + N * (version >= 3 ? 4 : 3));
   p.alphas.assign(alphas, alphas + N);

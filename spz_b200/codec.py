@@ -25,7 +25,7 @@ def float_plane_widths(sh_degree: int):
 
 
 def byte_plane_widths(sh_degree: int, version: int = 3):
-    return (6 if version == 1 else 9, 3, 4 if version >= 3 else 3, 1, 3, 3 * SH_DIM[sh_degree])
+    return (6 if version in (1, 4) else 9, 3, 4 if version >= 3 else 3, 1, 3, 3 * SH_DIM[sh_degree])
 
 
 def float_bytes_per_gaussian(sh_degree: int) -> int:

@@ -168,8 +168,8 @@ int checkPacked(const SpzB200Packed *p, const char *who, bool needVersion) {
   if (!p) return fail(SPZB200_ERR_INVALID, "%s: null packed view", who);
   if (p->num_points < 0) return fail(SPZB200_ERR_INVALID, "%s: num_points < 0", who);
   if (!validDegree(p->sh_degree)) return fail(SPZB200_ERR_INVALID, "%s: sh_degree %d not in 0..3", who, p->sh_degree);
-  if (needVersion && (p->version < 1 || p->version > 3))
-    return fail(SPZB200_ERR_INVALID, "%s: version %d not in 1..3", who, p->version);
+  if (needVersion && (p->version < 1 || p->version > SPZB200_STREAM_HALF_POSITIONS_SMALLEST_THREE))
+    return fail(SPZB200_ERR_INVALID, "%s: version %d not in 1..4", who, p->version);
   if (p->num_points > 0) {
     if (!p->positions || !p->scales || !p->rotations || !p->alphas || !p->colors)
       return fail(SPZB200_ERR_INVALID, "%s: null plane pointer", who);
@@ -233,7 +233,7 @@ void floatPlaneBytes(int shDim, size_t b[6]) {
   b[0] = 12; b[1] = 12; b[2] = 16; b[3] = 4; b[4] = 12; b[5] = (size_t)12 * shDim;
 }
 void bytePlaneBytes(int shDim, int version, size_t b[6]) {
-  b[0] = version == 1 ? 6 : 9; b[1] = 3; b[2] = version >= 3 ? 4 : 3; b[3] = 1; b[4] = 3;
+  b[0] = (version == 1 || version == 4) ? 6 : 9; b[1] = 3; b[2] = version >= 3 ? 4 : 3; b[3] = 1; b[4] = 3;
   b[5] = (size_t)3 * shDim;
 }
 
@@ -435,7 +435,7 @@ SpzB200Packed slicePacked(const SpzB200Packed &p, int64_t a, int64_t b) {
   const int d = shDimOf(p.sh_degree);
   SpzB200Packed s = p;
   s.num_points = b - a;
-  s.positions = p.positions + (p.version == 1 ? 6 : 9) * a; s.scales = p.scales + 3 * a;
+  s.positions = p.positions + ((p.version == 1 || p.version == 4) ? 6 : 9) * a; s.scales = p.scales + 3 * a;
   s.rotations = p.rotations + (p.version >= 3 ? 4 : 3) * a; s.alphas = p.alphas + a;
   s.colors = p.colors + 3 * a; s.sh = p.sh ? p.sh + (int64_t)3 * d * a : nullptr;
   return s;

@@ -270,16 +270,19 @@ encodeGenericKernel(const EncodeArgs a, const long long first) {
 
 // =================================================================================================
 // decode, vector path.  VER: 1 = half positions + first-three quaternion, 2 = 24-bit positions +
-// first-three, 3 = 24-bit + smallest-three (load-spz.cc:571-572).
+// first-three, 3 = 24-bit + smallest-three (load-spz.cc:571-572); 4 = half positions +
+// smallest-three, which no file produces but a hand-built PackedGaussians can (load-spz.cc:465,509).
 // =================================================================================================
 template <int D, int VER>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
   constexpr int S = kThreads;
   constexpr int M = Geo<D>::M;
-  __shared__ float sTab[VER == 3 ? kDecodeTableFloats : 512];
+  constexpr bool kHalf = (VER == 1 || VER == 4);  // float16 positions
+  constexpr bool kS3 = (VER >= 3);                // smallest-three rotations
+  __shared__ float sTab[kS3 ? kDecodeTableFloats : 512];
   __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
-  for (int i = threadIdx.x; i < (VER == 3 ? kDecodeTableFloats : 512); i += kThreads) sTab[i] = __ldg(a.tables + i);
+  for (int i = threadIdx.x; i < (kS3 ? kDecodeTableFloats : 512); i += kThreads) sTab[i] = __ldg(a.tables + i);
   const float *sAlpha = sTab, *sColor = sTab + 256, *sMag = sTab + 512;
   __syncthreads();
   const int t = threadIdx.x;
@@ -302,7 +305,7 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
       // ---- positions ------------------------------------------------------------------------
       {
         float4 *out = reinterpret_cast<float4 *>(a.oPositions) + q * (3 * S) + t;
-        if (VER == 1) {
+        if (kHalf) {
           const uint2 *in = reinterpret_cast<const uint2 *>(a.positions) + q * (3 * S) + t;
           uint2 w[3];
 #pragma unroll
@@ -389,7 +392,7 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
         stStream(reinterpret_cast<float4 *>(a.oAlphas) + q * S + t, o);
       }
       // ---- rotations ----------------------------------------------------------------------------
-      if (VER == 3) {
+      if (kS3) {
         const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (4 * S) + t;
         float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + t;
         uint32_t w[4];
@@ -464,7 +467,7 @@ decodeGenericKernel(const DecodeArgs a, const long long first) {
   for (int ax = 0; ax < 3; ax++) {
     const uint32_t flip = ((a.flipP >> ax) & 1u) << 31;
     float p;
-    if (a.version == 1) {
+    if (a.version == 1 || a.version == 4) {
       const uint8_t *h = a.positions + (g * 3 + ax) * 2;
       p = __uint_as_float(__float_as_uint(m::half_bits_to_float((uint32_t)h[0] | ((uint32_t)h[1] << 8))) ^ flip);
     } else {
@@ -535,6 +538,7 @@ cudaError_t launchDecodeTiles(const DecodeArgs &a, long long tiles, int grid, cu
   switch (a.version) {
     case 1: decodeTilesKernel<D, 1><<<grid, kThreads, 0, s>>>(a, tiles); break;
     case 2: decodeTilesKernel<D, 2><<<grid, kThreads, 0, s>>>(a, tiles); break;
+    case 4: decodeTilesKernel<D, 4><<<grid, kThreads, 0, s>>>(a, tiles); break;
     default: decodeTilesKernel<D, 3><<<grid, kThreads, 0, s>>>(a, tiles); break;
   }
   return cudaGetLastError();
@@ -591,7 +595,7 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
   int count = 0;
   if (launches) *launches = 0;
   if (a.n <= 0) return cudaSuccess;
-  const bool vec = !plan.forceGeneric && aligned(a.positions, a.version == 1 ? 8 : 4) &&
+  const bool vec = !plan.forceGeneric && aligned(a.positions, (a.version == 1 || a.version == 4) ? 8 : 4) &&
                    aligned(a.scales, 4) && aligned(a.rotations, 4) && aligned(a.alphas, 4) &&
                    aligned(a.colors, 4) && (a.shDim == 0 || aligned(a.sh, 4)) &&
                    aligned(a.oPositions, 16) && aligned(a.oScales, 16) &&

@@ -1,0 +1,677 @@
+// Host side of the drop-in C++ API (include/spz_b200/spz.hpp): namespace spz as the reference
+// exports it.  packGaussians / unpackGaussians marshal the std::vector planes into the C-ABI
+// (include/spz_b200.h) where the sm_100a kernels do all codec arithmetic; the rest of this file is
+// the host glue the reference also keeps on the host -- container header and plane order
+// (load-spz.cc:131-139, 533-596), zlib gzip framing (:141-214), file I/O (:598-668), one-element
+// accessors (:383-465) and the small math of splat-types.cc.
+//
+// Error behaviour follows the reference: nothing throws; a failed check prints one line to stdout
+// and the function returns false / an empty struct (load-spz.cc:94-100).
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <mutex>
+#include <ostream>
+#include <string>
+#include <vector>
+
+#include "../../include/spz_b200.h"
+#include "../../include/spz_b200/spz.hpp"
+
+namespace spz {
+namespace {
+
+void logLine(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vprintf(fmt, ap);
+  va_end(ap);
+  printf("\n");
+  fflush(stdout);
+}
+
+// The reference prints "[SPZ: ERROR] Check failed: file:line: expr" (load-spz.cc:94-100).
+#define SPZ_REQUIRE(cond)                                                                \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      logLine("[SPZ: ERROR] Check failed: %s:%d: %s", __FILE__, __LINE__, #cond);        \
+      return false;                                                                      \
+    }                                                                                    \
+  } while (0)
+
+int shDimOf(int degree) { return degree == 0 ? 0 : degree == 1 ? 3 : degree == 2 ? 8 : degree == 3 ? 15 : 0; }
+
+constexpr uint32_t kMagic = 0x5053474e;  // "NGSP"
+constexpr uint8_t kFlagAntialiased = 0x1;
+constexpr size_t kHeaderBytes = 16;
+
+// ---- devices and contexts -----------------------------------------------------------------------
+// SPZ_B200_DEVICES="0,1,2,3" shards every call by point range over those GPUs (no collective);
+// default is device 0 (or SPZ_B200_DEVICE).  One context per host thread and device, created on
+// first use and kept until the thread exits.
+
+std::vector<int32_t> configuredDevices() {
+  std::vector<int32_t> devs;
+  if (const char *list = std::getenv("SPZ_B200_DEVICES")) {
+    const char *p = list;
+    while (*p) {
+      char *end = nullptr;
+      const long v = std::strtol(p, &end, 10);
+      if (end == p) break;
+      devs.push_back((int32_t)v);
+      p = (*end == ',') ? end + 1 : end;
+    }
+  }
+  if (devs.empty()) {
+    const char *one = std::getenv("SPZ_B200_DEVICE");
+    devs.push_back(one ? (int32_t)std::atoi(one) : 0);
+  }
+  return devs;
+}
+
+struct ThreadContext {
+  SpzB200Context *ctx = nullptr;
+  int32_t device = -1;
+  ~ThreadContext() {
+    if (ctx) spzb200_destroy(ctx);
+  }
+};
+
+SpzB200Context *contextFor(int32_t device) {
+  thread_local ThreadContext tc;
+  if (tc.ctx && tc.device == device) return tc.ctx;
+  if (tc.ctx) {
+    spzb200_destroy(tc.ctx);
+    tc.ctx = nullptr;
+  }
+  if (spzb200_create(device, &tc.ctx) != SPZB200_OK) {
+    logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
+    tc.ctx = nullptr;
+    return nullptr;
+  }
+  tc.device = device;
+  return tc.ctx;
+}
+
+bool checkCloudSizes(const GaussianCloud &g) {
+  // the reference's checks (load-spz.cc:106-117) with the products taken in 64 bits
+  const int64_t n = g.numPoints;
+  SPZ_REQUIRE(g.numPoints >= 0);
+  SPZ_REQUIRE(g.shDegree >= 0);
+  SPZ_REQUIRE(g.shDegree <= 3);
+  SPZ_REQUIRE((int64_t)g.positions.size() == n * 3);
+  SPZ_REQUIRE((int64_t)g.scales.size() == n * 3);
+  SPZ_REQUIRE((int64_t)g.rotations.size() == n * 4);
+  SPZ_REQUIRE((int64_t)g.alphas.size() == n);
+  SPZ_REQUIRE((int64_t)g.colors.size() == n * 3);
+  SPZ_REQUIRE((int64_t)g.sh.size() == n * shDimOf(g.shDegree) * 3);
+  return true;
+}
+
+bool checkPackedSizes(const PackedGaussians &p, int64_t n, int shDim, bool usesFloat16) {
+  // load-spz.cc:119-127
+  SPZ_REQUIRE((int64_t)p.positions.size() == n * 3 * (usesFloat16 ? 2 : 3));
+  SPZ_REQUIRE((int64_t)p.scales.size() == n * 3);
+  SPZ_REQUIRE((int64_t)p.rotations.size() == n * (p.usesQuaternionSmallestThree ? 4 : 3));
+  SPZ_REQUIRE((int64_t)p.alphas.size() == n);
+  SPZ_REQUIRE((int64_t)p.colors.size() == n * 3);
+  SPZ_REQUIRE((int64_t)p.sh.size() == n * shDim * 3);
+  return true;
+}
+
+int32_t streamFlavour(bool usesFloat16, bool smallestThree) {
+  if (usesFloat16) return smallestThree ? SPZB200_STREAM_HALF_POSITIONS_SMALLEST_THREE : SPZB200_STREAM_V1;
+  return smallestThree ? SPZB200_STREAM_V3 : SPZB200_STREAM_V2;
+}
+
+SpzB200Packed viewOf(const PackedGaussians &p, int32_t flavour) {
+  SpzB200Packed v;
+  std::memset(&v, 0, sizeof v);
+  v.num_points = p.numPoints;
+  v.sh_degree = p.shDegree;
+  v.fractional_bits = p.fractionalBits;
+  v.version = flavour;
+  v.positions = const_cast<uint8_t *>(p.positions.data());
+  v.scales = const_cast<uint8_t *>(p.scales.data());
+  v.rotations = const_cast<uint8_t *>(p.rotations.data());
+  v.alphas = const_cast<uint8_t *>(p.alphas.data());
+  v.colors = const_cast<uint8_t *>(p.colors.data());
+  v.sh = const_cast<uint8_t *>(p.sh.data());
+  return v;
+}
+
+SpzB200Cloud viewOf(const GaussianCloud &g) {
+  SpzB200Cloud v;
+  std::memset(&v, 0, sizeof v);
+  v.num_points = g.numPoints;
+  v.sh_degree = g.shDegree;
+  v.positions = const_cast<float *>(g.positions.data());
+  v.scales = const_cast<float *>(g.scales.data());
+  v.rotations = const_cast<float *>(g.rotations.data());
+  v.alphas = const_cast<float *>(g.alphas.data());
+  v.colors = const_cast<float *>(g.colors.data());
+  v.sh = const_cast<float *>(g.sh.data());
+  return v;
+}
+
+// ---- container ------------------------------------------------------------------------------------
+
+// The 16 header bytes, little endian (load-spz.cc:131-139).  The writer always says version 3
+// (load-spz.cc:133,533-539), also for a struct that came from a version-1/2 file.
+void writeHeader(const PackedGaussians &p, uint8_t out[kHeaderBytes]) {
+  const uint32_t words[3] = {kMagic, 3u, (uint32_t)p.numPoints};
+  std::memcpy(out, words, 12);
+  out[12] = (uint8_t)p.shDegree;
+  out[13] = (uint8_t)p.fractionalBits;
+  out[14] = p.antialiased ? kFlagAntialiased : 0;
+  out[15] = 0;
+}
+
+// plane order in the stream: positions, alphas, colors, scales, rotations, sh
+const std::vector<uint8_t> *streamOrder(const PackedGaussians &p, int i) {
+  const std::vector<uint8_t> *order[6] = {&p.positions, &p.alphas, &p.colors, &p.scales, &p.rotations, &p.sh};
+  return order[i];
+}
+
+size_t serializedBytes(const PackedGaussians &p) {
+  size_t total = kHeaderBytes;
+  for (int i = 0; i < 6; i++) total += streamOrder(p, i)->size();
+  return total;
+}
+
+void serializeInto(const PackedGaussians &p, uint8_t *dst) {
+  writeHeader(p, dst);
+  dst += kHeaderBytes;
+  for (int i = 0; i < 6; i++) {
+    const std::vector<uint8_t> *v = streamOrder(p, i);
+    if (!v->empty()) std::memcpy(dst, v->data(), v->size());
+    dst += v->size();
+  }
+}
+
+int64_t maxPointsToRead() {
+  // The reference refuses more than 10,000,000 points (load-spz.cc:549).  Lifted here so the large
+  // configurations round-trip; SPZ_B200_MAX_POINTS restores any cap.
+  if (const char *env = std::getenv("SPZ_B200_MAX_POINTS")) return std::atoll(env);
+  return std::numeric_limits<int32_t>::max();
+}
+
+PackedGaussians deserialize(const uint8_t *data, size_t size) {
+  if (size < kHeaderBytes) {
+    logLine("[SPZ ERROR] deserializePackedGaussians: header not found");
+    return {};
+  }
+  uint32_t words[3];
+  std::memcpy(words, data, 12);
+  if (words[0] != kMagic) {
+    logLine("[SPZ ERROR] deserializePackedGaussians: header not found");
+    return {};
+  }
+  const uint32_t version = words[1], numPointsU = words[2];
+  const uint8_t shDegree = data[12], fractionalBits = data[13], flags = data[14];
+  if (version < 1 || version > 3) {
+    logLine("[SPZ ERROR] deserializePackedGaussians: version not supported: %d", (int)version);
+    return {};
+  }
+  if ((int64_t)numPointsU > maxPointsToRead()) {
+    logLine("[SPZ ERROR] deserializePackedGaussians: Too many points: %d", (int)numPointsU);
+    return {};
+  }
+  if (shDegree > 3) {
+    logLine("[SPZ ERROR] deserializePackedGaussians: Unsupported SH degree: %d", (int)shDegree);
+    return {};
+  }
+  const size_t n = numPointsU;
+  const size_t shDim = (size_t)shDimOf(shDegree);
+  const bool half = version == 1, s3 = version >= 3;
+  const size_t sizes[6] = {n * (half ? 6 : 9), n, n * 3, n * 3, n * (s3 ? 4 : 3), n * shDim * 3};  // stream order
+  size_t need = kHeaderBytes;
+  for (size_t s : sizes) need += s;
+  if (size < need) {  // checked before anything is allocated: a corrupt count cannot exhaust memory
+    logLine("[SPZ ERROR] deserializePackedGaussians: read error");
+    return {};
+  }
+  PackedGaussians r;
+  r.numPoints = (int32_t)numPointsU;
+  r.shDegree = shDegree;
+  r.fractionalBits = fractionalBits;
+  r.antialiased = (flags & kFlagAntialiased) != 0;
+  r.usesQuaternionSmallestThree = s3;
+  std::vector<uint8_t> *dst[6] = {&r.positions, &r.alphas, &r.colors, &r.scales, &r.rotations, &r.sh};
+  const uint8_t *src = data + kHeaderBytes;
+  for (int i = 0; i < 6; i++) {
+    dst[i]->assign(src, src + sizes[i]);
+    src += sizes[i];
+  }
+  return r;
+}
+
+// gzip member -> bytes (windowBits 16 + MAX_WBITS: gzip framing only, load-spz.cc:169-173).  The
+// ISIZE trailer sizes the first allocation; the loop still grows if it lied.  Stops at the end of
+// the first member, like the reference.
+bool gunzip(const uint8_t *data, size_t size, std::vector<uint8_t> *out) {
+  out->clear();
+  z_stream zs;
+  std::memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, 16 | MAX_WBITS) != Z_OK) return false;
+  size_t capacity = 1 << 16;
+  if (size >= 18) {
+    uint32_t isize;
+    std::memcpy(&isize, data + size - 4, 4);
+    capacity = std::max<size_t>(capacity, isize);
+  }
+  out->resize(capacity);
+  constexpr size_t kChunk = (size_t)1 << 30;  // zlib counts in 32 bits
+  size_t fed = 0, produced = 0;
+  bool ok = false;
+  while (true) {
+    if (zs.avail_in == 0 && fed < size) {
+      const size_t take = std::min(size - fed, kChunk);
+      zs.next_in = const_cast<Bytef *>(data + fed);
+      zs.avail_in = (uInt)take;
+      fed += take;
+    }
+    if (produced == out->size()) out->resize(out->size() + out->size() / 2);
+    const size_t room = std::min(out->size() - produced, kChunk);
+    zs.next_out = out->data() + produced;
+    zs.avail_out = (uInt)room;
+    const int rc = inflate(&zs, Z_NO_FLUSH);
+    produced += room - zs.avail_out;
+    if (rc == Z_STREAM_END) {
+      ok = true;
+      break;
+    }
+    if (rc == Z_OK) continue;
+    if (rc == Z_BUF_ERROR && (zs.avail_out == 0 || fed < size)) continue;  // wants room or input
+    break;  // corrupt, or the input ended inside the member
+  }
+  inflateEnd(&zs);
+  if (!ok) {
+    out->clear();
+    return false;
+  }
+  out->resize(produced);
+  return true;
+}
+
+bool readFile(const std::string &filename, std::vector<uint8_t> *out) {
+  std::ifstream in(filename, std::ios::binary | std::ios::ate);
+  if (!in.good()) return false;
+  const std::streamoff len = in.tellg();
+  if (len < 0) return false;
+  out->resize((size_t)len);
+  in.seekg(0, std::ios::beg);
+  if (len > 0) in.read(reinterpret_cast<char *>(out->data()), len);
+  return in.good();
+}
+
+}  // namespace
+
+// =================================================================================================
+// the codec: GPU only
+// =================================================================================================
+
+namespace {
+enum class PackStatus { Ok, Rejected, DeviceError };
+PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussians *result);
+}  // namespace
+
+PackedGaussians packGaussians(const GaussianCloud &g, const PackOptions &o) {
+  PackedGaussians packed;
+  if (packImpl(g, o, &packed) != PackStatus::Ok) return {};
+  return packed;
+}
+
+namespace {
+PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussians *result) {
+  PackedGaussians &packed = *result;
+  if (!checkCloudSizes(g)) return PackStatus::Rejected;
+  const size_t n = (size_t)g.numPoints;
+  const size_t shDim = (size_t)shDimOf(g.shDegree);
+  packed.numPoints = g.numPoints;
+  packed.shDegree = g.shDegree;
+  packed.fractionalBits = 12;  // load-spz.cc:270
+  packed.antialiased = g.antialiased;
+  packed.usesQuaternionSmallestThree = true;
+  packed.positions.resize(n * 9);
+  packed.scales.resize(n * 3);
+  packed.rotations.resize(n * 4);
+  packed.alphas.resize(n);
+  packed.colors.resize(n * 3);
+  packed.sh.resize(n * shDim * 3);
+  if (n == 0) return PackStatus::Ok;  // nothing to encode; no device needed (load_spz_test.py:753)
+
+  const SpzB200Cloud in = viewOf(g);
+  SpzB200Packed out = viewOf(packed, SPZB200_STREAM_V3);
+  const std::vector<int32_t> devs = configuredDevices();
+  int rc;
+  if (devs.size() > 1) {
+    rc = spzb200_encode_host_multi(devs.data(), (int32_t)devs.size(), &in, (int32_t)o.from, &out, nullptr);
+  } else {
+    SpzB200Context *ctx = contextFor(devs[0]);
+    if (!ctx) return PackStatus::DeviceError;
+    rc = spzb200_encode_host(ctx, &in, (int32_t)o.from, &out, nullptr);
+  }
+  if (rc != SPZB200_OK) {
+    logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
+    return PackStatus::DeviceError;
+  }
+  return PackStatus::Ok;
+}
+}  // namespace
+
+GaussianCloud unpackGaussians(const PackedGaussians &packed, const UnpackOptions &o) {
+  const int64_t n = packed.numPoints;
+  const int shDim = shDimOf(packed.shDegree);
+  const bool usesFloat16 = packed.usesFloat16();
+  if (n < 0 || packed.shDegree < 0 || packed.shDegree > 3) {
+    // the reference indexes with these unchecked; refusing is the defined version of that
+    logLine("[SPZ ERROR] unpackGaussians: invalid numPoints / shDegree");
+    return {};
+  }
+  if (!checkPackedSizes(packed, n, shDim, usesFloat16)) return {};
+
+  GaussianCloud result;
+  result.numPoints = packed.numPoints;
+  result.shDegree = packed.shDegree;
+  result.antialiased = packed.antialiased;
+  result.positions.resize((size_t)n * 3);
+  result.scales.resize((size_t)n * 3);
+  result.rotations.resize((size_t)n * 4);
+  result.alphas.resize((size_t)n);
+  result.colors.resize((size_t)n * 3);
+  result.sh.resize((size_t)n * shDim * 3);
+  if (n == 0) return result;
+
+  const SpzB200Packed in = viewOf(packed, streamFlavour(usesFloat16, packed.usesQuaternionSmallestThree));
+  SpzB200Cloud out = viewOf(result);
+  const std::vector<int32_t> devs = configuredDevices();
+  int rc;
+  if (devs.size() > 1) {
+    rc = spzb200_decode_host_multi(devs.data(), (int32_t)devs.size(), &in, (int32_t)o.to, &out, nullptr);
+  } else {
+    SpzB200Context *ctx = contextFor(devs[0]);
+    if (!ctx) return {};
+    rc = spzb200_decode_host(ctx, &in, (int32_t)o.to, &out, nullptr);
+  }
+  if (rc != SPZB200_OK) {
+    logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
+    return {};
+  }
+  return result;
+}
+
+// =================================================================================================
+// one-element accessors (load-spz.cc:383-465)
+// =================================================================================================
+
+bool PackedGaussians::usesFloat16() const { return (int64_t)positions.size() == (int64_t)numPoints * 3 * 2; }
+
+// Pure byte gather: the i-th gaussian's bytes, SH de-interleaved per channel and padded with 128
+// (the code of 0.0) up to 15 coefficients.
+PackedGaussian PackedGaussians::at(int32_t i) const {
+  PackedGaussian r;
+  const size_t idx = (size_t)i;
+  const size_t posBytes = usesFloat16() ? 6 : 9, rotBytes = usesQuaternionSmallestThree ? 4 : 3;
+  std::memcpy(r.position.data(), positions.data() + idx * posBytes, posBytes);
+  std::memcpy(r.scale.data(), scales.data() + idx * 3, 3);
+  std::memcpy(r.rotation.data(), rotations.data() + idx * rotBytes, rotBytes);
+  std::memcpy(r.color.data(), colors.data() + idx * 3, 3);
+  r.alpha = alphas[idx];
+  const size_t shDim = (size_t)shDimOf(shDegree);
+  const uint8_t *s = sh.data() + idx * shDim * 3;
+  for (size_t j = 0; j < 15; j++) {
+    const bool have = j < shDim;
+    r.shR[j] = have ? s[3 * j] : 128;
+    r.shG[j] = have ? s[3 * j + 1] : 128;
+    r.shB[j] = have ? s[3 * j + 2] : 128;
+  }
+  return r;
+}
+
+// One gaussian through the same decode kernel as the bulk path (a 1-point degree-3 stream, no
+// flips), then the caller's converter applied as plain multiplications, which is where the
+// reference applies it too (load-spz.cc:391,401,426-428; :377-379 for the quaternion).
+UnpackedGaussian PackedGaussian::unpack(bool usesFloat16, bool usesQuaternionSmallestThree,
+                                        int32_t fractionalBits, const CoordinateConverter &c) const {
+  UnpackedGaussian u;
+  std::memset(&u, 0, sizeof u);
+  uint8_t shBytes[45];
+  for (int j = 0; j < 15; j++) {
+    shBytes[3 * j] = shR[j];
+    shBytes[3 * j + 1] = shG[j];
+    shBytes[3 * j + 2] = shB[j];
+  }
+  float shOut[45], pos[3], rot[4], scl[3], col[3], alp[1];
+  SpzB200Packed in;
+  std::memset(&in, 0, sizeof in);
+  in.num_points = 1;
+  in.sh_degree = 3;
+  in.fractional_bits = fractionalBits;
+  in.version = streamFlavour(usesFloat16, usesQuaternionSmallestThree);
+  in.positions = const_cast<uint8_t *>(position.data());
+  in.scales = const_cast<uint8_t *>(scale.data());
+  in.rotations = const_cast<uint8_t *>(rotation.data());
+  in.alphas = const_cast<uint8_t *>(&alpha);
+  in.colors = const_cast<uint8_t *>(color.data());
+  in.sh = shBytes;
+  SpzB200Cloud out;
+  std::memset(&out, 0, sizeof out);
+  out.num_points = 1;
+  out.sh_degree = 3;
+  out.positions = pos; out.scales = scl; out.rotations = rot; out.alphas = alp; out.colors = col; out.sh = shOut;
+  SpzB200Context *ctx = contextFor(configuredDevices()[0]);
+  if (!ctx || spzb200_decode_host(ctx, &in, SPZB200_COORD_UNSPECIFIED, &out, nullptr) != SPZB200_OK) {
+    if (ctx) logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
+    return u;
+  }
+  for (int a = 0; a < 3; a++) {
+    u.position[a] = c.flipP[a] * pos[a];
+    u.scale[a] = scl[a];
+    u.color[a] = col[a];
+    u.rotation[a] = rot[a] * c.flipQ[a];
+  }
+  u.rotation[3] = rot[3];
+  u.alpha = alp[0];
+  for (int j = 0; j < 15; j++) {
+    u.shR[j] = c.flipSh[j] * shOut[3 * j];
+    u.shG[j] = c.flipSh[j] * shOut[3 * j + 1];
+    u.shB[j] = c.flipSh[j] * shOut[3 * j + 2];
+  }
+  return u;
+}
+
+UnpackedGaussian PackedGaussians::unpack(int32_t i, const CoordinateConverter &c) const {
+  return at(i).unpack(usesFloat16(), usesQuaternionSmallestThree, fractionalBits, c);
+}
+
+// =================================================================================================
+// container + gzip + files
+// =================================================================================================
+
+void serializePackedGaussians(const PackedGaussians &packed, std::ostream *out) {
+  uint8_t header[kHeaderBytes];
+  writeHeader(packed, header);
+  out->write(reinterpret_cast<const char *>(header), kHeaderBytes);
+  for (int i = 0; i < 6; i++) {
+    const std::vector<uint8_t> *v = streamOrder(packed, i);
+    out->write(reinterpret_cast<const char *>(v->data()), (std::streamsize)v->size());
+  }
+}
+
+// zlib deflate with the reference's parameters (default level, gzip wrapper, memLevel 9,
+// load-spz.cc:186-214), so the compressed bytes are the same for the same input.
+bool compressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out) {
+  z_stream zs;
+  std::memset(&zs, 0, sizeof zs);
+  if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 16 + MAX_WBITS, 9, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+  out->clear();
+  out->resize(std::max<size_t>(size / 4, 4096));
+  size_t produced = 0, consumed = 0;
+  bool ok = false;
+  while (true) {
+    const size_t inChunk = std::min<size_t>(size - consumed, (size_t)1 << 30);
+    const bool last = consumed + inChunk == size;
+    zs.next_in = const_cast<Bytef *>(reinterpret_cast<const Bytef *>(data) + consumed);
+    zs.avail_in = (uInt)inChunk;
+    if (produced == out->size()) out->resize(out->size() * 2);
+    const size_t outChunk = std::min<size_t>(out->size() - produced, (size_t)1 << 30);
+    zs.next_out = out->data() + produced;
+    zs.avail_out = (uInt)outChunk;
+    const int rc = deflate(&zs, last ? Z_FINISH : Z_NO_FLUSH);
+    consumed += inChunk - zs.avail_in;
+    produced += outChunk - zs.avail_out;
+    if (rc == Z_STREAM_END) {
+      ok = true;
+      break;
+    }
+    if (rc != Z_OK && rc != Z_BUF_ERROR) break;
+  }
+  deflateEnd(&zs);
+  if (!ok) {
+    out->clear();
+    return false;
+  }
+  out->resize(produced);
+  return true;
+}
+
+bool saveSpz(const GaussianCloud &g, const PackOptions &o, std::vector<uint8_t> *out) {
+  std::vector<uint8_t> stream;
+  {
+    PackedGaussians packed;
+    const PackStatus st = packImpl(g, o, &packed);
+    if (st == PackStatus::DeviceError) return false;  // no GPU: fail loudly, never write a file
+    // A cloud the size checks reject yields the empty struct, which the reference goes on to
+    // serialize as a 0-point file (load-spz.cc:598-607); same here.
+    if (st == PackStatus::Rejected) packed = PackedGaussians{};
+    stream.resize(serializedBytes(packed));
+    serializeInto(packed, stream.data());
+  }
+  return compressGzipped(stream.data(), stream.size(), out);
+}
+
+bool saveSpz(const GaussianCloud &g, const PackOptions &o, const std::string &filename) {
+  std::vector<uint8_t> bytes;
+  if (!saveSpz(g, o, &bytes)) return false;
+  std::ofstream out(filename, std::ios::binary | std::ios::out);
+  out.write(reinterpret_cast<const char *>(bytes.data()), (std::streamsize)bytes.size());
+  out.close();
+  return out.good();
+}
+
+PackedGaussians loadSpzPacked(const uint8_t *data, int32_t size) {
+  std::vector<uint8_t> stream;
+  if (size < 0 || !gunzip(data, (size_t)size, &stream)) return {};
+  return deserialize(stream.data(), stream.size());
+}
+
+PackedGaussians loadSpzPacked(const std::vector<uint8_t> &data) {
+  return loadSpzPacked(data.data(), static_cast<int>(data.size()));
+}
+
+PackedGaussians loadSpzPacked(const std::string &filename) {
+  std::vector<uint8_t> data;
+  if (!readFile(filename, &data)) return {};
+  return loadSpzPacked(data);
+}
+
+GaussianCloud loadSpz(const std::vector<uint8_t> &data, const UnpackOptions &o) {
+  return unpackGaussians(loadSpzPacked(data), o);
+}
+
+GaussianCloud loadSpz(const uint8_t *data, int32_t size, const UnpackOptions &o) {
+  return unpackGaussians(loadSpzPacked(data, size), o);
+}
+
+GaussianCloud loadSpz(const std::string &filename, const UnpackOptions &o) {
+  std::vector<uint8_t> data;
+  std::ifstream probe(filename, std::ios::binary);
+  if (!probe.good()) {
+    logLine("[SPZ ERROR] Unable to open: %s", filename.c_str());
+    return {};
+  }
+  probe.close();
+  if (!readFile(filename, &data)) {
+    logLine("[SPZ ERROR] Unable to load data from: %s", filename.c_str());
+    return {};
+  }
+  return loadSpz(data, o);
+}
+
+// =================================================================================================
+// small math (splat-types.cc)
+// =================================================================================================
+
+// IEEE binary16 -> binary32 by bit manipulation; every half value is exactly representable.
+float halfToFloat(Half h) {
+  const uint32_t sign = (uint32_t)(h >> 15) << 31, e = (h >> 10) & 0x1fu, mant = h & 0x3ffu;
+  uint32_t bits;
+  if (e == 0) {
+    const float v = std::ldexp((float)mant, -24);  // subnormal half
+    std::memcpy(&bits, &v, 4);
+    bits |= sign;
+  } else if (e == 31) {
+    if (mant) return std::numeric_limits<float>::quiet_NaN();
+    bits = sign | 0x7f800000u;
+  } else {
+    bits = sign | ((e + 112u) << 23) | (mant << 13);
+  }
+  float f;
+  std::memcpy(&f, &bits, 4);
+  return f;
+}
+
+// binary32 -> binary16 with truncation of the mantissa, the reference's conversion
+// (splat-types.cc:30-60): NaN -> 0x7c01 | sign, overflow -> Inf, tiny values flush through the
+// subnormal range by shifting.
+Half floatToHalf(float f) {
+  uint32_t b;
+  std::memcpy(&b, &f, 4);
+  const uint32_t sign = (b >> 16) & 0x8000u;
+  const int32_t e = (int32_t)((b >> 23) & 0xffu);
+  const uint32_t mant = b & 0x7fffffu;
+  if (e == 0xff) return (Half)(sign | (mant ? 0x7c01u : 0x7c00u));
+  const int32_t unbiased = e - 127;
+  if (unbiased > 15) return (Half)(sign | 0x7c00u);
+  if (unbiased > -15) return (Half)(sign | (uint32_t)((unbiased + 15) << 10) | (mant >> 13));
+  const int32_t shift = -(unbiased + 14);
+  const uint32_t full = 0x800000u | mant;
+  // For |f| < 2^-32 the reference shifts a 32-bit value by 32..113 places, which C leaves
+  // undefined; its x86-64 build takes the count modulo 32 (SHR/SAR), and so does this.
+  const uint32_t shifted = full >> (shift & 31);
+  return (Half)(sign | (shifted >> 13));
+}
+
+float norm(const Vec3f &a) { return std::sqrt(squaredNorm(a)); }
+
+Vec3f normalized(const Vec3f &v) {
+  const float n = norm(v);
+  return {v[0] / n, v[1] / n, v[2] / n};
+}
+
+float norm(const Quat4f &q) { return std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]); }
+
+Quat4f normalized(const Quat4f &v) {
+  const float n = norm(v);
+  return {v[0] / n, v[1] / n, v[2] / n, v[3] / n};
+}
+
+Quat4f axisAngleQuat(const Vec3f &scaledAxis) {
+  const float t2 = squaredNorm(scaledAxis);
+  float c = 1.0f, k = 0.5f;  // first-order series at the origin, where sin(t/2)/t -> 1/2
+  if (t2 > 0.0f) {
+    const float t = std::sqrt(t2);
+    c = std::cos(0.5f * t);
+    k = std::sin(0.5f * t) / t;
+  }
+  return normalized(Quat4f{c, scaledAxis[0] * k, scaledAxis[1] * k, scaledAxis[2] * k});
+}
+
+}  // namespace spz

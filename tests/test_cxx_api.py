@@ -1,0 +1,444 @@
+"""The drop-in C++ API (include/spz_b200/spz.hpp, spz_b200/csrc/spz_api.cc) against the reference's
+own C++ through one consumer source compiled against both (tests/cxx/api_shim.cc).
+
+not-gpu tests: everything that is host glue in both implementations -- container writer/reader and
+plane order, gzip bytes, loadSpzPacked of v1/v2/v3 files, PackedGaussians::at, coordinateConverter,
+convertCoordinates, medianVolume, data(), half conversions, small math, error behaviour, and that
+the codec entry points fail loudly without a device.
+gpu tests: packGaussians / unpackGaussians / saveSpz / loadSpz / unpack(i) vs the reference, bit for bit."""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import SH_DIM, Cloud, Packed, bits
+from util import PLANES, assert_cloud_bits_equal, assert_packed_equal, random_cloud, random_stream
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CXX = os.path.join(ROOT, "tests", "cxx")
+
+_f32p, _u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+
+
+class Shim:
+    """ctypes front end of one build of tests/cxx/api_shim.cc."""
+
+    def __init__(self, prefix: str):
+        self.prefix = prefix
+        so = os.path.join(CXX, "_build", f"libshim_{prefix}.so")
+        target = "all" if prefix == "b200" else "ref"
+        can_build = prefix == "b200" or os.path.isdir("/root/reference/src/cc")
+        if can_build:
+            from spz_b200 import _native
+            _native.lib()  # make sure libspz_b200.so exists before linking against it
+            subprocess.run(["make", "-s", "-C", CXX, target], check=True)
+        if not os.path.exists(so):
+            pytest.skip(f"{so} not built and cannot be built here")
+        self.lib = C.CDLL(so)
+        for name, res in (("save_spz", C.c_void_p), ("load_spz", C.c_void_p), ("load_spz_file", C.c_void_p),
+                          ("load_packed", C.c_void_p), ("serialize", C.c_void_p), ("gzip", C.c_void_p),
+                          ("cloud_ops", C.c_float)):
+            self.fn(name).restype = res
+
+    def fn(self, name):
+        return getattr(self.lib, f"{self.prefix}_{name}")
+
+    @staticmethod
+    def _fplanes(arrs):
+        arrs = [np.ascontiguousarray(a, np.float32).reshape(-1) for a in arrs]
+        return arrs, (_f32p * 6)(*[a.ctypes.data_as(_f32p) for a in arrs])
+
+    @staticmethod
+    def _bplanes(arrs):
+        arrs = [np.ascontiguousarray(a, np.uint8).reshape(-1) for a in arrs]
+        return arrs, (_u8p * 6)(*[a.ctypes.data_as(_u8p) for a in arrs])
+
+    def _take(self, ptr, size):
+        try:
+            return C.string_at(ptr, size.value)
+        finally:
+            self.fn("free")(C.c_void_p(ptr))
+
+    # ---- codec ------------------------------------------------------------------------------
+    def pack(self, c: Cloud, frm=0):
+        d = SH_DIM.get(c.sh_degree, 0) * 3
+        out = [np.zeros(c.n * w, np.uint8) for w in (9, 3, 4, 1, 3, d)]
+        _, ip = self._fplanes(c.planes())
+        _, op = self._bplanes(out)
+        meta = (C.c_int32 * 5)()
+        rc = self.fn("pack")(C.c_int32(c.n), C.c_int32(c.sh_degree), C.c_int32(frm), ip, op, meta)
+        return rc, Packed(c.n, c.sh_degree, meta[2], 3, *out), list(meta)
+
+    def unpack(self, p: Packed, to=0):
+        d = SH_DIM.get(p.sh_degree, 0) * 3
+        out = [np.zeros(p.n * w, np.float32) for w in (3, 3, 4, 1, 3, d)]
+        _, ip = self._bplanes(p.planes())
+        _, op = self._fplanes(out)
+        # _fplanes copies; rebuild pointer table over the real outputs
+        op = (_f32p * 6)(*[a.ctypes.data_as(_f32p) for a in out])
+        meta = (C.c_int32 * 3)()
+        rc = self.fn("unpack")(C.c_int32(p.n), C.c_int32(p.sh_degree), C.c_int32(p.fractional_bits), C.c_int32(p.version),
+                               C.c_int32(to), ip, op, meta)
+        return rc, Cloud(p.n, p.sh_degree, *out), list(meta)
+
+    def save_spz(self, c: Cloud, frm=0):
+        _, ip = self._fplanes(c.planes())
+        size = C.c_uint64(0)
+        ptr = self.fn("save_spz")(C.c_int32(c.n), C.c_int32(c.sh_degree), C.c_int32(int(c.antialiased)), C.c_int32(frm), ip, C.byref(size))
+        return None if not ptr else self._take(ptr, size)
+
+    def save_spz_file(self, c: Cloud, path: str, frm=0) -> bool:
+        _, ip = self._fplanes(c.planes())
+        return bool(self.fn("save_spz_file")(C.c_int32(c.n), C.c_int32(c.sh_degree), C.c_int32(int(c.antialiased)), C.c_int32(frm), ip, path.encode()))
+
+    def _cloud_from_handle(self, h):
+        try:
+            m = (C.c_int64 * 9)()
+            self.fn("cloud_info")(C.c_void_p(h), m)
+            out = [np.zeros(m[3 + k], np.float32) for k in range(6)]
+            op = (_f32p * 6)(*[a.ctypes.data_as(_f32p) for a in out])
+            self.fn("cloud_copy")(C.c_void_p(h), op)
+            return Cloud(int(m[0]), int(m[1]), *out, antialiased=bool(m[2]))
+        finally:
+            self.fn("cloud_free")(C.c_void_p(h))
+
+    def load_spz(self, blob: bytes, to=0, via_vector=False) -> Cloud:
+        buf = np.frombuffer(blob, np.uint8)
+        h = self.fn("load_spz")(buf.ctypes.data_as(_u8p), C.c_int32(buf.size), C.c_int32(to), C.c_int32(int(via_vector)))
+        return self._cloud_from_handle(h)
+
+    def load_spz_file(self, path: str, to=0) -> Cloud:
+        return self._cloud_from_handle(self.fn("load_spz_file")(path.encode(), C.c_int32(to)))
+
+    # ---- host glue --------------------------------------------------------------------------
+    def load_packed(self, blob: bytes, which=0):
+        buf = np.frombuffer(blob, np.uint8) if blob else np.zeros(0, np.uint8)
+        h = self.fn("load_packed")(buf.ctypes.data_as(_u8p), C.c_int32(buf.size), C.c_int32(which))
+        try:
+            m = (C.c_int64 * 12)()
+            self.fn("packed_info")(C.c_void_p(h), m)
+            out = [np.zeros(m[6 + k], np.uint8) for k in range(6)]
+            op = (_u8p * 6)(*[a.ctypes.data_as(_u8p) for a in out])
+            self.fn("packed_copy")(C.c_void_p(h), op)
+            return dict(n=int(m[0]), deg=int(m[1]), fb=int(m[2]), aa=bool(m[3]), s3=bool(m[4]), half=bool(m[5])), out
+        finally:
+            self.fn("packed_free")(C.c_void_p(h))
+
+    def serialize(self, p: Packed) -> bytes:
+        _, ip = self._bplanes(p.planes())
+        size = C.c_uint64(0)
+        ptr = self.fn("serialize")(C.c_int32(p.n), C.c_int32(p.sh_degree), C.c_int32(p.fractional_bits), C.c_int32(p.version),
+                                   C.c_int32(int(p.antialiased)), ip, C.byref(size))
+        return self._take(ptr, size)
+
+    def gzip(self, data: bytes):
+        buf = np.frombuffer(data, np.uint8) if data else np.zeros(0, np.uint8)
+        size = C.c_uint64(0)
+        ptr = self.fn("gzip")(buf.ctypes.data_as(_u8p), C.c_uint64(buf.size), C.byref(size))
+        return None if not ptr else self._take(ptr, size)
+
+    def at(self, p: Packed, i: int) -> np.ndarray:
+        _, ip = self._bplanes(p.planes())
+        out = np.zeros(65, np.uint8)
+        self.fn("packed_at")(C.c_int32(p.n), C.c_int32(p.sh_degree), C.c_int32(p.fractional_bits), C.c_int32(p.version), ip, C.c_int32(i), out.ctypes.data_as(_u8p))
+        return out
+
+    def unpack_one(self, p: Packed, i: int, frm: int, to: int) -> np.ndarray:
+        _, ip = self._bplanes(p.planes())
+        out = np.zeros(59, np.float32)
+        self.fn("packed_unpack_one")(C.c_int32(p.n), C.c_int32(p.sh_degree), C.c_int32(p.fractional_bits), C.c_int32(p.version), ip,
+                                     C.c_int32(i), C.c_int32(frm), C.c_int32(to), out.ctypes.data_as(_f32p))
+        return out
+
+    def converter(self, frm, to) -> np.ndarray:
+        out = np.zeros(21, np.float32)
+        self.fn("converter")(C.c_int32(frm), C.c_int32(to), out.ctypes.data_as(_f32p))
+        return out
+
+    def cloud_ops(self, c: Cloud, frm, to):
+        arrs = [np.ascontiguousarray(a, np.float32).copy() for a in c.planes()]
+        ip = (_f32p * 6)(*[a.ctypes.data_as(_f32p) for a in arrs])
+        vol = self.fn("cloud_ops")(C.c_int32(c.n), C.c_int32(c.sh_degree), C.c_int32(frm), C.c_int32(to), ip)
+        return Cloud(c.n, c.sh_degree, *arrs), float(vol)
+
+    def half_tables(self, samples: np.ndarray):
+        to_float = np.zeros(65536, np.float32)
+        samples = np.ascontiguousarray(samples, np.float32)
+        to_half = np.zeros(samples.size, np.uint16)
+        self.fn("half_tables")(to_float.ctypes.data_as(_f32p), samples.ctypes.data_as(_f32p), C.c_int32(samples.size),
+                               to_half.ctypes.data_as(C.POINTER(C.c_uint16)))
+        return to_float, to_half
+
+    def math(self, axis, qa, qb, v) -> np.ndarray:
+        a = [np.ascontiguousarray(x, np.float32) for x in (axis, qa, qb, v)]
+        out = np.zeros(16, np.float32)
+        self.fn("math")(*[x.ctypes.data_as(_f32p) for x in a], out.ctypes.data_as(_f32p))
+        return out
+
+
+@pytest.fixture(scope="module")
+def mine():
+    return Shim("b200")
+
+
+@pytest.fixture(scope="module")
+def theirs():
+    return Shim("ref")
+
+
+def container(p: Packed, version=None, n_override=None, magic=0x5053474e) -> bytes:
+    """Header + planes in stream order, written by hand (load-spz.cc:131-139, 533-546)."""
+    ver = p.version if version is None else version
+    hdr = struct.pack("<IIIBBBB", magic, ver, p.n if n_override is None else n_override, p.sh_degree, p.fractional_bits & 255,
+                      1 if p.antialiased else 0, 0)
+    return hdr + b"".join(np.ascontiguousarray(a).tobytes() for a in (p.positions, p.alphas, p.colors, p.scales, p.rotations, p.sh))
+
+
+# =================================================================================================
+# host glue (no GPU)
+# =================================================================================================
+
+@pytest.mark.parametrize("ver", [1, 2, 3])
+def test_serialize_and_gzip_bytes_match_reference(mine, theirs, ver):
+    rng = np.random.default_rng(ver)
+    p = random_stream(rng, 1000, 2, ver, 12)
+    p.antialiased = bool(ver % 2)
+    a, b = mine.serialize(p), theirs.serialize(p)
+    assert a == b
+    assert a[:4] == b"NGSP" and a[4] == 3  # the writer always stamps version 3 (load-spz.cc:133)
+    assert a[16:] == container(p)[16:]
+    for data in (a, b"", b"x" * 100000, rng.integers(0, 256, 300000).astype(np.uint8).tobytes()):
+        za, zb = mine.gzip(data), theirs.gzip(data)
+        assert za == zb
+        assert gzip.decompress(za) == data
+
+
+@pytest.mark.parametrize("ver", [1, 2, 3])
+@pytest.mark.parametrize("which", [0, 1])
+def test_load_packed_all_versions(mine, theirs, ver, which):
+    rng = np.random.default_rng(10 + ver)
+    for deg in range(4):
+        p = random_stream(rng, 333, deg, ver, 11)
+        p.antialiased = True
+        blob = gzip.compress(container(p), 6)
+        ma, pa = mine.load_packed(blob, which)
+        mb, pb = theirs.load_packed(blob, which)
+        assert ma == mb == dict(n=333, deg=deg, fb=11, aa=True, s3=ver >= 3, half=ver == 1)
+        for x, y, z in zip(pa, pb, p.planes()):
+            assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
+def test_load_packed_rejects_what_the_reference_rejects(mine, theirs, tmp_path):
+    rng = np.random.default_rng(20)
+    p = random_stream(rng, 50, 1, 3)
+    good = container(p)
+    empty = dict(n=0, deg=0, fb=0, aa=False, s3=True, half=True)  # a default PackedGaussians
+    cases = {
+        "not gzip": good,
+        "empty input": b"",
+        "truncated gzip": gzip.compress(good)[:40],
+        "bad magic": gzip.compress(container(p, magic=0x12345678)),
+        "version 0": gzip.compress(container(p, version=0)),
+        "version 4": gzip.compress(container(p, version=4)),
+        "sh degree 4": gzip.compress(good[:12] + bytes([4]) + good[13:]),
+        "short planes": gzip.compress(good[:-7]),
+        "short header": gzip.compress(good[:9]),
+        "count larger than data": gzip.compress(container(p, n_override=51)),
+    }
+    for name, blob in cases.items():
+        ma, _ = mine.load_packed(blob)
+        mb, _ = theirs.load_packed(blob)
+        assert ma == mb == empty, name
+    # trailing bytes after the planes are ignored by both
+    ma, pa = mine.load_packed(gzip.compress(good + b"tail"))
+    mb, pb = theirs.load_packed(gzip.compress(good + b"tail"))
+    assert ma == mb and ma["n"] == 50 and all(np.array_equal(x, y) for x, y in zip(pa, pb))
+    # file variant: missing file -> empty; real file -> same as bytes
+    path = str(tmp_path / "a.spz")
+    assert mine.load_packed(path.encode(), 2)[0] == empty
+    open(path, "wb").write(gzip.compress(good))
+    assert mine.load_packed(path.encode(), 2)[0] == theirs.load_packed(path.encode(), 2)[0] == ma
+
+
+def test_point_cap_is_lifted_and_restorable(mine, theirs):
+    """Documented divergence: the reference refuses > 10,000,000 points (load-spz.cc:549)."""
+    n = 10_000_001
+    z = lambda k: np.zeros(k, np.uint8)  # noqa: E731
+    p = Packed(n, 0, 12, 3, z(9 * n), z(3 * n), z(4 * n), z(n), z(3 * n), z(0))
+    blob = gzip.compress(container(p), 1)
+    assert theirs.load_packed(blob)[0]["n"] == 0
+    assert mine.load_packed(blob)[0]["n"] == n
+    os.environ["SPZ_B200_MAX_POINTS"] = "10000000"
+    try:
+        assert mine.load_packed(blob)[0]["n"] == 0
+    finally:
+        del os.environ["SPZ_B200_MAX_POINTS"]
+
+
+def test_at_gathers_the_same_65_bytes(mine, theirs):
+    rng = np.random.default_rng(30)
+    for ver in (1, 2, 3):
+        for deg in range(4):
+            p = random_stream(rng, 17, deg, ver)
+            for i in (0, 5, 16):
+                a, b = mine.at(p, i), theirs.at(p, i)
+                if ver == 1:  # only 6 of the 9 position bytes are defined for float16 positions
+                    a[6:9] = b[6:9] = 0
+                if ver < 3:   # and 3 of the 4 rotation bytes
+                    a[12] = b[12] = 0
+                assert np.array_equal(a, b), (ver, deg, i)
+
+
+def test_converter_cloud_ops_and_math(mine, theirs):
+    for frm in range(9):
+        for to in range(9):
+            assert np.array_equal(bits(mine.converter(frm, to)), bits(theirs.converter(frm, to)))
+    rng = np.random.default_rng(40)
+    for deg in range(4):
+        c = random_cloud(rng, 501, deg, True)
+        for frm, to in ((4, 6), (6, 7), (0, 8), (1, 8), (5, 5)):
+            (ca, va), (cb, vb) = mine.cloud_ops(c, frm, to), theirs.cloud_ops(c, frm, to)
+            assert_cloud_bits_equal(ca, cb, f"convertCoordinates deg{deg} {frm}->{to}")
+            assert va == vb or (np.isnan(va) and np.isnan(vb))
+    empty = Cloud(0, 0, *[np.zeros(0, np.float32)] * 6)
+    assert mine.cloud_ops(empty, 4, 6)[1] == theirs.cloud_ops(empty, 4, 6)[1] == np.float32(0.01)
+    samples = np.concatenate([rng.normal(size=5000).astype(np.float32) * np.float32(10.0) ** rng.integers(-12, 8, 5000).astype(np.float32),
+                              np.array([0, -0.0, np.inf, -np.inf, np.nan, 65504, 65520, 1e-8, 6e-8, 6.1e-5, -6.1e-5, 1e-45], np.float32)])
+    (fa, ha), (fb, hb) = mine.half_tables(samples), theirs.half_tables(samples)
+    assert np.array_equal(bits(fa), bits(fb)) and np.array_equal(ha, hb)
+    for _ in range(20):
+        axis, qa, qb, v = (rng.normal(size=k).astype(np.float32) for k in (3, 4, 4, 3))
+        assert np.array_equal(bits(mine.math(axis, qa, qb, v)), bits(theirs.math(axis, qa, qb, v)))
+    z3 = np.zeros(3, np.float32)
+    assert np.array_equal(bits(mine.math(z3, qa, qb, v)), bits(theirs.math(z3, qa, qb, v)))
+
+
+def test_size_checks_and_empty_cloud_need_no_device(mine, theirs):
+    """Rejections happen before any device work, so they behave the same with and without a GPU."""
+    rng = np.random.default_rng(50)
+    c = random_cloud(rng, 10, 1, False)
+    bad = Cloud(10, 1, c.positions, c.scales, c.rotations, c.alphas, c.colors, c.sh[:-3])
+    # the shim's makeCloud assigns by the declared sizes, so build the mismatch through sh_degree
+    wrong_degree = Cloud(10, 4, *c.planes())
+    for cloud in (wrong_degree,):
+        ra, _, ma = mine.pack(cloud, 0)
+        rb, _, mb = theirs.pack(cloud, 0)
+        assert ra == rb == 1 and ma == mb
+    del bad
+    # empty cloud: packs to an empty v3 struct and saves to the reference's bytes, no GPU touched
+    empty = Cloud(0, 0, *[np.zeros(0, np.float32)] * 6, antialiased=True)
+    ra, pa, ma = mine.pack(empty, 6)
+    rb, pb, mb = theirs.pack(empty, 6)
+    assert ra == rb == 0 and ma == mb == [0, 0, 12, 1, 1]
+    assert mine.save_spz(empty, 6) == theirs.save_spz(empty, 6)
+    g = mine.load_spz(theirs.save_spz(empty, 6), 8)
+    assert g.n == 0 and g.antialiased
+    # garbage in -> empty cloud out, no exception (load_spz_test.py:842-863)
+    assert mine.load_spz(b"garbage", 0).n == 0
+    assert mine.load_spz_file("/nonexistent/file.spz", 0).n == 0
+
+
+def test_codec_fails_loudly_without_a_device(mine):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    rng = np.random.default_rng(60)
+    c = random_cloud(rng, 10, 1, False)
+    rc, _, meta = mine.pack(c, 0)
+    assert rc == 1 and meta[0] == 0          # empty struct, like any rejected call
+    assert mine.save_spz(c, 0) is None       # and saveSpz returns false rather than writing an empty file
+    p = random_stream(rng, 10, 1, 3)
+    rc, _, meta = mine.unpack(p, 0)
+    assert rc == 1 and meta[0] == 0
+
+
+# =================================================================================================
+# the codec through the C++ API (GPU)
+# =================================================================================================
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_pack_unpack_match_reference(mine, theirs, deg):
+    rng = np.random.default_rng(100 + deg)
+    for special in (False, True):
+        c = random_cloud(rng, 20011, deg, special)
+        for frm in (0, 4, 6, 7, 8):
+            (ra, pa, ma), (rb, pb, mb) = mine.pack(c, frm), theirs.pack(c, frm)
+            assert ra == rb == 0 and ma == mb
+            assert_packed_equal(pa, pb, f"deg{deg} from{frm}")
+        for to in (0, 4, 6, 7, 8):
+            (ra, ga, ma), (rb, gb, mb) = mine.unpack(pb, to), theirs.unpack(pb, to)
+            assert ra == rb == 0 and ma == mb
+            assert_cloud_bits_equal(ga, gb, f"deg{deg} to{to}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ver", [1, 2, 3, 4])
+def test_unpack_legacy_flavours(mine, theirs, ver):
+    rng = np.random.default_rng(200 + ver)
+    for fb in (12, 7):
+        s = random_stream(rng, 7001, 2, ver, fb)
+        for to in (0, 7):
+            (ra, ga, _), (rb, gb, _) = mine.unpack(s, to), theirs.unpack(s, to)
+            assert ra == rb == 0
+            assert_cloud_bits_equal(ga, gb, f"v{ver} fb{fb} to{to}")
+
+
+@pytest.mark.gpu
+def test_save_load_spz_bytes_and_files(mine, theirs, tmp_path):
+    rng = np.random.default_rng(300)
+    for deg in (0, 3):
+        c = random_cloud(rng, 5003, deg, False)
+        c.antialiased = True
+        blob_a, blob_b = mine.save_spz(c, 6), theirs.save_spz(c, 6)
+        assert blob_a == blob_b  # same planes, same container, same zlib parameters
+        for via_vector in (False, True):
+            ga, gb = mine.load_spz(blob_b, 8, via_vector), theirs.load_spz(blob_b, 8, via_vector)
+            assert ga.n == gb.n == 5003 and ga.antialiased and ga.sh_degree == deg
+            assert_cloud_bits_equal(ga, gb, "loadSpz")
+        pa, pb = str(tmp_path / "a.spz"), str(tmp_path / "b.spz")
+        assert mine.save_spz_file(c, pa, 6) and theirs.save_spz_file(c, pb, 6)
+        assert open(pa, "rb").read() == open(pb, "rb").read()
+        assert_cloud_bits_equal(mine.load_spz_file(pb, 7), theirs.load_spz_file(pb, 7), "loadSpz(file)")
+        assert not mine.save_spz_file(c, "/nonexistent_dir/x.spz", 0)
+
+
+@pytest.mark.gpu
+def test_unpack_one_matches_reference(mine, theirs):
+    rng = np.random.default_rng(400)
+    for ver in (1, 2, 3):
+        for deg in (0, 2, 3):
+            s = random_stream(rng, 9, deg, ver, 12)
+            if ver == 3:
+                # keep smallest-three payloads valid so sqrt(1 - sum) is a number in both
+                comp = s.rotations.view("<u4")
+                comp &= np.uint32(0xDFF7FDFF)
+            for i in (0, 8):
+                for frm, to in ((0, 0), (4, 6), (4, 7)):
+                    a, b = mine.unpack_one(s, i, frm, to), theirs.unpack_one(s, i, frm, to)
+                    assert np.array_equal(bits(a), bits(b)), (ver, deg, i, frm, to)
+
+
+@pytest.mark.gpu
+def test_reference_suite_fixture_roundtrip(mine, theirs):
+    """The reference test-suite's canonical 2-gaussian fixture (load_spz_test.py:72-147) through
+    saveSpz -> loadSpz, with its tolerances, and bit-equality with the reference itself."""
+    c = Cloud(2, 3, np.array([0, .1, -.2, .3, .4, .5], np.float32), np.array([-3, -2, -1.5, -1, 0, .1], np.float32),
+              np.array([-.5, .2, 1, -.2, .1, -.4, -.3, .5], np.float32), np.array([-1, 1], np.float32),
+              np.array([-1, 0, 1, -.5, .5, .1], np.float32), (np.arange(90, dtype=np.float32) / 45.0 - 1.0).astype(np.float32), True)
+    blob = mine.save_spz(c, 0)
+    assert len(blob) == 126 and blob == theirs.save_spz(c, 0)
+    g = mine.load_spz(blob, 0)
+    assert g.n == 2 and g.sh_degree == 3 and g.antialiased
+    assert np.allclose(g.positions, c.positions, atol=1 / 2048)
+    assert np.allclose(g.scales, c.scales, atol=1 / 32)
+    assert np.allclose(g.alphas, c.alphas, atol=0.01 * 8)
+    assert np.allclose(g.sh, np.clip(c.sh, -1, 0.9922), atol=2 / 32 + 0.5 / 255)
+    assert_cloud_bits_equal(g, theirs.load_spz(blob, 0), "fixture")

@@ -37,7 +37,7 @@ def random_cloud(rng, n, deg, special=False) -> Cloud:
 def random_stream(rng, n, deg, ver, fb=12) -> Packed:
     d = SH_DIM[deg] * 3
     r = lambda k: rng.integers(0, 256, k).astype(np.uint8)  # noqa: E731
-    return Packed(n, deg, fb, ver, r(n * (6 if ver == 1 else 9)), r(n * 3), r(n * (4 if ver == 3 else 3)),
+    return Packed(n, deg, fb, ver, r(n * (6 if ver in (1, 4) else 9)), r(n * 3), r(n * (4 if ver >= 3 else 3)),
                   r(n), r(n * 3), r(n * d))
 
 
