@@ -146,6 +146,21 @@ void SHIM(cloud_copy)(const CloudHandle *h, float *const out[6]) {
 }
 void SHIM(cloud_free)(CloudHandle *h) { delete h; }
 
+int SHIM(save_ply)(int32_t n, int32_t deg, int32_t from, const float *const planes[6], const char *path) {
+  const spz::GaussianCloud g = makeCloud(n, deg, 0, planes);
+  spz::PackOptions o;
+  o.from = (spz::CoordinateSystem)from;
+  return spz::saveSplatToPly(g, o, std::string(path)) ? 1 : 0;
+}
+
+CloudHandle *SHIM(load_ply)(const char *path, int32_t to) {
+  spz::UnpackOptions o;
+  o.to = (spz::CoordinateSystem)to;
+  auto *h = new CloudHandle;
+  h->g = spz::loadSplatFromPly(std::string(path), o);
+  return h;
+}
+
 // ---- host glue, no GPU involved ------------------------------------------------------------------
 // which: 0 = bytes, 1 = vector, 2 = file (data = path)
 PackedHandle *SHIM(load_packed)(const uint8_t *data, int32_t size, int32_t which) {

@@ -42,7 +42,7 @@ class Shim:
         if not os.path.exists(so):
             pytest.skip(f"{so} not built and cannot be built here")
         self.lib = C.CDLL(so)
-        for name, res in (("save_spz", C.c_void_p), ("load_spz", C.c_void_p), ("load_spz_file", C.c_void_p),
+        for name, res in (("save_spz", C.c_void_p), ("load_spz", C.c_void_p), ("load_spz_file", C.c_void_p), ("load_ply", C.c_void_p),
                           ("load_packed", C.c_void_p), ("serialize", C.c_void_p), ("gzip", C.c_void_p),
                           ("cloud_ops", C.c_float)):
             self.fn(name).restype = res
@@ -116,6 +116,13 @@ class Shim:
 
     def load_spz_file(self, path: str, to=0) -> Cloud:
         return self._cloud_from_handle(self.fn("load_spz_file")(path.encode(), C.c_int32(to)))
+
+    def save_ply(self, c: Cloud, path: str, frm=0) -> bool:
+        _, ip = self._fplanes(c.planes())
+        return bool(self.fn("save_ply")(C.c_int32(c.n), C.c_int32(c.sh_degree), C.c_int32(frm), ip, path.encode()))
+
+    def load_ply(self, path: str, to=0) -> Cloud:
+        return self._cloud_from_handle(self.fn("load_ply")(path.encode(), C.c_int32(to)))
 
     # ---- host glue --------------------------------------------------------------------------
     def load_packed(self, blob: bytes, which=0):
@@ -318,6 +325,44 @@ def test_converter_cloud_ops_and_math(mine, theirs):
         assert np.array_equal(bits(mine.math(axis, qa, qb, v)), bits(theirs.math(axis, qa, qb, v)))
     z3 = np.zeros(3, np.float32)
     assert np.array_equal(bits(mine.math(z3, qa, qb, v)), bits(theirs.math(z3, qa, qb, v)))
+
+
+def test_ply_io_matches_reference(mine, theirs, tmp_path):
+    rng = np.random.default_rng(70)
+    for deg in range(4):
+        c = random_cloud(rng, 257, deg, False)
+        for frm in (0, 4, 6):
+            pa, pb = str(tmp_path / f"a{deg}{frm}.ply"), str(tmp_path / f"b{deg}{frm}.ply")
+            assert mine.save_ply(c, pa, frm) and theirs.save_ply(c, pb, frm)
+            assert open(pa, "rb").read() == open(pb, "rb").read()
+            for to in (0, 4, 8):
+                ga, gb = mine.load_ply(pb, to), theirs.load_ply(pb, to)
+                assert ga.n == gb.n == 257 and ga.sh_degree == gb.sh_degree == deg
+                assert_cloud_bits_equal(ga, gb, f"ply deg{deg} from{frm} to{to}")
+    assert not mine.save_ply(c, "/nonexistent_dir/x.ply", 0)
+    # malformed files: both hand back an empty cloud
+    good = open(pb, "rb").read()
+    body = good.index(b"end_header\n") + len(b"end_header\n")
+    variants = {
+        "missing": None,
+        "not ply": b"plx\n" + good[4:],
+        "ascii": good.replace(b"binary_little_endian", b"ascii"),
+        "double property": good.replace(b"property float opacity", b"property double opacity"),
+        "missing field": good.replace(b"property float rot_3\n", b""),
+        "truncated body": good[:body + 100],
+        "zero vertices": good.replace(b"element vertex 257", b"element vertex 0"),
+        "comment and blank lines ok": good.replace(b"format binary", b"comment hello\n\n  format binary", 1),
+    }
+    for name, data in variants.items():
+        path = str(tmp_path / "v.ply")
+        if data is None:
+            path = str(tmp_path / "nope.ply")
+        else:
+            open(path, "wb").write(data)
+        ga, gb = mine.load_ply(path, 0), theirs.load_ply(path, 0)
+        assert ga.n == gb.n, name
+        if gb.n:
+            assert_cloud_bits_equal(ga, gb, name)
 
 
 def test_size_checks_and_empty_cloud_need_no_device(mine, theirs):
