@@ -154,6 +154,7 @@ struct GaussianCloud {
     std::vector<float> sums;
     sums.reserve(scales.size() / 3);
     for (size_t i = 0; i + 2 < scales.size(); i += 3) sums.push_back(scales[i] + scales[i + 1] + scales[i + 2]);
+    if (sums.empty()) return 0.01f;  // inconsistent cloud (points but no scales): the reference reads out of bounds
     std::sort(sums.begin(), sums.end());
     const float median = sums[sums.size() / 2];
     return (3.14159265358979323846 * 4 / 3) * exp(median);

@@ -91,5 +91,35 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str |
     return lib_path
 
 
+PY_DIR = os.path.join(HERE, "pyspz")
+
+
+def python_module_path() -> str:
+    import sysconfig
+    return os.path.join(PY_DIR, "spz" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_python_module(force: bool = False) -> str:
+    """The Python module `spz` (csrc/py_spz.cc, pybind11) next to spz_b200/pyspz/__init__.py,
+    linked against the in-tree libspz_b200.so."""
+    import sysconfig
+
+    import pybind11
+    out = python_module_path()
+    src = os.path.join(CSRC, "py_spz.cc")
+    hdr = os.path.join(HERE, "..", "include", "spz_b200", "spz.hpp")
+    lib = build()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(p) for p in (src, hdr, lib)):
+        return out
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-ffp-contract=off",
+           "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], src, "-o", out,
+           "-L", OUT_DIR, "-lspz_b200", "-Wl,-rpath,$ORIGIN/../_lib"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("python module build failed:\n" + r.stdout)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_python_module(force="--force" in sys.argv))
