@@ -183,6 +183,31 @@ def traffic_for(kernel, gaussians, override):
         return None
 
 
+def time_host_zlib(packed, deg, sample_points):
+    """gzip stays on the host (north star) and is reported apart from the codec: deflate / inflate of
+    the container bytes of the first `sample_points` encoded gaussians with the reference's zlib
+    parameters (default level, gzip wrapper, memLevel 9; load-spz.cc:186-214), one thread."""
+    import struct
+    import zlib
+
+    from spz_b200 import codec
+    widths = codec.byte_plane_widths(deg, 3)
+    planes = [p[:w * sample_points].cpu().numpy().tobytes() for p, w in zip(packed.planes(), widths)]
+    order = [planes[0], planes[3], planes[4], planes[1], planes[2], planes[5]]  # stream order
+    stream = struct.pack("<IIIBBBB", 0x5053474e, 3, sample_points, deg, 12, 0, 0) + b"".join(order)
+    t0 = time.perf_counter()
+    co = zlib.compressobj(-1, zlib.DEFLATED, 16 + zlib.MAX_WBITS, 9)
+    gz = co.compress(stream) + co.flush()
+    t1 = time.perf_counter()
+    back = zlib.decompress(gz, 16 + zlib.MAX_WBITS)
+    t2 = time.perf_counter()
+    assert back == stream
+    return {"sample": f"container of the first {sample_points} encoded gaussians ({len(stream)} bytes), zlib {zlib.ZLIB_RUNTIME_VERSION}, 1 thread",
+            "deflate_mb_s": len(stream) / (t1 - t0) / 1e6, "inflate_mb_s": len(stream) / (t2 - t1) / 1e6,
+            "deflate_mgaussians_s": sample_points / (t1 - t0) / 1e6, "inflate_mgaussians_s": sample_points / (t2 - t1) / 1e6,
+            "ratio": len(gz) / len(stream)}
+
+
 def host_memory_available():
     """min(MemAvailable, cgroup limit - usage) in bytes, or None."""
     vals = []
@@ -230,6 +255,25 @@ def run_reference_arm(args):
 
 
 # -------------------------------------------------------------------------------------------------
+# multi-rank plumbing (no data-path collective: only the barrier and these scalar reductions)
+# -------------------------------------------------------------------------------------------------
+def reduce_scalar(dist, x, op, device):
+    """max / sum of a python scalar over all ranks; identity when not distributed."""
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return t.item()
+
+
+def rank_shard(points_total, sh_degree, world, rank):
+    """[a, b) of this rank: contiguous point range with tile-aligned boundaries (spzb200_shard_range)."""
+    from spz_b200 import codec
+    return codec.shard_range(points_total, sh_degree, world, rank)
+
+
+# -------------------------------------------------------------------------------------------------
 # the B200 arm
 # -------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
@@ -259,7 +303,7 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
 
     deg, n_total = args.sh_degree, args.points
-    a, b = codec.shard_range(n_total, deg, world, rank)
+    a, b = rank_shard(n_total, deg, world, rank)
     n = b - a
     ctx = codec.Context(local)
     dev = torch.device("cuda", local)
@@ -342,18 +386,10 @@ def run_b200_arm(args):
 
     # ---- reduce over ranks (max time; sums of bytes and launches) -----------------------------------
     def allmax(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
+        return reduce_scalar(dist, x, "max", dev)
 
     def allsum(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return t.item()
+        return reduce_scalar(dist, x, "sum", dev)
 
     total_ms = allmax(total_ms)
     enc_ms_max, dec_ms_max = allmax(enc_ms), allmax(dec_ms)
@@ -362,6 +398,10 @@ def run_b200_arm(args):
         e2e["s"] = allmax(e2e["s"])
         e2e["h2d"] = int(allsum(e2e["h2d"]))
         e2e["d2h"] = int(allsum(e2e["d2h"]))
+
+    host_zlib = None
+    if rank == 0 and not args.no_cpu_baseline:
+        host_zlib = time_host_zlib(packed, deg, min(n, 100_000))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -409,6 +449,8 @@ def run_b200_arm(args):
                            "encode_phases_ms": e2e["enc"], "decode_phases_ms": e2e["dec"]}
         if cpu:
             line["cpu_baseline"] = cpu
+        if host_zlib:
+            line["host_zlib"] = host_zlib
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist is not None:

@@ -1,0 +1,60 @@
+"""The N>1 path of bench.py on CPU: two gloo ranks agree on a partition of the cloud, reduce their
+timings as max and their counters as sum, and the reference arm runs on rank 0 only.  (The data
+path itself has no collective; these are the only cross-rank operations it uses.)"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import os, sys, json
+sys.path.insert(0, os.environ["REPO"])
+import torch, torch.distributed as dist
+import bench
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n, deg = 100_000_000, 3
+a, b = bench.rank_shard(n, deg, world, rank)
+edges = [None] * world
+dist.all_gather_object(edges, (a, b))
+mx = bench.reduce_scalar(dist, 10.0 + rank, "max", "cpu")
+sm = bench.reduce_scalar(dist, 40 + rank, "sum", "cpu")
+dist.barrier()
+if rank == 0:
+    print(json.dumps({"edges": edges, "max": mx, "sum": sm}))
+dist.destroy_process_group()
+"""
+
+
+def test_two_gloo_ranks_partition_and_reduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, REPO=ROOT, SPZB200_NO_REBUILD="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    (a0, b0), (a1, b1) = out["edges"]
+    assert a0 == 0 and b0 == a1 and b1 == 100_000_000
+    assert b0 % 1280 == 0 and abs((b0 - a0) - (b1 - a1)) <= 2 * 1280
+    assert out["max"] == 11.0 and out["sum"] == 81.0
+
+
+def test_reference_arm_runs_on_rank0_only():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+                        "--cpu-sample-points", "20000"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
