@@ -58,11 +58,39 @@ struct Geo {
 };
 
 // ---- memory helpers ---------------------------------------------------------------------------
-__device__ __forceinline__ float4 ldStream(const float4 *p) { return __ldcs(p); }
-__device__ __forceinline__ uint32_t ldStream(const uint32_t *p) { return __ldcs(p); }
-__device__ __forceinline__ uint2 ldStream(const uint2 *p) { return __ldcs(p); }
-__device__ __forceinline__ void stStream(uint32_t *p, uint32_t v) { __stcs(p, v); }
-__device__ __forceinline__ void stStream(float4 *p, float4 v) { __stcs(p, v); }
+// Every byte is touched once, so loads and stores carry the streaming (evict-first) hint.  The
+// SPZ_LD_MODE / SPZ_ST_MODE macros exist so scripts/ can build and time the alternatives
+// (profiles/ records the comparison); the defaults are what ships.
+#ifndef SPZ_LD_MODE
+#define SPZ_LD_MODE 1  // 0: ld.global.cs   1: ld.global.nc   2: ld.global   3: ld.global.lu
+#endif
+#ifndef SPZ_ST_MODE
+#define SPZ_ST_MODE 0  // 0: st.global.cs   1: st.global      2: st.global.wt   3: st.global.cg
+#endif
+template <class T>
+__device__ __forceinline__ T ldStream(const T *p) {
+#if SPZ_LD_MODE == 0
+  return __ldcs(p);
+#elif SPZ_LD_MODE == 1
+  return __ldg(p);
+#elif SPZ_LD_MODE == 2
+  return *p;
+#else
+  return __ldlu(p);
+#endif
+}
+template <class T>
+__device__ __forceinline__ void stStream(T *p, T v) {
+#if SPZ_ST_MODE == 0
+  __stcs(p, v);
+#elif SPZ_ST_MODE == 1
+  *p = v;
+#elif SPZ_ST_MODE == 2
+  __stwt(p, v);
+#else
+  __stcg(p, v);
+#endif
+}
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
