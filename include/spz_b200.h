@@ -104,6 +104,9 @@ typedef struct {
   int64_t d2h_bytes;
   int32_t kernel_launches;
   int32_t chunks;
+  double host_copy_ms;     /* host-thread time spent bouncing pageable planes through pinned buffers */
+  int32_t staged;          /* bit 0: input planes were pageable and bounced, bit 1: output planes */
+  int32_t reserved;
 } SpzB200Timings;
 
 /* One context per (thread, device): immutable codec tables resident on the device, two worker
@@ -135,10 +138,11 @@ int spzb200_decode_device(SpzB200Context *ctx, const SpzB200Packed *in, int32_t 
 
 /* ---- host-pointer codec: what the C++ / Python drop-in API calls ----------------------------
  *
- * Same contracts with HOST pointers (pinned or pageable; pinned copies overlap).  The cloud is
- * cut into contiguous point ranges; each range is copied in, transformed and copied out on
- * alternating streams so H2D, kernel and D2H overlap.  Synchronous: returns when `out` is
- * complete.  timings may be NULL. */
+ * Same contracts with HOST pointers.  The cloud is cut into contiguous point ranges; each range is
+ * copied in, transformed and copied out on one of three streams so H2D, kernel and D2H of
+ * neighbouring ranges overlap.  Pinned planes (spzb200_alloc_pinned, cudaHostRegister) are copied
+ * directly; pageable planes are bounced through pinned buffers by a few host threads.
+ * Synchronous: returns when `out` is complete.  timings may be NULL. */
 int spzb200_encode_host(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from,
                         SpzB200Packed *out, SpzB200Timings *timings);
 int spzb200_decode_host(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to,
@@ -190,8 +194,15 @@ int spzb200_info(const SpzB200Context *ctx, int32_t *sm_count, int32_t *pack_mod
 /* Test hooks: force the scalar kernels (1) / restore (0); choose the byte packer. */
 void spzb200_set_force_generic(SpzB200Context *ctx, int32_t on);
 void spzb200_set_pack_mode(SpzB200Context *ctx, int32_t mode);
-/* Point ranges of at most this many gaussians per pipeline stage of the *_host calls. */
+/* Point ranges of at most this many gaussians per pipeline stage of the *_host calls; 0 restores
+ * the defaults (2M points for pinned planes, 256K for pageable ones). */
 void spzb200_set_chunk_points(SpzB200Context *ctx, int64_t points);
+/* Pageable host planes (plain malloc / std::vector memory) are bounced through pinned buffers by
+ * `copy_threads` host threads (0 = auto: up to 8) so their transfers overlap: ~3x the speed of
+ * handing them to cudaMemcpyAsync as they are (driver-staged, synchronous).  bounce: 0 = never,
+ * 1 = calls of >= 1 GiB (SPZB200_BOUNCE_MIN_MB) or once the buffers exist (default: the pinned
+ * allocation is a one-time cost small one-shot calls would not earn back), 2 = always. */
+void spzb200_set_host_staging(SpzB200Context *ctx, int32_t bounce, int32_t copy_threads);
 
 /* Thread-local message of the last failing call on this thread ("" if none). */
 const char *spzb200_last_error(void);

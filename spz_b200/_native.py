@@ -32,7 +32,8 @@ class Packed(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("wall_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("kernel_launches", C.c_int32), ("chunks", C.c_int32)]
+                ("kernel_launches", C.c_int32), ("chunks", C.c_int32), ("host_copy_ms", C.c_double),
+                ("staged", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -61,6 +62,7 @@ SIGNATURES = {
     "spzb200_set_force_generic": (None, [C.c_void_p, C.c_int32]),
     "spzb200_set_pack_mode": (None, [C.c_void_p, C.c_int32]),
     "spzb200_set_chunk_points": (None, [C.c_void_p, C.c_int64]),
+    "spzb200_set_host_staging": (None, [C.c_void_p, C.c_int32, C.c_int32]),
     "spzb200_last_error": (C.c_char_p, []),
     "spzb200_version": (C.c_int32, []),
 }

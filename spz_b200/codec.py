@@ -240,6 +240,10 @@ class Context:
     def set_chunk_points(self, points: int):
         N.lib().spzb200_set_chunk_points(self._h, int(points))
 
+    def set_host_staging(self, bounce: int = 1, copy_threads: int = 0):
+        """bounce: 0 never, 1 auto (large calls), 2 always -- see spzb200_set_host_staging."""
+        N.lib().spzb200_set_host_staging(self._h, int(bounce), int(copy_threads))
+
     # ---- device-resident ---------------------------------------------------------------------
     @staticmethod
     def _stream_handle(stream) -> int:

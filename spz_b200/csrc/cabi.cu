@@ -13,8 +13,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -119,12 +121,87 @@ void buildAlphaLut(float lut[256]) {
   }
 }
 
+constexpr int kStages = 3;
+
 struct Stage {
   cudaStream_t stream = nullptr;
-  uint8_t *dFloats = nullptr;  // float planes of one chunk
-  uint8_t *dBytes = nullptr;   // byte planes of one chunk
+  uint8_t *dFloats = nullptr;  // float planes of one chunk (device)
+  uint8_t *dBytes = nullptr;   // byte planes of one chunk (device)
   size_t floatsCap = 0, bytesCap = 0;
+  uint8_t *hIn = nullptr;      // pinned bounce buffers, used only when the caller's planes are pageable
+  uint8_t *hOut = nullptr;
+  size_t hInCap = 0, hOutCap = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+// A few host threads that copy between the caller's pageable planes and the pinned bounce buffers
+// (one memcpy thread moves ~10 GB/s; the PCIe link wants ~50).  Created on first pageable call.
+class CopyPool {
+ public:
+  explicit CopyPool(int threads) {
+    for (int i = 0; i < threads; i++) workers_.emplace_back([this] { loop(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+  struct Job { void *dst; const void *src; size_t bytes; };
+  // Splits the jobs into <= 4 MiB pieces, runs them on the pool (the caller helps) and returns
+  // when all are done.
+  void run(const std::vector<Job> &jobs) {
+    constexpr size_t kPiece = (size_t)4 << 20;
+    {
+      std::lock_guard<std::mutex> g(m_);
+      for (const Job &j : jobs)
+        for (size_t off = 0; off < j.bytes; off += kPiece)
+          queue_.push_back({(uint8_t *)j.dst + off, (const uint8_t *)j.src + off, std::min(kPiece, j.bytes - off)});
+      pending_ += queue_.size();
+    }
+    cv_.notify_all();
+    Job j;
+    while (take(&j, false)) {
+      std::memcpy(j.dst, j.src, j.bytes);
+      done();
+    }
+    std::unique_lock<std::mutex> g(m_);
+    idle_.wait(g, [this] { return pending_ == 0; });
+  }
+
+ private:
+  bool take(Job *j, bool wait) {
+    std::unique_lock<std::mutex> g(m_);
+    if (wait) cv_.wait(g, [this] { return stop_ || !queue_.empty(); });
+    if (queue_.empty()) return false;
+    *j = queue_.back();
+    queue_.pop_back();
+    return true;
+  }
+  void done() {
+    std::lock_guard<std::mutex> g(m_);
+    if (--pending_ == 0) idle_.notify_all();
+  }
+  void loop() {
+    Job j;
+    while (true) {
+      if (!take(&j, true)) {
+        std::lock_guard<std::mutex> g(m_);
+        if (stop_) return;
+        continue;
+      }
+      std::memcpy(j.dst, j.src, j.bytes);
+      done();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::vector<Job> queue_;
+  std::mutex m_;
+  std::condition_variable cv_, idle_;
+  size_t pending_ = 0;
+  bool stop_ = false;
 };
 
 size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -138,14 +215,19 @@ struct SpzB200Context {
   bool cvtPackOk = false;  // the init-time probe of cvt.pack.sat.u8.s32 agreed with the ALU packer
   bool forceGeneric = false;
   int ctasPerSm = 0;
+  int bounceMode = 1;     // pageable planes: 0 never bounce, 1 bounce large calls (see bounceMinBytes), 2 always
+  size_t bounceMinBytes = (size_t)1 << 30;
   bool flatGrid = true;  // one CTA per tile: the block scheduler keeps the tile frontier compact
-  long long chunkPoints = 1 << 21;
+  long long chunkPoints = 1 << 21;        // pinned / registered host planes: copied straight from the caller
+  long long pageableChunkPoints = 1 << 18;  // pageable planes: bounced through pinned buffers of this many points
+  int copyThreads = 0;                      // 0 = auto (min(8, hardware threads))
+  CopyPool *pool = nullptr;
   long long kernelLaunches = 0;
   float hThr[256];
   float hLut[256];
   float *dThr = nullptr;
   float *dLut = nullptr;
-  Stage stage[2];
+  Stage stage[kStages];
 };
 
 namespace {
@@ -253,6 +335,15 @@ int ensureStage(Stage &s, size_t floatsBytes, size_t bytesBytes) {
   return SPZB200_OK;
 }
 
+int ensureBounce(uint8_t *&buf, size_t &cap, size_t bytes) {
+  if (cap >= bytes) return SPZB200_OK;
+  if (buf) cudaFreeHost(buf);
+  buf = nullptr; cap = 0;
+  CU(cudaHostAlloc(&buf, bytes, cudaHostAllocDefault));
+  cap = bytes;
+  return SPZB200_OK;
+}
+
 // carve six 256-byte-aligned sub-buffers for `points` gaussians
 size_t carve(uint8_t *base, const size_t per[6], long long points, uint8_t *out[6]) {
   size_t off = 0;
@@ -267,10 +358,27 @@ double nowMs() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-struct ChunkRec { int stage; };
+// true when cudaMemcpyAsync from/to p would be staged by the driver (plain malloc'd memory)
+bool isPageable(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
+}
 
 // The chunked H2D || kernel || D2H pipeline shared by encode_host and decode_host.
 // isEncode: float planes in, byte planes out; otherwise the reverse.
+//
+// The cloud is cut into contiguous point ranges.  Range c uses stage c % kStages: its own stream,
+// device staging buffers and events, so the copy-in of one range overlaps the kernel and the
+// copy-out of its predecessors.  Pinned (or registered) caller memory is copied directly.
+// Pageable caller memory -- what std::vector hands the C++ API -- would make every cudaMemcpyAsync
+// a synchronous, driver-staged ~10 GB/s copy; instead the ranges are bounced through pinned buffers
+// owned by the stage, filled and drained by a small pool of host threads while the GPU works on
+// the neighbouring ranges.
 int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &cloud,
                     const SpzB200Packed &packed, int32_t coord, SpzB200Timings *timings) {
   const double w0 = nowMs();
@@ -281,54 +389,98 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
   size_t fper[6], bper[6];
   floatPlaneBytes(shDim, fper);
   bytePlaneBytes(shDim, version, bper);
+  const size_t *inPer = isEncode ? fper : bper, *outPer = isEncode ? bper : fper;
+  uint8_t *const cloudPlanes[6] = {(uint8_t *)cloud.positions, (uint8_t *)cloud.scales, (uint8_t *)cloud.rotations,
+                                   (uint8_t *)cloud.alphas, (uint8_t *)cloud.colors, (uint8_t *)cloud.sh};
+  uint8_t *const packedPlanes[6] = {packed.positions, packed.scales, packed.rotations, packed.alphas, packed.colors, packed.sh};
+  uint8_t *const *userIn = isEncode ? cloudPlanes : packedPlanes;
+  uint8_t *const *userOut = isEncode ? packedPlanes : cloudPlanes;
+
+  // Bouncing costs a one-time pinned allocation per context (~1 GB/s on a VM), so small one-shot
+  // calls are cheaper through the driver's own staging; once the buffers exist they are always used.
+  const size_t callBytes = (size_t)n * (fper[0] + fper[1] + fper[2] + fper[3] + fper[4] + fper[5] +
+                                                                           bper[0] + bper[1] + bper[2] + bper[3] + bper[4] + bper[5]);
+  const bool wantBounce = ctx->bounceMode == 2 ||
+                          (ctx->bounceMode == 1 && (callBytes >= ctx->bounceMinBytes || ctx->stage[0].hIn || ctx->stage[0].hOut));
+  const bool bounceIn = n > 0 && wantBounce && isPageable(userIn[0]);
+  const bool bounceOut = n > 0 && wantBounce && isPageable(userOut[0]);
   const long long tg = spzb200::tileGaussians(shDim);
-  long long chunk = std::max<long long>(tg, ctx->chunkPoints / tg * tg);
+  const long long want = (bounceIn || bounceOut) ? ctx->pageableChunkPoints : ctx->chunkPoints;
+  long long chunk = std::max<long long>(tg, want / tg * tg);
   if (chunk > n) chunk = std::max<long long>(n, 1);
   const long long numChunks = n == 0 ? 0 : (n + chunk - 1) / chunk;
+  const int stages = (int)std::min<long long>(kStages, numChunks);
 
   SpzB200Timings tm;
   std::memset(&tm, 0, sizeof tm);
+  tm.staged = (bounceIn ? 1 : 0) | (bounceOut ? 2 : 0);
   if (numChunks > 0) {
     uint8_t *unused[6];
     const size_t fBytes = carve(nullptr, fper, chunk, unused);
     const size_t bBytes = carve(nullptr, bper, chunk, unused);
-    const int stages = numChunks > 1 ? 2 : 1;
     for (int s = 0; s < stages; s++) {
-      int rc = ensureStage(ctx->stage[s], fBytes, bBytes);
+      Stage &st = ctx->stage[s];
+      int rc = ensureStage(st, fBytes, bBytes);
+      if (rc == SPZB200_OK && bounceIn) rc = ensureBounce(st.hIn, st.hInCap, isEncode ? fBytes : bBytes);
+      if (rc == SPZB200_OK && bounceOut) rc = ensureBounce(st.hOut, st.hOutCap, isEncode ? bBytes : fBytes);
       if (rc != SPZB200_OK) return rc;
     }
+    if ((bounceIn || bounceOut) && !ctx->pool) {
+      int t = ctx->copyThreads > 0 ? ctx->copyThreads : (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+      ctx->pool = new CopyPool(std::max(0, t - 1));  // the calling thread copies too
+    }
   }
-
-  float *const cloudPlanes[6] = {cloud.positions, cloud.scales, cloud.rotations, cloud.alphas, cloud.colors, cloud.sh};
-  uint8_t *const packedPlanes[6] = {packed.positions, packed.scales, packed.rotations, packed.alphas, packed.colors, packed.sh};
   const spzb200::LaunchPlan plan = planOf(ctx);
 
-  for (long long c = 0; c < numChunks; c++) {
-    Stage &st = ctx->stage[c & 1];
-    const long long a = c * chunk, b = std::min(n, a + chunk), pts = b - a;
-    if (c >= 2) {
-      // the stage's previous chunk (c-2) has fully drained once its last event completed; collect
-      // its timings before the events are re-recorded
-      CU(cudaEventSynchronize(st.ev[3]));
-      float ms;
-      CU(cudaEventElapsedTime(&ms, st.ev[0], st.ev[1])); tm.h2d_ms += ms;
-      CU(cudaEventElapsedTime(&ms, st.ev[1], st.ev[2])); tm.kernel_ms += ms;
-      CU(cudaEventElapsedTime(&ms, st.ev[2], st.ev[3])); tm.d2h_ms += ms;
+  // Completes the range that last used `st`: waits for its copy-out, books its timings and, when
+  // the output is bounced, drains the pinned buffer into the caller's planes.
+  auto finish = [&](Stage &st, long long c) -> int {
+    const long long a = c * chunk, pts = std::min(n, a + chunk) - a;
+    CU(cudaEventSynchronize(st.ev[3]));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, st.ev[0], st.ev[1])); tm.h2d_ms += ms;
+    CU(cudaEventElapsedTime(&ms, st.ev[1], st.ev[2])); tm.kernel_ms += ms;
+    CU(cudaEventElapsedTime(&ms, st.ev[2], st.ev[3])); tm.d2h_ms += ms;
+    if (bounceOut) {
+      const double t0 = nowMs();
+      uint8_t *ho[6];
+      carve(st.hOut, outPer, chunk, ho);
+      std::vector<CopyPool::Job> jobs;
+      for (int i = 0; i < 6; i++)
+        if (outPer[i] * (size_t)pts) jobs.push_back({userOut[i] + outPer[i] * (size_t)a, ho[i], outPer[i] * (size_t)pts});
+      ctx->pool->run(jobs);
+      tm.host_copy_ms += nowMs() - t0;
     }
-    uint8_t *df[6], *db[6];
+    return SPZB200_OK;
+  };
+
+  for (long long c = 0; c < numChunks; c++) {
+    Stage &st = ctx->stage[c % kStages];
+    const long long a = c * chunk, b = std::min(n, a + chunk), pts = b - a;
+    if (c >= kStages) {
+      int rc = finish(st, c - kStages);
+      if (rc != SPZB200_OK) return rc;
+    }
+    uint8_t *df[6], *db[6], *hi[6], *ho[6];
     carve(st.dFloats, fper, chunk, df);
     carve(st.dBytes, bper, chunk, db);
+    uint8_t **dIn = isEncode ? df : db, **dOut = isEncode ? db : df;
+    if (bounceIn) {
+      const double t0 = nowMs();
+      carve(st.hIn, inPer, chunk, hi);
+      std::vector<CopyPool::Job> jobs;
+      for (int i = 0; i < 6; i++)
+        if (inPer[i] * (size_t)pts) jobs.push_back({hi[i], userIn[i] + inPer[i] * (size_t)a, inPer[i] * (size_t)pts});
+      ctx->pool->run(jobs);
+      tm.host_copy_ms += nowMs() - t0;
+    }
+    if (bounceOut) carve(st.hOut, outPer, chunk, ho);
     CU(cudaEventRecord(st.ev[0], st.stream));
     for (int i = 0; i < 6; i++) {
-      if (isEncode) {
-        const size_t bytes = fper[i] * (size_t)pts;
-        if (bytes) CU(cudaMemcpyAsync(df[i], reinterpret_cast<const uint8_t *>(cloudPlanes[i]) + fper[i] * (size_t)a, bytes, cudaMemcpyHostToDevice, st.stream));
-        tm.h2d_bytes += (int64_t)bytes;
-      } else {
-        const size_t bytes = bper[i] * (size_t)pts;
-        if (bytes) CU(cudaMemcpyAsync(db[i], packedPlanes[i] + bper[i] * (size_t)a, bytes, cudaMemcpyHostToDevice, st.stream));
-        tm.h2d_bytes += (int64_t)bytes;
-      }
+      const size_t bytes = inPer[i] * (size_t)pts;
+      const uint8_t *src = bounceIn ? hi[i] : userIn[i] + inPer[i] * (size_t)a;
+      if (bytes) CU(cudaMemcpyAsync(dIn[i], src, bytes, cudaMemcpyHostToDevice, st.stream));
+      tm.h2d_bytes += (int64_t)bytes;
     }
     CU(cudaEventRecord(st.ev[1], st.stream));
     SpzB200Cloud dc = cloud;
@@ -349,26 +501,17 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
     tm.kernel_launches += launches;
     CU(cudaEventRecord(st.ev[2], st.stream));
     for (int i = 0; i < 6; i++) {
-      if (isEncode) {
-        const size_t bytes = bper[i] * (size_t)pts;
-        if (bytes) CU(cudaMemcpyAsync(packedPlanes[i] + bper[i] * (size_t)a, db[i], bytes, cudaMemcpyDeviceToHost, st.stream));
-        tm.d2h_bytes += (int64_t)bytes;
-      } else {
-        const size_t bytes = fper[i] * (size_t)pts;
-        if (bytes) CU(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(cloudPlanes[i]) + fper[i] * (size_t)a, df[i], bytes, cudaMemcpyDeviceToHost, st.stream));
-        tm.d2h_bytes += (int64_t)bytes;
-      }
+      const size_t bytes = outPer[i] * (size_t)pts;
+      uint8_t *dst = bounceOut ? ho[i] : userOut[i] + outPer[i] * (size_t)a;
+      if (bytes) CU(cudaMemcpyAsync(dst, dOut[i], bytes, cudaMemcpyDeviceToHost, st.stream));
+      tm.d2h_bytes += (int64_t)bytes;
     }
     CU(cudaEventRecord(st.ev[3], st.stream));
   }
-  // drain: the last (up to two) chunks still hold unread events
-  for (long long c = std::max<long long>(0, numChunks - 2); c < numChunks; c++) {
-    Stage &st = ctx->stage[c & 1];
-    CU(cudaEventSynchronize(st.ev[3]));
-    float ms;
-    CU(cudaEventElapsedTime(&ms, st.ev[0], st.ev[1])); tm.h2d_ms += ms;
-    CU(cudaEventElapsedTime(&ms, st.ev[1], st.ev[2])); tm.kernel_ms += ms;
-    CU(cudaEventElapsedTime(&ms, st.ev[2], st.ev[3])); tm.d2h_ms += ms;
+  // drain the ranges still in flight, oldest first
+  for (long long c = std::max<long long>(0, numChunks - kStages); c < numChunks; c++) {
+    int rc = finish(ctx->stage[c % kStages], c);
+    if (rc != SPZB200_OK) return rc;
   }
   tm.chunks = (int32_t)numChunks;
   tm.wall_ms = nowMs() - w0;
@@ -481,7 +624,7 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   if ((e = cudaMalloc(&ctx->dLut, spzb200::kDecodeTableFloats * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc tables");
   if ((e = cudaMemcpy(ctx->dThr, ctx->hThr, sizeof ctx->hThr, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "table upload");
   if ((e = cudaMemcpy(ctx->dLut, ctx->hLut, sizeof ctx->hLut, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "table upload");
-  for (int s = 0; s < 2; s++) {
+  for (int s = 0; s < kStages; s++) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stage[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (int k = 0; k < 4; k++)
       if ((e = cudaEventCreate(&ctx->stage[s].ev[k])) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -496,6 +639,7 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
     if (!std::strcmp(env, "alu")) ctx->packMode = spzb200::kPackAlu;
   }
   if (const char *env = std::getenv("SPZB200_CTAS_PER_SM")) ctx->ctasPerSm = std::atoi(env);
+  if (const char *env = std::getenv("SPZB200_BOUNCE_MIN_MB")) ctx->bounceMinBytes = (size_t)std::atoll(env) << 20;
   if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = std::strcmp(env, "persistent") != 0;
   *out = ctx;
   return SPZB200_OK;
@@ -504,9 +648,12 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
 void spzb200_destroy(SpzB200Context *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  for (int s = 0; s < 2; s++) {
+  delete ctx->pool;
+  for (int s = 0; s < kStages; s++) {
     Stage &st = ctx->stage[s];
     if (st.stream) cudaStreamSynchronize(st.stream);
+    if (st.hIn) cudaFreeHost(st.hIn);
+    if (st.hOut) cudaFreeHost(st.hOut);
     for (int k = 0; k < 4; k++) if (st.ev[k]) cudaEventDestroy(st.ev[k]);
     if (st.dFloats) cudaFree(st.dFloats);
     if (st.dBytes) cudaFree(st.dBytes);
@@ -699,6 +846,23 @@ void spzb200_set_force_generic(SpzB200Context *ctx, int32_t on) { if (ctx) ctx->
 void spzb200_set_pack_mode(SpzB200Context *ctx, int32_t mode) {
   if (ctx) ctx->packMode = (mode && ctx->cvtPackOk) ? spzb200::kPackCvt : spzb200::kPackAlu;
 }
-void spzb200_set_chunk_points(SpzB200Context *ctx, int64_t points) { if (ctx && points > 0) ctx->chunkPoints = points; }
+void spzb200_set_chunk_points(SpzB200Context *ctx, int64_t points) {
+  if (!ctx) return;
+  if (points > 0) {
+    ctx->chunkPoints = ctx->pageableChunkPoints = points;
+  } else {  // back to the defaults
+    ctx->chunkPoints = 1 << 21;
+    ctx->pageableChunkPoints = 1 << 18;
+  }
+}
+void spzb200_set_host_staging(SpzB200Context *ctx, int32_t bounce, int32_t copy_threads) {
+  if (!ctx) return;
+  ctx->bounceMode = bounce < 0 ? 0 : (bounce > 2 ? 2 : bounce);
+  if (copy_threads >= 0 && copy_threads != ctx->copyThreads) {
+    ctx->copyThreads = copy_threads;
+    delete ctx->pool;
+    ctx->pool = nullptr;
+  }
+}
 
 }  // extern "C"

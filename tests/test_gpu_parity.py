@@ -328,7 +328,37 @@ def test_host_pipeline_chunked(gpu_ctx, oracle, deg):
         assert tm2["chunks"] == 4
         assert_cloud_bits_equal(Cloud(n, deg, *back.planes()), oracle.unpack(want, 7), "decode_host")
     finally:
-        gpu_ctx.set_chunk_points(1 << 21)
+        gpu_ctx.set_chunk_points(0)
+
+
+def test_host_pipeline_pageable_pinned_and_unstaged_agree(gpu_ctx, oracle):
+    """Pageable planes are bounced through pinned buffers by host threads, pinned planes are copied
+    directly, and the bounce can be switched off: three routes, one result."""
+    from spz_b200.codec import CloudPlanes, PackedPlanes, alloc_cloud, alloc_packed, tile_gaussians
+    rng = np.random.default_rng(4200)
+    deg = 2
+    n = 11 * tile_gaussians(deg) + 17
+    c = random_cloud(rng, n, deg, False)
+    want = oracle.pack(c, 7)
+    want_back = oracle.unpack(want, 5)
+    try:
+        gpu_ctx.set_chunk_points(3 * tile_gaussians(deg))  # 4 ranges over 3 stages
+        for label, pinned, bounce, staged in (("pageable", False, 2, 3), ("pinned", True, 2, 0), ("unstaged", False, 0, 0), ("auto-small", False, 1, 3)):
+            gpu_ctx.set_host_staging(bounce, 3)
+            src = alloc_cloud(n, deg, numpy_arrays=True, pinned=pinned)
+            for a, b in zip(src.planes(), c.planes()):
+                a[...] = b
+            out = alloc_packed(n, deg, 3, numpy_arrays=True, pinned=pinned)
+            got, tm = gpu_ctx.encode_host(src, 7, out=out)
+            assert tm["staged"] == staged and tm["chunks"] == 4, (label, tm)
+            assert_packed_equal(Packed(n, deg, 12, 3, *got.planes()), want, label)
+            back = alloc_cloud(n, deg, numpy_arrays=True, pinned=pinned)
+            got_back, tm = gpu_ctx.decode_host(out, 5, out=back)
+            assert tm["staged"] == staged
+            assert_cloud_bits_equal(Cloud(n, deg, *got_back.planes()), want_back, label)
+    finally:
+        gpu_ctx.set_chunk_points(0)
+        gpu_ctx.set_host_staging(1, 0)
 
 
 def test_host_multi_entry_point_single_device(oracle):
