@@ -165,6 +165,15 @@ void spzb200_free_pinned(void *ptr);
 
 /* ---- host-side helpers (no GPU needed) ------------------------------------------------------ */
 
+/* The container's gzip stage (load-spz.cc:141-214) for FFI callers: zlib with the reference's
+ * parameters.  threads <= 1 gives the reference's byte-identical single-thread stream; threads > 1
+ * deflates independent blocks concurrently into one standard gzip member (same inflated bytes,
+ * different compressed bytes) and inflates such members block-parallel.  *out is malloc'd; release
+ * it with spzb200_free. */
+int spzb200_gzip(const uint8_t *data, size_t size, int32_t threads, uint8_t **out, size_t *out_size);
+int spzb200_gunzip(const uint8_t *data, size_t size, int32_t threads, uint8_t **out, size_t *out_size);
+void spzb200_free(void *ptr);
+
 /* Point range [*begin, *end) of shard `index` out of `num_shards` over n gaussians of the given
  * SH degree.  Boundaries are multiples of the kernel tile, so every shard but the last runs
  * entirely on the vector path and every plane slice stays 16-byte aligned. */

@@ -279,4 +279,14 @@ GaussianCloud loadSplatFromPly(const std::string &filename, const UnpackOptions 
 void serializePackedGaussians(const PackedGaussians &packed, std::ostream *out);
 bool compressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out);
 
+// ---- extensions (not in the reference's headers) --------------------------------------------------
+// The inverse of compressGzipped (the reference keeps it file-local, load-spz.cc:169-182).
+bool decompressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out);
+// zlib on several host threads: one standard gzip member made of independently deflated blocks,
+// readable by any inflater; the inflated bytes equal compressGzipped's input, the compressed bytes
+// do not equal its output.  decompressGzippedParallel inflates such members block-parallel and
+// anything else serially.  saveSpz / loadSpz* use them when SPZ_B200_GZIP_THREADS > 1.
+bool compressGzippedParallel(const uint8_t *data, size_t size, int threads, std::vector<uint8_t> *out);
+bool decompressGzippedParallel(const uint8_t *data, size_t size, int threads, std::vector<uint8_t> *out);
+
 }  // namespace spz

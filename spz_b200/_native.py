@@ -53,6 +53,9 @@ SIGNATURES = {
     "spzb200_decode_host_multi": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(Packed), C.c_int32, C.POINTER(Cloud), C.POINTER(Timings)]),
     "spzb200_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "spzb200_free_pinned": (None, [C.c_void_p]),
+    "spzb200_gzip": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "spzb200_gunzip": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "spzb200_free": (None, [C.c_void_p]),
     "spzb200_shard_range": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "spzb200_tile_gaussians": (C.c_int32, [C.c_int32]),
     "spzb200_flip_bits": (None, [C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

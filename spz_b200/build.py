@@ -19,7 +19,7 @@ OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libspz_b200.so")
 
 CUDA_SOURCES = ["codec_kernels.cu", "cabi.cu"]
-CXX_SOURCES = ["spz_api.cc", "spz_ply.cc"]
+CXX_SOURCES = ["spz_api.cc", "spz_ply.cc", "spz_gzip.cc"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

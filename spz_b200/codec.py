@@ -174,6 +174,25 @@ def alloc_packed(n: int, sh_degree: int, version: int = 3, device=None, pinned: 
     return PackedPlanes(n, sh_degree, *planes, fractional_bits=fractional_bits, version=version)
 
 
+def _host_bytes_call(fn, data, threads: int) -> bytes:
+    buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+    out, size = C.c_void_p(None), C.c_size_t(0)
+    N.check(fn(buf.ctypes.data if buf.size else None, buf.size, int(threads), C.byref(out), C.byref(size)))
+    try:
+        return C.string_at(out.value, size.value)
+    finally:
+        N.lib().spzb200_free(out)
+
+
+def gzip_bytes(data, threads: int = 1) -> bytes:
+    """The container's gzip stage on the host (spzb200_gzip): threads <= 1 is the reference's stream."""
+    return _host_bytes_call(N.lib().spzb200_gzip, data, threads)
+
+
+def gunzip_bytes(data, threads: int = 1) -> bytes:
+    return _host_bytes_call(N.lib().spzb200_gunzip, data, threads)
+
+
 def shard_range(n: int, sh_degree: int, num_shards: int, index: int):
     """Contiguous point range of one shard (host logic, no GPU): spzb200_shard_range."""
     a, b = C.c_int64(0), C.c_int64(0)

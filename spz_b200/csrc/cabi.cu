@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/spz_b200.h"
+#include "../../include/spz_b200/spz.hpp"
 #include "codec_kernels.cuh"
 #include "codec_math.cuh"
 
@@ -793,6 +794,32 @@ int spzb200_alloc_pinned(size_t bytes, void **out) {
 void spzb200_free_pinned(void *ptr) {
   if (ptr) cudaFreeHost(ptr);
 }
+
+static int handOverBytes(bool ok, const char *who, std::vector<uint8_t> &bytes, uint8_t **out, size_t *outSize) {
+  if (!out || !outSize) return fail(SPZB200_ERR_INVALID, "%s: null output arguments", who);
+  *out = nullptr;
+  *outSize = 0;
+  if (!ok) return fail(SPZB200_ERR_INVALID, "%s: zlib rejected the input", who);
+  *out = static_cast<uint8_t *>(std::malloc(bytes.size() ? bytes.size() : 1));
+  if (!*out) return fail(SPZB200_ERR_NOMEM, "%s: out of memory (%zu bytes)", who, bytes.size());
+  if (!bytes.empty()) std::memcpy(*out, bytes.data(), bytes.size());
+  *outSize = bytes.size();
+  return SPZB200_OK;
+}
+
+int spzb200_gzip(const uint8_t *data, size_t size, int32_t threads, uint8_t **out, size_t *out_size) {
+  std::vector<uint8_t> bytes;
+  const bool ok = (data || size == 0) && spz::compressGzippedParallel(data, size, threads, &bytes);
+  return handOverBytes(ok, "spzb200_gzip", bytes, out, out_size);
+}
+
+int spzb200_gunzip(const uint8_t *data, size_t size, int32_t threads, uint8_t **out, size_t *out_size) {
+  std::vector<uint8_t> bytes;
+  const bool ok = data && spz::decompressGzippedParallel(data, size, threads, &bytes);
+  return handOverBytes(ok, "spzb200_gunzip", bytes, out, out_size);
+}
+
+void spzb200_free(void *ptr) { std::free(ptr); }
 
 int32_t spzb200_tile_gaussians(int32_t sh_degree) {
   return validDegree(sh_degree) ? spzb200::tileGaussians(shDimOf(sh_degree)) : 0;

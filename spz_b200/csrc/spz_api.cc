@@ -195,6 +195,13 @@ void serializeInto(const PackedGaussians &p, uint8_t *dst) {
   }
 }
 
+// SPZ_B200_GZIP_THREADS > 1 switches saveSpz / loadSpz* to the block-parallel zlib framing of
+// spz_gzip.cc; unset (or 1) keeps the reference's single-thread byte-identical output.
+int gzipThreads() {
+  const char *env = std::getenv("SPZ_B200_GZIP_THREADS");
+  return env ? std::atoi(env) : 1;
+}
+
 int64_t maxPointsToRead() {
   // The reference refuses more than 10,000,000 points (load-spz.cc:549).  Lifted here so the large
   // configurations round-trip; SPZ_B200_MAX_POINTS restores any cap.
@@ -250,54 +257,6 @@ PackedGaussians deserialize(const uint8_t *data, size_t size) {
     src += sizes[i];
   }
   return r;
-}
-
-// gzip member -> bytes (windowBits 16 + MAX_WBITS: gzip framing only, load-spz.cc:169-173).  The
-// ISIZE trailer sizes the first allocation; the loop still grows if it lied.  Stops at the end of
-// the first member, like the reference.
-bool gunzip(const uint8_t *data, size_t size, std::vector<uint8_t> *out) {
-  out->clear();
-  z_stream zs;
-  std::memset(&zs, 0, sizeof zs);
-  if (inflateInit2(&zs, 16 | MAX_WBITS) != Z_OK) return false;
-  size_t capacity = 1 << 16;
-  if (size >= 18) {
-    uint32_t isize;
-    std::memcpy(&isize, data + size - 4, 4);
-    capacity = std::max<size_t>(capacity, isize);
-  }
-  out->resize(capacity);
-  constexpr size_t kChunk = (size_t)1 << 30;  // zlib counts in 32 bits
-  size_t fed = 0, produced = 0;
-  bool ok = false;
-  while (true) {
-    if (zs.avail_in == 0 && fed < size) {
-      const size_t take = std::min(size - fed, kChunk);
-      zs.next_in = const_cast<Bytef *>(data + fed);
-      zs.avail_in = (uInt)take;
-      fed += take;
-    }
-    if (produced == out->size()) out->resize(out->size() + out->size() / 2);
-    const size_t room = std::min(out->size() - produced, kChunk);
-    zs.next_out = out->data() + produced;
-    zs.avail_out = (uInt)room;
-    const int rc = inflate(&zs, Z_NO_FLUSH);
-    produced += room - zs.avail_out;
-    if (rc == Z_STREAM_END) {
-      ok = true;
-      break;
-    }
-    if (rc == Z_OK) continue;
-    if (rc == Z_BUF_ERROR && (zs.avail_out == 0 || fed < size)) continue;  // wants room or input
-    break;  // corrupt, or the input ended inside the member
-  }
-  inflateEnd(&zs);
-  if (!ok) {
-    out->clear();
-    return false;
-  }
-  out->resize(produced);
-  return true;
 }
 
 bool readFile(const std::string &filename, std::vector<uint8_t> *out) {
@@ -505,6 +464,54 @@ void serializePackedGaussians(const PackedGaussians &packed, std::ostream *out) 
   }
 }
 
+// gzip member -> bytes (windowBits 16 + MAX_WBITS: gzip framing only, load-spz.cc:169-173).  The
+// ISIZE trailer sizes the first allocation; the loop still grows if it lied.  Stops at the end of
+// the first member, like the reference.
+bool decompressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out) {
+  out->clear();
+  z_stream zs;
+  std::memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, 16 | MAX_WBITS) != Z_OK) return false;
+  size_t capacity = 1 << 16;
+  if (size >= 18) {
+    uint32_t isize;
+    std::memcpy(&isize, data + size - 4, 4);
+    capacity = std::max<size_t>(capacity, isize);
+  }
+  out->resize(capacity);
+  constexpr size_t kChunk = (size_t)1 << 30;  // zlib counts in 32 bits
+  size_t fed = 0, produced = 0;
+  bool ok = false;
+  while (true) {
+    if (zs.avail_in == 0 && fed < size) {
+      const size_t take = std::min(size - fed, kChunk);
+      zs.next_in = const_cast<Bytef *>(data + fed);
+      zs.avail_in = (uInt)take;
+      fed += take;
+    }
+    if (produced == out->size()) out->resize(out->size() + out->size() / 2);
+    const size_t room = std::min(out->size() - produced, kChunk);
+    zs.next_out = out->data() + produced;
+    zs.avail_out = (uInt)room;
+    const int rc = inflate(&zs, Z_NO_FLUSH);
+    produced += room - zs.avail_out;
+    if (rc == Z_STREAM_END) {
+      ok = true;
+      break;
+    }
+    if (rc == Z_OK) continue;
+    if (rc == Z_BUF_ERROR && (zs.avail_out == 0 || fed < size)) continue;  // wants room or input
+    break;  // corrupt, or the input ended inside the member
+  }
+  inflateEnd(&zs);
+  if (!ok) {
+    out->clear();
+    return false;
+  }
+  out->resize(produced);
+  return true;
+}
+
 // zlib deflate with the reference's parameters (default level, gzip wrapper, memLevel 9,
 // load-spz.cc:186-214), so the compressed bytes are the same for the same input.
 bool compressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out) {
@@ -554,6 +561,8 @@ bool saveSpz(const GaussianCloud &g, const PackOptions &o, std::vector<uint8_t> 
     stream.resize(serializedBytes(packed));
     serializeInto(packed, stream.data());
   }
+  const int threads = gzipThreads();
+  if (threads > 1) return compressGzippedParallel(stream.data(), stream.size(), threads, out);
   return compressGzipped(stream.data(), stream.size(), out);
 }
 
@@ -568,7 +577,7 @@ bool saveSpz(const GaussianCloud &g, const PackOptions &o, const std::string &fi
 
 PackedGaussians loadSpzPacked(const uint8_t *data, int32_t size) {
   std::vector<uint8_t> stream;
-  if (size < 0 || !gunzip(data, (size_t)size, &stream)) return {};
+  if (size < 0 || !decompressGzippedParallel(data, (size_t)size, gzipThreads(), &stream)) return {};
   return deserialize(stream.data(), stream.size());
 }
 

@@ -198,6 +198,20 @@ uint8_t *SHIM(gzip)(const uint8_t *data, uint64_t size, uint64_t *outSize) {
   return dupBytes(out.data(), out.size(), outSize);
 }
 
+#ifdef SHIM_HAS_EXTENSIONS  // this repo only: block-parallel zlib (spz_gzip.cc)
+uint8_t *SHIM(gzip_parallel)(const uint8_t *data, uint64_t size, int32_t threads, uint64_t *outSize) {
+  std::vector<uint8_t> out;
+  if (!spz::compressGzippedParallel(data, size, threads, &out)) return nullptr;
+  return dupBytes(out.data(), out.size(), outSize);
+}
+uint8_t *SHIM(gunzip)(const uint8_t *data, uint64_t size, int32_t threads, uint64_t *outSize) {
+  std::vector<uint8_t> out;
+  const bool ok = threads > 0 ? spz::decompressGzippedParallel(data, size, threads, &out) : spz::decompressGzipped(data, size, &out);
+  if (!ok) return nullptr;
+  return dupBytes(out.data(), out.size(), outSize);
+}
+#endif
+
 // PackedGaussians::at(i): 65 bytes out in member order position9 rotation4 scale3 color3 alpha1 shR15 shG15 shB15
 void SHIM(packed_at)(int32_t n, int32_t deg, int32_t fb, int32_t version, const uint8_t *const planes[6], int32_t i, uint8_t *out65) {
   const spz::PackedGaussians p = makePacked(n, deg, fb, version, 0, planes);

@@ -151,6 +151,20 @@ class Shim:
         ptr = self.fn("gzip")(buf.ctypes.data_as(_u8p), C.c_uint64(buf.size), C.byref(size))
         return None if not ptr else self._take(ptr, size)
 
+    def gzip_parallel(self, data: bytes, threads: int):
+        self.fn("gzip_parallel").restype = C.c_void_p
+        buf = np.frombuffer(data, np.uint8) if data else np.zeros(0, np.uint8)
+        size = C.c_uint64(0)
+        ptr = self.fn("gzip_parallel")(buf.ctypes.data_as(_u8p), C.c_uint64(buf.size), C.c_int32(threads), C.byref(size))
+        return None if not ptr else self._take(ptr, size)
+
+    def gunzip(self, data: bytes, threads: int):
+        self.fn("gunzip").restype = C.c_void_p
+        buf = np.frombuffer(data, np.uint8) if data else np.zeros(0, np.uint8)
+        size = C.c_uint64(0)
+        ptr = self.fn("gunzip")(buf.ctypes.data_as(_u8p), C.c_uint64(buf.size), C.c_int32(threads), C.byref(size))
+        return None if not ptr else self._take(ptr, size)
+
     def at(self, p: Packed, i: int) -> np.ndarray:
         _, ip = self._bplanes(p.planes())
         out = np.zeros(65, np.uint8)
@@ -365,6 +379,65 @@ def test_ply_io_matches_reference(mine, theirs, tmp_path):
             assert_cloud_bits_equal(ga, gb, name)
 
 
+def test_parallel_gzip_is_a_standard_member_with_identical_content(mine, theirs):
+    """Block-parallel zlib (spz_gzip.cc): every inflater recovers the exact input -- Python's gzip,
+    the reference's loadSpzPacked, this repo's serial and parallel inflaters -- and the parallel
+    inflater also reads members it did not write."""
+    rng = np.random.default_rng(80)
+    # a real container so the reference's loader can be the judge: 120k SH3 points = 7.8 MB, 8 blocks
+    p = random_stream(rng, 120_000, 3, 3)
+    # compressible planes (real splats are): quantise the noise
+    p.sh = (p.sh & 0xF0).astype(np.uint8)
+    p.scales = (p.scales & 0xFC).astype(np.uint8)
+    stream = container(p)
+    for threads in (2, 5, 16):
+        z = mine.gzip_parallel(stream, threads)
+        assert z[:4] == b"\x1f\x8b\x08\x04"            # one member, FEXTRA set
+        assert gzip.decompress(z) == stream
+        assert zlib.decompress(z, 16 + zlib.MAX_WBITS) == stream
+        assert mine.gunzip(z, 0) == stream                 # serial inflater
+        assert mine.gunzip(z, threads) == stream           # block-parallel inflater
+        meta, planes = theirs.load_packed(z)               # the unmodified reference reads it
+        assert meta["n"] == 120_000 and all(np.array_equal(a, b) for a, b in zip(planes, p.planes()))
+        serial = mine.gzip(stream)
+        assert len(z) < len(serial) * 1.02                 # independent 1 MiB blocks cost < 2 % in ratio
+    # one thread, or an input below two blocks: the reference's byte-identical serial stream
+    assert mine.gzip_parallel(stream, 1) == theirs.gzip(stream)
+    small = stream[:1_500_000]
+    assert mine.gzip_parallel(small, 8) == theirs.gzip(small)
+    # sizes around the block boundaries
+    for size in (2 << 20, (2 << 20) + 1, (3 << 20) - 1, 5 * (1 << 20)):
+        data = rng.integers(0, 64, size).astype(np.uint8).tobytes()
+        z = mine.gzip_parallel(data, 4)
+        assert gzip.decompress(z) == data and mine.gunzip(z, 4) == data
+    # members written by others (no block table) go down the serial path
+    assert mine.gunzip(theirs.gzip(stream), 8) == stream
+    assert mine.gunzip(gzip.compress(stream, 1), 8) == stream
+    # damage: flipped payload byte, truncated tail, lying table -> the same refusal as a serial inflater
+    z = bytearray(mine.gzip_parallel(stream, 4))
+    bad = bytes(z[:len(z) // 2]) + bytes([z[len(z) // 2] ^ 0x55]) + bytes(z[len(z) // 2 + 1:])
+    assert mine.gunzip(bad, 4) is None and mine.gunzip(bad, 0) is None
+    assert mine.gunzip(bytes(z[:-9]), 4) is None
+    lying = bytearray(z)
+    lying[20] ^= 0x10  # block size field
+    assert mine.gunzip(bytes(lying), 4) in (None, stream)  # falls back to the serial inflater, which ignores FEXTRA
+    assert mine.gunzip(b"", 4) is None and mine.gunzip(b"\x1f\x8b", 4) is None
+
+
+def test_save_load_use_parallel_gzip_when_asked(mine, theirs, tmp_path):
+    """SPZ_B200_GZIP_THREADS switches loadSpzPacked to the parallel inflater (the save side needs the
+    GPU for its planes and is covered by the gpu test below)."""
+    rng = np.random.default_rng(81)
+    p = random_stream(rng, 100_000, 3, 3)
+    z = mine.gzip_parallel(container(p), 4)
+    os.environ["SPZ_B200_GZIP_THREADS"] = "4"
+    try:
+        meta, planes = mine.load_packed(z)
+    finally:
+        del os.environ["SPZ_B200_GZIP_THREADS"]
+    assert meta["n"] == 100_000 and all(np.array_equal(a, b) for a, b in zip(planes, p.planes()))
+
+
 def test_size_checks_and_empty_cloud_need_no_device(mine, theirs):
     """Rejections happen before any device work, so they behave the same with and without a GPU."""
     rng = np.random.default_rng(50)
@@ -453,6 +526,22 @@ def test_save_load_spz_bytes_and_files(mine, theirs, tmp_path):
         assert open(pa, "rb").read() == open(pb, "rb").read()
         assert_cloud_bits_equal(mine.load_spz_file(pb, 7), theirs.load_spz_file(pb, 7), "loadSpz(file)")
         assert not mine.save_spz_file(c, "/nonexistent_dir/x.spz", 0)
+
+
+@pytest.mark.gpu
+def test_save_spz_with_parallel_gzip_is_readable_by_the_reference(mine, theirs):
+    rng = np.random.default_rng(310)
+    c = random_cloud(rng, 150_000, 3, False)
+    serial = mine.save_spz(c, 6)
+    os.environ["SPZ_B200_GZIP_THREADS"] = "8"
+    try:
+        par = mine.save_spz(c, 6)
+        back = mine.load_spz(par, 8)
+    finally:
+        del os.environ["SPZ_B200_GZIP_THREADS"]
+    assert par != serial and gzip.decompress(par) == gzip.decompress(serial)
+    assert_cloud_bits_equal(theirs.load_spz(par, 8), theirs.load_spz(serial, 8), "reference reads the parallel member")
+    assert_cloud_bits_equal(back, theirs.load_spz(serial, 8), "parallel inflate + decode")
 
 
 @pytest.mark.gpu
