@@ -181,6 +181,36 @@ def test_under_aligned_pointers_take_the_scalar_path(gpu_ctx, oracle):
     del t
 
 
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_kernels_write_only_their_planes(gpu_ctx, oracle, deg):
+    """Guard bands (compute-sanitizer is closed on this GPU pool): every output plane sits inside a
+    larger 0xA5-filled buffer; after encode and decode of assorted sizes -- tile multiples, one off
+    either side, sub-tile, odd counts that end in the scalar kernel -- the bands are untouched."""
+    from spz_b200.codec import CloudPlanes, PackedPlanes, byte_plane_widths, float_plane_widths, tile_gaussians
+    t = _torch()
+    tg = tile_gaussians(deg)
+    rng = np.random.default_rng(3300 + deg)
+    pad = 4096
+    for n in (1, 3, 31, tg - 1, tg, tg + 1, 2 * tg + 7, 3 * tg):
+        c = random_cloud(rng, n, deg, False)
+        want = oracle.pack(c, 6)
+        bufs = [t.full((n * w + 2 * pad,), 0xA5, dtype=t.uint8, device="cuda") for w in byte_plane_widths(deg, 3)]
+        out = PackedPlanes(n, deg, *[b[pad:pad + n * w] for b, w in zip(bufs, byte_plane_widths(deg, 3))])
+        gpu_ctx.encode_device(to_dev_cloud(c), 6, out=out)
+        t.cuda.synchronize()
+        for name, b, w, exp in zip(PLANES, bufs, byte_plane_widths(deg, 3), want.planes()):
+            assert bool((b[:pad] == 0xA5).all()) and bool((b[pad + n * w:] == 0xA5).all()), (n, name, "encode wrote outside its plane")
+            assert np.array_equal(b[pad:pad + n * w].cpu().numpy(), exp), (n, name)
+        fb = [t.full((n * w + 2 * pad,), float("nan"), dtype=t.float32, device="cuda") for w in float_plane_widths(deg)]
+        fout = CloudPlanes(n, deg, *[b[pad:pad + n * w] for b, w in zip(fb, float_plane_widths(deg))])
+        gpu_ctx.decode_device(to_dev_packed(want), 8, out=fout)
+        t.cuda.synchronize()
+        back = oracle.unpack(want, 8)
+        for name, b, w, exp in zip(PLANES, fb, float_plane_widths(deg), back.planes()):
+            assert bool(t.isnan(b[:pad]).all()) and bool(t.isnan(b[pad + n * w:]).all()), (n, name, "decode wrote outside its plane")
+            assert np.array_equal(bits(b[pad:pad + n * w].cpu().numpy()), bits(exp)), (n, name)
+
+
 def test_empty_cloud(gpu_ctx):
     from spz_b200.codec import alloc_cloud, alloc_packed
     for deg in range(4):
