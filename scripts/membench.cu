@@ -1,0 +1,393 @@
+// Development microbenchmark (not part of the product): the memory pattern of the decode kernel's
+// SH section -- read one packed word, write one float4, rows of 320, 45-row tiles -- with the
+// arithmetic stripped, in several store/load styles, to find what the access pattern itself allows.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/_build/membench scripts/membench.cu
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+constexpr int S = 320, ROWS = 45, CYC = 9, U = 5;
+
+__device__ __forceinline__ float4 expand(uint32_t w) {
+  return make_float4(__uint_as_float(0x4b000000u | (w & 255u)), __uint_as_float(0x4b000000u | ((w >> 8) & 255u)),
+                     __uint_as_float(0x4b000000u | ((w >> 16) & 255u)), __uint_as_float(0x4b000000u | (w >> 24)));
+}
+
+// A: what the shipped kernel does
+__global__ void __launch_bounds__(S, 4) kDirect(const uint32_t *in, float4 *out) {
+  const long long base = (long long)blockIdx.x * ROWS * S + threadIdx.x;
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    uint32_t w[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) w[u] = __ldg(in + base + (c + u * CYC) * S);
+#pragma unroll
+    for (int u = 0; u < U; u++) __stcs(out + base + (c + u * CYC) * S, expand(w[u]));
+  }
+}
+
+// A2: consecutive rows instead of rows 9 apart
+__global__ void __launch_bounds__(S, 4) kDirectSeq(const uint32_t *in, float4 *out) {
+  const long long base = (long long)blockIdx.x * ROWS * S + threadIdx.x;
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    uint32_t w[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) w[u] = __ldg(in + base + (c * U + u) * S);
+#pragma unroll
+    for (int u = 0; u < U; u++) __stcs(out + base + (c * U + u) * S, expand(w[u]));
+  }
+}
+
+// D: stores only (ceiling of the write side with this pattern)
+__global__ void __launch_bounds__(S, 4) kWriteOnly(const uint32_t *in, float4 *out) {
+  const long long base = (long long)blockIdx.x * ROWS * S + threadIdx.x;
+  const uint32_t w = threadIdx.x;
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+#pragma unroll
+    for (int u = 0; u < U; u++) __stcs(out + base + (c + u * CYC) * S, expand(w + u));
+  }
+}
+
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// B: direct loads, results staged in shared memory, rows written with bulk async copies (UBLKCP)
+__global__ void __launch_bounds__(S, 4) kBulkStore(const uint32_t *in, float4 *out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4 *buf = reinterpret_cast<float4 *>(smem);  // [2][U][S]
+  const long long base = (long long)blockIdx.x * ROWS * S;
+  const int t = threadIdx.x;
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    float4 *b = buf + (c & 1) * U * S;
+    uint32_t w[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) w[u] = __ldg(in + base + t + (c * U + u) * S);
+    if (c >= 2) {
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) b[u * S + t] = expand(w[u]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+      // the U rows of this class are consecutive here: one 25.6 KB bulk store
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + base + (long long)c * U * S),
+                   "r"(smemAddr(b)), "r"(U * S * 16)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// C: bulk loads (mbarrier) + bulk stores; the whole tile's words (57.6 KB) arrive with one copy
+__global__ void __launch_bounds__(S, 2) kBulkBoth(const uint32_t *in, float4 *out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t *win = reinterpret_cast<uint32_t *>(smem);                       // [ROWS][S] words
+  float4 *buf = reinterpret_cast<float4 *>(smem + ROWS * S * 4);            // [2][U][S]
+  __shared__ __align__(8) unsigned long long bar;
+  const long long base = (long long)blockIdx.x * ROWS * S;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(&bar)), "r"(ROWS * S * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(win)),
+                 "l"(in + base), "r"(ROWS * S * 4), "r"(smemAddr(&bar))
+                 : "memory");
+  }
+  {  // wait for phase 0
+    uint32_t done = 0;
+    for (int spin = 0; !done && spin < (1 << 24); spin++) {  // bounded: a wrong byte count must not hang the GPU
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done)
+                   : "r"(smemAddr(&bar)), "r"(0)
+                   : "memory");
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    float4 *b = buf + (c & 1) * U * S;
+    if (c >= 2) {
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) b[u * S + t] = expand(win[(c * U + u) * S + t]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + base + (long long)c * U * S),
+                   "r"(smemAddr(b)), "r"(U * S * 16)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+
+// C5: as C but each class is written as five separate 5 KB rows (what rows-9-apart would need)
+__global__ void __launch_bounds__(S, 2) kBulkBothRows(const uint32_t *in, float4 *out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t *win = reinterpret_cast<uint32_t *>(smem);
+  float4 *buf = reinterpret_cast<float4 *>(smem + ROWS * S * 4);
+  __shared__ __align__(8) unsigned long long bar;
+  const long long base = (long long)blockIdx.x * ROWS * S;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(&bar)), "r"(ROWS * S * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(win)),
+                 "l"(in + base), "r"(ROWS * S * 4), "r"(smemAddr(&bar)) : "memory");
+  }
+  {
+    uint32_t done = 0;
+    for (int spin = 0; !done && spin < (1 << 24); spin++) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smemAddr(&bar)), "r"(0) : "memory");
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    float4 *b = buf + (c & 1) * U * S;
+    if (c >= 2) {
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) b[u * S + t] = expand(win[(c + u * CYC) * S + t]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + base + (long long)(c + u * CYC) * S),
+                     "r"(smemAddr(b + u * S)), "r"(S * 16) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// C3: persistent CTAs (grid = SMs x 2), next tile's words prefetched while this one is expanded
+__global__ void __launch_bounds__(S, 2) kBulkPersistent(const uint32_t *in, float4 *out, long long tiles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t *win = reinterpret_cast<uint32_t *>(smem);                          // [2][ROWS][S]
+  float4 *buf = reinterpret_cast<float4 *>(smem + 2 * ROWS * S * 4);           // [2][U][S]
+  __shared__ __align__(8) unsigned long long bar[2];
+  const int t = threadIdx.x;
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto fetch = [&](long long tile, int slot) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(&bar[slot])), "r"(ROWS * S * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(win + slot * ROWS * S)),
+                 "l"(in + tile * ROWS * S), "r"(ROWS * S * 4), "r"(smemAddr(&bar[slot])) : "memory");
+  };
+  if (t == 0 && blockIdx.x < tiles) fetch(blockIdx.x, 0);
+  int it = 0, stores = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+    const int slot = it & 1;
+    const long long next = tile + gridDim.x;
+    if (t == 0 && next < tiles) fetch(next, slot ^ 1);  // slot^1 was fully read one iteration ago (syncthreads below)
+    {
+      uint32_t done = 0;
+      const uint32_t parity = (it >> 1) & 1;
+      for (int spin = 0; !done && spin < (1 << 24); spin++) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smemAddr(&bar[slot])), "r"(parity) : "memory");
+      }
+    }
+    const uint32_t *w = win + slot * ROWS * S;
+    const long long base = tile * ROWS * S;
+#pragma unroll 1
+    for (int c = 0; c < CYC; c++, stores++) {
+      float4 *b = buf + (stores & 1) * U * S;
+      if (stores >= 2) {
+        if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) b[u * S + t] = expand(w[(c * U + u) * S + t]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (t == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + base + (long long)c * U * S),
+                     "r"(smemAddr(b)), "r"(U * S * 16) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---- the encode direction: read float4, write one word --------------------------------------------
+__device__ __forceinline__ uint32_t squeeze(float4 v) {
+  return (__float_as_uint(v.x) & 255u) | ((__float_as_uint(v.y) & 255u) << 8) | ((__float_as_uint(v.z) & 255u) << 16) | (__float_as_uint(v.w) << 24);
+}
+__global__ void __launch_bounds__(S, 4) kEncDirect(const float4 *in, uint32_t *out) {
+  const long long base = (long long)blockIdx.x * ROWS * S + threadIdx.x;
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) v[u] = __ldg(in + base + (c + u * CYC) * S);
+#pragma unroll
+    for (int u = 0; u < U; u++) __stcs(out + base + (c + u * CYC) * S, squeeze(v[u]));
+  }
+}
+__global__ void __launch_bounds__(S, 4) kEncReadOnly(const float4 *in, uint32_t *out) {
+  const long long base = (long long)blockIdx.x * ROWS * S + threadIdx.x;
+  uint32_t acc = 0;
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) v[u] = __ldg(in + base + (c + u * CYC) * S);
+#pragma unroll
+    for (int u = 0; u < U; u++) acc ^= squeeze(v[u]);
+  }
+  if (acc == 0x12345678u) out[base] = acc;
+}
+// bulk loads of 25.6 KB (5 rows) double-buffered, words collected in smem, one 57.6 KB bulk store per tile
+__global__ void __launch_bounds__(S, 2) kEncBulk(const float4 *in, uint32_t *out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4 *fin = reinterpret_cast<float4 *>(smem);                            // [2][U][S]
+  uint32_t *wout = reinterpret_cast<uint32_t *>(smem + 2 * U * S * 16);     // [ROWS][S]
+  __shared__ __align__(8) unsigned long long bar[2];
+  const long long base = (long long)blockIdx.x * ROWS * S;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto fetch = [&](int c) {
+    const int slot = c & 1;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(&bar[slot])), "r"(U * S * 16) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(fin + slot * U * S)),
+                 "l"(in + base + (long long)c * U * S), "r"(U * S * 16), "r"(smemAddr(&bar[slot])) : "memory");
+  };
+  if (t == 0) { fetch(0); fetch(1); }
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    const int slot = c & 1;
+    uint32_t done = 0;
+    const uint32_t parity = (c >> 1) & 1;
+    for (int spin = 0; !done && spin < (1 << 24); spin++) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smemAddr(&bar[slot])), "r"(parity) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) wout[(c * U + u) * S + t] = squeeze(fin[slot * U * S + u * S + t]);
+    __syncthreads();  // everyone has read this slot
+    if (t == 0 && c + 2 < CYC) fetch(c + 2);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (t == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + base), "r"(smemAddr(wout)), "r"(ROWS * S * 4) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
+
+template <class K>
+int run(const char *name, K kernel, int smemBytes, const uint32_t *in, float4 *out, long long tiles, double bytes, float4 *check) {
+  if (smemBytes) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; i++) kernel<<<(unsigned)tiles, S, smemBytes>>>(in, out);
+  CK(cudaDeviceSynchronize());
+  float best = 1e9f;
+  for (int i = 0; i < 8; i++) {
+    CK(cudaEventRecord(e0));
+    kernel<<<(unsigned)tiles, S, smemBytes>>>(in, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = ms < best ? ms : best;
+  }
+  CK(cudaGetLastError());
+  // spot check against the direct kernel's output
+  int bad = 0;
+  if (check) {
+    float4 a[4], b[4];
+    const long long where[2] = {0, tiles * ROWS * S - 4};
+    for (long long off : where) {
+      CK(cudaMemcpy(a, out + off, sizeof a, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(b, check + off, sizeof b, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < 4; i++) bad += (a[i].x != b[i].x || a[i].w != b[i].w);
+    }
+  }
+  printf("%-44s %8.3f ms  %7.0f GB/s%s\n", name, best, bytes / best / 1e6, bad ? "  MISMATCH" : "");
+  return 0;
+}
+
+template <class L>
+int timeIt(const char *name, L launch, double bytes) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; i++) launch();
+  CK(cudaDeviceSynchronize());
+  float best = 1e9f;
+  for (int i = 0; i < 8; i++) {
+    CK(cudaEventRecord(e0)); launch(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = ms < best ? ms : best;
+  }
+  CK(cudaGetLastError());
+  printf("%-44s %8.3f ms  %7.0f GB/s\n", name, best, bytes / best / 1e6);
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  const long long gaussians = argc > 1 ? atoll(argv[1]) : 100000000LL;
+  const long long tiles = gaussians / 1280;
+  const long long words = tiles * ROWS * S;
+  uint32_t *in; float4 *out, *ref;
+  CK(cudaMalloc(&in, words * 4)); CK(cudaMalloc(&out, words * 16)); CK(cudaMalloc(&ref, words * 16));
+  CK(cudaMemset(in, 0x5a, words * 4));
+  const double rw = words * 20.0, wo = words * 16.0;
+  printf("# decode SH-section memory pattern, %lld gaussians: %lld words in (%.2f GB), %.2f GB out\n", tiles * 1280, words, words * 4e-9, words * 16e-9);
+  if (run("A  direct LDG.32 / STG.128, rows 9 apart", kDirect, 0, in, ref, tiles, rw, nullptr)) return 1;
+  if (run("A2 direct, consecutive rows", kDirectSeq, 0, in, out, tiles, rw, ref)) return 1;
+  if (run("D  stores only (STG.128)", kWriteOnly, 0, in, out, tiles, wo, nullptr)) return 1;
+  if (run("B  LDG.32 -> smem -> bulk store 25.6 KB", kBulkStore, 2 * U * S * 16, in, out, tiles, rw, ref)) return 1;
+  if (run("C  bulk load 57.6 KB + bulk stores", kBulkBoth, ROWS * S * 4 + 2 * U * S * 16, in, out, tiles, rw, ref)) return 1;
+  if (run("C5 bulk load + 5 KB row stores, rows 9 apart", kBulkBothRows, ROWS * S * 4 + 2 * U * S * 16, in, out, tiles, rw, ref)) return 1;
+  {
+    const int smemP = 2 * ROWS * S * 4 + 2 * U * S * 16;
+    CK(cudaFuncSetAttribute(kBulkPersistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smemP));
+    int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    if (timeIt("C3 persistent, 1 CTA/SM, next tile prefetched", [&] { kBulkPersistent<<<sms, S, smemP>>>(in, out, tiles); }, rw)) return 1;
+  }
+  // encode direction: `out` (18 GB) is the float input, `in` (4.5 GB) the word output
+  const float4 *fin = out; uint32_t *wout = in;
+  if (timeIt("E_A encode direct LDG.128 / STG.32", [&] { kEncDirect<<<(unsigned)tiles, S>>>(fin, wout); }, rw)) return 1;
+  if (timeIt("E_R loads only (LDG.128)", [&] { kEncReadOnly<<<(unsigned)tiles, S>>>(fin, wout); }, wo)) return 1;
+  {
+    const int smemE = 2 * U * S * 16 + ROWS * S * 4;
+    CK(cudaFuncSetAttribute(kEncBulk, cudaFuncAttributeMaxDynamicSharedMemorySize, smemE));
+    if (timeIt("E_C bulk loads 25.6 KB x2 + one 57.6 KB bulk store", [&] { kEncBulk<<<(unsigned)tiles, S, smemE>>>(fin, wout); }, rw)) return 1;
+  }
+  return 0;
+}

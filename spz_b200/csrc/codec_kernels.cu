@@ -64,6 +64,9 @@ struct Geo {
 #ifndef SPZ_LD_MODE
 #define SPZ_LD_MODE 1  // 0: ld.global.cs   1: ld.global.nc   2: ld.global   3: ld.global.lu
 #endif
+#ifndef SPZ_DEC_PREFETCH
+#define SPZ_DEC_PREFETCH 0
+#endif
 #ifndef SPZ_ST_MODE
 #define SPZ_ST_MODE 0  // 0: st.global.cs   1: st.global      2: st.global.wt   3: st.global.cg
 #endif
@@ -301,157 +304,175 @@ encodeGenericKernel(const EncodeArgs a, const long long first) {
 // first-three, 3 = 24-bit + smallest-three (load-spz.cc:571-572); 4 = half positions +
 // smallest-three, which no file produces but a hand-built PackedGaussians can (load-spz.cc:465,509).
 // =================================================================================================
+
+// Per-thread constants of the xyz planes: sign bit / signed scale for the phase (t + k) mod 3.
+struct DecodePosConsts {
+  uint32_t posFlip3[3];
+  float posScale3[3];
+  __device__ __forceinline__ void init(const DecodeArgs &a, int t) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      posFlip3[k] = ((a.flipP >> ((t + k) % 3)) & 1u) << 31;
+      posScale3[k] = __uint_as_float(__float_as_uint(a.positionScale) ^ posFlip3[k]);
+    }
+  }
+};
+
+// positions, scales, colours, alphas and rotations of sub-tile q (gaussians [q*1280, (q+1)*1280)):
+// direct 128-byte-aligned loads and stores, shared by both decode kernels.  `stage` is this warp's
+// 288-word scratch.
+template <int VER>
+__device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const long long q, const int t, uint32_t *stage,
+                                                  const float *sAlpha, const float *sColor, const float *sMag,
+                                                  const DecodePosConsts &pc) {
+  constexpr int S = kThreads;
+  constexpr bool kHalf = (VER == 1 || VER == 4);  // float16 positions
+  constexpr bool kS3 = (VER >= 3);                // smallest-three rotations
+  const int lane = t & 31, warp = t >> 5;
+  const uint32_t *posFlip3 = pc.posFlip3;
+  const float *posScale3 = pc.posScale3;
+  // ---- positions ------------------------------------------------------------------------
+  {
+    float4 *out = reinterpret_cast<float4 *>(a.oPositions) + q * (3 * S) + t;
+    if (kHalf) {
+      const uint2 *in = reinterpret_cast<const uint2 *>(a.positions) + q * (3 * S) + t;
+      uint2 w[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) w[i] = ldStream(in + i * S);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float4 o;
+        o.x = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x & 0xffffu)) ^ posFlip3[(0 + 2 * i) % 3]);
+        o.y = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x >> 16)) ^ posFlip3[(1 + 2 * i) % 3]);
+        o.z = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y & 0xffffu)) ^ posFlip3[(2 + 2 * i) % 3]);
+        o.w = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y >> 16)) ^ posFlip3[(3 + 2 * i) % 3]);
+        stStream(out + i * S, o);
+      }
+    } else {
+      // contiguous 128-byte loads of the 96 words a warp needs per row, re-dealt through the
+      // per-warp stage so each lane gets the three words of its four 24-bit values
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.positions) + q * (9 * S) + warp * 96 + lane;
+      uint32_t g[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) g[i][k] = ldStream(in + i * (3 * S) + k * 32);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) stage[i * 96 + k * 32 + lane] = g[i][k];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const uint32_t *sp = stage + i * 96 + 3 * lane;
+        const uint32_t w0 = sp[0], w1 = sp[1], w2 = sp[2];
+        // PRMT with the sign-replicate bit (selector nibble 8|idx) sign-extends 24 -> 32 bits
+        const int32_t f0 = (int32_t)prmt(w0, w0, 0xA210u);
+        const int32_t f1 = (int32_t)prmt(w0, w1, 0xD543u);
+        const int32_t f2 = (int32_t)prmt(w1, w2, 0xC432u);
+        const int32_t f3 = (int32_t)prmt(w2, w2, 0xB321u);
+        float4 o;
+        o.x = m::mul(m::i2f(f0), posScale3[(0 + 2 * i) % 3]);
+        o.y = m::mul(m::i2f(f1), posScale3[(1 + 2 * i) % 3]);
+        o.z = m::mul(m::i2f(f2), posScale3[(2 + 2 * i) % 3]);
+        o.w = m::mul(m::i2f(f3), posScale3[(3 + 2 * i) % 3]);
+        stStream(out + i * S, o);
+      }
+      __syncwarp();
+    }
+  }
+  // ---- scales (exact FMA on the magic float) and colours (table) ---------------------------
+  {
+    const uint32_t *inS = reinterpret_cast<const uint32_t *>(a.scales) + q * (3 * S) + t;
+    const uint32_t *inC = reinterpret_cast<const uint32_t *>(a.colors) + q * (3 * S) + t;
+    float4 *outS = reinterpret_cast<float4 *>(a.oScales) + q * (3 * S) + t;
+    float4 *outC = reinterpret_cast<float4 *>(a.oColors) + q * (3 * S) + t;
+    uint32_t ws[3], wc[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { ws[i] = ldStream(inS + i * S); wc[i] = ldStream(inC + i * S); }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      // (2^23 + s) / 16 - (2^19 + 10) = s/16 - 10: both steps exact, so the fused form equals
+      // the reference's s / 16.0f - 10.0f (load-spz.cc:506) bit for bit, +0 at s = 160.
+      float4 o;
+      o.x = __fmaf_rn(byteAsMagicFloat<0>(ws[i]), 0.0625f, -524298.0f);
+      o.y = __fmaf_rn(byteAsMagicFloat<1>(ws[i]), 0.0625f, -524298.0f);
+      o.z = __fmaf_rn(byteAsMagicFloat<2>(ws[i]), 0.0625f, -524298.0f);
+      o.w = __fmaf_rn(byteAsMagicFloat<3>(ws[i]), 0.0625f, -524298.0f);
+      stStream(outS + i * S, o);
+      float4 c;
+      c.x = sColor[wc[i] & 0xffu];
+      c.y = sColor[(wc[i] >> 8) & 0xffu];
+      c.z = sColor[(wc[i] >> 16) & 0xffu];
+      c.w = sColor[wc[i] >> 24];
+      stStream(outC + i * S, c);
+    }
+  }
+  // ---- alphas (table) ---------------------------------------------------------------------
+  {
+    const uint32_t w = ldStream(reinterpret_cast<const uint32_t *>(a.alphas) + q * S + t);
+    float4 o;
+    o.x = sAlpha[w & 0xffu];
+    o.y = sAlpha[(w >> 8) & 0xffu];
+    o.z = sAlpha[(w >> 16) & 0xffu];
+    o.w = sAlpha[w >> 24];
+    stStream(reinterpret_cast<float4 *>(a.oAlphas) + q * S + t, o);
+  }
+  // ---- rotations ----------------------------------------------------------------------------
+  if (kS3) {
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (4 * S) + t;
+    float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + t;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = ldStream(in + i * S);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float r[4];
+      m::dequant_rotation_smallest3(w[i], sMag, a.flipQ, r);
+      stStream(out + i * S, make_float4(r[0], r[1], r[2], r[3]));
+    }
+  } else {
+    // 3 bytes per quaternion.  A warp owns 128 consecutive quaternions = 96 words, loaded as
+    // three contiguous lines into the stage; lane L then decodes quaternions L, L+32, L+64,
+    // L+96 so that each of its four float4 stores is a contiguous 512-byte warp store.
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (3 * S) + warp * 96 + lane;
+    float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + warp * 128 + lane;
+#pragma unroll
+    for (int k = 0; k < 3; k++) stage[k * 32 + lane] = ldStream(in + k * 32);
+    __syncwarp();
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(stage);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int qi = 3 * (lane + 32 * i);
+      float r[4];
+      m::dequant_rotation_first3(sb[qi], sb[qi + 1], sb[qi + 2], a.flipQ, r);
+      stStream(out + 32 * i, make_float4(r[0], r[1], r[2], r[3]));
+    }
+    __syncwarp();
+  }
+}
+
 template <int D, int VER>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
   constexpr int S = kThreads;
   constexpr int M = Geo<D>::M;
-  constexpr bool kHalf = (VER == 1 || VER == 4);  // float16 positions
-  constexpr bool kS3 = (VER >= 3);                // smallest-three rotations
+  constexpr bool kS3 = (VER >= 3);
   __shared__ float sTab[kS3 ? kDecodeTableFloats : 512];
   __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
   for (int i = threadIdx.x; i < (kS3 ? kDecodeTableFloats : 512); i += kThreads) sTab[i] = __ldg(a.tables + i);
   const float *sAlpha = sTab, *sColor = sTab + 256, *sMag = sTab + 512;
   __syncthreads();
   const int t = threadIdx.x;
-  const int lane = t & 31, warp = t >> 5;
-  uint32_t *stage = sStage[warp];
-
-  // sign bit / signed scale for the xyz phase (t + k) mod 3 (see the encoder)
-  uint32_t posFlip3[3];
-  float posScale3[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    posFlip3[k] = ((a.flipP >> ((t + k) % 3)) & 1u) << 31;
-    posScale3[k] = __uint_as_float(__float_as_uint(a.positionScale) ^ posFlip3[k]);
-  }
+  uint32_t *stage = sStage[t >> 5];
+  DecodePosConsts pc;
+  pc.init(a, t);
 
   for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
 #pragma unroll 1
-    for (int mm = 0; mm < M; mm++) {
-      const long long q = tile * M + mm;
-      // ---- positions ------------------------------------------------------------------------
-      {
-        float4 *out = reinterpret_cast<float4 *>(a.oPositions) + q * (3 * S) + t;
-        if (kHalf) {
-          const uint2 *in = reinterpret_cast<const uint2 *>(a.positions) + q * (3 * S) + t;
-          uint2 w[3];
-#pragma unroll
-          for (int i = 0; i < 3; i++) w[i] = ldStream(in + i * S);
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-            float4 o;
-            o.x = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x & 0xffffu)) ^ posFlip3[(0 + 2 * i) % 3]);
-            o.y = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x >> 16)) ^ posFlip3[(1 + 2 * i) % 3]);
-            o.z = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y & 0xffffu)) ^ posFlip3[(2 + 2 * i) % 3]);
-            o.w = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y >> 16)) ^ posFlip3[(3 + 2 * i) % 3]);
-            stStream(out + i * S, o);
-          }
-        } else {
-          // contiguous 128-byte loads of the 96 words a warp needs per row, re-dealt through the
-          // per-warp stage so each lane gets the three words of its four 24-bit values
-          const uint32_t *in = reinterpret_cast<const uint32_t *>(a.positions) + q * (9 * S) + warp * 96 + lane;
-          uint32_t g[3][3];
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) g[i][k] = ldStream(in + i * (3 * S) + k * 32);
-          }
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) stage[i * 96 + k * 32 + lane] = g[i][k];
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-            const uint32_t *sp = stage + i * 96 + 3 * lane;
-            const uint32_t w0 = sp[0], w1 = sp[1], w2 = sp[2];
-            // PRMT with the sign-replicate bit (selector nibble 8|idx) sign-extends 24 -> 32 bits
-            const int32_t f0 = (int32_t)prmt(w0, w0, 0xA210u);
-            const int32_t f1 = (int32_t)prmt(w0, w1, 0xD543u);
-            const int32_t f2 = (int32_t)prmt(w1, w2, 0xC432u);
-            const int32_t f3 = (int32_t)prmt(w2, w2, 0xB321u);
-            float4 o;
-            o.x = m::mul(m::i2f(f0), posScale3[(0 + 2 * i) % 3]);
-            o.y = m::mul(m::i2f(f1), posScale3[(1 + 2 * i) % 3]);
-            o.z = m::mul(m::i2f(f2), posScale3[(2 + 2 * i) % 3]);
-            o.w = m::mul(m::i2f(f3), posScale3[(3 + 2 * i) % 3]);
-            stStream(out + i * S, o);
-          }
-          __syncwarp();
-        }
-      }
-      // ---- scales (exact FMA on the magic float) and colours (table) ---------------------------
-      {
-        const uint32_t *inS = reinterpret_cast<const uint32_t *>(a.scales) + q * (3 * S) + t;
-        const uint32_t *inC = reinterpret_cast<const uint32_t *>(a.colors) + q * (3 * S) + t;
-        float4 *outS = reinterpret_cast<float4 *>(a.oScales) + q * (3 * S) + t;
-        float4 *outC = reinterpret_cast<float4 *>(a.oColors) + q * (3 * S) + t;
-        uint32_t ws[3], wc[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) { ws[i] = ldStream(inS + i * S); wc[i] = ldStream(inC + i * S); }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          // (2^23 + s) / 16 - (2^19 + 10) = s/16 - 10: both steps exact, so the fused form equals
-          // the reference's s / 16.0f - 10.0f (load-spz.cc:506) bit for bit, +0 at s = 160.
-          float4 o;
-          o.x = __fmaf_rn(byteAsMagicFloat<0>(ws[i]), 0.0625f, -524298.0f);
-          o.y = __fmaf_rn(byteAsMagicFloat<1>(ws[i]), 0.0625f, -524298.0f);
-          o.z = __fmaf_rn(byteAsMagicFloat<2>(ws[i]), 0.0625f, -524298.0f);
-          o.w = __fmaf_rn(byteAsMagicFloat<3>(ws[i]), 0.0625f, -524298.0f);
-          stStream(outS + i * S, o);
-          float4 c;
-          c.x = sColor[wc[i] & 0xffu];
-          c.y = sColor[(wc[i] >> 8) & 0xffu];
-          c.z = sColor[(wc[i] >> 16) & 0xffu];
-          c.w = sColor[wc[i] >> 24];
-          stStream(outC + i * S, c);
-        }
-      }
-      // ---- alphas (table) ---------------------------------------------------------------------
-      {
-        const uint32_t w = ldStream(reinterpret_cast<const uint32_t *>(a.alphas) + q * S + t);
-        float4 o;
-        o.x = sAlpha[w & 0xffu];
-        o.y = sAlpha[(w >> 8) & 0xffu];
-        o.z = sAlpha[(w >> 16) & 0xffu];
-        o.w = sAlpha[w >> 24];
-        stStream(reinterpret_cast<float4 *>(a.oAlphas) + q * S + t, o);
-      }
-      // ---- rotations ----------------------------------------------------------------------------
-      if (kS3) {
-        const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (4 * S) + t;
-        float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + t;
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) w[i] = ldStream(in + i * S);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          float r[4];
-          m::dequant_rotation_smallest3(w[i], sMag, a.flipQ, r);
-          stStream(out + i * S, make_float4(r[0], r[1], r[2], r[3]));
-        }
-      } else {
-        // 3 bytes per quaternion.  A warp owns 128 consecutive quaternions = 96 words, loaded as
-        // three contiguous lines into the stage; lane L then decodes quaternions L, L+32, L+64,
-        // L+96 so that each of its four float4 stores is a contiguous 512-byte warp store.
-        const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (3 * S) + warp * 96 + lane;
-        float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + warp * 128 + lane;
-#pragma unroll
-        for (int k = 0; k < 3; k++) stage[k * 32 + lane] = ldStream(in + k * 32);
-        __syncwarp();
-        const uint8_t *sb = reinterpret_cast<const uint8_t *>(stage);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int qi = 3 * (lane + 32 * i);
-          float r[4];
-          m::dequant_rotation_first3(sb[qi], sb[qi + 1], sb[qi + 2], a.flipQ, r);
-          stStream(out + 32 * i, make_float4(r[0], r[1], r[2], r[3]));
-        }
-        __syncwarp();
-      }
-    }
+    for (int mm = 0; mm < M; mm++) decodeSmallPlanes<VER>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc);
     // ---- spherical harmonics: word -> float4 -------------------------------------------------
     if (D > 0) {
       constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS;
@@ -459,11 +480,24 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
       float4 *out = reinterpret_cast<float4 *>(a.oSh) + tile * ((long long)ROWS * S) + t;
       ShPhase<D> ph;
       ph.init(t);
+#if SPZ_DEC_PREFETCH
+      // software pipeline: the words of class c+1 are requested before class c is expanded
+      uint32_t w[U], wn[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) w[u] = ldStream(in + (u * CYC) * S);
+#pragma unroll 1
+      for (int c = 0; c < CYC; c++) {
+        if (c + 1 < CYC) {
+#pragma unroll
+          for (int u = 0; u < U; u++) wn[u] = ldStream(in + (c + 1 + u * CYC) * S);
+        }
+#else
 #pragma unroll 1
       for (int c = 0; c < CYC; c++) {
         uint32_t w[U];
 #pragma unroll
         for (int u = 0; u < U; u++) w[u] = ldStream(in + (c + u * CYC) * S);
+#endif
         float shMul[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) shMul[e] = signedConst(0.0078125f, ph.flip(e, a.flipSh));
@@ -479,9 +513,135 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
           stStream(out + (c + u * CYC) * S, o);
         }
         ph.advance();
+#if SPZ_DEC_PREFETCH
+#pragma unroll
+        for (int u = 0; u < U; u++) w[u] = wn[u];
+#endif
       }
     }
+    }
+}
+
+// ---- bulk-copy (TMA) staging of the SH plane ---------------------------------------------------------
+// scripts/membench.cu (profiles/r1_membench_patterns.txt): for decode's write-heavy mix, moving the
+// packed words in with ONE bulk async copy per tile (UBLKCP.S.G, completion on an mbarrier) and
+// the expanded rows out with bulk async stores from shared memory (UBLKCP.G.S) sustains 6.76 TB/s
+// where LDG.32 / STG.128 from registers sustains 6.09; for encode's read-heavy mix the two are
+// equal (7.12 vs 7.06), so the encoder keeps its register path.
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbarInit(unsigned long long *bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
+               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long *bar, uint32_t parity) {
+  uint32_t done = 0;
+  // bounded so a lost completion surfaces as a launch failure instead of a hung GPU
+  for (uint32_t spin = 0; !done; spin++) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(smemAddr(bar)), "r"(parity)
+                 : "memory");
+    if (spin > (1u << 28)) __trap();
   }
+}
+__device__ __forceinline__ void bulkStore(void *dstGlobal, const void *srcSmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGlobal), "r"(smemAddr(srcSmem)), "r"(bytes)
+               : "memory");
+}
+
+template <int D>
+struct BulkGeo {
+  static constexpr int SB = (D == 8) ? 4 : 5;  // rows per store batch (a class has U = 5 or 8 rows)
+  static_assert(Geo<D>::U % SB == 0, "a class must split into whole store batches");
+  static constexpr int kTableBytes = kDecodeTableFloats * 4;
+  static constexpr int kWordBytes = Geo<D>::ROWS * kThreads * 4;  // the tile's packed SH words
+  static constexpr int kOutBytes = 2 * SB * kThreads * 16;        // two batches of expanded rows
+  static constexpr int kSmemBytes = kTableBytes + kWordBytes + kOutBytes;
+  static_assert(kOutBytes >= kWarps * 3 * 96 * 4, "the out buffers double as the per-warp word stage");
+};
+
+template <int D, int VER>
+__global__ void __launch_bounds__(kThreads, 2)
+decodeTilesBulkKernel(const DecodeArgs a, const long long numTiles) {
+  static_assert(D > 0, "SH-less clouds use decodeTilesKernel");
+  constexpr int S = kThreads;
+  constexpr int M = Geo<D>::M;
+  constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS, SB = BulkGeo<D>::SB;
+  extern __shared__ __align__(128) unsigned char dynSmem[];
+  __shared__ __align__(8) unsigned long long bar;
+  float *sTab = reinterpret_cast<float *>(dynSmem);
+  uint32_t *win = reinterpret_cast<uint32_t *>(dynSmem + BulkGeo<D>::kTableBytes);
+  float4 *obuf = reinterpret_cast<float4 *>(dynSmem + BulkGeo<D>::kTableBytes + BulkGeo<D>::kWordBytes);
+  const int t = threadIdx.x;
+  for (int i = t; i < kDecodeTableFloats; i += kThreads) sTab[i] = __ldg(a.tables + i);
+  if (t == 0) mbarInit(&bar);
+  const float *sAlpha = sTab, *sColor = sTab + 256, *sMag = sTab + 512;
+  __syncthreads();
+  uint32_t *stage = reinterpret_cast<uint32_t *>(obuf) + (t >> 5) * (3 * 96);
+  DecodePosConsts pc;
+  pc.init(a, t);
+
+  uint32_t parity = 0;
+  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
+    // the SH words of the whole tile: one bulk copy, in flight while the small planes are decoded
+    if (t == 0)
+      bulkLoad(win, reinterpret_cast<const uint32_t *>(a.sh) + tile * ((long long)ROWS * S), BulkGeo<D>::kWordBytes, &bar);
+#pragma unroll 1
+    for (int mm = 0; mm < M; mm++) decodeSmallPlanes<VER>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc);
+    mbarWait(&bar, parity);
+    __syncthreads();  // every warp is done with its word stage, which the out buffers overlay
+
+    float4 *out = reinterpret_cast<float4 *>(a.oSh) + tile * ((long long)ROWS * S);
+    ShPhase<D> ph;
+    ph.init(t);
+    int batch = 0;
+#pragma unroll 1
+    for (int c = 0; c < CYC; c++) {
+      float shMul[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) shMul[e] = signedConst(0.0078125f, ph.flip(e, a.flipSh));
+#pragma unroll 1
+      for (int h = 0; h < U / SB; h++, batch++) {
+        float4 *b = obuf + (batch & 1) * (SB * S);
+        if (batch >= 2) {  // the bulk stores that read this buffer two batches ago must be done with it
+          if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < SB; k++) {
+          const uint32_t w = win[(c + (h * SB + k) * CYC) * S + t];
+          // (2^23 + x) - (2^23 + 128) = x - 128 exactly (+0 at x = 128), then * +-1/128: the
+          // reference's ((float)x - 128.0f) / 128.0f followed by the flip (load-spz.cc:83).
+          float4 o;
+          o.x = m::mul(m::add(byteAsMagicFloat<0>(w), -8388736.0f), shMul[0]);
+          o.y = m::mul(m::add(byteAsMagicFloat<1>(w), -8388736.0f), shMul[1]);
+          o.z = m::mul(m::add(byteAsMagicFloat<2>(w), -8388736.0f), shMul[2]);
+          o.w = m::mul(m::add(byteAsMagicFloat<3>(w), -8388736.0f), shMul[3]);
+          b[k * S + t] = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the STS visible to the copy engine
+        __syncthreads();
+        if (t == 0) {
+#pragma unroll
+          for (int k = 0; k < SB; k++) bulkStore(out + (long long)(c + (h * SB + k) * CYC) * S, b + k * S, S * 16);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      ph.advance();
+    }
+    // before the buffers are reused (next tile's word stage / words): stores have read them, and
+    // every thread has read its last words
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // =================================================================================================
@@ -561,15 +721,29 @@ cudaError_t launchEncodeTiles(const EncodeArgs &a, long long tiles, int grid, cu
   return cudaGetLastError();
 }
 
-template <int D>
-cudaError_t launchDecodeTiles(const DecodeArgs &a, long long tiles, int grid, cudaStream_t s) {
-  switch (a.version) {
-    case 1: decodeTilesKernel<D, 1><<<grid, kThreads, 0, s>>>(a, tiles); break;
-    case 2: decodeTilesKernel<D, 2><<<grid, kThreads, 0, s>>>(a, tiles); break;
-    case 4: decodeTilesKernel<D, 4><<<grid, kThreads, 0, s>>>(a, tiles); break;
-    default: decodeTilesKernel<D, 3><<<grid, kThreads, 0, s>>>(a, tiles); break;
+template <int D, int VER>
+cudaError_t launchDecodeTilesVer(const DecodeArgs &a, long long tiles, int grid, bool bulk, cudaStream_t s) {
+  if constexpr (D > 0) {
+    if (bulk) {
+      static cudaError_t attr = cudaFuncSetAttribute(decodeTilesBulkKernel<D, VER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     BulkGeo<D>::kSmemBytes);  // once per instantiation
+      if (attr != cudaSuccess) return attr;
+      decodeTilesBulkKernel<D, VER><<<grid, kThreads, BulkGeo<D>::kSmemBytes, s>>>(a, tiles);
+      return cudaGetLastError();
+    }
   }
+  decodeTilesKernel<D, VER><<<grid, kThreads, 0, s>>>(a, tiles);
   return cudaGetLastError();
+}
+
+template <int D>
+cudaError_t launchDecodeTiles(const DecodeArgs &a, long long tiles, int grid, bool bulk, cudaStream_t s) {
+  switch (a.version) {
+    case 1: return launchDecodeTilesVer<D, 1>(a, tiles, grid, bulk, s);
+    case 2: return launchDecodeTilesVer<D, 2>(a, tiles, grid, bulk, s);
+    case 4: return launchDecodeTilesVer<D, 4>(a, tiles, grid, bulk, s);
+    default: return launchDecodeTilesVer<D, 3>(a, tiles, grid, bulk, s);
+  }
 }
 
 }  // namespace
@@ -635,12 +809,15 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
     const int per = plan.ctasPerSm >= 1 && plan.ctasPerSm <= kCtasPerSm ? plan.ctasPerSm : kCtasPerSm;
     const long long cap = plan.flatGrid ? 0x7fffffffLL : (long long)plan.smCount * per;
     const int grid = (int)(tiles < cap ? tiles : cap);
+    // the bulk-copy kernel needs the packed SH plane 16-byte aligned (cp.async.bulk); 4-byte aligned
+    // planes still take the register-path tile kernel
+    const bool bulk = plan.decodeBulk && aligned(a.sh, 16);
     cudaError_t e;
     switch (a.shDim) {
-      case 0: e = launchDecodeTiles<0>(a, tiles, grid, stream); break;
-      case 3: e = launchDecodeTiles<3>(a, tiles, grid, stream); break;
-      case 8: e = launchDecodeTiles<8>(a, tiles, grid, stream); break;
-      case 15: e = launchDecodeTiles<15>(a, tiles, grid, stream); break;
+      case 0: e = launchDecodeTiles<0>(a, tiles, grid, false, stream); break;
+      case 3: e = launchDecodeTiles<3>(a, tiles, grid, bulk, stream); break;
+      case 8: e = launchDecodeTiles<8>(a, tiles, grid, bulk, stream); break;
+      case 15: e = launchDecodeTiles<15>(a, tiles, grid, bulk, stream); break;
       default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

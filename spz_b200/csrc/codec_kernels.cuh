@@ -40,6 +40,7 @@ struct LaunchPlan {
   bool forceGeneric;   // test hook: route everything through the scalar kernels
   int ctasPerSm;       // persistent grid = smCount * ctasPerSm (1..3); 0 = default (3)
   bool flatGrid;       // experiment knob: one CTA per tile instead of persistent CTAs
+  bool decodeBulk;     // decode the SH plane through bulk async copies (TMA) instead of registers
 };
 
 // Number of kernels launched is returned through *launches (0, 1 or 2).
