@@ -11,5 +11,5 @@ $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'encode|decode' -c 40 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "list rc=$?"
 $CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'TilesKernel' -s 6 -c 2 -o gpurun_out/prof_${TAG} -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"Tiles.*Kernel" -s 6 -c 2 -o gpurun_out/prof_${TAG} -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full rc=$?"

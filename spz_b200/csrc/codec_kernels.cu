@@ -64,6 +64,9 @@ struct Geo {
 #ifndef SPZ_LD_MODE
 #define SPZ_LD_MODE 1  // 0: ld.global.cs   1: ld.global.nc   2: ld.global   3: ld.global.lu
 #endif
+#ifndef SPZ_DEC_HOIST
+#define SPZ_DEC_HOIST false  // true: request all small-plane words of a sub-tile up front (measured: no gain)
+#endif
 #ifndef SPZ_DEC_PREFETCH
 #define SPZ_DEC_PREFETCH 0
 #endif
@@ -321,7 +324,7 @@ struct DecodePosConsts {
 // positions, scales, colours, alphas and rotations of sub-tile q (gaussians [q*1280, (q+1)*1280)):
 // direct 128-byte-aligned loads and stores, shared by both decode kernels.  `stage` is this warp's
 // 288-word scratch.
-template <int VER>
+template <int VER, bool HOIST>
 __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const long long q, const int t, uint32_t *stage,
                                                   const float *sAlpha, const float *sColor, const float *sMag,
                                                   const DecodePosConsts &pc) {
@@ -331,14 +334,51 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
   const int lane = t & 31, warp = t >> 5;
   const uint32_t *posFlip3 = pc.posFlip3;
   const float *posScale3 = pc.posScale3;
+  // The packed words of the five planes: 20 registers.  HOIST requests all of them before the
+  // first value is expanded (the bulk kernel runs 20 warps per SM and has the registers to spare);
+  // otherwise each plane's words are requested right before use.
+  uint2 w[3];
+  uint32_t g[3][3], ws[3], wc[3], wa, wr[4];
+  auto loadPositions = [&] {
+    if (kHalf) {
+      const uint2 *in = reinterpret_cast<const uint2 *>(a.positions) + q * (3 * S) + t;
+#pragma unroll
+      for (int i = 0; i < 3; i++) w[i] = ldStream(in + i * S);
+    } else {
+      // contiguous 128-byte loads of the 96 words a warp needs per row (re-dealt through the stage below)
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.positions) + q * (9 * S) + warp * 96 + lane;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) g[i][k] = ldStream(in + i * (3 * S) + k * 32);
+      }
+    }
+  };
+  auto loadScalesColors = [&] {
+    const uint32_t *inS = reinterpret_cast<const uint32_t *>(a.scales) + q * (3 * S) + t;
+    const uint32_t *inC = reinterpret_cast<const uint32_t *>(a.colors) + q * (3 * S) + t;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { ws[i] = ldStream(inS + i * S); wc[i] = ldStream(inC + i * S); }
+  };
+  auto loadAlphas = [&] { wa = ldStream(reinterpret_cast<const uint32_t *>(a.alphas) + q * S + t); };
+  auto loadRotations = [&] {
+    if (kS3) {
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (4 * S) + t;
+#pragma unroll
+      for (int i = 0; i < 4; i++) wr[i] = ldStream(in + i * S);
+    }
+  };
+  if (HOIST) {
+    loadPositions();
+    loadScalesColors();
+    loadAlphas();
+    loadRotations();
+  }
   // ---- positions ------------------------------------------------------------------------
   {
     float4 *out = reinterpret_cast<float4 *>(a.oPositions) + q * (3 * S) + t;
+    if (!HOIST) loadPositions();
     if (kHalf) {
-      const uint2 *in = reinterpret_cast<const uint2 *>(a.positions) + q * (3 * S) + t;
-      uint2 w[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) w[i] = ldStream(in + i * S);
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         float4 o;
@@ -349,15 +389,7 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
         stStream(out + i * S, o);
       }
     } else {
-      // contiguous 128-byte loads of the 96 words a warp needs per row, re-dealt through the
-      // per-warp stage so each lane gets the three words of its four 24-bit values
-      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.positions) + q * (9 * S) + warp * 96 + lane;
-      uint32_t g[3][3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) g[i][k] = ldStream(in + i * (3 * S) + k * 32);
-      }
+      // re-deal through the per-warp stage so each lane gets the three words of its four 24-bit values
 #pragma unroll
       for (int i = 0; i < 3; i++) {
 #pragma unroll
@@ -385,13 +417,9 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
   }
   // ---- scales (exact FMA on the magic float) and colours (table) ---------------------------
   {
-    const uint32_t *inS = reinterpret_cast<const uint32_t *>(a.scales) + q * (3 * S) + t;
-    const uint32_t *inC = reinterpret_cast<const uint32_t *>(a.colors) + q * (3 * S) + t;
     float4 *outS = reinterpret_cast<float4 *>(a.oScales) + q * (3 * S) + t;
     float4 *outC = reinterpret_cast<float4 *>(a.oColors) + q * (3 * S) + t;
-    uint32_t ws[3], wc[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) { ws[i] = ldStream(inS + i * S); wc[i] = ldStream(inC + i * S); }
+    if (!HOIST) loadScalesColors();
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       // (2^23 + s) / 16 - (2^19 + 10) = s/16 - 10: both steps exact, so the fused form equals
@@ -412,25 +440,22 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
   }
   // ---- alphas (table) ---------------------------------------------------------------------
   {
-    const uint32_t w = ldStream(reinterpret_cast<const uint32_t *>(a.alphas) + q * S + t);
+    if (!HOIST) loadAlphas();
     float4 o;
-    o.x = sAlpha[w & 0xffu];
-    o.y = sAlpha[(w >> 8) & 0xffu];
-    o.z = sAlpha[(w >> 16) & 0xffu];
-    o.w = sAlpha[w >> 24];
+    o.x = sAlpha[wa & 0xffu];
+    o.y = sAlpha[(wa >> 8) & 0xffu];
+    o.z = sAlpha[(wa >> 16) & 0xffu];
+    o.w = sAlpha[wa >> 24];
     stStream(reinterpret_cast<float4 *>(a.oAlphas) + q * S + t, o);
   }
   // ---- rotations ----------------------------------------------------------------------------
   if (kS3) {
-    const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (4 * S) + t;
     float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + t;
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) w[i] = ldStream(in + i * S);
+    if (!HOIST) loadRotations();
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       float r[4];
-      m::dequant_rotation_smallest3(w[i], sMag, a.flipQ, r);
+      m::dequant_rotation_smallest3(wr[i], sMag, a.flipQ, r);
       stStream(out + i * S, make_float4(r[0], r[1], r[2], r[3]));
     }
   } else {
@@ -472,7 +497,7 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
 
   for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
 #pragma unroll 1
-    for (int mm = 0; mm < M; mm++) decodeSmallPlanes<VER>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc);
+    for (int mm = 0; mm < M; mm++) decodeSmallPlanes<VER, false>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc);
     // ---- spherical harmonics: word -> float4 -------------------------------------------------
     if (D > 0) {
       constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS;
@@ -594,7 +619,7 @@ decodeTilesBulkKernel(const DecodeArgs a, const long long numTiles) {
     if (t == 0)
       bulkLoad(win, reinterpret_cast<const uint32_t *>(a.sh) + tile * ((long long)ROWS * S), BulkGeo<D>::kWordBytes, &bar);
 #pragma unroll 1
-    for (int mm = 0; mm < M; mm++) decodeSmallPlanes<VER>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc);
+    for (int mm = 0; mm < M; mm++) decodeSmallPlanes<VER, SPZ_DEC_HOIST>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc);
     mbarWait(&bar, parity);
     __syncthreads();  // every warp is done with its word stage, which the out buffers overlay
 
