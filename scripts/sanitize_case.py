@@ -1,4 +1,5 @@
-"""Small end-to-end case for compute-sanitizer: every kernel variant once (tile + generic, all SH
+"""Small end-to-end case (written for compute-sanitizer, which this GPU pool keeps closed; now run
+by tests/test_gpu_parity.py::test_alternate_launch_shapes under each development knob): every kernel variant once (tile + generic, all SH
 degrees, every stream flavour, host pipeline with and without bounce buffers), checked against the
 oracle so the run also fails on wrong results."""
 import os, sys
@@ -10,11 +11,13 @@ import oracle as O
 from spz_b200 import codec
 from util import random_cloud, random_stream, assert_packed_equal, assert_cloud_bits_equal
 
+# enough tiles that persistent CTAs (148 x SPZB200_CTAS_PER_SM of them) each walk several
+TILES = 310 if os.environ.get("SPZB200_GRID") == "persistent" else 7
 chk = O.Oracle()
 rng = np.random.default_rng(9)
 with codec.Context(0) as ctx:
     for deg in range(4):
-        n = 2 * codec.tile_gaussians(deg) + 37
+        n = TILES * codec.tile_gaussians(deg) + 37
         c = random_cloud(rng, n, deg, True)
         dev = codec.CloudPlanes(n, deg, *[torch.from_numpy(p).cuda() for p in c.planes()])
         p = ctx.encode_device(dev, 6); torch.cuda.synchronize()

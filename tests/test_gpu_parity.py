@@ -211,6 +211,22 @@ def test_kernels_write_only_their_planes(gpu_ctx, oracle, deg):
             assert np.array_equal(bits(b[pad:pad + n * w].cpu().numpy()), bits(exp)), (n, name)
 
 
+@pytest.mark.parametrize("env", [{"SPZB200_GRID": "persistent"}, {"SPZB200_GRID": "persistent", "SPZB200_CTAS_PER_SM": "1"},
+                                 {"SPZB200_DECODE": "direct"}, {"SPZB200_PACK": "alu"}])
+def test_alternate_launch_shapes(env):
+    """The development knobs select other code paths of the same kernels (persistent multi-tile CTAs,
+    which exercise the bulk decoder's mbarrier phase flip and buffer hand-over between tiles; the
+    register-path decoder; the ALU byte packer).  scripts/sanitize_case.py runs every kernel variant
+    against the oracle under each."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "sanitize_case.py")], capture_output=True, text=True,
+                       env=dict(os.environ, SPZB200_NO_REBUILD="1", **env), timeout=600)
+    assert r.returncode == 0 and "sanitize_case ok" in r.stdout, (env, r.stdout[-1500:], r.stderr[-1500:])
+
+
 def test_empty_cloud(gpu_ctx):
     from spz_b200.codec import alloc_cloud, alloc_packed
     for deg in range(4):
