@@ -236,6 +236,106 @@ __global__ void __launch_bounds__(S, 2) kBulkPersistent(const uint32_t *in, floa
   if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+
+// C7: per-class bulk loads (5 rows of 1280 B, rows 9 apart, double buffered) + bulk row stores: 64 KB -> 3 CTAs/SM
+__global__ void __launch_bounds__(S, 3) kBulkPerClass(const uint32_t *in, float4 *out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t *win = reinterpret_cast<uint32_t *>(smem);                   // [2][U][S]
+  float4 *buf = reinterpret_cast<float4 *>(smem + 2 * U * S * 4);       // [2][U][S]
+  __shared__ __align__(8) unsigned long long bar[2];
+  const long long base = (long long)blockIdx.x * ROWS * S;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto fetch = [&](int c) {
+    const int slot = c & 1;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(&bar[slot])), "r"(U * S * 4) : "memory");
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(win + (slot * U + u) * S)),
+                   "l"(in + base + (long long)(c + u * CYC) * S), "r"(S * 4), "r"(smemAddr(&bar[slot])) : "memory");
+  };
+  if (t == 0) { fetch(0); fetch(1); }
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    const int slot = c & 1;
+    float4 *b = buf + slot * U * S;
+    uint32_t done = 0;
+    for (int spin = 0; !done && spin < (1 << 24); spin++) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smemAddr(&bar[slot])), "r"((c >> 1) & 1) : "memory");
+    }
+    if (c >= 2) {
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) b[u * S + t] = expand(win[(slot * U + u) * S + t]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+      if (c + 2 < CYC) fetch(c + 2);  // everyone has read this slot's words
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + base + (long long)(c + u * CYC) * S),
+                     "r"(smemAddr(b + u * S)), "r"(S * 16) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// C6: as C5 with three row buffers instead of two
+__global__ void __launch_bounds__(S, 1) kBulkBoth3(const uint32_t *in, float4 *out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t *win = reinterpret_cast<uint32_t *>(smem);
+  float4 *buf = reinterpret_cast<float4 *>(smem + ROWS * S * 4);  // [3][U][S]
+  __shared__ __align__(8) unsigned long long bar;
+  const long long base = (long long)blockIdx.x * ROWS * S;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(&bar)), "r"(ROWS * S * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(win)),
+                 "l"(in + base), "r"(ROWS * S * 4), "r"(smemAddr(&bar)) : "memory");
+  }
+  {
+    uint32_t done = 0;
+    for (int spin = 0; !done && spin < (1 << 24); spin++) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smemAddr(&bar)), "r"(0) : "memory");
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < CYC; c++) {
+    float4 *b = buf + (c % 3) * U * S;
+    if (c >= 3) {
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) b[u * S + t] = expand(win[(c + u * CYC) * S + t]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + base + (long long)(c + u * CYC) * S),
+                     "r"(smemAddr(b + u * S)), "r"(S * 16) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---- the encode direction: read float4, write one word --------------------------------------------
 __device__ __forceinline__ uint32_t squeeze(float4 v) {
   return (__float_as_uint(v.x) & 255u) | ((__float_as_uint(v.y) & 255u) << 8) | ((__float_as_uint(v.z) & 255u) << 16) | (__float_as_uint(v.w) << 24);
@@ -374,6 +474,8 @@ int main(int argc, char **argv) {
   if (run("B  LDG.32 -> smem -> bulk store 25.6 KB", kBulkStore, 2 * U * S * 16, in, out, tiles, rw, ref)) return 1;
   if (run("C  bulk load 57.6 KB + bulk stores", kBulkBoth, ROWS * S * 4 + 2 * U * S * 16, in, out, tiles, rw, ref)) return 1;
   if (run("C5 bulk load + 5 KB row stores, rows 9 apart", kBulkBothRows, ROWS * S * 4 + 2 * U * S * 16, in, out, tiles, rw, ref)) return 1;
+  if (run("C7 per-class bulk loads 5x1280 B, 3 CTAs/SM", kBulkPerClass, 2 * U * S * 4 + 2 * U * S * 16, in, out, tiles, rw, ref)) return 1;
+  if (run("C6 as C5 with 3 row buffers (1 CTA/SM)", kBulkBoth3, ROWS * S * 4 + 3 * U * S * 16, in, out, tiles, rw, ref)) return 1;
   {
     const int smemP = 2 * ROWS * S * 4 + 2 * U * S * 16;
     CK(cudaFuncSetAttribute(kBulkPersistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smemP));

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "load-spz.h"  // -I decides whose
@@ -145,6 +146,36 @@ void SHIM(cloud_copy)(const CloudHandle *h, float *const out[6]) {
   put(out[3], h->g.alphas); put(out[4], h->g.colors); put(out[5], h->g.sh);
 }
 void SHIM(cloud_free)(CloudHandle *h) { delete h; }
+
+// `threads` host threads pack and unpack the same cloud concurrently (the API is re-entrant: the
+// reference has no shared state; this repo keeps one GPU context per host thread).  Returns the
+// number of threads whose result differs from thread 0's, or -1 if any call failed.
+int SHIM(concurrent_roundtrip)(int32_t n, int32_t deg, int32_t from, int32_t to, const float *const planes[6], int32_t threads) {
+  const spz::GaussianCloud g = makeCloud(n, deg, 0, planes);
+  spz::PackOptions po; po.from = (spz::CoordinateSystem)from;
+  spz::UnpackOptions uo; uo.to = (spz::CoordinateSystem)to;
+  std::vector<spz::PackedGaussians> packed((size_t)threads);
+  std::vector<spz::GaussianCloud> back((size_t)threads);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++)
+    pool.emplace_back([&, t] {
+      for (int rep = 0; rep < 3; rep++) {
+        packed[t] = spz::packGaussians(g, po);
+        back[t] = spz::unpackGaussians(packed[t], uo);
+      }
+    });
+  for (auto &t : pool) t.join();
+  int different = 0;
+  for (int t = 0; t < threads; t++) {
+    if (packed[t].numPoints != n || back[t].numPoints != n) return -1;
+    const bool same = packed[t].positions == packed[0].positions && packed[t].rotations == packed[0].rotations &&
+                      packed[t].sh == packed[0].sh && packed[t].alphas == packed[0].alphas &&
+                      std::memcmp(back[t].sh.data(), back[0].sh.data(), back[0].sh.size() * 4) == 0 &&
+                      std::memcmp(back[t].rotations.data(), back[0].rotations.data(), back[0].rotations.size() * 4) == 0;
+    different += same ? 0 : 1;
+  }
+  return different;
+}
 
 int SHIM(save_ply)(int32_t n, int32_t deg, int32_t from, const float *const planes[6], const char *path) {
   const spz::GaussianCloud g = makeCloud(n, deg, 0, planes);

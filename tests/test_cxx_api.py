@@ -545,6 +545,16 @@ def test_save_spz_with_parallel_gzip_is_readable_by_the_reference(mine, theirs):
 
 
 @pytest.mark.gpu
+def test_concurrent_callers_each_get_their_own_context(mine, theirs):
+    rng = np.random.default_rng(320)
+    c = random_cloud(rng, 40_000, 3, False)
+    _, ip = mine._fplanes(c.planes())
+    for shim in (mine, theirs):
+        diff = shim.fn("concurrent_roundtrip")(C.c_int32(c.n), C.c_int32(3), C.c_int32(6), C.c_int32(8), ip, C.c_int32(4))
+        assert diff == 0, shim.prefix
+
+
+@pytest.mark.gpu
 def test_unpack_one_matches_reference(mine, theirs):
     rng = np.random.default_rng(400)
     for ver in (1, 2, 3):
