@@ -522,6 +522,31 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
   return SPZB200_OK;
 }
 
+// Contexts of the multi-GPU entry points: created on first use, kept for the life of the process
+// (a context owns device staging buffers, pinned bounce buffers and a copy pool -- re-creating them
+// per call costs more than a small cloud's whole encode).  A lease hands one out exclusively, so
+// concurrent *_host_multi calls that name the same device slot in behind each other on it.
+struct SharedContexts {
+  struct Slot {
+    std::mutex busy;
+    SpzB200Context *ctx = nullptr;
+  };
+  std::mutex m;
+  std::vector<std::pair<int32_t, Slot *>> slots;  // a device may be listed twice in one call: one slot per (device, ordinal)
+  Slot *slot(int32_t device, int ordinal) {
+    std::lock_guard<std::mutex> g(m);
+    int seen = 0;
+    for (auto &s : slots)
+      if (s.first == device && seen++ == ordinal) return s.second;
+    slots.emplace_back(device, new Slot);
+    return slots.back().second;
+  }
+};
+SharedContexts &sharedContexts() {
+  static SharedContexts *pool = new SharedContexts;  // intentionally never destroyed: no CUDA calls at exit
+  return *pool;
+}
+
 template <class Fn>
 int runSharded(const int32_t *devices, int32_t numDevices, int64_t n, int32_t shDegree, Fn &&perShard,
                SpzB200Timings *timings) {
@@ -537,12 +562,12 @@ int runSharded(const int32_t *devices, int32_t numDevices, int64_t n, int32_t sh
       int64_t a = 0, b = 0;
       rc[i] = spzb200_shard_range(n, shDegree, numDevices, i, &a, &b);
       if (rc[i] == SPZB200_OK && b > a) {
-        SpzB200Context *ctx = nullptr;
-        rc[i] = spzb200_create(devices[i], &ctx);
-        if (rc[i] == SPZB200_OK) {
-          rc[i] = perShard(ctx, a, b, &tms[i]);
-          spzb200_destroy(ctx);
-        }
+        int ordinal = 0;
+        for (int32_t k = 0; k < i; k++) ordinal += devices[k] == devices[i];
+        SharedContexts::Slot *slot = sharedContexts().slot(devices[i], ordinal);
+        std::lock_guard<std::mutex> lease(slot->busy);
+        if (!slot->ctx) rc[i] = spzb200_create(devices[i], &slot->ctx);
+        if (rc[i] == SPZB200_OK) rc[i] = perShard(slot->ctx, a, b, &tms[i]);
       }
       if (rc[i] != SPZB200_OK) msg[i] = spzb200_last_error();
     });
@@ -561,6 +586,8 @@ int runSharded(const int32_t *devices, int32_t numDevices, int64_t n, int32_t sh
       out.d2h_bytes += t.d2h_bytes;
       out.kernel_launches += t.kernel_launches;
       out.chunks += t.chunks;
+      out.host_copy_ms = std::max(out.host_copy_ms, t.host_copy_ms);
+      out.staged |= t.staged;
     }
     out.wall_ms = nowMs() - w0;
     *timings = out;

@@ -19,6 +19,7 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -50,11 +51,20 @@ void parallelFor(size_t count, int threads, Fn &&fn) {
   for (auto &t : pool) t.join();
 }
 
+// zlib level of the parallel path: the reference's default unless SPZ_B200_GZIP_LEVEL (0..9) says
+// otherwise (level 1 is ~3x faster for a few percent of ratio; the inflated bytes never change).
+int parallelLevel() {
+  const char *env = std::getenv("SPZ_B200_GZIP_LEVEL");
+  if (!env || !*env) return Z_DEFAULT_COMPRESSION;
+  const int v = std::atoi(env);
+  return v < 0 ? Z_DEFAULT_COMPRESSION : (v > 9 ? 9 : v);
+}
+
 // One block -> raw deflate bytes, reference parameters (default level, memLevel 9).
-bool deflateBlock(const uint8_t *src, size_t len, bool last, std::vector<uint8_t> *out) {
+bool deflateBlock(const uint8_t *src, size_t len, bool last, int level, std::vector<uint8_t> *out) {
   z_stream zs;
   std::memset(&zs, 0, sizeof zs);
-  if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -MAX_WBITS, 9, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+  if (deflateInit2(&zs, level, Z_DEFLATED, -MAX_WBITS, 9, Z_DEFAULT_STRATEGY) != Z_OK) return false;
   out->resize(deflateBound(&zs, (uLong)len) + 16);
   zs.next_in = const_cast<Bytef *>(src);
   zs.avail_in = (uInt)len;
@@ -124,9 +134,10 @@ bool compressGzippedParallel(const uint8_t *data, size_t size, int threads, std:
   std::vector<std::vector<uint8_t>> parts(blocks);
   std::vector<uint32_t> crcs(blocks);
   std::atomic<bool> ok{true};
+  const int level = parallelLevel();
   parallelFor(blocks, threads, [&](size_t i) {
     const size_t off = i * blockSize, len = std::min(blockSize, size - off);
-    if (!deflateBlock(data + off, len, i + 1 == blocks, &parts[i])) ok = false;
+    if (!deflateBlock(data + off, len, i + 1 == blocks, level, &parts[i])) ok = false;
     crcs[i] = (uint32_t)crc32(crc32(0L, Z_NULL, 0), data + off, (uInt)len);
   });
   if (!ok) {

@@ -401,6 +401,14 @@ def test_parallel_gzip_is_a_standard_member_with_identical_content(mine, theirs)
         assert meta["n"] == 120_000 and all(np.array_equal(a, b) for a, b in zip(planes, p.planes()))
         serial = mine.gzip(stream)
         assert len(z) < len(serial) * 1.02                 # independent 1 MiB blocks cost < 2 % in ratio
+    # a faster zlib level for the parallel path only; content unchanged
+    os.environ["SPZ_B200_GZIP_LEVEL"] = "1"
+    try:
+        fast = mine.gzip_parallel(stream, 4)
+        assert gzip.decompress(fast) == stream and mine.gunzip(fast, 4) == stream and len(fast) >= len(z)
+        assert mine.gzip(stream) == theirs.gzip(stream)    # the serial stream ignores the knob
+    finally:
+        del os.environ["SPZ_B200_GZIP_LEVEL"]
     # one thread, or an input below two blocks: the reference's byte-identical serial stream
     assert mine.gzip_parallel(stream, 1) == theirs.gzip(stream)
     small = stream[:1_500_000]
