@@ -33,7 +33,7 @@ class Shim:
     def __init__(self, prefix: str):
         self.prefix = prefix
         so = os.path.join(CXX, "_build", f"libshim_{prefix}.so")
-        target = "all" if prefix == "b200" else "ref"
+        target = {"b200": "all", "ref": "ref", "xlink": "xlink"}[prefix]
         can_build = prefix == "b200" or os.path.isdir("/root/reference/src/cc")
         if can_build:
             from spz_b200 import _native
@@ -212,6 +212,14 @@ def mine():
 @pytest.fixture(scope="module")
 def theirs():
     return Shim("ref")
+
+
+@pytest.fixture(scope="module")
+def relinked():
+    """The consumer compiled against the REFERENCE's headers but linked against libspz_b200.so: what
+    an existing application gets when only the library is swapped (layout-identical structs, same
+    mangled symbols)."""
+    return Shim("xlink")
 
 
 def container(p: Packed, version=None, n_override=None, magic=0x5053474e) -> bytes:
@@ -446,6 +454,30 @@ def test_save_load_use_parallel_gzip_when_asked(mine, theirs, tmp_path):
     assert meta["n"] == 100_000 and all(np.array_equal(a, b) for a, b in zip(planes, p.planes()))
 
 
+def test_relinked_consumer_host_glue(relinked, theirs, tmp_path):
+    rng = np.random.default_rng(90)
+    p = random_stream(rng, 777, 3, 3)
+    p.antialiased = True
+    assert relinked.serialize(p) == theirs.serialize(p)
+    assert relinked.gzip(container(p)) == theirs.gzip(container(p))
+    for ver in (1, 2, 3):
+        q = random_stream(rng, 99, 2, ver, 9)
+        blob = gzip.compress(container(q))
+        (ma, pa), (mb, pb) = relinked.load_packed(blob), theirs.load_packed(blob)
+        assert ma == mb and all(np.array_equal(x, y) for x, y in zip(pa, pb))
+        assert np.array_equal(relinked.at(q, 7)[13:], theirs.at(q, 7)[13:])
+    c = random_cloud(rng, 300, 3, False)
+    (ca, va), (cb, vb) = relinked.cloud_ops(c, 6, 7), theirs.cloud_ops(c, 6, 7)
+    assert_cloud_bits_equal(ca, cb, "convertCoordinates")
+    assert va == vb
+    pa, pb = str(tmp_path / "a.ply"), str(tmp_path / "b.ply")
+    assert relinked.save_ply(c, pa, 4) and theirs.save_ply(c, pb, 4)
+    assert open(pa, "rb").read() == open(pb, "rb").read()
+    assert_cloud_bits_equal(relinked.load_ply(pb, 8), theirs.load_ply(pb, 8), "ply")
+    empty = Cloud(0, 0, *[np.zeros(0, np.float32)] * 6, antialiased=True)
+    assert relinked.save_spz(empty, 6) == theirs.save_spz(empty, 6)
+
+
 def test_size_checks_and_empty_cloud_need_no_device(mine, theirs):
     """Rejections happen before any device work, so they behave the same with and without a GPU."""
     rng = np.random.default_rng(50)
@@ -550,6 +582,25 @@ def test_save_spz_with_parallel_gzip_is_readable_by_the_reference(mine, theirs):
     assert par != serial and gzip.decompress(par) == gzip.decompress(serial)
     assert_cloud_bits_equal(theirs.load_spz(par, 8), theirs.load_spz(serial, 8), "reference reads the parallel member")
     assert_cloud_bits_equal(back, theirs.load_spz(serial, 8), "parallel inflate + decode")
+
+
+@pytest.mark.gpu
+def test_relinked_consumer_codec(relinked, theirs, tmp_path):
+    rng = np.random.default_rng(330)
+    for deg in (0, 3):
+        c = random_cloud(rng, 30_011, deg, True)
+        c.antialiased = True
+        (ra, pa, ma), (rb, pb, mb) = relinked.pack(c, 6), theirs.pack(c, 6)
+        assert ra == rb == 0 and ma == mb
+        assert_packed_equal(pa, pb, f"relinked pack deg{deg}")
+        (ra, ga, ma), (rb, gb, mb) = relinked.unpack(pb, 8), theirs.unpack(pb, 8)
+        assert ra == rb == 0 and ma == mb
+        assert_cloud_bits_equal(ga, gb, f"relinked unpack deg{deg}")
+        assert relinked.save_spz(c, 6) == theirs.save_spz(c, 6)
+        assert_cloud_bits_equal(relinked.load_spz(theirs.save_spz(c, 6), 7), theirs.load_spz(theirs.save_spz(c, 6), 7), "relinked loadSpz")
+    s = random_stream(rng, 5, 3, 3)
+    s.rotations.view("<u4")[:] &= np.uint32(0xDFF7FDFF)
+    assert np.array_equal(bits(relinked.unpack_one(s, 3, 4, 6)), bits(theirs.unpack_one(s, 3, 4, 6)))
 
 
 @pytest.mark.gpu
