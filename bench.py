@@ -14,7 +14,9 @@ One "step" = encode the rank's shard (float planes -> byte planes), then decode 
 encode+decode round trip per second, whole job, inputs resident in HBM, timed with CUDA events on
 the launching stream, max over ranks.  `e2e` = the same step through the host-pointer C-ABI
 (spzb200_encode_host / spzb200_decode_host: pinned host planes in, pinned host planes out, H2D and
-D2H inside the timed region).  The working set (30.1 GB per step at N=1) is far larger than the
+D2H inside the timed region), issued full duplex -- step i's encode and the decode of step i-1's
+stream run concurrently from two host threads so both directions of the PCIe link are busy; the
+one-thread "encode, then decode its result" figure is reported beside it as e2e.sequential.  The working set (30.1 GB per step at N=1) is far larger than the
 126 MB L2, so no explicit flush is needed between iterations.
 
 The oracle / reference build under oracle/ is used here ONLY as the timed CPU baseline
@@ -383,7 +385,7 @@ def run_b200_arm(args):
 
     # ---- e2e: the same step through the host-pointer C-ABI with pinned host planes ---------------
     e2e = None
-    need = 2 * codec.float_bytes_per_gaussian(deg) * n + codec.packed_bytes_per_gaussian(deg) * n
+    need = 2 * codec.float_bytes_per_gaussian(deg) * n + 2 * codec.packed_bytes_per_gaussian(deg) * n
     avail = host_memory_available()
     if not args.no_e2e and avail is not None and need * world > 0.6 * avail:
         raise SystemExit(f"bench.py: e2e needs {need * world / 1e9:.1f} GB of pinned host memory, only {avail / 1e9:.1f} GB "
@@ -423,6 +425,38 @@ def run_b200_arm(args):
             if k and not torch.equal(torch.from_numpy(hp[:k]), dp[:k].cpu()):
                 raise SystemExit(f"bench.py: e2e plane {name} differs from the device-resident encode")
 
+        # Full-duplex form of the same step: a second host thread (own context) decodes the stream
+        # the previous step produced while this step's cloud is being encoded, so both directions of
+        # the PCIe link carry a step's worth of planes at once.  Same calls, same bytes per step.
+        from concurrent.futures import ThreadPoolExecutor
+        ctx2 = codec.Context(local)
+        h_packed2 = codec.alloc_packed(n, deg, 3, pinned=True, numpy_arrays=True)
+        streams = [h_packed, h_packed2]
+        ctx.encode_host(h_cloud, args.from_coord, out=streams[1])  # step 0 decodes this one
+        pool = ThreadPoolExecutor(2)
+
+        def duplex_step(i):
+            fa = pool.submit(ctx.encode_host, h_cloud, args.from_coord, streams[i % 2])
+            fb = pool.submit(ctx2.decode_host, streams[(i + 1) % 2], args.to_coord, h_back)
+            return fa.result()[1], fb.result()[1]
+
+        duplex_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        dphases = [duplex_step(1 + i) for i in range(args.e2e_steps)]
+        barrier()
+        e2e["duplex_s"] = (time.perf_counter() - t0) / args.e2e_steps
+        e2e["duplex_enc_wall_ms"] = statistics.mean(p[0]["wall_ms"] for p in dphases)
+        e2e["duplex_dec_wall_ms"] = statistics.mean(p[1]["wall_ms"] for p in dphases)
+        pool.shutdown()
+        ctx2.close()
+        hb, db = torch.from_numpy(h_back.sh[:1 << 20] if deg else h_back.alphas[:1 << 20]), None
+        ref_back = ctx.decode_device(packed, args.to_coord)
+        db = (ref_back.sh if deg else ref_back.alphas)[:hb.numel()].cpu()
+        if not torch.equal(hb.view(torch.int32), db.view(torch.int32)):
+            raise SystemExit("bench.py: duplex e2e decode differs from the device-resident decode")
+        del ref_back
+
     # ---- reduce over ranks (max time; sums of bytes and launches) -----------------------------------
     def allmax(x):
         return reduce_scalar(dist, x, "max", dev)
@@ -435,6 +469,7 @@ def run_b200_arm(args):
     launches = int(allsum(launches))
     if e2e:
         e2e["s"] = allmax(e2e["s"])
+        e2e["duplex_s"] = allmax(e2e["duplex_s"])
         e2e["h2d"] = int(allsum(e2e["h2d"]))
         e2e["d2h"] = int(allsum(e2e["d2h"]))
 
@@ -489,11 +524,16 @@ def run_b200_arm(args):
             "gpu_launches": launches, "clocks": clocks,
         }
         if e2e:
-            line["e2e"] = {"value": n_total / e2e["s"] / 1e6, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
-                           "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["s"] * 1e3, "steps": args.e2e_steps,
+            line["e2e"] = {"value": n_total / e2e["duplex_s"] / 1e6, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                           "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["duplex_s"] * 1e3, "steps": args.e2e_steps,
                            "api": "spzb200_encode_host + spzb200_decode_host (pinned host planes)",
-                           "phases_note": "h2d/kernel/d2h_ms are sums over point ranges of per-range stream time; ranges run on 3 streams and overlap, wall_ms is the call",
-                           "encode_phases_ms": e2e["enc"], "decode_phases_ms": e2e["dec"]}
+                           "mode": "full duplex: step i's encode_host and the decode_host of step i-1's stream are issued concurrently "
+                                   "from two host threads (one context each), so H2D and D2H of a step's planes overlap on the PCIe link",
+                           "encode_call_ms": e2e["duplex_enc_wall_ms"], "decode_call_ms": e2e["duplex_dec_wall_ms"],
+                           "sequential": {"value": n_total / e2e["s"] / 1e6, "ms_per_step": e2e["s"] * 1e3,
+                                          "mode": "one host thread: encode_host, then decode_host of its result",
+                                          "phases_note": "h2d/kernel/d2h_ms are sums over point ranges of per-range stream time; ranges run on 3 streams and overlap, wall_ms is the call",
+                                          "encode_phases_ms": e2e["enc"], "decode_phases_ms": e2e["dec"]}}
         if cpu:
             line["cpu_baseline"] = cpu
         if host_zlib:

@@ -1,4 +1,7 @@
 #!/bin/bash
+mkdir -p gpurun_out
 export SPZB200_NO_REBUILD=1
-timeout 300 python scripts/sanitize_case.py 2>&1 | tail -1
-echo "== sweep"; timeout 300 python scripts/kernel_sweep.py 1e7,1e8 3,2,1 2>&1 | cut -c1-100
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tmp.json 2>gpurun_out/bench_tmp.err; echo rc=$?; tail -3 gpurun_out/bench_tmp.err; python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/bench_tmp.json') if l.startswith('{')][-1])
+print(d['value']); print(json.dumps(d['e2e'], indent=1)[:1500])"
