@@ -22,9 +22,12 @@
 // they are loaded together (5 or 8 float4 in flight per thread) under one set of constants.
 // The 24-bit position words (3 per float4) are exchanged through a per-warp shared-memory
 // stage so that their global loads and stores are contiguous 128-byte lines as well.
-// CTAs are persistent (gridDim = SMs x resident CTAs) and stride over tiles.  The remainder
-// (< one tile) and any call with under-aligned pointers goes to a scalar one-thread-per-gaussian
-// kernel.
+// One CTA per tile (gridDim = tiles): the hardware block scheduler hands tiles out in order, which
+// keeps the set of pages being touched compact; persistent grid-stride CTAs drift apart over a
+// 100M-point cloud and lost 4-12 % (kept as the SPZB200_GRID=persistent knob).  The encoder works
+// from registers.  The decoder stages the SH plane -- three quarters of its bytes -- through shared
+// memory with bulk async copies (decodeTilesBulkKernel below).  The remainder (< one tile) and any
+// call with under-aligned pointers goes to a scalar one-thread-per-gaussian kernel.
 //
 // HBM traffic is exactly the algorithmic 301 B per gaussian at SH degree 3 (236 B floats + 65 B
 // packed); nothing is read twice.

@@ -38,8 +38,8 @@ struct LaunchPlan {
   int smCount;
   int packMode;        // encode only: how four bytes are saturated and packed into a word
   bool forceGeneric;   // test hook: route everything through the scalar kernels
-  int ctasPerSm;       // persistent grid = smCount * ctasPerSm (1..3); 0 = default (3)
-  bool flatGrid;       // experiment knob: one CTA per tile instead of persistent CTAs
+  int ctasPerSm;       // persistent grid only: smCount * ctasPerSm CTAs (1..4); 0 = default (4)
+  bool flatGrid;       // one CTA per tile (default) instead of persistent grid-stride CTAs
   bool decodeBulk;     // decode the SH plane through bulk async copies (TMA) instead of registers
 };
 
