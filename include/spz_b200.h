@@ -109,7 +109,7 @@ typedef struct {
   int32_t reserved;
 } SpzB200Timings;
 
-/* One context per (thread, device): immutable codec tables resident on the device, two worker
+/* One context per (thread, device): immutable codec tables resident on the device, three worker
  * streams and the staging buffers of the host-pointer pipeline.  A context is not thread-safe;
  * create one per host thread.  Creation fails (no CPU fallback) without an sm_100 device. */
 typedef struct SpzB200Context SpzB200Context;
