@@ -158,6 +158,27 @@ int spzb200_decode_host_multi(const int32_t *devices, int32_t num_devices,
                               const SpzB200Packed *in, int32_t to, SpzB200Cloud *out,
                               SpzB200Timings *timings);
 
+/* ---- fused PLY-rows encoder ------------------------------------------------------
+ *
+ * The vertex records of a gaussian-splat .ply -- row-major, `width` floats each, the layout
+ * loadSplatFromPly parses (load-spz.cc:691-844) -- straight to PackedGaussians planes.  Equals
+ * packGaussians(loadSplatFromPly(rows, to = X), from = X): the loader's [N,C,S] -> [N,S,C] SH shuffle and
+ * wxyz -> xyzw reorder, then the encoder.  `from` is the frame the records are in (RDF for PLY files;
+ * UNSPECIFIED = no flips, which is what the reference's ply_to_spz tool does).  Column indices are
+ * positions inside a record; col_rest lists f_rest_0 .. f_rest_{3*shDim-1} in file order. */
+typedef struct {
+  int64_t num_points;
+  int32_t width;      /* floats per record */
+  int32_t sh_degree;  /* 0..3 */
+  const float *rows;  /* device pointer for *_device, host pointer for *_host */
+  int32_t col_pos[3], col_scale[3], col_rot[4] /* x, y, z, w = rot_1, rot_2, rot_3, rot_0 */, col_alpha, col_color[3];
+  int32_t col_rest[45];
+} SpzB200PlyRows;
+
+int spzb200_encode_ply_device(SpzB200Context *ctx, const SpzB200PlyRows *in, int32_t from, SpzB200Packed *out, void *stream);
+int spzb200_encode_ply_host(SpzB200Context *ctx, const SpzB200PlyRows *in, int32_t from, SpzB200Packed *out,
+                            SpzB200Timings *timings);
+
 /* Page-locked host buffers for the *_host entry points (cudaHostAlloc, portable across devices).
  * Pageable memory works too but its copies neither overlap nor reach PCIe bandwidth. */
 int spzb200_alloc_pinned(size_t bytes, void **out);

@@ -286,6 +286,10 @@ bool decompressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *o
 // readable by any inflater; the inflated bytes equal compressGzipped's input, the compressed bytes
 // do not equal its output.  decompressGzippedParallel inflates such members block-parallel and
 // anything else serially.  saveSpz / loadSpz* use them when SPZ_B200_GZIP_THREADS > 1.
+// .ply file -> .spz bytes with the loader's column shuffle and the encoder fused in one GPU kernel
+// (no planar GaussianCloud in between).  options.from = RDF: the bytes of
+// saveSpz(loadSplatFromPly(f, {to}), {from = to}); UNSPECIFIED: what the reference's ply_to_spz writes.
+bool plyToSpz(const std::string &plyFilename, const PackOptions &options, std::vector<uint8_t> *output);
 bool compressGzippedParallel(const uint8_t *data, size_t size, int threads, std::vector<uint8_t> *out);
 bool decompressGzippedParallel(const uint8_t *data, size_t size, int threads, std::vector<uint8_t> *out);
 

@@ -29,6 +29,13 @@ class Packed(C.Structure):
                 ("alphas", C.c_void_p), ("colors", C.c_void_p), ("sh", C.c_void_p)]
 
 
+class PlyRows(C.Structure):
+    """SpzB200PlyRows: row-major .ply vertex records + the column map."""
+    _fields_ = [("num_points", C.c_int64), ("width", C.c_int32), ("sh_degree", C.c_int32), ("rows", C.c_void_p),
+                ("col_pos", C.c_int32 * 3), ("col_scale", C.c_int32 * 3), ("col_rot", C.c_int32 * 4), ("col_alpha", C.c_int32),
+                ("col_color", C.c_int32 * 3), ("col_rest", C.c_int32 * 45)]
+
+
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("wall_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
@@ -49,6 +56,8 @@ SIGNATURES = {
     "spzb200_decode_device": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_int32, C.POINTER(Cloud), C.c_void_p]),
     "spzb200_encode_host": (C.c_int, [C.c_void_p, C.POINTER(Cloud), C.c_int32, C.POINTER(Packed), C.POINTER(Timings)]),
     "spzb200_decode_host": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_int32, C.POINTER(Cloud), C.POINTER(Timings)]),
+    "spzb200_encode_ply_device": (C.c_int, [C.c_void_p, C.POINTER(PlyRows), C.c_int32, C.POINTER(Packed), C.c_void_p]),
+    "spzb200_encode_ply_host": (C.c_int, [C.c_void_p, C.POINTER(PlyRows), C.c_int32, C.POINTER(Packed), C.POINTER(Timings)]),
     "spzb200_encode_host_multi": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(Cloud), C.c_int32, C.POINTER(Packed), C.POINTER(Timings)]),
     "spzb200_decode_host_multi": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(Packed), C.c_int32, C.POINTER(Cloud), C.POINTER(Timings)]),
     "spzb200_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -217,6 +217,30 @@ def build_tables():
     return thr, lut
 
 
+def ply_property_names(sh_degree: int):
+    """Property order the reference's PLY writer emits (load-spz.cc:892-916)."""
+    d = SH_DIM[sh_degree]
+    return (["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"] + [f"f_rest_{i}" for i in range(3 * d)] +
+            ["opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"])
+
+
+def ply_rows_struct(rows, n: int, names, sh_degree: int, on_device: Optional[bool]) -> N.PlyRows:
+    """SpzB200PlyRows for row-major vertex records with the given property names (one float each)."""
+    col = {name: i for i, name in enumerate(names)}
+    width = len(names)
+    s = N.PlyRows()
+    s.num_points, s.width, s.sh_degree = n, width, sh_degree
+    s.rows = _ptr(rows, "f4", n * width, on_device, "rows")
+    s.col_pos[:] = [col["x"], col["y"], col["z"]]
+    s.col_scale[:] = [col["scale_0"], col["scale_1"], col["scale_2"]]
+    s.col_rot[:] = [col["rot_1"], col["rot_2"], col["rot_3"], col["rot_0"]]  # file is wxyz
+    s.col_alpha = col["opacity"]
+    s.col_color[:] = [col["f_dc_0"], col["f_dc_1"], col["f_dc_2"]]
+    rest = [col[f"f_rest_{i}"] for i in range(3 * SH_DIM[sh_degree])]
+    s.col_rest[:] = rest + [0] * (45 - len(rest))
+    return s
+
+
 class Context:
     """One per (thread, device).  Raises CodecError(ERR_NO_DEVICE) when there is no B200: the codec
     has no CPU path."""
@@ -287,6 +311,23 @@ class Context:
         ps, cs = _packed_struct(packed, True), _cloud_struct(out, True)
         N.check(N.lib().spzb200_decode_device(self._h, C.byref(ps), int(to), C.byref(cs), C.c_void_p(self._stream_handle(stream))))
         return out
+
+    # ---- fused PLY-rows encoder ---------------------------------------------------------------
+    def encode_ply_device(self, rows, n: int, names, sh_degree: int, frm: int = 0, out: Optional[PackedPlanes] = None, stream=None):
+        if out is None:
+            out = alloc_packed(n, sh_degree, 3, device=rows.device)
+        rs, ps = ply_rows_struct(rows, n, names, sh_degree, True), _packed_struct(out, True)
+        N.check(N.lib().spzb200_encode_ply_device(self._h, C.byref(rs), int(frm), C.byref(ps), C.c_void_p(self._stream_handle(stream))))
+        out.fractional_bits, out.version = ps.fractional_bits, ps.version
+        return out
+
+    def encode_ply_host(self, rows, n: int, names, sh_degree: int, frm: int = 0, out: Optional[PackedPlanes] = None):
+        if out is None:
+            out = alloc_packed(n, sh_degree, 3, numpy_arrays=True)
+        rs, ps, tm = ply_rows_struct(rows, n, names, sh_degree, False), _packed_struct(out, False), N.Timings()
+        N.check(N.lib().spzb200_encode_ply_host(self._h, C.byref(rs), int(frm), C.byref(ps), C.byref(tm)))
+        out.fractional_bits, out.version = ps.fractional_bits, ps.version
+        return out, tm.as_dict()
 
     # ---- host pointers (numpy arrays or CPU tensors, pinned for overlap) ----------------------
     def encode_host(self, cloud: CloudPlanes, frm: int = 0, out: Optional[PackedPlanes] = None):

@@ -126,9 +126,9 @@ constexpr int kStages = 3;
 
 struct Stage {
   cudaStream_t stream = nullptr;
-  uint8_t *dFloats = nullptr;  // float planes of one chunk (device)
-  uint8_t *dBytes = nullptr;   // byte planes of one chunk (device)
-  size_t floatsCap = 0, bytesCap = 0;
+  uint8_t *dIn = nullptr;   // input planes of one range (device)
+  uint8_t *dOut = nullptr;  // output planes of one range (device)
+  size_t dInCap = 0, dOutCap = 0;
   uint8_t *hIn = nullptr;      // pinned bounce buffers, used only when the caller's planes are pageable
   uint8_t *hOut = nullptr;
   size_t hInCap = 0, hOutCap = 0;
@@ -322,18 +322,18 @@ void bytePlaneBytes(int shDim, int version, size_t b[6]) {
   b[5] = (size_t)3 * shDim;
 }
 
-int ensureStage(Stage &s, size_t floatsBytes, size_t bytesBytes) {
-  if (s.floatsCap < floatsBytes) {
-    if (s.dFloats) cudaFree(s.dFloats);
-    s.dFloats = nullptr; s.floatsCap = 0;
-    CU(cudaMalloc(&s.dFloats, floatsBytes));
-    s.floatsCap = floatsBytes;
+int ensureStage(Stage &s, size_t inBytes_, size_t outBytes_) {
+  if (s.dInCap < inBytes_) {
+    if (s.dIn) cudaFree(s.dIn);
+    s.dIn = nullptr; s.dInCap = 0;
+    CU(cudaMalloc(&s.dIn, inBytes_));
+    s.dInCap = inBytes_;
   }
-  if (s.bytesCap < bytesBytes) {
-    if (s.dBytes) cudaFree(s.dBytes);
-    s.dBytes = nullptr; s.bytesCap = 0;
-    CU(cudaMalloc(&s.dBytes, bytesBytes));
-    s.bytesCap = bytesBytes;
+  if (s.dOutCap < outBytes_) {
+    if (s.dOut) cudaFree(s.dOut);
+    s.dOut = nullptr; s.dOutCap = 0;
+    CU(cudaMalloc(&s.dOut, outBytes_));
+    s.dOutCap = outBytes_;
   }
   return SPZB200_OK;
 }
@@ -345,16 +345,6 @@ int ensureBounce(uint8_t *&buf, size_t &cap, size_t bytes) {
   CU(cudaHostAlloc(&buf, bytes, cudaHostAllocDefault));
   cap = bytes;
   return SPZB200_OK;
-}
-
-// carve six 256-byte-aligned sub-buffers for `points` gaussians
-size_t carve(uint8_t *base, const size_t per[6], long long points, uint8_t *out[6]) {
-  size_t off = 0;
-  for (int i = 0; i < 6; i++) {
-    out[i] = base ? base + off : nullptr;
-    off += alignUp(per[i] * (size_t)points, 256);
-  }
-  return off;
 }
 
 double nowMs() {
@@ -372,44 +362,52 @@ bool isPageable(const void *p) {
   return at.type == cudaMemoryTypeUnregistered;
 }
 
-// The chunked H2D || kernel || D2H pipeline shared by encode_host and decode_host.
-// isEncode: float planes in, byte planes out; otherwise the reverse.
+// A set of per-gaussian planes on the host or the device: pointer + bytes per gaussian each.
+struct PlaneSet {
+  int count = 0;
+  uint8_t *ptr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t per[6] = {0, 0, 0, 0, 0, 0};
+  size_t bytesPerGaussian() const {
+    size_t t = 0;
+    for (int i = 0; i < count; i++) t += per[i];
+    return t;
+  }
+};
+
+// `count` 256-byte-aligned sub-buffers for `points` gaussians inside one allocation
+size_t carveSet(uint8_t *base, const PlaneSet &set, long long points, uint8_t *out[6]) {
+  size_t off = 0;
+  for (int i = 0; i < set.count; i++) {
+    out[i] = base ? base + off : nullptr;
+    off += alignUp(set.per[i] * (size_t)points, 256);
+  }
+  return off;
+}
+
+// The chunked H2D || kernel || D2H pipeline behind every *_host entry point.
 //
-// The cloud is cut into contiguous point ranges.  Range c uses stage c % kStages: its own stream,
-// device staging buffers and events, so the copy-in of one range overlaps the kernel and the
-// copy-out of its predecessors.  Pinned (or registered) caller memory is copied directly.
-// Pageable caller memory -- what std::vector hands the C++ API -- would make every cudaMemcpyAsync
-// a synchronous, driver-staged ~10 GB/s copy; instead the ranges are bounced through pinned buffers
-// owned by the stage, filled and drained by a small pool of host threads while the GPU works on
-// the neighbouring ranges.
-int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &cloud,
-                    const SpzB200Packed &packed, int32_t coord, SpzB200Timings *timings) {
+// The n gaussians are cut into contiguous point ranges (multiples of `granule`, the kernel tile).
+// Range c uses stage c % kStages: its own stream, device staging buffers and events, so the copy-in
+// of one range overlaps the kernel and the copy-out of its predecessors.  Pinned (or registered)
+// caller memory is copied directly.  Pageable caller memory -- what std::vector hands the C++ API --
+// would make every cudaMemcpyAsync a synchronous, driver-staged ~10 GB/s copy; instead the ranges
+// are bounced through pinned buffers owned by the stage, filled and drained by a small pool of host
+// threads while the GPU works on the neighbouring ranges.
+// launch(dIn, dOut, points, stream, &launches) queues the kernel(s) for one range.
+template <class Launch>
+int runPipeline(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, long long n, long long granule,
+                Launch &&launch, SpzB200Timings *timings) {
   const double w0 = nowMs();
   CU(cudaSetDevice(ctx->device));
-  const long long n = cloud.num_points;
-  const int shDim = shDimOf(cloud.sh_degree);
-  const int version = isEncode ? 3 : packed.version;
-  size_t fper[6], bper[6];
-  floatPlaneBytes(shDim, fper);
-  bytePlaneBytes(shDim, version, bper);
-  const size_t *inPer = isEncode ? fper : bper, *outPer = isEncode ? bper : fper;
-  uint8_t *const cloudPlanes[6] = {(uint8_t *)cloud.positions, (uint8_t *)cloud.scales, (uint8_t *)cloud.rotations,
-                                   (uint8_t *)cloud.alphas, (uint8_t *)cloud.colors, (uint8_t *)cloud.sh};
-  uint8_t *const packedPlanes[6] = {packed.positions, packed.scales, packed.rotations, packed.alphas, packed.colors, packed.sh};
-  uint8_t *const *userIn = isEncode ? cloudPlanes : packedPlanes;
-  uint8_t *const *userOut = isEncode ? packedPlanes : cloudPlanes;
-
   // Bouncing costs a one-time pinned allocation per context (~1 GB/s on a VM), so small one-shot
   // calls are cheaper through the driver's own staging; once the buffers exist they are always used.
-  const size_t callBytes = (size_t)n * (fper[0] + fper[1] + fper[2] + fper[3] + fper[4] + fper[5] +
-                                                                           bper[0] + bper[1] + bper[2] + bper[3] + bper[4] + bper[5]);
+  const size_t callBytes = (size_t)n * (in.bytesPerGaussian() + out.bytesPerGaussian());
   const bool wantBounce = ctx->bounceMode == 2 ||
                           (ctx->bounceMode == 1 && (callBytes >= ctx->bounceMinBytes || ctx->stage[0].hIn || ctx->stage[0].hOut));
-  const bool bounceIn = n > 0 && wantBounce && isPageable(userIn[0]);
-  const bool bounceOut = n > 0 && wantBounce && isPageable(userOut[0]);
-  const long long tg = spzb200::tileGaussians(shDim);
+  const bool bounceIn = n > 0 && wantBounce && isPageable(in.ptr[0]);
+  const bool bounceOut = n > 0 && wantBounce && isPageable(out.ptr[0]);
   const long long want = (bounceIn || bounceOut) ? ctx->pageableChunkPoints : ctx->chunkPoints;
-  long long chunk = std::max<long long>(tg, want / tg * tg);
+  long long chunk = std::max<long long>(granule, want / granule * granule);
   if (chunk > n) chunk = std::max<long long>(n, 1);
   const long long numChunks = n == 0 ? 0 : (n + chunk - 1) / chunk;
   const int stages = (int)std::min<long long>(kStages, numChunks);
@@ -419,13 +417,13 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
   tm.staged = (bounceIn ? 1 : 0) | (bounceOut ? 2 : 0);
   if (numChunks > 0) {
     uint8_t *unused[6];
-    const size_t fBytes = carve(nullptr, fper, chunk, unused);
-    const size_t bBytes = carve(nullptr, bper, chunk, unused);
+    const size_t inBytes = carveSet(nullptr, in, chunk, unused);
+    const size_t outBytes = carveSet(nullptr, out, chunk, unused);
     for (int s = 0; s < stages; s++) {
       Stage &st = ctx->stage[s];
-      int rc = ensureStage(st, fBytes, bBytes);
-      if (rc == SPZB200_OK && bounceIn) rc = ensureBounce(st.hIn, st.hInCap, isEncode ? fBytes : bBytes);
-      if (rc == SPZB200_OK && bounceOut) rc = ensureBounce(st.hOut, st.hOutCap, isEncode ? bBytes : fBytes);
+      int rc = ensureStage(st, inBytes, outBytes);
+      if (rc == SPZB200_OK && bounceIn) rc = ensureBounce(st.hIn, st.hInCap, inBytes);
+      if (rc == SPZB200_OK && bounceOut) rc = ensureBounce(st.hOut, st.hOutCap, outBytes);
       if (rc != SPZB200_OK) return rc;
     }
     if ((bounceIn || bounceOut) && !ctx->pool) {
@@ -433,7 +431,6 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
       ctx->pool = new CopyPool(std::max(0, t - 1));  // the calling thread copies too
     }
   }
-  const spzb200::LaunchPlan plan = planOf(ctx);
 
   // Completes the range that last used `st`: waits for its copy-out, books its timings and, when
   // the output is bounced, drains the pinned buffer into the caller's planes.
@@ -447,10 +444,10 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
     if (bounceOut) {
       const double t0 = nowMs();
       uint8_t *ho[6];
-      carve(st.hOut, outPer, chunk, ho);
+      carveSet(st.hOut, out, chunk, ho);
       std::vector<CopyPool::Job> jobs;
-      for (int i = 0; i < 6; i++)
-        if (outPer[i] * (size_t)pts) jobs.push_back({userOut[i] + outPer[i] * (size_t)a, ho[i], outPer[i] * (size_t)pts});
+      for (int i = 0; i < out.count; i++)
+        if (out.per[i] * (size_t)pts) jobs.push_back({out.ptr[i] + out.per[i] * (size_t)a, ho[i], out.per[i] * (size_t)pts});
       ctx->pool->run(jobs);
       tm.host_copy_ms += nowMs() - t0;
     }
@@ -464,48 +461,35 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
       int rc = finish(st, c - kStages);
       if (rc != SPZB200_OK) return rc;
     }
-    uint8_t *df[6], *db[6], *hi[6], *ho[6];
-    carve(st.dFloats, fper, chunk, df);
-    carve(st.dBytes, bper, chunk, db);
-    uint8_t **dIn = isEncode ? df : db, **dOut = isEncode ? db : df;
+    uint8_t *dIn[6], *dOut[6], *hi[6], *ho[6];
+    carveSet(st.dIn, in, chunk, dIn);
+    carveSet(st.dOut, out, chunk, dOut);
     if (bounceIn) {
       const double t0 = nowMs();
-      carve(st.hIn, inPer, chunk, hi);
+      carveSet(st.hIn, in, chunk, hi);
       std::vector<CopyPool::Job> jobs;
-      for (int i = 0; i < 6; i++)
-        if (inPer[i] * (size_t)pts) jobs.push_back({hi[i], userIn[i] + inPer[i] * (size_t)a, inPer[i] * (size_t)pts});
+      for (int i = 0; i < in.count; i++)
+        if (in.per[i] * (size_t)pts) jobs.push_back({hi[i], in.ptr[i] + in.per[i] * (size_t)a, in.per[i] * (size_t)pts});
       ctx->pool->run(jobs);
       tm.host_copy_ms += nowMs() - t0;
     }
-    if (bounceOut) carve(st.hOut, outPer, chunk, ho);
+    if (bounceOut) carveSet(st.hOut, out, chunk, ho);
     CU(cudaEventRecord(st.ev[0], st.stream));
-    for (int i = 0; i < 6; i++) {
-      const size_t bytes = inPer[i] * (size_t)pts;
-      const uint8_t *src = bounceIn ? hi[i] : userIn[i] + inPer[i] * (size_t)a;
+    for (int i = 0; i < in.count; i++) {
+      const size_t bytes = in.per[i] * (size_t)pts;
+      const uint8_t *src = bounceIn ? hi[i] : in.ptr[i] + in.per[i] * (size_t)a;
       if (bytes) CU(cudaMemcpyAsync(dIn[i], src, bytes, cudaMemcpyHostToDevice, st.stream));
       tm.h2d_bytes += (int64_t)bytes;
     }
     CU(cudaEventRecord(st.ev[1], st.stream));
-    SpzB200Cloud dc = cloud;
-    SpzB200Packed dp = packed;
-    dc.num_points = dp.num_points = pts;
-    dc.positions = (float *)df[0]; dc.scales = (float *)df[1]; dc.rotations = (float *)df[2];
-    dc.alphas = (float *)df[3]; dc.colors = (float *)df[4]; dc.sh = (float *)df[5];
-    dp.positions = db[0]; dp.scales = db[1]; dp.rotations = db[2]; dp.alphas = db[3];
-    dp.colors = db[4]; dp.sh = db[5];
-    dp.version = version;
     int launches = 0;
-    if (isEncode) {
-      CU(spzb200::launchEncode(makeEncodeArgs(ctx, dc, dp, coord), plan, st.stream, &launches));
-    } else {
-      CU(spzb200::launchDecode(makeDecodeArgs(ctx, dp, dc, coord), plan, st.stream, &launches));
-    }
+    CU(launch(dIn, dOut, pts, st.stream, &launches));
     ctx->kernelLaunches += launches;
     tm.kernel_launches += launches;
     CU(cudaEventRecord(st.ev[2], st.stream));
-    for (int i = 0; i < 6; i++) {
-      const size_t bytes = outPer[i] * (size_t)pts;
-      uint8_t *dst = bounceOut ? ho[i] : userOut[i] + outPer[i] * (size_t)a;
+    for (int i = 0; i < out.count; i++) {
+      const size_t bytes = out.per[i] * (size_t)pts;
+      uint8_t *dst = bounceOut ? ho[i] : out.ptr[i] + out.per[i] * (size_t)a;
       if (bytes) CU(cudaMemcpyAsync(dst, dOut[i], bytes, cudaMemcpyDeviceToHost, st.stream));
       tm.d2h_bytes += (int64_t)bytes;
     }
@@ -520,6 +504,61 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
   tm.wall_ms = nowMs() - w0;
   if (timings) *timings = tm;
   return SPZB200_OK;
+}
+
+PlaneSet cloudPlaneSet(const SpzB200Cloud &c) {
+  PlaneSet s;
+  s.count = 6;
+  float *const p[6] = {c.positions, c.scales, c.rotations, c.alphas, c.colors, c.sh};
+  floatPlaneBytes(shDimOf(c.sh_degree), s.per);
+  for (int i = 0; i < 6; i++) s.ptr[i] = reinterpret_cast<uint8_t *>(p[i]);
+  return s;
+}
+
+PlaneSet packedPlaneSet(const SpzB200Packed &p, int version) {
+  PlaneSet s;
+  s.count = 6;
+  uint8_t *const q[6] = {p.positions, p.scales, p.rotations, p.alphas, p.colors, p.sh};
+  bytePlaneBytes(shDimOf(p.sh_degree), version, s.per);
+  for (int i = 0; i < 6; i++) s.ptr[i] = q[i];
+  return s;
+}
+
+SpzB200Cloud cloudOn(const SpzB200Cloud &like, uint8_t *const d[6], long long pts) {
+  SpzB200Cloud c = like;
+  c.num_points = pts;
+  c.positions = (float *)d[0]; c.scales = (float *)d[1]; c.rotations = (float *)d[2];
+  c.alphas = (float *)d[3]; c.colors = (float *)d[4]; c.sh = (float *)d[5];
+  return c;
+}
+
+SpzB200Packed packedOn(const SpzB200Packed &like, uint8_t *const d[6], long long pts, int version) {
+  SpzB200Packed p = like;
+  p.num_points = pts;
+  p.version = version;
+  p.positions = d[0]; p.scales = d[1]; p.rotations = d[2]; p.alphas = d[3]; p.colors = d[4]; p.sh = d[5];
+  return p;
+}
+
+// encode_host / decode_host: float planes in and byte planes out, or the reverse.
+int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &cloud,
+                    const SpzB200Packed &packed, int32_t coord, SpzB200Timings *timings) {
+  const int version = isEncode ? 3 : packed.version;
+  const PlaneSet fl = cloudPlaneSet(cloud), by = packedPlaneSet(packed, version);
+  const long long granule = spzb200::tileGaussians(shDimOf(cloud.sh_degree));
+  const spzb200::LaunchPlan plan = planOf(ctx);
+  if (isEncode) {
+    return runPipeline(ctx, fl, by, cloud.num_points, granule,
+                       [&](uint8_t *const dIn[6], uint8_t *const dOut[6], long long pts, cudaStream_t s, int *launches) {
+                         return spzb200::launchEncode(makeEncodeArgs(ctx, cloudOn(cloud, dIn, pts), packedOn(packed, dOut, pts, version), coord),
+                                                      plan, s, launches);
+                       }, timings);
+  }
+  return runPipeline(ctx, by, fl, cloud.num_points, granule,
+                     [&](uint8_t *const dIn[6], uint8_t *const dOut[6], long long pts, cudaStream_t s, int *launches) {
+                       return spzb200::launchDecode(makeDecodeArgs(ctx, packedOn(packed, dIn, pts, version), cloudOn(cloud, dOut, pts), coord),
+                                                    plan, s, launches);
+                     }, timings);
 }
 
 // Contexts of the multi-GPU entry points: created on first use, kept for the life of the process
@@ -686,8 +725,8 @@ void spzb200_destroy(SpzB200Context *ctx) {
     if (st.hIn) cudaFreeHost(st.hIn);
     if (st.hOut) cudaFreeHost(st.hOut);
     for (int k = 0; k < 4; k++) if (st.ev[k]) cudaEventDestroy(st.ev[k]);
-    if (st.dFloats) cudaFree(st.dFloats);
-    if (st.dBytes) cudaFree(st.dBytes);
+    if (st.dIn) cudaFree(st.dIn);
+    if (st.dOut) cudaFree(st.dOut);
     if (st.stream) cudaStreamDestroy(st.stream);
   }
   if (ctx->dThr) cudaFree(ctx->dThr);
@@ -802,6 +841,87 @@ int spzb200_decode_host_multi(const int32_t *devices, int32_t num_devices,
                       SpzB200Cloud co = sliceCloud(cout, a, b);
                       return spzb200_decode_host(ctx, &pi, to, &co, tm);
                     }, timings);
+}
+
+static int checkPlyRows(const SpzB200PlyRows *in, const char *who) {
+  if (!in) return fail(SPZB200_ERR_INVALID, "%s: null rows view", who);
+  if (in->num_points < 0) return fail(SPZB200_ERR_INVALID, "%s: num_points < 0", who);
+  if (!validDegree(in->sh_degree)) return fail(SPZB200_ERR_INVALID, "%s: sh_degree %d not in 0..3", who, in->sh_degree);
+  if (in->width < 14 || in->width > 4096) return fail(SPZB200_ERR_INVALID, "%s: width %d out of range", who, in->width);
+  if (in->num_points > 0 && !in->rows) return fail(SPZB200_ERR_INVALID, "%s: null rows pointer", who);
+  auto ok = [&](int32_t c) { return c >= 0 && c < in->width; };
+  bool cols = ok(in->col_alpha);
+  for (int i = 0; i < 3; i++) cols = cols && ok(in->col_pos[i]) && ok(in->col_scale[i]) && ok(in->col_color[i]);
+  for (int i = 0; i < 4; i++) cols = cols && ok(in->col_rot[i]);
+  for (int i = 0; i < 3 * shDimOf(in->sh_degree); i++) cols = cols && ok(in->col_rest[i]);
+  if (!cols) return fail(SPZB200_ERR_INVALID, "%s: column index outside the record", who);
+  return SPZB200_OK;
+}
+
+static spzb200::PlyEncodeArgs makePlyArgs(const SpzB200Context *ctx, const SpzB200PlyRows &in, const float *rows, long long n,
+                                          const SpzB200Packed &out, int32_t from) {
+  spzb200::PlyEncodeArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.rows = rows;
+  a.n = n;
+  a.width = in.width;
+  a.shDim = shDimOf(in.sh_degree);
+  for (int i = 0; i < 3; i++) { a.colPos[i] = in.col_pos[i]; a.colScale[i] = in.col_scale[i]; a.colColor[i] = in.col_color[i]; }
+  for (int i = 0; i < 4; i++) a.colRot[i] = in.col_rot[i];
+  a.colAlpha = in.col_alpha;
+  for (int i = 0; i < 3 * a.shDim; i++) a.colRest[i] = in.col_rest[i];
+  a.oPositions = out.positions; a.oScales = out.scales; a.oRotations = out.rotations;
+  a.oAlphas = out.alphas; a.oColors = out.colors; a.oSh = out.sh;
+  const spzb200::m::FlipBits f = spzb200::m::make_flip_bits(from, SPZB200_COORD_RUB);
+  a.flipP = f.p; a.flipQ = f.q; a.flipSh = f.sh;
+  a.alphaThresholds = ctx->dThr;
+  return a;
+}
+
+static int preparePlyOut(const SpzB200PlyRows *in, SpzB200Packed *out, int32_t from, const char *who) {
+  if (!out) return fail(SPZB200_ERR_INVALID, "%s: null out", who);
+  out->num_points = in->num_points;
+  out->sh_degree = in->sh_degree;
+  out->fractional_bits = 12;
+  out->version = 3;
+  int rc = checkPacked(out, who, true);
+  if (rc) return rc;
+  if (from < 0 || from > 8) return fail(SPZB200_ERR_INVALID, "%s: coordinate system %d", who, from);
+  return SPZB200_OK;
+}
+
+int spzb200_encode_ply_device(SpzB200Context *ctx, const SpzB200PlyRows *in, int32_t from, SpzB200Packed *out, void *stream) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_encode_ply_device: null context");
+  int rc = checkPlyRows(in, "spzb200_encode_ply_device");
+  if (rc) return rc;
+  rc = preparePlyOut(in, out, from, "spzb200_encode_ply_device");
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  int launches = 0;
+  CU(spzb200::launchEncodePly(makePlyArgs(ctx, *in, in->rows, in->num_points, *out, from), planOf(ctx), (cudaStream_t)stream, &launches));
+  ctx->kernelLaunches += launches;
+  return SPZB200_OK;
+}
+
+int spzb200_encode_ply_host(SpzB200Context *ctx, const SpzB200PlyRows *in, int32_t from, SpzB200Packed *out,
+                            SpzB200Timings *timings) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_encode_ply_host: null context");
+  int rc = checkPlyRows(in, "spzb200_encode_ply_host");
+  if (rc) return rc;
+  rc = preparePlyOut(in, out, from, "spzb200_encode_ply_host");
+  if (rc) return rc;
+  PlaneSet rows;
+  rows.count = 1;
+  rows.ptr[0] = reinterpret_cast<uint8_t *>(const_cast<float *>(in->rows));
+  rows.per[0] = (size_t)in->width * 4;
+  const PlaneSet by = packedPlaneSet(*out, 3);
+  const spzb200::LaunchPlan plan = planOf(ctx);
+  return runPipeline(ctx, rows, by, in->num_points, spzb200::plyTileGaussians(),
+                     [&](uint8_t *const dIn[6], uint8_t *const dOut[6], long long pts, cudaStream_t s, int *launches) {
+                       const SpzB200Packed dp = packedOn(*out, dOut, pts, 3);
+                       return spzb200::launchEncodePly(makePlyArgs(ctx, *in, reinterpret_cast<const float *>(dIn[0]), pts, dp, from),
+                                                       plan, s, launches);
+                     }, timings);
 }
 
 int spzb200_alloc_pinned(size_t bytes, void **out) {

@@ -32,6 +32,20 @@ struct DecodeArgs {
 
 constexpr int kDecodeTableFloats = 1024;
 
+// PLY vertex records (row-major, `width` floats per vertex) -> PackedGaussians planes, both
+// device-resident: loadSplatFromPly's column shuffle (load-spz.cc:808-838) fused with packGaussians.
+struct PlyEncodeArgs {
+  const float *rows;
+  long long n;
+  int width;   // floats per record
+  int shDim;   // 0, 3, 8, 15
+  int colPos[3], colScale[3], colRot[4] /* x, y, z, w */, colAlpha, colColor[3];
+  int colRest[45];  // f_rest_0 .. : channel-major [C][S], as the file stores them
+  uint8_t *oPositions, *oScales, *oRotations, *oAlphas, *oColors, *oSh;
+  uint32_t flipP, flipQ, flipSh;  // sign-bit sets of coordinateConverter(from, RUB)
+  const float *alphaThresholds;
+};
+
 enum PackMode { kPackAlu = 0, kPackCvt = 1 };
 
 struct LaunchPlan {
@@ -48,6 +62,9 @@ cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream
                          int *launches);
 cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream,
                          int *launches);
+
+cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, int *launches);
+int plyTileGaussians();
 
 // Gaussians per tile of the vector kernels for a given shDim (the sharding granule).
 int tileGaussians(int shDim);

@@ -1,0 +1,216 @@
+// Fused PLY-rows encoder: the vertex records of a gaussian-splat .ply (row-major, `width` floats
+// per vertex, the layout load-spz.cc:691-844 parses) straight to PackedGaussians planes, skipping
+// the planar float GaussianCloud in between.  It computes exactly
+//
+//     packGaussians(loadSplatFromPly(rows, to = X), from = X)          
+//
+// i.e. the [N,C,S] -> [N,S,C] SH shuffle and wxyz -> xyzw quaternion reorder of the PLY loader
+// (load-spz.cc:808-838), its RDF -> X flips and the encoder's X -> RUB flips (both are sign
+// products, so they compose into one set of sign bits), then the quantizers of codec_math.cuh.
+//
+// This IS a transposition: a vertex record is 62 consecutive floats (248 B at SH degree 3) while
+// every output plane wants consecutive gaussians.  A CTA therefore brings 128 records (31.7 KB,
+// contiguous in memory) into shared memory with one bulk async copy and gathers from there: thread
+// t produces output word t, t + 256, ... of each plane, picking its four source floats by
+// (gaussian, column) -- record stride 62 words is 2-way bank conflicted at worst -- so all global
+// stores are contiguous words and nothing is read from HBM twice: 313 B per gaussian at degree 3.
+#include "codec_kernels.cuh"
+
+#include "codec_math.cuh"
+
+namespace spzb200 {
+namespace {
+
+constexpr int kPlyThreads = 256;
+constexpr int kPlyTile = 128;  // gaussians per CTA
+
+__device__ __forceinline__ uint32_t smemAddrPly(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float signedConstPly(float magnitude, uint32_t negate) {
+  return __uint_as_float(__float_as_uint(magnitude) | (negate << 31));
+}
+
+// value of output element `i` of a plane for the tile, gathered from the staged records
+struct RowGather {
+  const float *rows;  // shared memory (tile kernel) or global memory (scalar kernel)
+  int width;
+  __device__ __forceinline__ float at(int g, int col) const { return rows[g * width + col]; }
+};
+
+// One packed SH word: elements 4j .. 4j+3 of the tile's [G][3*D] SH block.
+template <int D>
+__device__ __forceinline__ uint32_t shWord(const RowGather &r, const PlyEncodeArgs &a, int j) {
+  uint32_t word = 0;
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int i = 4 * j + e;
+    const int g = i / (3 * D), k = i - g * (3 * D);  // k = 3 * coefficient + channel
+    const int sCoef = k / 3, ch = k - 3 * sCoef;
+    const float x = r.at(g, a.colRest[ch * D + sCoef]);  // file order is [channel][coefficient]
+    const uint32_t bucket = k < 9 ? 8u : 16u;            // load-spz.cc:312-326
+    word |= m::quant_sh(x, signedConstPly(128.0f, (a.flipSh >> sCoef) & 1u), 128u + bucket / 2u, ~(bucket - 1u)) << (8 * e);
+  }
+  return word;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kPlyThreads)
+encodePlyTilesKernel(const PlyEncodeArgs a, const long long numTiles) {
+  extern __shared__ __align__(128) unsigned char dynSmem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ float sThr[256];
+  float *rows = reinterpret_cast<float *>(dynSmem);
+  const int t = threadIdx.x;
+  for (int i = t; i < 256; i += kPlyThreads) sThr[i] = a.alphaThresholds[i];
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddrPly(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const RowGather r{rows, a.width};
+  constexpr int G = kPlyTile;
+  const uint32_t tileBytes = (uint32_t)(G * a.width * 4);
+
+  uint32_t parity = 0;
+  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
+    if (t == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddrPly(&bar)), "r"(tileBytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddrPly(rows)),
+                   "l"(a.rows + tile * (long long)G * a.width), "r"(tileBytes), "r"(smemAddrPly(&bar))
+                   : "memory");
+    }
+    {
+      uint32_t done = 0;
+      for (uint32_t spin = 0; !done; spin++) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smemAddrPly(&bar)), "r"(parity)
+                     : "memory");
+        if (spin > (1u << 28)) __trap();
+      }
+    }
+    const long long g0 = tile * G;
+    // ---- positions: 3G values -> 3G/4 groups of three words --------------------------------------
+    for (int j = t; j < 3 * G / 4; j += kPlyThreads) {
+      uint32_t n[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int i = 4 * j + e, g = i / 3, ax = i - 3 * g;
+        n[e] = m::quant_position24(r.at(g, a.colPos[ax]), signedConstPly(4096.0f, (a.flipP >> ax) & 1u));
+      }
+      uint32_t *o = reinterpret_cast<uint32_t *>(a.oPositions + g0 * 9) + 3 * j;
+      o[0] = n[0] | (n[1] << 24);
+      o[1] = (n[1] >> 8) | (n[2] << 16);
+      o[2] = (n[2] >> 16) | (n[3] << 8);
+    }
+    // ---- scales, colours: 3G values -> 3G/4 words each -------------------------------------------
+    for (int j = t; j < 3 * G / 4; j += kPlyThreads) {
+      uint32_t ws = 0, wc = 0;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int i = 4 * j + e, g = i / 3, ax = i - 3 * g;
+        ws |= m::quant_scale(r.at(g, a.colScale[ax])) << (8 * e);
+        wc |= m::quant_color(r.at(g, a.colColor[ax])) << (8 * e);
+      }
+      reinterpret_cast<uint32_t *>(a.oScales + g0 * 3)[j] = ws;
+      reinterpret_cast<uint32_t *>(a.oColors + g0 * 3)[j] = wc;
+    }
+    // ---- alphas: G values -> G/4 words;  rotations: one word per gaussian ---------------------------
+    for (int j = t; j < G / 4; j += kPlyThreads) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int e = 0; e < 4; e++) w |= m::quant_alpha(r.at(4 * j + e, a.colAlpha), sThr) << (8 * e);
+      reinterpret_cast<uint32_t *>(a.oAlphas + g0)[j] = w;
+    }
+    for (int g = t; g < G; g += kPlyThreads) {
+      reinterpret_cast<uint32_t *>(a.oRotations + g0 * 4)[g] = m::quant_rotation_smallest3(
+          r.at(g, a.colRot[0]), r.at(g, a.colRot[1]), r.at(g, a.colRot[2]), r.at(g, a.colRot[3]), a.flipQ);
+    }
+    // ---- spherical harmonics: 3*D*G values -> 3*D*G/4 words ---------------------------------------------
+    if constexpr (D > 0) {
+      uint32_t *o = reinterpret_cast<uint32_t *>(a.oSh + g0 * (3 * D));
+      for (int j = t; j < 3 * D * G / 4; j += kPlyThreads) o[j] = shWord<D>(r, a, j);
+    }
+    __syncthreads();  // everyone is done with the records before the next tile's copy lands
+  }
+}
+
+// remainder / under-aligned rows: one thread per gaussian straight from global memory
+__global__ void __launch_bounds__(128)
+encodePlyGenericKernel(const PlyEncodeArgs a, const long long first) {
+  const long long g = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.n) return;
+  const float *row = a.rows + g * a.width;
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    const uint32_t n = m::quant_position24(row[a.colPos[ax]], signedConstPly(4096.0f, (a.flipP >> ax) & 1u));
+    uint8_t *o = a.oPositions + (g * 3 + ax) * 3;
+    o[0] = (uint8_t)n; o[1] = (uint8_t)(n >> 8); o[2] = (uint8_t)(n >> 16);
+    a.oScales[g * 3 + ax] = (uint8_t)m::quant_scale(row[a.colScale[ax]]);
+    a.oColors[g * 3 + ax] = (uint8_t)m::quant_color(row[a.colColor[ax]]);
+  }
+  a.oAlphas[g] = (uint8_t)m::quant_alpha(row[a.colAlpha], a.alphaThresholds);
+  const uint32_t comp = m::quant_rotation_smallest3(row[a.colRot[0]], row[a.colRot[1]], row[a.colRot[2]], row[a.colRot[3]], a.flipQ);
+  uint8_t *ro = a.oRotations + g * 4;
+  ro[0] = (uint8_t)comp; ro[1] = (uint8_t)(comp >> 8); ro[2] = (uint8_t)(comp >> 16); ro[3] = (uint8_t)(comp >> 24);
+  const int D = a.shDim;
+  uint8_t *so = a.oSh + g * (3 * D);
+  for (int k = 0; k < 3 * D; k++) {
+    const int sCoef = k / 3, ch = k - 3 * sCoef;
+    const uint32_t bucket = k < 9 ? 8u : 16u;
+    so[k] = (uint8_t)m::quant_sh(row[a.colRest[ch * D + sCoef]], signedConstPly(128.0f, (a.flipSh >> sCoef) & 1u),
+                                 128u + bucket / 2u, ~(bucket - 1u));
+  }
+}
+
+bool alignedTo(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+template <int D>
+cudaError_t launchPlyTiles(const PlyEncodeArgs &a, long long tiles, cudaStream_t s) {
+  const int smem = kPlyTile * a.width * 4;
+  cudaError_t e = cudaFuncSetAttribute(encodePlyTilesKernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  encodePlyTilesKernel<D><<<(unsigned)(tiles < 0x7fffffffLL ? tiles : 0x7fffffffLL), kPlyThreads, smem, s>>>(a, tiles);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, int *launches) {
+  int count = 0;
+  if (launches) *launches = 0;
+  if (a.n <= 0) return cudaSuccess;
+  // the bulk copy wants 16-byte aligned records; 128 records of `width` floats always are a
+  // multiple of 16 bytes, so only the base pointer matters.  227 KB of shared memory bound the width.
+  const bool vec = !plan.forceGeneric && alignedTo(a.rows, 16) && alignedTo(a.oPositions, 4) && alignedTo(a.oScales, 4) &&
+                   alignedTo(a.oRotations, 4) && alignedTo(a.oAlphas, 4) && alignedTo(a.oColors, 4) &&
+                   (a.shDim == 0 || alignedTo(a.oSh, 4)) && (long long)kPlyTile * a.width * 4 <= 200 * 1024;
+  const long long tiles = vec ? a.n / kPlyTile : 0;
+  if (tiles > 0) {
+    cudaError_t e;
+    switch (a.shDim) {
+      case 0: e = launchPlyTiles<0>(a, tiles, stream); break;
+      case 3: e = launchPlyTiles<3>(a, tiles, stream); break;
+      case 8: e = launchPlyTiles<8>(a, tiles, stream); break;
+      case 15: e = launchPlyTiles<15>(a, tiles, stream); break;
+      default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    count++;
+  }
+  const long long first = tiles * kPlyTile;
+  if (first < a.n) {
+    const long long blocks = (a.n - first + 127) / 128;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    encodePlyGenericKernel<<<(unsigned)blocks, 128, 0, stream>>>(a, first);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    count++;
+  }
+  if (launches) *launches = count;
+  return cudaSuccess;
+}
+
+int plyTileGaussians() { return kPlyTile; }
+
+}  // namespace spzb200

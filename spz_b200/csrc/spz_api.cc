@@ -21,12 +21,10 @@
 #include <string>
 #include <vector>
 
-#include "../../include/spz_b200.h"
-#include "../../include/spz_b200/spz.hpp"
+#include "spz_internal.hpp"
 
 namespace spz {
-namespace {
-
+namespace detail {
 void logLine(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -35,6 +33,9 @@ void logLine(const char *fmt, ...) {
   printf("\n");
   fflush(stdout);
 }
+}  // namespace detail
+namespace {
+using detail::logLine;
 
 // The reference prints "[SPZ: ERROR] Check failed: file:line: expr" (load-spz.cc:94-100).
 #define SPZ_REQUIRE(cond)                                                                \
@@ -56,6 +57,9 @@ constexpr size_t kHeaderBytes = 16;
 // default is device 0 (or SPZ_B200_DEVICE).  One context per host thread and device, created on
 // first use and kept until the thread exits.
 
+}  // namespace
+
+namespace detail {
 std::vector<int32_t> configuredDevices() {
   std::vector<int32_t> devs;
   if (const char *list = std::getenv("SPZ_B200_DEVICES")) {
@@ -98,6 +102,12 @@ SpzB200Context *contextFor(int32_t device) {
   tc.device = device;
   return tc.ctx;
 }
+
+}  // namespace detail
+
+namespace {
+using detail::configuredDevices;
+using detail::contextFor;
 
 bool checkCloudSizes(const GaussianCloud &g) {
   // the reference's checks (load-spz.cc:106-117) with the products taken in 64 bits
@@ -548,6 +558,16 @@ bool compressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out
   out->resize(produced);
   return true;
 }
+
+namespace detail {
+bool finishSpz(const PackedGaussians &packed, std::vector<uint8_t> *out) {
+  std::vector<uint8_t> stream(serializedBytes(packed));
+  serializeInto(packed, stream.data());
+  const int threads = gzipThreads();
+  if (threads > 1) return compressGzippedParallel(stream.data(), stream.size(), threads, out);
+  return compressGzipped(stream.data(), stream.size(), out);
+}
+}  // namespace detail
 
 bool saveSpz(const GaussianCloud &g, const PackOptions &o, std::vector<uint8_t> *out) {
   std::vector<uint8_t> stream;

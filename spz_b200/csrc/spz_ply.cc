@@ -12,7 +12,7 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/spz_b200/spz.hpp"
+#include "spz_internal.hpp"
 
 namespace spz {
 namespace {
@@ -42,37 +42,38 @@ int degreeForShDim(int dim) { return dim < 3 ? 0 : dim < 8 ? 1 : dim < 15 ? 2 : 
 
 }  // namespace
 
-GaussianCloud loadSplatFromPly(const std::string &filename, const UnpackOptions &o) {
+namespace detail {
+
+bool readPlyRows(const std::string &filename, PlyLayout *layout, std::vector<float> *rows) {
   const char *name = filename.c_str();
   say("[SPZ] Loading: %s", name);
   std::ifstream in(filename, std::ios::binary);
   if (!in.good()) {
     say("[SPZ ERROR] Unable to open: %s", name);
-    return {};
+    return false;
   }
   std::string line;
   std::getline(in, line);
   if (line != "ply") {
     say("[SPZ ERROR] %s: not a .ply file", name);
-    return {};
+    return false;
   }
   if (!nextHeaderLine(in, &line) || line != "format binary_little_endian 1.0") {
     say("[SPZ ERROR] %s: unsupported .ply format", name);
-    return {};
+    return false;
   }
   static const char kVertex[] = "element vertex ";
   if (!nextHeaderLine(in, &line) || !startsWith(line, kVertex)) {
     say("[SPZ ERROR] %s: missing vertex count", name);
-    return {};
+    return false;
   }
   char *end = nullptr;
   const long long count = std::strtoll(line.c_str() + sizeof(kVertex) - 1, &end, 10);
   if (end == line.c_str() + sizeof(kVertex) - 1 || count <= 0 || count > 10LL * 1024 * 1024) {
     printf("[SPZ ERROR] %s: invalid vertex count: %lld\n", name, count);
     fflush(stdout);
-    return {};
+    return false;
   }
-  const size_t numPoints = (size_t)count;
   printf("[SPZ] Loading %lld points\n", count);
   fflush(stdout);
 
@@ -82,12 +83,12 @@ GaussianCloud loadSplatFromPly(const std::string &filename, const UnpackOptions 
   for (int i = 0;; i++) {
     if (!nextHeaderLine(in, &line)) {
       say("[SPZ ERROR] %s: unexpected EOF while reading header properties.", name);
-      return {};
+      return false;
     }
     if (line == "end_header") break;
     if (!startsWith(line, kProp)) {
       say("[SPZ ERROR] %s: unsupported property data type: %s", name, line.c_str());
-      return {};
+      return false;
     }
     column[line.substr(sizeof(kProp) - 1)] = i;
   }
@@ -101,27 +102,39 @@ GaussianCloud loadSplatFromPly(const std::string &filename, const UnpackOptions 
     }
     return it->second;
   };
-  const int pos[3] = {col("x"), col("y"), col("z")};
-  const int scl[3] = {col("scale_0"), col("scale_1"), col("scale_2")};
-  const int rot[4] = {col("rot_1"), col("rot_2"), col("rot_3"), col("rot_0")};  // file is wxyz
-  const int alp = col("opacity");
-  const int dc[3] = {col("f_dc_0"), col("f_dc_1"), col("f_dc_2")};
-  if (missing) return {};
-  std::vector<int> rest;
+  PlyLayout &L = *layout;
+  L.pos[0] = col("x"); L.pos[1] = col("y"); L.pos[2] = col("z");
+  L.scale[0] = col("scale_0"); L.scale[1] = col("scale_1"); L.scale[2] = col("scale_2");
+  L.rot[0] = col("rot_1"); L.rot[1] = col("rot_2"); L.rot[2] = col("rot_3"); L.rot[3] = col("rot_0");  // file is wxyz
+  L.alpha = col("opacity");
+  L.color[0] = col("f_dc_0"); L.color[1] = col("f_dc_1"); L.color[2] = col("f_dc_2");
+  if (missing) return false;
+  L.rest.clear();
   for (int i = 0; i < 45; i++) {
     const auto it = column.find("f_rest_" + std::to_string(i));
     if (it == column.end()) break;
-    rest.push_back(it->second);
+    L.rest.push_back(it->second);
   }
-  const size_t shDim = rest.size() / 3;
-  const size_t width = column.size();
+  L.shDim = (int)(L.rest.size() / 3);
+  L.width = (int)column.size();
+  L.numPoints = count;
 
-  std::vector<float> rows(numPoints * width);
-  in.read(reinterpret_cast<char *>(rows.data()), (std::streamsize)(rows.size() * sizeof(float)));
+  rows->resize((size_t)count * (size_t)L.width);
+  in.read(reinterpret_cast<char *>(rows->data()), (std::streamsize)(rows->size() * sizeof(float)));
   if (!in.good()) {
     say("[SPZ ERROR] Unable to load data from: %s", name);
-    return {};
+    return false;
   }
+  return true;
+}
+
+}  // namespace detail
+
+GaussianCloud loadSplatFromPly(const std::string &filename, const UnpackOptions &o) {
+  detail::PlyLayout L;
+  std::vector<float> rows;
+  if (!detail::readPlyRows(filename, &L, &rows)) return {};
+  const size_t numPoints = (size_t)L.numPoints, shDim = (size_t)L.shDim, width = (size_t)L.width;
 
   GaussianCloud g;
   g.numPoints = (int32_t)numPoints;
@@ -135,18 +148,76 @@ GaussianCloud loadSplatFromPly(const std::string &filename, const UnpackOptions 
   for (size_t p = 0; p < numPoints; p++) {
     const float *row = rows.data() + p * width;
     for (int a = 0; a < 3; a++) {
-      g.positions[p * 3 + a] = row[pos[a]];
-      g.scales[p * 3 + a] = row[scl[a]];
-      g.colors[p * 3 + a] = row[dc[a]];
+      g.positions[p * 3 + a] = row[L.pos[a]];
+      g.scales[p * 3 + a] = row[L.scale[a]];
+      g.colors[p * 3 + a] = row[L.color[a]];
     }
-    for (int a = 0; a < 4; a++) g.rotations[p * 4 + a] = row[rot[a]];
-    g.alphas[p] = row[alp];
+    for (int a = 0; a < 4; a++) g.rotations[p * 4 + a] = row[L.rot[a]];
+    g.alphas[p] = row[L.alpha];
     float *sh = g.sh.data() + p * shDim * 3;
     for (size_t s = 0; s < shDim; s++)
-      for (size_t c = 0; c < 3; c++) sh[s * 3 + c] = row[rest[c * shDim + s]];  // [C][S] -> [S][C]
+      for (size_t c = 0; c < 3; c++) sh[s * 3 + c] = row[L.rest[c * shDim + s]];  // [C][S] -> [S][C]
   }
   g.convertCoordinates(CoordinateSystem::RDF, o.to);
   return g;
+}
+
+// Extension: .ply file -> .spz bytes without materialising the planar GaussianCloud.  The vertex
+// records go to the GPU as they lie in the file and the fused kernel (ply_kernels.cu) shuffles and
+// quantises them: same bytes as saveSpz(loadSplatFromPly(file, {to}), {from = to}) for any `to`
+// when options.from == RDF, and as the reference's ply_to_spz tool (no conversion either way) when
+// options.from == UNSPECIFIED.
+bool plyToSpz(const std::string &plyFilename, const PackOptions &options, std::vector<uint8_t> *output) {
+  detail::PlyLayout L;
+  std::vector<float> rows;
+  if (!detail::readPlyRows(plyFilename, &L, &rows)) return false;
+  const int degree = degreeForShDim(L.shDim);
+  const int usedDim = degree == 0 ? 0 : degree == 1 ? 3 : degree == 2 ? 8 : 15;
+  if (usedDim != L.shDim) {
+    // a file with e.g. 4 coefficients per channel: the loader would keep them all while declaring
+    // degree 1, which packGaussians then rejects (load-spz.cc:115); same verdict here
+    detail::logLine("[SPZ: ERROR] Check failed: %s:%d: sh coefficient count %d does not match a degree", __FILE__, __LINE__, L.shDim);
+    return detail::finishSpz(PackedGaussians{}, output);
+  }
+  const size_t n = (size_t)L.numPoints;
+  PackedGaussians packed;
+  packed.numPoints = (int32_t)n;
+  packed.shDegree = degree;
+  packed.fractionalBits = 12;
+  packed.antialiased = false;
+  packed.usesQuaternionSmallestThree = true;
+  packed.positions.resize(n * 9);
+  packed.scales.resize(n * 3);
+  packed.rotations.resize(n * 4);
+  packed.alphas.resize(n);
+  packed.colors.resize(n * 3);
+  packed.sh.resize(n * (size_t)usedDim * 3);
+
+  SpzB200PlyRows in;
+  std::memset(&in, 0, sizeof in);
+  in.num_points = (int64_t)n;
+  in.width = L.width;
+  in.sh_degree = degree;
+  in.rows = rows.data();
+  for (int a = 0; a < 3; a++) { in.col_pos[a] = L.pos[a]; in.col_scale[a] = L.scale[a]; in.col_color[a] = L.color[a]; }
+  for (int a = 0; a < 4; a++) in.col_rot[a] = L.rot[a];
+  in.col_alpha = L.alpha;
+  // the loader reads channel c, coefficient s from rest[c * shDim + s] with shDim = coefficients in the FILE
+  for (int c = 0; c < 3; c++)
+    for (int s = 0; s < usedDim; s++) in.col_rest[c * usedDim + s] = L.rest[(size_t)(c * L.shDim + s)];
+  SpzB200Packed out;
+  std::memset(&out, 0, sizeof out);
+  out.num_points = (int64_t)n;
+  out.sh_degree = degree;
+  out.positions = packed.positions.data(); out.scales = packed.scales.data(); out.rotations = packed.rotations.data();
+  out.alphas = packed.alphas.data(); out.colors = packed.colors.data(); out.sh = packed.sh.data();
+  SpzB200Context *ctx = detail::contextFor(detail::configuredDevices()[0]);
+  if (!ctx) return false;
+  if (spzb200_encode_ply_host(ctx, &in, (int32_t)options.from, &out, nullptr) != SPZB200_OK) {
+    detail::logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
+    return false;
+  }
+  return detail::finishSpz(packed, output);
 }
 
 bool saveSplatToPly(const GaussianCloud &g, const PackOptions &o, const std::string &filename) {

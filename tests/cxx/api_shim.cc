@@ -229,7 +229,14 @@ uint8_t *SHIM(gzip)(const uint8_t *data, uint64_t size, uint64_t *outSize) {
   return dupBytes(out.data(), out.size(), outSize);
 }
 
-#ifdef SHIM_HAS_EXTENSIONS  // this repo only: block-parallel zlib (spz_gzip.cc)
+#ifdef SHIM_HAS_EXTENSIONS  // this repo only: fused .ply -> .spz, block-parallel zlib (spz_gzip.cc)
+uint8_t *SHIM(ply_to_spz)(const char *path, int32_t from, uint64_t *outSize) {
+  spz::PackOptions o;
+  o.from = (spz::CoordinateSystem)from;
+  std::vector<uint8_t> out;
+  if (!spz::plyToSpz(std::string(path), o, &out)) return nullptr;
+  return dupBytes(out.data(), out.size(), outSize);
+}
 uint8_t *SHIM(gzip_parallel)(const uint8_t *data, uint64_t size, int32_t threads, uint64_t *outSize) {
   std::vector<uint8_t> out;
   if (!spz::compressGzippedParallel(data, size, threads, &out)) return nullptr;

@@ -151,6 +151,12 @@ class Shim:
         ptr = self.fn("gzip")(buf.ctypes.data_as(_u8p), C.c_uint64(buf.size), C.byref(size))
         return None if not ptr else self._take(ptr, size)
 
+    def ply_to_spz(self, path: str, frm: int):
+        self.fn("ply_to_spz").restype = C.c_void_p
+        size = C.c_uint64(0)
+        ptr = self.fn("ply_to_spz")(path.encode(), C.c_int32(frm), C.byref(size))
+        return None if not ptr else self._take(ptr, size)
+
     def gzip_parallel(self, data: bytes, threads: int):
         self.fn("gzip_parallel").restype = C.c_void_p
         buf = np.frombuffer(data, np.uint8) if data else np.zeros(0, np.uint8)
@@ -582,6 +588,24 @@ def test_save_spz_with_parallel_gzip_is_readable_by_the_reference(mine, theirs):
     assert par != serial and gzip.decompress(par) == gzip.decompress(serial)
     assert_cloud_bits_equal(theirs.load_spz(par, 8), theirs.load_spz(serial, 8), "reference reads the parallel member")
     assert_cloud_bits_equal(back, theirs.load_spz(serial, 8), "parallel inflate + decode")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_fused_ply_to_spz_matches_load_then_save(mine, theirs, tmp_path, deg):
+    """plyToSpz (records -> GPU -> packed planes, ply_kernels.cu) against the reference's two-step
+    loadSplatFromPly + saveSpz: identical container bytes for every frame choice."""
+    rng = np.random.default_rng(340 + deg)
+    n = 3 * 128 + 57  # three tiles on the staged kernel + a scalar remainder
+    c = random_cloud(rng, n, deg, deg == 3)
+    path = str(tmp_path / "in.ply")
+    assert theirs.save_ply(c, path, 0)
+    for to in (4, 7, 8):  # records are RDF; the loader converts to X, the encoder from X back to RUB
+        want = theirs.save_spz(theirs.load_ply(path, to), to)
+        got = mine.ply_to_spz(path, 6)
+        assert gzip.decompress(got) == gzip.decompress(want), (deg, to)
+    assert gzip.decompress(mine.ply_to_spz(path, 0)) == gzip.decompress(theirs.save_spz(theirs.load_ply(path, 0), 0))
+    assert mine.ply_to_spz(str(tmp_path / "missing.ply"), 0) is None
 
 
 @pytest.mark.gpu

@@ -227,6 +227,50 @@ def test_alternate_launch_shapes(env):
     assert r.returncode == 0 and "sanitize_case ok" in r.stdout, (env, r.stdout[-1500:], r.stderr[-1500:])
 
 
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_fused_ply_rows_encoder(gpu_ctx, oracle, deg):
+    """spzb200_encode_ply_device / _host: row-major .ply records -> packed planes, against the oracle's
+    pack of the same cloud; shuffled column order, extra columns, tile multiples and remainders,
+    an unaligned base pointer (scalar kernel) and the chunked host pipeline."""
+    from spz_b200.codec import SH_DIM as DIM, ply_property_names
+    t = _torch()
+    rng = np.random.default_rng(3400 + deg)
+    names = ply_property_names(deg)
+    d = DIM[deg]
+    for n, shuffle in ((128 * 5, False), (128 * 3 + 77, True), (90, False)):
+        c = random_cloud(rng, n, deg, True)
+        cols = {"x": c.positions[0::3], "y": c.positions[1::3], "z": c.positions[2::3],
+                "nx": np.zeros(n, np.float32), "ny": np.zeros(n, np.float32), "nz": np.zeros(n, np.float32),
+                "f_dc_0": c.colors[0::3], "f_dc_1": c.colors[1::3], "f_dc_2": c.colors[2::3], "opacity": c.alphas,
+                "scale_0": c.scales[0::3], "scale_1": c.scales[1::3], "scale_2": c.scales[2::3],
+                "rot_0": c.rotations[3::4], "rot_1": c.rotations[0::4], "rot_2": c.rotations[1::4], "rot_3": c.rotations[2::4]}
+        sh = c.sh.reshape(n, d, 3) if d else np.zeros((n, 0, 3), np.float32)
+        for ch in range(3):
+            for s in range(d):
+                cols[f"f_rest_{ch * d + s}"] = sh[:, s, ch]
+        order = list(names)
+        if shuffle:
+            order = list(rng.permutation(order)) + ["extra_a", "extra_b"]
+            cols["extra_a"] = rng.normal(size=n).astype(np.float32)
+            cols["extra_b"] = rng.normal(size=n).astype(np.float32)
+        rows = np.ascontiguousarray(np.stack([cols[k] for k in order], axis=1), np.float32).reshape(-1)
+        for frm in (0, 6, 7):
+            want = oracle.pack(c, frm)
+            got = host_packed(gpu_ctx.encode_ply_device(t.from_numpy(rows).cuda(), n, order, deg, frm))
+            assert_packed_equal(got, want, f"ply device deg{deg} n{n} from{frm}")
+        # base pointer off by one float: not 16-byte aligned -> scalar kernel
+        padded = t.from_numpy(np.concatenate([np.zeros(1, np.float32), rows])).cuda()
+        got = host_packed(gpu_ctx.encode_ply_device(padded[1:], n, order, deg, 6))
+        assert_packed_equal(got, oracle.pack(c, 6), "ply device unaligned")
+        try:
+            gpu_ctx.set_chunk_points(256)
+            got, tm = gpu_ctx.encode_ply_host(rows, n, order, deg, 6)
+            assert tm["chunks"] == (n + 255) // 256
+            assert_packed_equal(Packed(n, deg, 12, 3, *got.planes()), oracle.pack(c, 6), "ply host")
+        finally:
+            gpu_ctx.set_chunk_points(0)
+
+
 def test_empty_cloud(gpu_ctx):
     from spz_b200.codec import alloc_cloud, alloc_packed
     for deg in range(4):
