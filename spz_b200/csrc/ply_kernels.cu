@@ -22,7 +22,10 @@ namespace spzb200 {
 namespace {
 
 constexpr int kPlyThreads = 256;
-constexpr int kPlyTile = 128;  // gaussians per CTA
+constexpr int kPlyTileBase = 128;  // tile sizes are multiples of this
+// gaussians per CTA: about 32 KB of records at the standard widths (62 / 41 / 26 / 17 floats)
+template <int D>
+constexpr int kPlyTileFor = D == 15 ? 128 : D == 8 ? 256 : D == 3 ? 256 : 512;
 
 __device__ __forceinline__ uint32_t smemAddrPly(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -30,53 +33,47 @@ __device__ __forceinline__ float signedConstPly(float magnitude, uint32_t negate
   return __uint_as_float(__float_as_uint(magnitude) | (negate << 31));
 }
 
-// value of output element `i` of a plane for the tile, gathered from the staged records
-struct RowGather {
-  const float *rows;  // shared memory (tile kernel) or global memory (scalar kernel)
-  int width;
-  __device__ __forceinline__ float at(int g, int col) const { return rows[g * width + col]; }
-};
-
-// One packed SH word: elements 4j .. 4j+3 of the tile's [G][3*D] SH block.
-template <int D>
-__device__ __forceinline__ uint32_t shWord(const RowGather &r, const PlyEncodeArgs &a, int j) {
-  uint32_t word = 0;
-#pragma unroll
-  for (int e = 0; e < 4; e++) {
-    const int i = 4 * j + e;
-    const int g = i / (3 * D), k = i - g * (3 * D);  // k = 3 * coefficient + channel
-    const int sCoef = k / 3, ch = k - 3 * sCoef;
-    const float x = r.at(g, a.colRest[ch * D + sCoef]);  // file order is [channel][coefficient]
-    const uint32_t bucket = k < 9 ? 8u : 16u;            // load-spz.cc:312-326
-    word |= m::quant_sh(x, signedConstPly(128.0f, (a.flipSh >> sCoef) & 1u), 128u + bucket / 2u, ~(bucket - 1u)) << (8 * e);
-  }
-  return word;
-}
-
+// Column maps live in shared memory: indexing the kernel-parameter arrays with a lane-dependent
+// index turns into divergent constant-bank loads, which replay once per distinct address (the first
+// version did that and ran at 0.9 TB/s).
+//   shMap[k], k = 3 * coefficient + channel: bits 0..15 source column, bit 30 = 5-bit band, bit 31 = flip
+//   xyzMap[plane][axis]: source column (| flip << 31 for positions)
 template <int D>
 __global__ void __launch_bounds__(kPlyThreads)
 encodePlyTilesKernel(const PlyEncodeArgs a, const long long numTiles) {
   extern __shared__ __align__(128) unsigned char dynSmem[];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ float sThr[256];
+  __shared__ uint32_t shMap[D > 0 ? 3 * D : 1];
+  __shared__ uint32_t xyzMap[3][3];
   float *rows = reinterpret_cast<float *>(dynSmem);
   const int t = threadIdx.x;
   for (int i = t; i < 256; i += kPlyThreads) sThr[i] = a.alphaThresholds[i];
+  if (D > 0 && t < 3 * D) {
+    const int sCoef = t / 3, ch = t - 3 * sCoef;
+    shMap[t] = (uint32_t)a.colRest[ch * D + sCoef] | (t < 9 ? 1u << 30 : 0u) | (((a.flipSh >> sCoef) & 1u) << 31);
+  }
+  if (t < 3) {
+    xyzMap[0][t] = (uint32_t)a.colPos[t] | (((a.flipP >> t) & 1u) << 31);
+    xyzMap[1][t] = (uint32_t)a.colScale[t];
+    xyzMap[2][t] = (uint32_t)a.colColor[t];
+  }
   if (t == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddrPly(&bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const RowGather r{rows, a.width};
-  constexpr int G = kPlyTile;
-  const uint32_t tileBytes = (uint32_t)(G * a.width * 4);
+  const int width = a.width;
+  constexpr int G = kPlyTileFor<D>;
+  const uint32_t tileBytes = (uint32_t)(G * width * 4);
+  const int colAlpha = a.colAlpha, colRx = a.colRot[0], colRy = a.colRot[1], colRz = a.colRot[2], colRw = a.colRot[3];
 
   uint32_t parity = 0;
   for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
     if (t == 0) {
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddrPly(&bar)), "r"(tileBytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddrPly(rows)),
-                   "l"(a.rows + tile * (long long)G * a.width), "r"(tileBytes), "r"(smemAddrPly(&bar))
+                   "l"(a.rows + tile * (long long)G * width), "r"(tileBytes), "r"(smemAddrPly(&bar))
                    : "memory");
     }
     {
@@ -96,7 +93,8 @@ encodePlyTilesKernel(const PlyEncodeArgs a, const long long numTiles) {
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         const int i = 4 * j + e, g = i / 3, ax = i - 3 * g;
-        n[e] = m::quant_position24(r.at(g, a.colPos[ax]), signedConstPly(4096.0f, (a.flipP >> ax) & 1u));
+        const uint32_t mp = xyzMap[0][ax];
+        n[e] = m::quant_position24(rows[g * width + (int)(mp & 0xffffu)], __uint_as_float(0x45800000u | (mp & 0x80000000u)));  // +-4096
       }
       uint32_t *o = reinterpret_cast<uint32_t *>(a.oPositions + g0 * 9) + 3 * j;
       o[0] = n[0] | (n[1] << 24);
@@ -109,8 +107,8 @@ encodePlyTilesKernel(const PlyEncodeArgs a, const long long numTiles) {
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         const int i = 4 * j + e, g = i / 3, ax = i - 3 * g;
-        ws |= m::quant_scale(r.at(g, a.colScale[ax])) << (8 * e);
-        wc |= m::quant_color(r.at(g, a.colColor[ax])) << (8 * e);
+        ws |= m::quant_scale(rows[g * width + (int)xyzMap[1][ax]]) << (8 * e);
+        wc |= m::quant_color(rows[g * width + (int)xyzMap[2][ax]]) << (8 * e);
       }
       reinterpret_cast<uint32_t *>(a.oScales + g0 * 3)[j] = ws;
       reinterpret_cast<uint32_t *>(a.oColors + g0 * 3)[j] = wc;
@@ -119,17 +117,31 @@ encodePlyTilesKernel(const PlyEncodeArgs a, const long long numTiles) {
     for (int j = t; j < G / 4; j += kPlyThreads) {
       uint32_t w = 0;
 #pragma unroll
-      for (int e = 0; e < 4; e++) w |= m::quant_alpha(r.at(4 * j + e, a.colAlpha), sThr) << (8 * e);
+      for (int e = 0; e < 4; e++) w |= m::quant_alpha(rows[(4 * j + e) * width + colAlpha], sThr) << (8 * e);
       reinterpret_cast<uint32_t *>(a.oAlphas + g0)[j] = w;
     }
     for (int g = t; g < G; g += kPlyThreads) {
-      reinterpret_cast<uint32_t *>(a.oRotations + g0 * 4)[g] = m::quant_rotation_smallest3(
-          r.at(g, a.colRot[0]), r.at(g, a.colRot[1]), r.at(g, a.colRot[2]), r.at(g, a.colRot[3]), a.flipQ);
+      const float *row = rows + g * width;
+      reinterpret_cast<uint32_t *>(a.oRotations + g0 * 4)[g] =
+          m::quant_rotation_smallest3(row[colRx], row[colRy], row[colRz], row[colRw], a.flipQ);
     }
     // ---- spherical harmonics: 3*D*G values -> 3*D*G/4 words ---------------------------------------------
     if constexpr (D > 0) {
       uint32_t *o = reinterpret_cast<uint32_t *>(a.oSh + g0 * (3 * D));
-      for (int j = t; j < 3 * D * G / 4; j += kPlyThreads) o[j] = shWord<D>(r, a, j);
+      for (int j = t; j < 3 * D * G / 4; j += kPlyThreads) {
+        const int i0 = 4 * j;
+        int g = i0 / (3 * D), k = i0 - g * (3 * D);  // element 0 of the word; the others follow, wrapping into the next gaussian
+        uint32_t word = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const uint32_t mp = shMap[k];
+          const float x = rows[g * width + (int)(mp & 0xffffu)];
+          const uint32_t fine = (mp >> 30) & 1u;
+          word |= m::quant_sh(x, __uint_as_float(0x43000000u | (mp & 0x80000000u)), 136u - (fine << 2), ~15u | (fine << 3)) << (8 * e);
+          if (++k == 3 * D) { k = 0; g++; }
+        }
+        o[j] = word;
+      }
     }
     __syncthreads();  // everyone is done with the records before the next tile's copy lands
   }
@@ -167,7 +179,7 @@ bool alignedTo(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>
 
 template <int D>
 cudaError_t launchPlyTiles(const PlyEncodeArgs &a, long long tiles, cudaStream_t s) {
-  const int smem = kPlyTile * a.width * 4;
+  const int smem = kPlyTileFor<D> * a.width * 4;
   cudaError_t e = cudaFuncSetAttribute(encodePlyTilesKernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   encodePlyTilesKernel<D><<<(unsigned)(tiles < 0x7fffffffLL ? tiles : 0x7fffffffLL), kPlyThreads, smem, s>>>(a, tiles);
@@ -180,12 +192,14 @@ cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cuda
   int count = 0;
   if (launches) *launches = 0;
   if (a.n <= 0) return cudaSuccess;
-  // the bulk copy wants 16-byte aligned records; 128 records of `width` floats always are a
-  // multiple of 16 bytes, so only the base pointer matters.  227 KB of shared memory bound the width.
+  // the bulk copy wants 16-byte aligned records; a tile of `width`-float records always is a
+  // multiple of 16 bytes, so only the base pointer matters
   const bool vec = !plan.forceGeneric && alignedTo(a.rows, 16) && alignedTo(a.oPositions, 4) && alignedTo(a.oScales, 4) &&
                    alignedTo(a.oRotations, 4) && alignedTo(a.oAlphas, 4) && alignedTo(a.oColors, 4) &&
-                   (a.shDim == 0 || alignedTo(a.oSh, 4)) && (long long)kPlyTile * a.width * 4 <= 200 * 1024;
-  const long long tiles = vec ? a.n / kPlyTile : 0;
+                   (a.shDim == 0 || alignedTo(a.oSh, 4));
+  const int tileG = a.shDim == 15 ? kPlyTileFor<15> : a.shDim == 8 ? kPlyTileFor<8> : a.shDim == 3 ? kPlyTileFor<3> : kPlyTileFor<0>;
+  // 200 KB of shared memory bound the record width the staged kernel accepts (wider: scalar kernel)
+  const long long tiles = vec && (long long)tileG * a.width * 4 <= 200 * 1024 ? a.n / tileG : 0;
   if (tiles > 0) {
     cudaError_t e;
     switch (a.shDim) {
@@ -198,7 +212,7 @@ cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cuda
     if (e != cudaSuccess) return e;
     count++;
   }
-  const long long first = tiles * kPlyTile;
+  const long long first = tiles * tileG;
   if (first < a.n) {
     const long long blocks = (a.n - first + 127) / 128;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -211,6 +225,6 @@ cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cuda
   return cudaSuccess;
 }
 
-int plyTileGaussians() { return kPlyTile; }
+int plyTileGaussians() { return kPlyTileFor<0>; }  // the largest tile: a granule every tile size divides
 
 }  // namespace spzb200

@@ -596,7 +596,7 @@ def test_fused_ply_to_spz_matches_load_then_save(mine, theirs, tmp_path, deg):
     """plyToSpz (records -> GPU -> packed planes, ply_kernels.cu) against the reference's two-step
     loadSplatFromPly + saveSpz: identical container bytes for every frame choice."""
     rng = np.random.default_rng(340 + deg)
-    n = 3 * 128 + 57  # three tiles on the staged kernel + a scalar remainder
+    n = 3 * 512 + 57  # full tiles on the staged kernel (128..512 gaussians by degree) + a scalar remainder
     c = random_cloud(rng, n, deg, deg == 3)
     path = str(tmp_path / "in.ply")
     assert theirs.save_ply(c, path, 0)

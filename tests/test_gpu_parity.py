@@ -237,7 +237,7 @@ def test_fused_ply_rows_encoder(gpu_ctx, oracle, deg):
     rng = np.random.default_rng(3400 + deg)
     names = ply_property_names(deg)
     d = DIM[deg]
-    for n, shuffle in ((128 * 5, False), (128 * 3 + 77, True), (90, False)):
+    for n, shuffle in ((512 * 3, False), (512 * 2 + 128 * 3 + 77, True), (90, False)):
         c = random_cloud(rng, n, deg, True)
         cols = {"x": c.positions[0::3], "y": c.positions[1::3], "z": c.positions[2::3],
                 "nx": np.zeros(n, np.float32), "ny": np.zeros(n, np.float32), "nz": np.zeros(n, np.float32),
@@ -263,9 +263,9 @@ def test_fused_ply_rows_encoder(gpu_ctx, oracle, deg):
         got = host_packed(gpu_ctx.encode_ply_device(padded[1:], n, order, deg, 6))
         assert_packed_equal(got, oracle.pack(c, 6), "ply device unaligned")
         try:
-            gpu_ctx.set_chunk_points(256)
+            gpu_ctx.set_chunk_points(512)
             got, tm = gpu_ctx.encode_ply_host(rows, n, order, deg, 6)
-            assert tm["chunks"] == (n + 255) // 256
+            assert tm["chunks"] == (n + 511) // 512
             assert_packed_equal(Packed(n, deg, 12, 3, *got.planes()), oracle.pack(c, 6), "ply host")
         finally:
             gpu_ctx.set_chunk_points(0)
