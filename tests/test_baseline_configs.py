@@ -204,3 +204,44 @@ def test_config5_100m_sh3_sharded(oracle):
         return all(oracle.fnv1a64(bits(exp)) == oracle.fnv1a64(bits(plane[w * a:w * b]))
                    for exp, plane, w in zip(want.planes(), back.planes(), WF + (d,)))
     assert all(chunked(check_unpack, n, block))
+
+
+def test_config5_100m_sh3_device_resident_far_end(gpu_ctx, oracle):
+    """The same 100M SH3 cloud resident in one GPU's HBM (what bench.py times): plane offsets pass
+    2^32 elements, so the blocks at the far end are the ones a 32-bit index would corrupt.  Sampled
+    64k-point blocks -- first, middle, straddling element 2^32 of the SH plane, last -- against the
+    oracle, for the encoder and both decoders."""
+    import torch
+    from spz_b200.synth import torch_cloud
+    n, deg = 100_000_000, 3
+    c = torch_cloud(n, deg, "cuda", seed=9)
+    p = gpu_ctx.encode_device(c, 6)
+    g = gpu_ctx.decode_device(p, 8)
+    torch.cuda.synchronize()
+    blk = 65_536
+    sh_overflow_point = (1 << 32) // 45 - blk // 2   # the SH plane's element 2^32 lies inside this block
+    starts = (0, n // 2 + 17, sh_overflow_point, n - blk)
+    wf, wb = WF + (45,), WB + (45,)
+    for a in starts:
+        cb = Cloud(blk, deg, *[pl[w * a:w * (a + blk)].cpu().numpy() for pl, w in zip(c.planes(), wf)])
+        want = oracle.pack(cb, 6)
+        for name, pl, w, exp in zip(PLANES, p.planes(), wb, want.planes()):
+            assert np.array_equal(pl[w * a:w * (a + blk)].cpu().numpy(), exp), (a, name)
+        want_g = oracle.unpack(want, 8)
+        for name, pl, w, exp in zip(PLANES, g.planes(), wf, want_g.planes()):
+            assert np.array_equal(bits(pl[w * a:w * (a + blk)].cpu().numpy()), bits(exp)), (a, name)
+    del g
+    import os
+    os.environ["SPZB200_DECODE"] = "direct"   # the register-path decoder, through a fresh context
+    try:
+        from spz_b200.codec import Context
+        with Context(0) as ctx2:
+            g2 = ctx2.decode_device(p, 8)
+            torch.cuda.synchronize()
+            for a in starts[2:]:
+                pb = Packed(blk, deg, 12, 3, *[pl[w * a:w * (a + blk)].cpu().numpy() for pl, w in zip(p.planes(), wb)])
+                want_g = oracle.unpack(pb, 8)
+                for name, pl, w, exp in zip(PLANES, g2.planes(), wf, want_g.planes()):
+                    assert np.array_equal(bits(pl[w * a:w * (a + blk)].cpu().numpy()), bits(exp)), ("direct", a, name)
+    finally:
+        del os.environ["SPZB200_DECODE"]
