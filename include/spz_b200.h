@@ -170,13 +170,21 @@ typedef struct {
   int64_t num_points;
   int32_t width;      /* floats per record */
   int32_t sh_degree;  /* 0..3 */
-  const float *rows;  /* device pointer for *_device, host pointer for *_host */
+  float *rows;        /* device pointer for *_device, host pointer for *_host; read by the encoder, written by the decoder */
   int32_t col_pos[3], col_scale[3], col_rot[4] /* x, y, z, w = rot_1, rot_2, rot_3, rot_0 */, col_alpha, col_color[3];
   int32_t col_rest[45];
 } SpzB200PlyRows;
 
 int spzb200_encode_ply_device(SpzB200Context *ctx, const SpzB200PlyRows *in, int32_t from, SpzB200Packed *out, void *stream);
 int spzb200_encode_ply_host(SpzB200Context *ctx, const SpzB200PlyRows *in, int32_t from, SpzB200Packed *out,
+                            SpzB200Timings *timings);
+
+/* The mirror image: PackedGaussians planes -> vertex records, i.e. saveSplatToPly(unpackGaussians(in, to = X),
+ * from = X)'s body (load-spz.cc:846-934) in one kernel.  `to` is the frame of the records (RDF for a
+ * PLY file, UNSPECIFIED = no flips).  out->rows receives num_points * width floats; columns no
+ * plane maps to (nx, ny, nz, anything extra) are written as 0.  in->version as for spzb200_decode_*. */
+int spzb200_decode_ply_device(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to, SpzB200PlyRows *out, void *stream);
+int spzb200_decode_ply_host(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to, SpzB200PlyRows *out,
                             SpzB200Timings *timings);
 
 /* Page-locked host buffers for the *_host entry points (cudaHostAlloc, portable across devices).

@@ -290,6 +290,9 @@ bool decompressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *o
 // (no planar GaussianCloud in between).  options.from = RDF: the bytes of
 // saveSpz(loadSplatFromPly(f, {to}), {from = to}); UNSPECIFIED: what the reference's ply_to_spz writes.
 bool plyToSpz(const std::string &plyFilename, const PackOptions &options, std::vector<uint8_t> *output);
+// The mirror: .spz bytes -> .ply file, decoder and the writer's record layout fused in one kernel.
+// options.to = RDF: the file of saveSplatToPly(loadSpz(bytes, {to}), {from = to}, f); UNSPECIFIED: spz_to_ply's.
+bool spzToPly(const std::vector<uint8_t> &spzBytes, const UnpackOptions &options, const std::string &plyFilename);
 bool compressGzippedParallel(const uint8_t *data, size_t size, int threads, std::vector<uint8_t> *out);
 bool decompressGzippedParallel(const uint8_t *data, size_t size, int threads, std::vector<uint8_t> *out);
 

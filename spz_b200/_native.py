@@ -58,6 +58,8 @@ SIGNATURES = {
     "spzb200_decode_host": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_int32, C.POINTER(Cloud), C.POINTER(Timings)]),
     "spzb200_encode_ply_device": (C.c_int, [C.c_void_p, C.POINTER(PlyRows), C.c_int32, C.POINTER(Packed), C.c_void_p]),
     "spzb200_encode_ply_host": (C.c_int, [C.c_void_p, C.POINTER(PlyRows), C.c_int32, C.POINTER(Packed), C.POINTER(Timings)]),
+    "spzb200_decode_ply_device": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_int32, C.POINTER(PlyRows), C.c_void_p]),
+    "spzb200_decode_ply_host": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_int32, C.POINTER(PlyRows), C.POINTER(Timings)]),
     "spzb200_encode_host_multi": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(Cloud), C.c_int32, C.POINTER(Packed), C.POINTER(Timings)]),
     "spzb200_decode_host_multi": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(Packed), C.c_int32, C.POINTER(Cloud), C.POINTER(Timings)]),
     "spzb200_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -329,6 +329,22 @@ class Context:
         out.fractional_bits, out.version = ps.fractional_bits, ps.version
         return out, tm.as_dict()
 
+    def decode_ply_device(self, packed: PackedPlanes, names, to: int = 0, out=None, stream=None):
+        """Packed planes -> row-major .ply records (one float per name); returns the rows tensor."""
+        import torch
+        if out is None:
+            out = torch.empty(packed.n * len(names), dtype=torch.float32, device=packed.positions.device)
+        ps, rs = _packed_struct(packed, True), ply_rows_struct(out, packed.n, names, packed.sh_degree, True)
+        N.check(N.lib().spzb200_decode_ply_device(self._h, C.byref(ps), int(to), C.byref(rs), C.c_void_p(self._stream_handle(stream))))
+        return out
+
+    def decode_ply_host(self, packed: PackedPlanes, names, to: int = 0, out=None):
+        if out is None:
+            out = np.empty(packed.n * len(names), np.float32)
+        ps, rs, tm = _packed_struct(packed, False), ply_rows_struct(out, packed.n, names, packed.sh_degree, False), N.Timings()
+        N.check(N.lib().spzb200_decode_ply_host(self._h, C.byref(ps), int(to), C.byref(rs), C.byref(tm)))
+        return out, tm.as_dict()
+
     # ---- host pointers (numpy arrays or CPU tensors, pinned for overlap) ----------------------
     def encode_host(self, cloud: CloudPlanes, frm: int = 0, out: Optional[PackedPlanes] = None):
         if out is None:

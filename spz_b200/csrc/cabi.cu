@@ -912,7 +912,7 @@ int spzb200_encode_ply_host(SpzB200Context *ctx, const SpzB200PlyRows *in, int32
   if (rc) return rc;
   PlaneSet rows;
   rows.count = 1;
-  rows.ptr[0] = reinterpret_cast<uint8_t *>(const_cast<float *>(in->rows));
+  rows.ptr[0] = reinterpret_cast<uint8_t *>(in->rows);
   rows.per[0] = (size_t)in->width * 4;
   const PlaneSet by = packedPlaneSet(*out, 3);
   const spzb200::LaunchPlan plan = planOf(ctx);
@@ -920,6 +920,70 @@ int spzb200_encode_ply_host(SpzB200Context *ctx, const SpzB200PlyRows *in, int32
                      [&](uint8_t *const dIn[6], uint8_t *const dOut[6], long long pts, cudaStream_t s, int *launches) {
                        const SpzB200Packed dp = packedOn(*out, dOut, pts, 3);
                        return spzb200::launchEncodePly(makePlyArgs(ctx, *in, reinterpret_cast<const float *>(dIn[0]), pts, dp, from),
+                                                       plan, s, launches);
+                     }, timings);
+}
+
+static spzb200::PlyDecodeArgs makePlyDecodeArgs(const SpzB200Context *ctx, const SpzB200Packed &in, const SpzB200PlyRows &out, float *rows,
+                                                long long n, int32_t to) {
+  spzb200::PlyDecodeArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.positions = in.positions; a.scales = in.scales; a.rotations = in.rotations;
+  a.alphas = in.alphas; a.colors = in.colors; a.sh = in.sh;
+  a.rows = rows;
+  a.n = n;
+  a.width = out.width;
+  a.shDim = shDimOf(in.sh_degree);
+  a.version = in.version;
+  a.positionScale = positionScaleFor(in.fractional_bits);
+  for (int i = 0; i < 3; i++) { a.colPos[i] = out.col_pos[i]; a.colScale[i] = out.col_scale[i]; a.colColor[i] = out.col_color[i]; }
+  for (int i = 0; i < 4; i++) a.colRot[i] = out.col_rot[i];
+  a.colAlpha = out.col_alpha;
+  for (int i = 0; i < 3 * a.shDim; i++) a.colRest[i] = out.col_rest[i];
+  const spzb200::m::FlipBits f = spzb200::m::make_flip_bits(SPZB200_COORD_RUB, to);
+  a.flipP = f.p; a.flipQ = f.q; a.flipSh = f.sh;
+  a.tables = ctx->dLut;
+  return a;
+}
+
+static int preparePlyDecode(const SpzB200Packed *in, int32_t to, SpzB200PlyRows *out, const char *who) {
+  int rc = checkPacked(in, who, true);
+  if (rc) return rc;
+  if (!out) return fail(SPZB200_ERR_INVALID, "%s: null out", who);
+  out->num_points = in->num_points;
+  out->sh_degree = in->sh_degree;
+  rc = checkPlyRows(out, who);
+  if (rc) return rc;
+  if (to < 0 || to > 8) return fail(SPZB200_ERR_INVALID, "%s: coordinate system %d", who, to);
+  return SPZB200_OK;
+}
+
+int spzb200_decode_ply_device(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to, SpzB200PlyRows *out, void *stream) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_decode_ply_device: null context");
+  int rc = preparePlyDecode(in, to, out, "spzb200_decode_ply_device");
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  int launches = 0;
+  CU(spzb200::launchDecodePly(makePlyDecodeArgs(ctx, *in, *out, out->rows, in->num_points, to), planOf(ctx), (cudaStream_t)stream, &launches));
+  ctx->kernelLaunches += launches;
+  return SPZB200_OK;
+}
+
+int spzb200_decode_ply_host(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to, SpzB200PlyRows *out,
+                            SpzB200Timings *timings) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_decode_ply_host: null context");
+  int rc = preparePlyDecode(in, to, out, "spzb200_decode_ply_host");
+  if (rc) return rc;
+  PlaneSet rows;
+  rows.count = 1;
+  rows.ptr[0] = reinterpret_cast<uint8_t *>(out->rows);
+  rows.per[0] = (size_t)out->width * 4;
+  const PlaneSet by = packedPlaneSet(*in, in->version);
+  const spzb200::LaunchPlan plan = planOf(ctx);
+  return runPipeline(ctx, by, rows, in->num_points, spzb200::plyTileGaussians(),
+                     [&](uint8_t *const dIn[6], uint8_t *const dOut[6], long long pts, cudaStream_t s, int *launches) {
+                       const SpzB200Packed dp = packedOn(*in, dIn, pts, in->version);
+                       return spzb200::launchDecodePly(makePlyDecodeArgs(ctx, dp, *out, reinterpret_cast<float *>(dOut[0]), pts, to),
                                                        plan, s, launches);
                      }, timings);
 }

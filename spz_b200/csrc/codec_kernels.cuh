@@ -46,6 +46,20 @@ struct PlyEncodeArgs {
   const float *alphaThresholds;
 };
 
+// PackedGaussians planes -> PLY vertex records: unpackGaussians fused with saveSplatToPly's row
+// layout (load-spz.cc:846-934).  Columns no plane maps to (nx, ny, nz, extras) are written as 0.
+struct PlyDecodeArgs {
+  const uint8_t *positions, *scales, *rotations, *alphas, *colors, *sh;
+  float *rows;
+  long long n;
+  int width, shDim, version;
+  float positionScale;
+  int colPos[3], colScale[3], colRot[4] /* x, y, z, w */, colAlpha, colColor[3];
+  int colRest[45];
+  uint32_t flipP, flipQ, flipSh;  // sign-bit sets of coordinateConverter(RUB, to)
+  const float *tables;
+};
+
 enum PackMode { kPackAlu = 0, kPackCvt = 1 };
 
 struct LaunchPlan {
@@ -64,6 +78,7 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
                          int *launches);
 
 cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, int *launches);
+cudaError_t launchDecodePly(const PlyDecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, int *launches);
 int plyTileGaussians();
 
 // Gaussians per tile of the vector kernels for a given shDim (the sharding granule).

@@ -175,6 +175,171 @@ encodePlyGenericKernel(const PlyEncodeArgs a, const long long first) {
   }
 }
 
+// =================================================================================================
+// decode to PLY rows: the mirror image.  The records of a tile are assembled in shared memory
+// (scatter by column, 2-way bank conflicts at worst) and leave with one bulk async store.
+// =================================================================================================
+__device__ __forceinline__ float unpackS3Component(uint32_t field, const float *magLut) {
+  return __uint_as_float(__float_as_uint(magLut[field & 511u]) | ((field & 512u) << 22));
+}
+
+// rotation of gaussian g (global index) -> out[4] = x, y, z, w with flips applied
+__device__ __forceinline__ void decodeRotationAt(const PlyDecodeArgs &a, long long g, const float *sMag, float out[4]) {
+  if (a.version >= 3) {
+    const uint32_t comp = __ldg(reinterpret_cast<const uint32_t *>(a.rotations) + g);
+    m::dequant_rotation_smallest3(comp, sMag, a.flipQ, out);
+  } else {
+    const uint8_t *b = a.rotations + g * 3;
+    m::dequant_rotation_first3(b[0], b[1], b[2], a.flipQ, out);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kPlyThreads)
+decodePlyTilesKernel(const PlyDecodeArgs a, const long long numTiles) {
+  extern __shared__ __align__(128) unsigned char dynSmem[];
+  __shared__ float sTab[kDecodeTableFloats];
+  __shared__ uint32_t shMap[D > 0 ? 3 * D : 1];  // k = 3 * coefficient + channel: column | flip << 31
+  __shared__ uint32_t xyzMap[3][3];
+  float *rows = reinterpret_cast<float *>(dynSmem);
+  const int t = threadIdx.x;
+  for (int i = t; i < kDecodeTableFloats; i += kPlyThreads) sTab[i] = __ldg(a.tables + i);
+  if (D > 0 && t < 3 * D) {
+    const int sCoef = t / 3, ch = t - 3 * sCoef;
+    shMap[t] = (uint32_t)a.colRest[ch * D + sCoef] | (((a.flipSh >> sCoef) & 1u) << 31);
+  }
+  if (t < 3) {
+    xyzMap[0][t] = (uint32_t)a.colPos[t] | (((a.flipP >> t) & 1u) << 31);
+    xyzMap[1][t] = (uint32_t)a.colScale[t];
+    xyzMap[2][t] = (uint32_t)a.colColor[t];
+  }
+  __syncthreads();
+  const float *sAlpha = sTab, *sColor = sTab + 256, *sMag = sTab + 512;
+  const int width = a.width;
+  constexpr int G = kPlyTileFor<D>;
+  const bool half = a.version == 1 || a.version == 4;
+
+  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+    const long long g0 = tile * G;
+    for (int i = t; i < G * width; i += kPlyThreads) rows[i] = 0.0f;  // normals and unmapped columns
+    __syncthreads();
+    // ---- positions --------------------------------------------------------------------------------------
+    if (!half) {
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.positions + g0 * 9);
+      for (int j = t; j < 3 * G / 4; j += kPlyThreads) {
+        const uint32_t w0 = __ldg(in + 3 * j), w1 = __ldg(in + 3 * j + 1), w2 = __ldg(in + 3 * j + 2);
+        const uint32_t lo[4] = {w0 & 0xffffffu, (w0 >> 24) | ((w1 & 0xffffu) << 8), (w1 >> 16) | ((w2 & 0xffu) << 16), w2 >> 8};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int i = 4 * j + e, g = i / 3, ax = i - 3 * g;
+          const uint32_t mp = xyzMap[0][ax];
+          rows[g * width + (int)(mp & 0xffffu)] = m::dequant_position24(lo[e], __uint_as_float(__float_as_uint(a.positionScale) ^ (mp & 0x80000000u)));
+        }
+      }
+    } else {
+      const uint16_t *in = reinterpret_cast<const uint16_t *>(a.positions + g0 * 6);
+      for (int i = t; i < 3 * G; i += kPlyThreads) {
+        const int g = i / 3, ax = i - 3 * g;
+        const uint32_t mp = xyzMap[0][ax];
+        rows[g * width + (int)(mp & 0xffffu)] = __uint_as_float(__float_as_uint(m::half_bits_to_float(in[i])) ^ (mp & 0x80000000u));
+      }
+    }
+    // ---- scales, colours -----------------------------------------------------------------------------------
+    for (int j = t; j < 3 * G / 4; j += kPlyThreads) {
+      const uint32_t ws = __ldg(reinterpret_cast<const uint32_t *>(a.scales + g0 * 3) + j);
+      const uint32_t wc = __ldg(reinterpret_cast<const uint32_t *>(a.colors + g0 * 3) + j);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int i = 4 * j + e, g = i / 3, ax = i - 3 * g;
+        rows[g * width + (int)xyzMap[1][ax]] = m::dequant_scale((ws >> (8 * e)) & 0xffu);
+        rows[g * width + (int)xyzMap[2][ax]] = sColor[(wc >> (8 * e)) & 0xffu];
+      }
+    }
+    // ---- alphas, rotations -------------------------------------------------------------------------------
+    for (int j = t; j < G / 4; j += kPlyThreads) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(a.alphas + g0) + j);
+#pragma unroll
+      for (int e = 0; e < 4; e++) rows[(4 * j + e) * width + a.colAlpha] = sAlpha[(w >> (8 * e)) & 0xffu];
+    }
+    for (int g = t; g < G; g += kPlyThreads) {
+      float r[4];
+      decodeRotationAt(a, g0 + g, sMag, r);
+      float *row = rows + g * width;
+      row[a.colRot[0]] = r[0]; row[a.colRot[1]] = r[1]; row[a.colRot[2]] = r[2]; row[a.colRot[3]] = r[3];
+    }
+    // ---- spherical harmonics --------------------------------------------------------------------------------
+    if constexpr (D > 0) {
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(a.sh + g0 * (3 * D));
+      for (int j = t; j < 3 * D * G / 4; j += kPlyThreads) {
+        const uint32_t w = __ldg(in + j);
+        const int i0 = 4 * j;
+        int g = i0 / (3 * D), k = i0 - g * (3 * D);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const uint32_t mp = shMap[k];
+          rows[g * width + (int)(mp & 0xffffu)] =
+              m::dequant_sh((w >> (8 * e)) & 0xffu, __uint_as_float(0x3c000000u | (mp & 0x80000000u)));  // +-1/128
+          if (++k == 3 * D) { k = 0; g++; }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.rows + g0 * width), "r"(smemAddrPly(rows)),
+                   "r"((uint32_t)(G * width * 4))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the records are reused by the next tile
+    }
+    __syncthreads();
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// remainder / under-aligned rows: one thread per gaussian
+__global__ void __launch_bounds__(128)
+decodePlyGenericKernel(const PlyDecodeArgs a, const long long first) {
+  const long long g = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.n) return;
+  float *row = a.rows + g * a.width;
+  for (int i = 0; i < a.width; i++) row[i] = 0.0f;
+  const bool half = a.version == 1 || a.version == 4;
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    const uint32_t flip = ((a.flipP >> ax) & 1u) << 31;
+    float p;
+    if (half) {
+      const uint8_t *h = a.positions + (g * 3 + ax) * 2;
+      p = __uint_as_float(__float_as_uint(m::half_bits_to_float((uint32_t)h[0] | ((uint32_t)h[1] << 8))) ^ flip);
+    } else {
+      const uint8_t *b = a.positions + (g * 3 + ax) * 3;
+      p = m::dequant_position24((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16),
+                                __uint_as_float(__float_as_uint(a.positionScale) ^ flip));
+    }
+    row[a.colPos[ax]] = p;
+    row[a.colScale[ax]] = m::dequant_scale(a.scales[g * 3 + ax]);
+    row[a.colColor[ax]] = a.tables[256 + a.colors[g * 3 + ax]];
+  }
+  row[a.colAlpha] = a.tables[a.alphas[g]];
+  float r[4];
+  if (a.version >= 3) {
+    const uint8_t *b = a.rotations + g * 4;
+    m::dequant_rotation_smallest3((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24),
+                                  a.tables + 512, a.flipQ, r);
+  } else {
+    const uint8_t *b = a.rotations + g * 3;
+    m::dequant_rotation_first3(b[0], b[1], b[2], a.flipQ, r);
+  }
+  for (int i = 0; i < 4; i++) row[a.colRot[i]] = r[i];
+  const int D = a.shDim;
+  const uint8_t *s = a.sh + g * (3 * D);
+  for (int k = 0; k < 3 * D; k++) {
+    const int sCoef = k / 3, ch = k - 3 * sCoef;
+    row[a.colRest[ch * D + sCoef]] = m::dequant_sh(s[k], signedConstPly(0.0078125f, (a.flipSh >> sCoef) & 1u));
+  }
+}
+
 bool alignedTo(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 template <int D>
@@ -217,6 +382,50 @@ cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cuda
     const long long blocks = (a.n - first + 127) / 128;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
     encodePlyGenericKernel<<<(unsigned)blocks, 128, 0, stream>>>(a, first);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    count++;
+  }
+  if (launches) *launches = count;
+  return cudaSuccess;
+}
+
+template <int D>
+cudaError_t launchPlyDecodeTiles(const PlyDecodeArgs &a, long long tiles, cudaStream_t s) {
+  const int smem = kPlyTileFor<D> * a.width * 4;
+  cudaError_t e = cudaFuncSetAttribute(decodePlyTilesKernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  decodePlyTilesKernel<D><<<(unsigned)(tiles < 0x7fffffffLL ? tiles : 0x7fffffffLL), kPlyThreads, smem, s>>>(a, tiles);
+  return cudaGetLastError();
+}
+
+cudaError_t launchDecodePly(const PlyDecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, int *launches) {
+  int count = 0;
+  if (launches) *launches = 0;
+  if (a.n <= 0) return cudaSuccess;
+  const bool half = a.version == 1 || a.version == 4;
+  const bool vec = !plan.forceGeneric && alignedTo(a.rows, 16) && alignedTo(a.positions, half ? 2 : 4) && alignedTo(a.scales, 4) &&
+                   alignedTo(a.alphas, 4) && alignedTo(a.colors, 4) && (a.version < 3 || alignedTo(a.rotations, 4)) &&
+                   (a.shDim == 0 || alignedTo(a.sh, 4));
+  const int tileG = a.shDim == 15 ? kPlyTileFor<15> : a.shDim == 8 ? kPlyTileFor<8> : a.shDim == 3 ? kPlyTileFor<3> : kPlyTileFor<0>;
+  const long long tiles = vec && (long long)tileG * a.width * 4 <= 200 * 1024 ? a.n / tileG : 0;
+  if (tiles > 0) {
+    cudaError_t e;
+    switch (a.shDim) {
+      case 0: e = launchPlyDecodeTiles<0>(a, tiles, stream); break;
+      case 3: e = launchPlyDecodeTiles<3>(a, tiles, stream); break;
+      case 8: e = launchPlyDecodeTiles<8>(a, tiles, stream); break;
+      case 15: e = launchPlyDecodeTiles<15>(a, tiles, stream); break;
+      default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    count++;
+  }
+  const long long first = tiles * tileG;
+  if (first < a.n) {
+    const long long blocks = (a.n - first + 127) / 128;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    decodePlyGenericKernel<<<(unsigned)blocks, 128, 0, stream>>>(a, first);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     count++;

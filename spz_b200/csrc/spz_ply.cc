@@ -40,6 +40,17 @@ bool startsWith(const std::string &s, const char *prefix) { return s.compare(0, 
 
 int degreeForShDim(int dim) { return dim < 3 ? 0 : dim < 8 ? 1 : dim < 15 ? 2 : 3; }
 
+// The header saveSplatToPly writes (load-spz.cc:892-918): x y z, zero normals, f_dc, f_rest
+// channel-major, opacity, scales, rot wxyz -- 17 + 3 * shDim float properties.
+std::string plyHeader(long long numPoints, size_t shDim) {
+  std::string header = "ply\nformat binary_little_endian 1.0\nelement vertex " + std::to_string(numPoints) + "\n";
+  for (const char *f : {"x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"}) header += std::string("property float ") + f + "\n";
+  for (size_t i = 0; i < shDim * 3; i++) header += "property float f_rest_" + std::to_string(i) + "\n";
+  for (const char *f : {"opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"}) header += std::string("property float ") + f + "\n";
+  header += "end_header\n";
+  return header;
+}
+
 }  // namespace
 
 namespace detail {
@@ -220,6 +231,65 @@ bool plyToSpz(const std::string &plyFilename, const PackOptions &options, std::v
   return detail::finishSpz(packed, output);
 }
 
+// Extension: .spz bytes -> .ply file without materialising the planar GaussianCloud: the packed
+// planes go to the GPU and come back as finished vertex records (ply_kernels.cu).  Same file as
+// saveSplatToPly(loadSpz(bytes, {to = X}), {from = X}, f) when options.to == RDF, and as the
+// reference's spz_to_ply tool (no conversion either way) when options.to == UNSPECIFIED.
+bool spzToPly(const std::vector<uint8_t> &spzBytes, const UnpackOptions &options, const std::string &plyFilename) {
+  const PackedGaussians packed = loadSpzPacked(spzBytes);
+  const size_t n = packed.numPoints < 0 ? 0 : (size_t)packed.numPoints;
+  const int degree = packed.shDegree;
+  const size_t shDim = degree == 0 ? 0 : degree == 1 ? 3 : degree == 2 ? 8 : 15;
+  const size_t width = 17 + 3 * shDim;
+  std::vector<float> rows(n * width);
+  if (n > 0) {
+    SpzB200Packed in;
+    std::memset(&in, 0, sizeof in);
+    in.num_points = (int64_t)n;
+    in.sh_degree = degree;
+    in.fractional_bits = packed.fractionalBits;
+    const bool half = packed.usesFloat16();
+    in.version = half ? (packed.usesQuaternionSmallestThree ? SPZB200_STREAM_HALF_POSITIONS_SMALLEST_THREE : SPZB200_STREAM_V1)
+                      : (packed.usesQuaternionSmallestThree ? SPZB200_STREAM_V3 : SPZB200_STREAM_V2);
+    in.positions = const_cast<uint8_t *>(packed.positions.data()); in.scales = const_cast<uint8_t *>(packed.scales.data());
+    in.rotations = const_cast<uint8_t *>(packed.rotations.data()); in.alphas = const_cast<uint8_t *>(packed.alphas.data());
+    in.colors = const_cast<uint8_t *>(packed.colors.data()); in.sh = const_cast<uint8_t *>(packed.sh.data());
+    SpzB200PlyRows out;
+    std::memset(&out, 0, sizeof out);
+    out.num_points = (int64_t)n;
+    out.width = (int32_t)width;
+    out.sh_degree = degree;
+    out.rows = rows.data();
+    // the writer's column order: x y z nx ny nz f_dc[3] f_rest[3 * shDim] opacity scale[3] rot_0(w) rot_1..3(xyz)
+    for (int a = 0; a < 3; a++) { out.col_pos[a] = a; out.col_color[a] = 6 + a; out.col_scale[a] = (int32_t)(10 + 3 * shDim) + a; }
+    for (size_t i = 0; i < 3 * shDim; i++) out.col_rest[i] = (int32_t)(9 + i);
+    out.col_alpha = (int32_t)(9 + 3 * shDim);
+    const int32_t rot0 = (int32_t)(13 + 3 * shDim);
+    out.col_rot[3] = rot0;  // w
+    for (int a = 0; a < 3; a++) out.col_rot[a] = rot0 + 1 + a;
+    SpzB200Context *ctx = detail::contextFor(detail::configuredDevices()[0]);
+    if (!ctx) return false;
+    if (spzb200_decode_ply_host(ctx, &in, (int32_t)options.to, &out, nullptr) != SPZB200_OK) {
+      detail::logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
+      return false;
+    }
+  }
+  std::ofstream file(plyFilename, std::ios::binary);
+  if (!file.good()) {
+    say("[SPZ ERROR] Unable to open for writing: %s", plyFilename.c_str());
+    return false;
+  }
+  const std::string header = plyHeader((long long)n, shDim);
+  file.write(header.data(), (std::streamsize)header.size());
+  file.write(reinterpret_cast<const char *>(rows.data()), (std::streamsize)(rows.size() * sizeof(float)));
+  file.close();
+  if (!file.good()) {
+    say("[SPZ ERROR] Failed to write to: %s", plyFilename.c_str());
+    return false;
+  }
+  return true;
+}
+
 bool saveSplatToPly(const GaussianCloud &g, const PackOptions &o, const std::string &filename) {
   const size_t n = g.numPoints < 0 ? 0 : (size_t)g.numPoints;
   auto sized = [&](const std::vector<float> &v, size_t per, const char *what) {
@@ -241,11 +311,7 @@ bool saveSplatToPly(const GaussianCloud &g, const PackOptions &o, const std::str
     say("[SPZ ERROR] Unable to open for writing: %s", filename.c_str());
     return false;
   }
-  std::string header = "ply\nformat binary_little_endian 1.0\nelement vertex " + std::to_string(g.numPoints) + "\n";
-  for (const char *f : {"x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"}) header += std::string("property float ") + f + "\n";
-  for (size_t i = 0; i < shDim * 3; i++) header += "property float f_rest_" + std::to_string(i) + "\n";
-  for (const char *f : {"opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"}) header += std::string("property float ") + f + "\n";
-  header += "end_header\n";
+  const std::string header = plyHeader(g.numPoints, shDim);
   out.write(header.data(), (std::streamsize)header.size());
 
   constexpr size_t kBatch = 4096;  // points per write

@@ -237,6 +237,11 @@ uint8_t *SHIM(ply_to_spz)(const char *path, int32_t from, uint64_t *outSize) {
   if (!spz::plyToSpz(std::string(path), o, &out)) return nullptr;
   return dupBytes(out.data(), out.size(), outSize);
 }
+int SHIM(spz_to_ply)(const uint8_t *data, uint64_t size, int32_t to, const char *path) {
+  spz::UnpackOptions o;
+  o.to = (spz::CoordinateSystem)to;
+  return spz::spzToPly(std::vector<uint8_t>(data, data + size), o, std::string(path)) ? 1 : 0;
+}
 uint8_t *SHIM(gzip_parallel)(const uint8_t *data, uint64_t size, int32_t threads, uint64_t *outSize) {
   std::vector<uint8_t> out;
   if (!spz::compressGzippedParallel(data, size, threads, &out)) return nullptr;

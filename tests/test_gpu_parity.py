@@ -271,6 +271,45 @@ def test_fused_ply_rows_encoder(gpu_ctx, oracle, deg):
             gpu_ctx.set_chunk_points(0)
 
 
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+@pytest.mark.parametrize("ver", [1, 2, 3, 4])
+def test_fused_ply_rows_decoder(gpu_ctx, oracle, deg, ver):
+    """spzb200_decode_ply_device / _host: packed planes -> row-major records, against the oracle's
+    unpack scattered into the same column layout."""
+    from spz_b200.codec import SH_DIM as DIM, ply_property_names
+    rng = np.random.default_rng(3500 + 4 * deg + ver)
+    names = ply_property_names(deg) + ["extra"]
+    d, w = DIM[deg], len(ply_property_names(deg)) + 1
+    col = {k: i for i, k in enumerate(names)}
+    for n in (512 * 2 + 300, 77):
+        s = random_stream(rng, n, deg, ver, 11)
+        for to in (0, 6):
+            g = oracle.unpack(s, to)
+            want = np.zeros((n, w), np.float32)
+            for ax, k in enumerate("xyz"):
+                want[:, col[k]] = g.positions[ax::3]
+                want[:, col[f"scale_{ax}"]] = g.scales[ax::3]
+                want[:, col[f"f_dc_{ax}"]] = g.colors[ax::3]
+            want[:, col["opacity"]] = g.alphas
+            for i, k in enumerate(("rot_1", "rot_2", "rot_3", "rot_0")):
+                want[:, col[k]] = g.rotations[i::4]
+            sh = g.sh.reshape(n, d, 3) if d else None
+            for ch in range(3):
+                for c in range(d):
+                    want[:, col[f"f_rest_{ch * d + c}"]] = sh[:, c, ch]
+            got = gpu_ctx.decode_ply_device(to_dev_packed(s), names, to)
+            _torch().cuda.synchronize()
+            assert np.array_equal(bits(got.cpu().numpy()), bits(want.reshape(-1))), (deg, ver, n, to)
+        try:
+            gpu_ctx.set_chunk_points(512)
+            from spz_b200.codec import PackedPlanes
+            got, tm = gpu_ctx.decode_ply_host(PackedPlanes(n, deg, *s.planes(), fractional_bits=11, version=ver), names, 6)
+            assert tm["chunks"] == (n + 511) // 512
+            assert np.array_equal(bits(got), bits(want.reshape(-1)))
+        finally:
+            gpu_ctx.set_chunk_points(0)
+
+
 def test_empty_cloud(gpu_ctx):
     from spz_b200.codec import alloc_cloud, alloc_packed
     for deg in range(4):
