@@ -22,6 +22,9 @@ namespace spzb200 {
 namespace {
 
 constexpr int kPlyThreads = 256;
+#ifndef SPZ_PLY_CTAS
+#define SPZ_PLY_CTAS 6  // 40 registers: 4 -> 6 resident CTAs was +8 % at SH degree 3
+#endif
 constexpr int kPlyTileBase = 128;  // tile sizes are multiples of this
 // gaussians per CTA: about 32 KB of records at the standard widths (62 / 41 / 26 / 17 floats)
 template <int D>
@@ -39,7 +42,7 @@ __device__ __forceinline__ float signedConstPly(float magnitude, uint32_t negate
 //   shMap[k], k = 3 * coefficient + channel: bits 0..15 source column, bit 30 = 5-bit band, bit 31 = flip
 //   xyzMap[plane][axis]: source column (| flip << 31 for positions)
 template <int D>
-__global__ void __launch_bounds__(kPlyThreads)
+__global__ void __launch_bounds__(kPlyThreads, SPZ_PLY_CTAS)
 encodePlyTilesKernel(const PlyEncodeArgs a, const long long numTiles) {
   extern __shared__ __align__(128) unsigned char dynSmem[];
   __shared__ __align__(8) unsigned long long bar;
