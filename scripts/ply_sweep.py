@@ -20,7 +20,18 @@ def run(ctx, n, deg):
         ts.append(e[0].elapsed_time(e[1]))
     b = (4 * w + codec.packed_bytes_per_gaussian(deg)) * n
     ms = statistics.median(ts)
-    print(json.dumps({"points": n, "sh_degree": deg, "bytes_per_gaussian": 4 * w + codec.packed_bytes_per_gaussian(deg), "ms": round(ms, 3), "gbs": round(b / ms / 1e6), "mgs": round(n / ms / 1e3)}), flush=True)
+    print(json.dumps({"op": "rows->packed", "points": n, "sh_degree": deg, "bytes_per_gaussian": 4 * w + codec.packed_bytes_per_gaussian(deg), "ms": round(ms, 3), "gbs": round(b / ms / 1e6), "mgs": round(n / ms / 1e3)}), flush=True)
+    back = torch.empty_like(rows)
+    for _ in range(3):
+        ctx.decode_ply_device(out, names, 6, out=back)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(8):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e[0].record(); ctx.decode_ply_device(out, names, 6, out=back); e[1].record(); torch.cuda.synchronize()
+        ts.append(e[0].elapsed_time(e[1]))
+    ms = statistics.median(ts)
+    print(json.dumps({"op": "packed->rows", "points": n, "sh_degree": deg, "ms": round(ms, 3), "gbs": round(b / ms / 1e6), "mgs": round(n / ms / 1e3)}), flush=True)
 
 with codec.Context(0) as ctx:
     for deg in (3, 0):

@@ -940,6 +940,18 @@ static spzb200::PlyDecodeArgs makePlyDecodeArgs(const SpzB200Context *ctx, const
   for (int i = 0; i < 4; i++) a.colRot[i] = out.col_rot[i];
   a.colAlpha = out.col_alpha;
   for (int i = 0; i < 3 * a.shDim; i++) a.colRest[i] = out.col_rest[i];
+  // the columns nothing is decoded into (normals, extras): the kernel writes zeros there
+  std::vector<bool> used((size_t)out.width, false);
+  used[(size_t)a.colAlpha] = true;
+  for (int i = 0; i < 3; i++) used[(size_t)a.colPos[i]] = used[(size_t)a.colScale[i]] = used[(size_t)a.colColor[i]] = true;
+  for (int i = 0; i < 4; i++) used[(size_t)a.colRot[i]] = true;
+  for (int i = 0; i < 3 * a.shDim; i++) used[(size_t)a.colRest[i]] = true;
+  a.numUnmapped = 0;
+  for (int c = 0; c < out.width && a.numUnmapped >= 0; c++) {
+    if (used[(size_t)c]) continue;
+    if (a.numUnmapped == spzb200::kMaxUnmappedColumns) a.numUnmapped = -1;
+    else a.unmapped[a.numUnmapped++] = (uint16_t)c;
+  }
   const spzb200::m::FlipBits f = spzb200::m::make_flip_bits(SPZB200_COORD_RUB, to);
   a.flipP = f.p; a.flipQ = f.q; a.flipSh = f.sh;
   a.tables = ctx->dLut;

@@ -46,6 +46,8 @@ struct PlyEncodeArgs {
   const float *alphaThresholds;
 };
 
+constexpr int kMaxUnmappedColumns = 64;
+
 // PackedGaussians planes -> PLY vertex records: unpackGaussians fused with saveSplatToPly's row
 // layout (load-spz.cc:846-934).  Columns no plane maps to (nx, ny, nz, extras) are written as 0.
 struct PlyDecodeArgs {
@@ -56,6 +58,8 @@ struct PlyDecodeArgs {
   float positionScale;
   int colPos[3], colScale[3], colRot[4] /* x, y, z, w */, colAlpha, colColor[3];
   int colRest[45];
+  int numUnmapped;                          // columns no plane maps to, or -1 if more than the list holds
+  uint16_t unmapped[kMaxUnmappedColumns];
   uint32_t flipP, flipQ, flipSh;  // sign-bit sets of coordinateConverter(RUB, to)
   const float *tables;
 };

@@ -216,6 +216,11 @@ decodePlyTilesKernel(const PlyDecodeArgs a, const long long numTiles) {
     xyzMap[1][t] = (uint32_t)a.colScale[t];
     xyzMap[2][t] = (uint32_t)a.colColor[t];
   }
+  // columns no plane writes (the three normals, anything extra) must read 0; the host lists them so
+  // only they are cleared per tile, not the whole 32 KB of records
+  __shared__ uint16_t unmapped[kMaxUnmappedColumns];
+  const int numUnmapped = a.numUnmapped;  // -1: too many for the list, clear everything
+  if (t < numUnmapped) unmapped[t] = a.unmapped[t];
   __syncthreads();
   const float *sAlpha = sTab, *sColor = sTab + 256, *sMag = sTab + 512;
   const int width = a.width;
@@ -224,8 +229,15 @@ decodePlyTilesKernel(const PlyDecodeArgs a, const long long numTiles) {
 
   for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
     const long long g0 = tile * G;
-    for (int i = t; i < G * width; i += kPlyThreads) rows[i] = 0.0f;  // normals and unmapped columns
-    __syncthreads();
+    if (numUnmapped < 0) {
+      for (int i = t; i < G * width; i += kPlyThreads) rows[i] = 0.0f;
+      __syncthreads();  // the scatter below overwrites some of these
+    } else {
+      for (int i = t; i < G * numUnmapped; i += kPlyThreads) {
+        const int g = i / numUnmapped;
+        rows[g * width + unmapped[i - g * numUnmapped]] = 0.0f;
+      }
+    }
     // ---- positions --------------------------------------------------------------------------------------
     if (!half) {
       const uint32_t *in = reinterpret_cast<const uint32_t *>(a.positions + g0 * 9);
