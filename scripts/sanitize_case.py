@@ -9,7 +9,7 @@ import numpy as np
 import torch
 import oracle as O
 from spz_b200 import codec
-from util import random_cloud, random_stream, assert_packed_equal, assert_cloud_bits_equal
+from util import random_cloud, random_stream, assert_packed_equal, assert_cloud_bits_equal, cloud_to_ply_rows
 
 # enough tiles that persistent CTAs (148 x SPZB200_CTAS_PER_SM of them) each walk several
 TILES = 310 if os.environ.get("SPZB200_GRID") == "persistent" else 7
@@ -27,6 +27,20 @@ with codec.Context(0) as ctx:
             sd = codec.PackedPlanes(n, deg, *[torch.from_numpy(a).cuda() for a in s.planes()], fractional_bits=12, version=ver)
             g = ctx.decode_device(sd, 7); torch.cuda.synchronize()
             assert_cloud_bits_equal(O.Cloud(n, deg, *[a.cpu().numpy() for a in g.planes()]), chk.unpack(s, 7), f"dec deg{deg} v{ver}")
+    # fused PLY-rows kernels, canonical property order (compile-time columns unless SPZB200_PLY=mapped)
+    for deg in range(4):
+        names = codec.ply_property_names(deg)
+        n = TILES * 128 + 37
+        c = random_cloud(rng, n, deg, True)
+        rows = torch.from_numpy(cloud_to_ply_rows(c, names).reshape(-1)).cuda()
+        p = ctx.encode_ply_device(rows, n, names, deg, 6); torch.cuda.synchronize()
+        assert_packed_equal(O.Packed(n, deg, 12, 3, *[a.cpu().numpy() for a in p.planes()]), chk.pack(c, 6), f"ply enc deg{deg}")
+        for ver in (1, 2, 3, 4):
+            s = random_stream(rng, n, deg, ver, 12)
+            sd = codec.PackedPlanes(n, deg, *[torch.from_numpy(a).cuda() for a in s.planes()], fractional_bits=12, version=ver)
+            got = ctx.decode_ply_device(sd, names, 7); torch.cuda.synchronize()
+            want = cloud_to_ply_rows(chk.unpack(s, 7), names).reshape(-1)
+            assert np.array_equal(O.bits(got.cpu().numpy()), O.bits(want)), f"ply dec deg{deg} v{ver}"
     n, deg = 5 * codec.tile_gaussians(3) + 11, 3
     c = random_cloud(rng, n, deg, False)
     ctx.set_chunk_points(2 * codec.tile_gaussians(3))

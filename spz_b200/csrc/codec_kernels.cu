@@ -34,6 +34,7 @@
 #include "codec_kernels.cuh"
 
 #include "codec_math.cuh"
+#include "kernel_utils.cuh"
 
 namespace spzb200 {
 namespace {
@@ -99,36 +100,6 @@ __device__ __forceinline__ void stStream(T *p, T v) {
 #else
   __stcg(p, v);
 #endif
-}
-
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-  return d;
-}
-
-// Saturate four int32 to [0,255] and pack them little-endian (v0 lowest byte).
-template <int MODE>
-__device__ __forceinline__ uint32_t packSat4(int32_t v0, int32_t v1, int32_t v2, int32_t v3) {
-  if (MODE == kPackCvt) {
-    // cvt.pack.sat.u8.s32.b32 d, a, b, c:  d = sat(a) << 8 | sat(b) | c << 16   (I2IP in SASS)
-    uint32_t hi, r;
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v1), "r"(v0), "r"(hi));
-    return r;
-  }
-  return (uint32_t)m::clamp_u8(v0) | ((uint32_t)m::clamp_u8(v1) << 8) |
-         ((uint32_t)m::clamp_u8(v2) << 16) | ((uint32_t)m::clamp_u8(v3) << 24);
-}
-
-// byte k of w as the float 2^23 + byte (exact), built with one PRMT
-template <int K>
-__device__ __forceinline__ float byteAsMagicFloat(uint32_t w) {
-  return __uint_as_float(prmt(w, 0x4b000000u, 0x7650u + K));
-}
-
-__device__ __forceinline__ float signedConst(float magnitude, uint32_t negate) {
-  return __uint_as_float(__float_as_uint(magnitude) | (negate << 31));
 }
 
 // Phase bookkeeping of the SH plane: pos[e] = index of the thread's element e inside its
@@ -556,34 +527,6 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
 // the expanded rows out with bulk async stores from shared memory (UBLKCP.G.S) sustains 6.76 TB/s
 // where LDG.32 / STG.128 from registers sustains 6.09; for encode's read-heavy mix the two are
 // equal (7.12 vs 7.06), so the encoder keeps its register path.
-__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbarInit(unsigned long long *bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(bar)));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, uint32_t bytes, unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
-               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbarWait(unsigned long long *bar, uint32_t parity) {
-  uint32_t done = 0;
-  // bounded so a lost completion surfaces as a launch failure instead of a hung GPU
-  for (uint32_t spin = 0; !done; spin++) {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done)
-                 : "r"(smemAddr(bar)), "r"(parity)
-                 : "memory");
-    if (spin > (1u << 28)) __trap();
-  }
-}
-__device__ __forceinline__ void bulkStore(void *dstGlobal, const void *srcSmem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGlobal), "r"(smemAddr(srcSmem)), "r"(bytes)
-               : "memory");
-}
-
 template <int D>
 struct BulkGeo {
   static constexpr int SB = (D == 8) ? 4 : 5;  // rows per store batch (a class has U = 5 or 8 rows)

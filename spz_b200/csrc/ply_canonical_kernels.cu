@@ -1,0 +1,425 @@
+// Fused PLY-rows kernels for the CANONICAL record layout -- the property order the reference's
+// saveSplatToPly writes (load-spz.cc:892-916) and the 3DGS trainers emit:
+//
+//     x y z  nx ny nz  f_dc_0..2  f_rest_0..3D-1 (channel-major)  opacity  scale_0..2  rot_0..3 (w x y z)
+//
+// so every column index is a compile-time constant and the column maps of ply_kernels.cu (which
+// stay for any other property order) disappear.  One thread per gaussian, 128 gaussians per CTA:
+//
+//   rows -> packed (encodePlyCanonKernel): the tile's records (31.7 KB at SH degree 3) arrive with
+//     one bulk async copy; thread g reads record g from shared memory (64-bit loads, conflict
+//     free at the even widths, 32-bit at the odd ones), quantises its 59 values with immediate
+//     constants and deposits its bytes into a shared-memory image of the six packed planes, which
+//     leaves with six bulk async stores.
+//   packed -> rows (decodePlyCanonKernel): the mirror image; six bulk loads bring the tile's packed
+//     planes in, thread g expands gaussian g into record g of the shared-memory tile, one bulk
+//     async store writes the records.
+//
+// A gaussian's bytes in a packed plane start at byte B*g (B = 9, 3, 3 or 3D), i.e. at a lane-
+// dependent offset (B*g) mod 4 inside a word.  loadRecord/emitRecord do the realignment with funnel
+// shifts; on the way out the word a lane shares with its predecessor is completed from the
+// predecessor's last four bytes, passed down with one warp shuffle (B*32 is a multiple of 4, so lane
+// 0 of every warp starts a word).  All shared-memory traffic is therefore whole words.
+#include "codec_kernels.cuh"
+
+#include "codec_math.cuh"
+#include "kernel_utils.cuh"
+
+namespace spzb200 {
+namespace {
+
+#ifndef SPZ_PLYC_CTAS
+#define SPZ_PLYC_CTAS 4
+#endif
+constexpr int kG = 128;  // gaussians per tile = threads per CTA
+
+template <int D>
+struct Canon {
+  static constexpr int W = 17 + 3 * D;  // floats per record
+  static constexpr int kColor = 6, kRest = 9, kAlpha = 9 + 3 * D, kScale = 10 + 3 * D, kRot = 13 + 3 * D;
+  static constexpr int kRowBytes = kG * W * 4;
+  // the tile's packed planes in shared memory, in the container's order (load-spz.cc:533-546);
+  // every offset and size is a multiple of 16 bytes, as the bulk copies require
+  static constexpr int oPos = 0, oAlpha = 9 * kG, oColor = 10 * kG, oScale = 13 * kG, oRot = 16 * kG, oSh = 20 * kG;
+  static constexpr int kPackedBytes = (20 + 3 * D) * kG + 16;  // + one granule: loadRecord<3> of the last lane reads a word ahead
+  static constexpr int kSmemBytes = kRowBytes + kPackedBytes;
+};
+
+template <int B>
+struct Rec {
+  static constexpr int kMaxShift = (B % 4 == 0) ? 0 : (B % 2 == 0) ? 2 : 3;
+  static constexpr int NL = (B + kMaxShift + 3) / 4;  // words a lane reads to cover its B bytes at any alignment
+  static constexpr int NV = (B + 3) / 4;              // words holding one record, byte 0 first
+};
+
+// v <- the B bytes of gaussian g of a packed plane (record byte k = byte k & 3 of v[k >> 2])
+template <int B>
+__device__ __forceinline__ void loadRecord(const uint32_t *plane, int g, uint32_t (&v)[Rec<B>::NL]) {
+  constexpr int NL = Rec<B>::NL;
+  const uint32_t *p = plane + ((B * g) >> 2);
+  uint32_t w[NL];
+#pragma unroll
+  for (int i = 0; i < NL; i++) w[i] = p[i];
+  if constexpr (B % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < NL; i++) v[i] = w[i];
+  } else {
+    const uint32_t sh = ((uint32_t)(B * g) & 3u) * 8u;
+#pragma unroll
+    for (int i = 0; i + 1 < NL; i++) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    v[NL - 1] = w[NL - 1] >> sh;
+  }
+}
+
+// the B bytes in v -> gaussian g's place in a packed plane.  Lane g stores the words that END inside
+// its byte range [B*g, B*(g+1)); bytes at or above B in v's last word are never stored.  Must be
+// called by all 32 lanes of a warp, g = consecutive per lane, lane 0's g a multiple of 32.
+template <int B>
+__device__ __forceinline__ void emitRecord(uint32_t *plane, int g, const uint32_t (&v)[Rec<B>::NV]) {
+  constexpr int NV = Rec<B>::NV;
+  uint32_t *p = plane + ((B * g) >> 2);
+  if constexpr (B % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) p[i] = v[i];
+  } else {
+    uint32_t tail;  // record bytes B-4 .. B-1
+    if constexpr (B >= 4) {
+      constexpr int j = (B - 4) >> 2;
+      constexpr uint32_t s = ((B - 4) & 3) * 8;
+      tail = __funnelshift_r(v[j], v[j + 1 < NV ? j + 1 : j], s);
+    } else {
+      tail = v[0] << (8 * (4 - B));
+    }
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, tail, 1);
+    const uint32_t sh = ((uint32_t)(B * g) & 3u) * 8u;
+    uint32_t w[NV];
+    w[0] = __funnelshift_l(prev, v[0], sh);
+#pragma unroll
+    for (int i = 1; i < NV; i++) w[i] = __funnelshift_l(v[i - 1], v[i], sh);
+#pragma unroll
+    for (int i = 0; i + 1 < NV; i++) p[i] = w[i];
+    if (((B * (g + 1)) >> 2) - ((B * g) >> 2) == NV) p[NV - 1] = w[NV - 1];
+  }
+}
+
+__device__ __forceinline__ uint32_t byteOf(const uint32_t *v, int k) { return (v[k >> 2] >> (8 * (k & 3))) & 0xffu; }
+// record byte k as the float 2^23 + byte (one PRMT; k is a constant after unrolling)
+__device__ __forceinline__ float magicByte(const uint32_t *v, int k) {
+  return __uint_as_float(prmt(v[k >> 2], 0x4b000000u, 0x7650u + (uint32_t)(k & 3)));
+}
+
+__device__ __forceinline__ void mbarExpect(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoadOn(void *dstSmem, const void *srcGlobal, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
+               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+
+// =================================================================================================
+// rows -> packed:  packGaussians(loadSplatFromPly(rows, to = X), from = X), load-spz.cc:808-838 + :257-331
+// =================================================================================================
+template <int D, int MODE>
+__global__ void __launch_bounds__(kG, SPZ_PLYC_CTAS)
+encodePlyCanonKernel(const PlyEncodeArgs a, const long long numTiles) {
+  using C = Canon<D>;
+  constexpr int W = C::W;
+  extern __shared__ __align__(128) unsigned char dynSmem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ float sThr[256];
+  float *rows = reinterpret_cast<float *>(dynSmem);
+  unsigned char *stage = dynSmem + C::kRowBytes;
+  const int t = threadIdx.x;
+  if (t == 0) mbarInit(&bar);
+  __syncthreads();
+  uint32_t parity = 0;
+  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
+    if (tile != blockIdx.x) {  // multi-tile CTAs only: the previous tile's stores are done reading the stage
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncthreads();
+    }
+    if (t == 0) bulkLoad(rows, a.rows + tile * (long long)(kG * W), C::kRowBytes, &bar);
+    if (tile == blockIdx.x) {  // the threshold table arrives while the records are in flight
+      sThr[t] = __ldg(a.alphaThresholds + t);
+      sThr[t + kG] = __ldg(a.alphaThresholds + t + kG);
+      __syncthreads();
+    }
+    mbarWait(&bar, parity);
+
+    float r[W];
+    {
+      const float *row = rows + t * W;
+      if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < W / 2; j++) {
+          const float2 p = reinterpret_cast<const float2 *>(row)[j];
+          r[2 * j] = p.x;
+          r[2 * j + 1] = p.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < W; c++) r[c] = row[c];
+      }
+    }
+    // positions: 3 x 24 bit
+    uint32_t pv[3];
+    {
+      const uint32_t n0 = m::quant_position24(r[0], signedConst(4096.0f, a.flipP & 1u));
+      const uint32_t n1 = m::quant_position24(r[1], signedConst(4096.0f, (a.flipP >> 1) & 1u));
+      const uint32_t n2 = m::quant_position24(r[2], signedConst(4096.0f, (a.flipP >> 2) & 1u));
+      pv[0] = prmt(n0, n1, 0x4210u);
+      pv[1] = prmt(n1, n2, 0x5421u);
+      pv[2] = n2 >> 16;
+    }
+    const uint32_t cv[1] = {packSat4<MODE>(m::quant_color_raw(r[C::kColor]), m::quant_color_raw(r[C::kColor + 1]),
+                                           m::quant_color_raw(r[C::kColor + 2]), 0)};
+    const uint32_t sv[1] = {packSat4<MODE>(m::quant_scale_raw(r[C::kScale]), m::quant_scale_raw(r[C::kScale + 1]),
+                                           m::quant_scale_raw(r[C::kScale + 2]), 0)};
+    const uint32_t av = m::quant_alpha(r[C::kAlpha], sThr);
+    // the file stores w first (load-spz.cc:826-829)
+    const uint32_t rv = m::quant_rotation_smallest3(r[C::kRot + 1], r[C::kRot + 2], r[C::kRot + 3], r[C::kRot], a.flipQ);
+    uint32_t hv[D > 0 ? Rec<3 * D>::NV : 1];
+    if constexpr (D > 0) {
+#pragma unroll
+      for (int k4 = 0; k4 < Rec<3 * D>::NV; k4++) {
+        int32_t q[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int k = 4 * k4 + e;  // packed order: coefficient-major, channel innermost
+          if (k < 3 * D) {
+            const int coef = k / 3, ch = k - 3 * coef;
+            q[e] = m::quant_sh_raw(r[C::kRest + ch * D + coef], signedConst(128.0f, (a.flipSh >> coef) & 1u), k < 9 ? 132u : 136u,
+                                   k < 9 ? ~7u : ~15u);
+          } else {
+            q[e] = 0;
+          }
+        }
+        hv[k4] = packSat4<MODE>(q[0], q[1], q[2], q[3]);
+      }
+    }
+
+    emitRecord<9>(reinterpret_cast<uint32_t *>(stage + C::oPos), t, pv);
+    stage[C::oAlpha + t] = (unsigned char)av;
+    emitRecord<3>(reinterpret_cast<uint32_t *>(stage + C::oColor), t, cv);
+    emitRecord<3>(reinterpret_cast<uint32_t *>(stage + C::oScale), t, sv);
+    reinterpret_cast<uint32_t *>(stage + C::oRot)[t] = rv;
+    if constexpr (D > 0) emitRecord<3 * D>(reinterpret_cast<uint32_t *>(stage + C::oSh), t, hv);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();  // also: everyone has read its record, the next tile's copy may land
+    if (t == 0) {
+      const long long g0 = tile * kG;
+      bulkStore(a.oPositions + g0 * 9, stage + C::oPos, 9 * kG);
+      bulkStore(a.oAlphas + g0, stage + C::oAlpha, kG);
+      bulkStore(a.oColors + g0 * 3, stage + C::oColor, 3 * kG);
+      bulkStore(a.oScales + g0 * 3, stage + C::oScale, 3 * kG);
+      bulkStore(a.oRotations + g0 * 4, stage + C::oRot, 4 * kG);
+      if constexpr (D > 0) bulkStore(a.oSh + g0 * (3 * D), stage + C::oSh, 3 * D * kG);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the stores' reads
+}
+
+// =================================================================================================
+// packed -> rows:  saveSplatToPly(unpackGaussians(in, to = X), from = X)'s vertex records, load-spz.cc:467-531 + :858-890
+// =================================================================================================
+template <int D>
+__global__ void __launch_bounds__(kG, SPZ_PLYC_CTAS)
+decodePlyCanonKernel(const PlyDecodeArgs a, const long long numTiles) {
+  using C = Canon<D>;
+  constexpr int W = C::W;
+  extern __shared__ __align__(128) unsigned char dynSmem[];
+  __shared__ __align__(8) unsigned long long bar;
+  float *rows = reinterpret_cast<float *>(dynSmem);
+  unsigned char *in = dynSmem + C::kRowBytes;
+  const int t = threadIdx.x;
+  const bool half = a.version == 1 || a.version == 4;
+  const bool s3 = a.version >= 3;
+  const uint32_t posBytes = half ? 6 * kG : 9 * kG, rotBytes = s3 ? 4 * kG : 3 * kG;
+  const float *tab = a.tables;  // 4 KB, read through L1 (the bulk copies do not pass through it)
+  if (t == 0) mbarInit(&bar);
+  __syncthreads();
+  uint32_t parity = 0;
+  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
+    if (tile != blockIdx.x) {  // multi-tile CTAs only: the previous tile's store is done reading the records
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncthreads();
+    }
+    if (t == 0) {
+      const long long g0 = tile * kG;
+      mbarExpect(&bar, posBytes + rotBytes + (uint32_t)((7 + 3 * D) * kG));
+      bulkLoadOn(in + C::oPos, a.positions + g0 * (half ? 6 : 9), posBytes, &bar);
+      bulkLoadOn(in + C::oAlpha, a.alphas + g0, kG, &bar);
+      bulkLoadOn(in + C::oColor, a.colors + g0 * 3, 3 * kG, &bar);
+      bulkLoadOn(in + C::oScale, a.scales + g0 * 3, 3 * kG, &bar);
+      bulkLoadOn(in + C::oRot, a.rotations + g0 * (s3 ? 4 : 3), rotBytes, &bar);
+      if constexpr (D > 0) bulkLoadOn(in + C::oSh, a.sh + g0 * (3 * D), 3 * D * kG, &bar);
+    }
+    mbarWait(&bar, parity);
+
+    // every shared-memory read of the inputs comes before the first store to the records
+    uint32_t pv[3], cv[2], sv[2], rv[2], hv[D > 0 ? Rec<3 * D>::NL : 1];
+    if (half) {
+      uint32_t h[2];
+      loadRecord<6>(reinterpret_cast<const uint32_t *>(in + C::oPos), t, h);
+      pv[0] = h[0]; pv[1] = h[1]; pv[2] = 0;
+    } else {
+      loadRecord<9>(reinterpret_cast<const uint32_t *>(in + C::oPos), t, pv);
+    }
+    loadRecord<3>(reinterpret_cast<const uint32_t *>(in + C::oColor), t, cv);
+    loadRecord<3>(reinterpret_cast<const uint32_t *>(in + C::oScale), t, sv);
+    const uint32_t av = in[C::oAlpha + t];
+    if (s3) {
+      rv[0] = reinterpret_cast<const uint32_t *>(in + C::oRot)[t];
+    } else {
+      loadRecord<3>(reinterpret_cast<const uint32_t *>(in + C::oRot), t, rv);
+    }
+    if constexpr (D > 0) loadRecord<3 * D>(reinterpret_cast<const uint32_t *>(in + C::oSh), t, hv);
+
+    float rec[W];
+    if (half) {
+      rec[0] = __uint_as_float(__float_as_uint(m::half_bits_to_float(pv[0] & 0xffffu)) ^ ((a.flipP & 1u) << 31));
+      rec[1] = __uint_as_float(__float_as_uint(m::half_bits_to_float(pv[0] >> 16)) ^ ((a.flipP & 2u) << 30));
+      rec[2] = __uint_as_float(__float_as_uint(m::half_bits_to_float(pv[1] & 0xffffu)) ^ ((a.flipP & 4u) << 29));
+    } else {
+      // PRMT with the sign-replicate bit (selector nibble 8|idx) sign-extends 24 -> 32 bits
+      const int32_t f0 = (int32_t)prmt(pv[0], pv[0], 0xA210u);
+      const int32_t f1 = (int32_t)prmt(pv[0], pv[1], 0xD543u);
+      const int32_t f2 = (int32_t)prmt(pv[1], pv[2], 0xC432u);
+      const uint32_t ps = __float_as_uint(a.positionScale);
+      rec[0] = m::mul(m::i2f(f0), __uint_as_float(ps ^ ((a.flipP & 1u) << 31)));
+      rec[1] = m::mul(m::i2f(f1), __uint_as_float(ps ^ ((a.flipP & 2u) << 30)));
+      rec[2] = m::mul(m::i2f(f2), __uint_as_float(ps ^ ((a.flipP & 4u) << 29)));
+    }
+    rec[3] = rec[4] = rec[5] = 0.0f;  // normals (load-spz.cc:866)
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      rec[C::kColor + i] = __ldg(tab + 256 + byteOf(cv, i));
+      // (2^23 + s) / 16 - (2^19 + 10) = s/16 - 10, both steps exact (load-spz.cc:506)
+      rec[C::kScale + i] = __fmaf_rn(magicByte(sv, i), 0.0625f, -524298.0f);
+    }
+    rec[C::kAlpha] = __ldg(tab + av);
+    {
+      float q[4];
+      if (s3) m::dequant_rotation_smallest3(rv[0], tab + 512, a.flipQ, q);
+      else m::dequant_rotation_first3(byteOf(rv, 0), byteOf(rv, 1), byteOf(rv, 2), a.flipQ, q);
+      rec[C::kRot] = q[3];
+      rec[C::kRot + 1] = q[0];
+      rec[C::kRot + 2] = q[1];
+      rec[C::kRot + 3] = q[2];
+    }
+    if constexpr (D > 0) {
+#pragma unroll
+      for (int k = 0; k < 3 * D; k++) {
+        const int coef = k / 3, ch = k - 3 * coef;
+        // (2^23 + x) - (2^23 + 128) = x - 128 exactly, then * +-1/128 (load-spz.cc:83, splat-types.h:158-161)
+        rec[C::kRest + ch * D + coef] =
+            m::mul(m::add(magicByte(hv, k), -8388736.0f), signedConst(0.0078125f, (a.flipSh >> coef) & 1u));
+      }
+    }
+    {
+      float *row = rows + t * W;
+      if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < W / 2; j++) reinterpret_cast<float2 *>(row)[j] = make_float2(rec[2 * j], rec[2 * j + 1]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < W; c++) row[c] = rec[c];
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+      bulkStore(a.rows + tile * (long long)(kG * W), rows, C::kRowBytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <class Args>
+bool canonicalColumns(const Args &a) {
+  const int D = a.shDim;
+  if (a.width != 17 + 3 * D) return false;
+  bool ok = a.colAlpha == 9 + 3 * D && a.colRot[3] == 13 + 3 * D;  // colRot = x, y, z, w; the file has w first
+  for (int i = 0; i < 3; i++) ok = ok && a.colPos[i] == i && a.colColor[i] == 6 + i && a.colScale[i] == 10 + 3 * D + i && a.colRot[i] == 14 + 3 * D + i;
+  for (int i = 0; i < 3 * D; i++) ok = ok && a.colRest[i] == 9 + i;
+  return ok;
+}
+
+unsigned gridFor(long long tiles, const LaunchPlan &plan) {
+  if (!plan.flatGrid) {
+    const long long g = (long long)plan.smCount * SPZ_PLYC_CTAS;
+    return (unsigned)(tiles < g ? tiles : g);
+  }
+  return (unsigned)(tiles < 0x7fffffffLL ? tiles : 0x7fffffffLL);
+}
+
+template <int D, int MODE>
+cudaError_t launchEncodeCanon(const PlyEncodeArgs &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+  constexpr int smem = Canon<D>::kSmemBytes;
+  cudaError_t e = cudaFuncSetAttribute(encodePlyCanonKernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  encodePlyCanonKernel<D, MODE><<<gridFor(tiles, plan), kG, smem, s>>>(a, tiles);
+  return cudaGetLastError();
+}
+
+template <int D>
+cudaError_t launchDecodeCanon(const PlyDecodeArgs &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+  constexpr int smem = Canon<D>::kSmemBytes;
+  cudaError_t e = cudaFuncSetAttribute(decodePlyCanonKernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  decodePlyCanonKernel<D><<<gridFor(tiles, plan), kG, smem, s>>>(a, tiles);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// Both return the number of leading gaussians handled (a multiple of 128; 0 when the layout is not
+// canonical, a pointer is not 16-byte aligned or the cloud is smaller than a tile); the caller
+// finishes the rest with the column-map / scalar kernels of ply_kernels.cu.
+cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done) {
+  *done = 0;
+  if (plan.forceGeneric || plan.plyMapped || !canonicalColumns(a)) return cudaSuccess;
+  if (!(aligned16(a.rows) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) && aligned16(a.oAlphas) &&
+        aligned16(a.oColors) && (a.shDim == 0 || aligned16(a.oSh))))
+    return cudaSuccess;
+  const long long tiles = a.n / kG;
+  if (tiles == 0) return cudaSuccess;
+  cudaError_t e;
+  const bool cvt = plan.packMode == kPackCvt;
+  switch (a.shDim) {
+    case 0: e = cvt ? launchEncodeCanon<0, kPackCvt>(a, tiles, plan, stream) : launchEncodeCanon<0, kPackAlu>(a, tiles, plan, stream); break;
+    case 3: e = cvt ? launchEncodeCanon<3, kPackCvt>(a, tiles, plan, stream) : launchEncodeCanon<3, kPackAlu>(a, tiles, plan, stream); break;
+    case 8: e = cvt ? launchEncodeCanon<8, kPackCvt>(a, tiles, plan, stream) : launchEncodeCanon<8, kPackAlu>(a, tiles, plan, stream); break;
+    case 15: e = cvt ? launchEncodeCanon<15, kPackCvt>(a, tiles, plan, stream) : launchEncodeCanon<15, kPackAlu>(a, tiles, plan, stream); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (e == cudaSuccess) *done = tiles * kG;
+  return e;
+}
+
+cudaError_t launchDecodePlyCanonical(const PlyDecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done) {
+  *done = 0;
+  if (plan.forceGeneric || plan.plyMapped || !canonicalColumns(a)) return cudaSuccess;
+  if (!(aligned16(a.rows) && aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) &&
+        aligned16(a.colors) && (a.shDim == 0 || aligned16(a.sh))))
+    return cudaSuccess;
+  const long long tiles = a.n / kG;
+  if (tiles == 0) return cudaSuccess;
+  cudaError_t e;
+  switch (a.shDim) {
+    case 0: e = launchDecodeCanon<0>(a, tiles, plan, stream); break;
+    case 3: e = launchDecodeCanon<3>(a, tiles, plan, stream); break;
+    case 8: e = launchDecodeCanon<8>(a, tiles, plan, stream); break;
+    case 15: e = launchDecodeCanon<15>(a, tiles, plan, stream); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (e == cudaSuccess) *done = tiles * kG;
+  return e;
+}
+
+}  // namespace spzb200

@@ -379,7 +379,11 @@ cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cuda
                    (a.shDim == 0 || alignedTo(a.oSh, 4));
   const int tileG = a.shDim == 15 ? kPlyTileFor<15> : a.shDim == 8 ? kPlyTileFor<8> : a.shDim == 3 ? kPlyTileFor<3> : kPlyTileFor<0>;
   // 200 KB of shared memory bound the record width the staged kernel accepts (wider: scalar kernel)
-  const long long tiles = vec && (long long)tileG * a.width * 4 <= 200 * 1024 ? a.n / tileG : 0;
+  // the property order the reference writes: compile-time columns (ply_canonical_kernels.cu)
+  long long canon = 0;
+  if (cudaError_t e = launchEncodePlyCanonical(a, plan, stream, &canon); e != cudaSuccess) return e;
+  if (canon > 0) count++;
+  const long long tiles = canon == 0 && vec && (long long)tileG * a.width * 4 <= 200 * 1024 ? a.n / tileG : 0;
   if (tiles > 0) {
     cudaError_t e;
     switch (a.shDim) {
@@ -392,7 +396,7 @@ cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cuda
     if (e != cudaSuccess) return e;
     count++;
   }
-  const long long first = tiles * tileG;
+  const long long first = canon + tiles * tileG;
   if (first < a.n) {
     const long long blocks = (a.n - first + 127) / 128;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -423,7 +427,10 @@ cudaError_t launchDecodePly(const PlyDecodeArgs &a, const LaunchPlan &plan, cuda
                    alignedTo(a.alphas, 4) && alignedTo(a.colors, 4) && (a.version < 3 || alignedTo(a.rotations, 4)) &&
                    (a.shDim == 0 || alignedTo(a.sh, 4));
   const int tileG = a.shDim == 15 ? kPlyTileFor<15> : a.shDim == 8 ? kPlyTileFor<8> : a.shDim == 3 ? kPlyTileFor<3> : kPlyTileFor<0>;
-  const long long tiles = vec && (long long)tileG * a.width * 4 <= 200 * 1024 ? a.n / tileG : 0;
+  long long canon = 0;
+  if (cudaError_t e = launchDecodePlyCanonical(a, plan, stream, &canon); e != cudaSuccess) return e;
+  if (canon > 0) count++;
+  const long long tiles = canon == 0 && vec && (long long)tileG * a.width * 4 <= 200 * 1024 ? a.n / tileG : 0;
   if (tiles > 0) {
     cudaError_t e;
     switch (a.shDim) {
@@ -436,7 +443,7 @@ cudaError_t launchDecodePly(const PlyDecodeArgs &a, const LaunchPlan &plan, cuda
     if (e != cudaSuccess) return e;
     count++;
   }
-  const long long first = tiles * tileG;
+  const long long first = canon + tiles * tileG;
   if (first < a.n) {
     const long long blocks = (a.n - first + 127) / 128;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;

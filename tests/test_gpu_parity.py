@@ -212,7 +212,7 @@ def test_kernels_write_only_their_planes(gpu_ctx, oracle, deg):
 
 
 @pytest.mark.parametrize("env", [{"SPZB200_GRID": "persistent"}, {"SPZB200_GRID": "persistent", "SPZB200_CTAS_PER_SM": "1"},
-                                 {"SPZB200_DECODE": "direct"}, {"SPZB200_PACK": "alu"}])
+                                 {"SPZB200_DECODE": "direct"}, {"SPZB200_PACK": "alu"}, {"SPZB200_PLY": "mapped"}])
 def test_alternate_launch_shapes(env):
     """The development knobs select other code paths of the same kernels (persistent multi-tile CTAs,
     which exercise the bulk decoder's mbarrier phase flip and buffer hand-over between tiles; the
@@ -278,8 +278,13 @@ def test_fused_ply_rows_decoder(gpu_ctx, oracle, deg, ver):
     unpack scattered into the same column layout."""
     from spz_b200.codec import SH_DIM as DIM, ply_property_names
     rng = np.random.default_rng(3500 + 4 * deg + ver)
-    names = ply_property_names(deg) + ["extra"]
-    d, w = DIM[deg], len(ply_property_names(deg)) + 1
+    _fused_ply_rows_decoder_case(gpu_ctx, oracle, deg, ver, rng, ply_property_names(deg) + ["extra"])  # column-map kernels
+    _fused_ply_rows_decoder_case(gpu_ctx, oracle, deg, ver, rng, ply_property_names(deg))  # canonical-layout kernel
+
+
+def _fused_ply_rows_decoder_case(gpu_ctx, oracle, deg, ver, rng, names):
+    from spz_b200.codec import SH_DIM as DIM
+    d, w = DIM[deg], len(names)
     col = {k: i for i, k in enumerate(names)}
     for n in (512 * 2 + 300, 77):
         s = random_stream(rng, n, deg, ver, 11)

@@ -59,3 +59,20 @@ def assert_cloud_bits_equal(a, b, what=""):
             i = np.flatnonzero(bx != by)
             raise AssertionError(f"{what} plane {name}: {i.size} float-bit mismatches, first at {i[:5]}: "
                                  f"{[hex(v) for v in bx[i[:5]]]} vs {[hex(v) for v in by[i[:5]]]}")
+
+
+def cloud_to_ply_rows(c, names):
+    """[n, len(names)] float32 vertex records of a .ply with the given property order (the layout
+    load-spz.cc:858-890 writes, flips aside); properties the cloud does not carry are 0."""
+    n = c.n if hasattr(c, "n") else c.num_points
+    d = c.sh.size // (3 * n) if n else 0
+    cols = {"x": c.positions[0::3], "y": c.positions[1::3], "z": c.positions[2::3],
+            "f_dc_0": c.colors[0::3], "f_dc_1": c.colors[1::3], "f_dc_2": c.colors[2::3], "opacity": c.alphas,
+            "scale_0": c.scales[0::3], "scale_1": c.scales[1::3], "scale_2": c.scales[2::3],
+            "rot_0": c.rotations[3::4], "rot_1": c.rotations[0::4], "rot_2": c.rotations[1::4], "rot_3": c.rotations[2::4]}
+    sh = c.sh.reshape(n, d, 3) if d else np.zeros((n, 0, 3), np.float32)
+    for ch in range(3):
+        for s in range(d):
+            cols[f"f_rest_{ch * d + s}"] = sh[:, s, ch]
+    zero = np.zeros(n, np.float32)
+    return np.ascontiguousarray(np.stack([cols.get(k, zero) for k in names], axis=1), np.float32)
