@@ -696,8 +696,9 @@ template <int D, int VER>
 cudaError_t launchDecodeTilesVer(const DecodeArgs &a, long long tiles, int grid, bool bulk, cudaStream_t s) {
   if constexpr (D > 0) {
     if (bulk) {
-      static cudaError_t attr = cudaFuncSetAttribute(decodeTilesBulkKernel<D, VER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     BulkGeo<D>::kSmemBytes);  // once per instantiation
+      // per launch, not once: the attribute belongs to the current device, and one process may drive several
+      const cudaError_t attr = cudaFuncSetAttribute(decodeTilesBulkKernel<D, VER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    BulkGeo<D>::kSmemBytes);
       if (attr != cudaSuccess) return attr;
       decodeTilesBulkKernel<D, VER><<<grid, kThreads, BulkGeo<D>::kSmemBytes, s>>>(a, tiles);
       return cudaGetLastError();
@@ -731,8 +732,16 @@ cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream
                    (a.shDim == 0 || aligned(a.sh, 16)) && aligned(a.oPositions, 4) &&
                    aligned(a.oScales, 4) && aligned(a.oRotations, 4) && aligned(a.oAlphas, 4) &&
                    aligned(a.oColors, 4) && (a.shDim == 0 || aligned(a.oSh, 4));
+  // opt-in (SPZB200_ENCODE=bulk): one thread per gaussian, planes in and out by bulk async copies
+  // (pergaussian_kernels.cu).  Measured 6357 vs 6853 GB/s at SH degree 3 and 4837 vs 6530 at degree 0
+  // against the register-path tiles below, so those stay the default.
+  long long bulkDone = 0;
+  if (plan.encodeBulk) {
+    if (cudaError_t e = launchEncodePerGaussianPlanar(a, plan, stream, &bulkDone); e != cudaSuccess) return e;
+    if (bulkDone > 0) count++;
+  }
   const long long tg = tileGaussians(a.shDim);
-  const long long tiles = vec ? a.n / tg : 0;
+  const long long tiles = vec && bulkDone == 0 ? a.n / tg : 0;
   if (tiles > 0) {
     const int per = plan.ctasPerSm >= 1 && plan.ctasPerSm <= kCtasPerSm ? plan.ctasPerSm : kCtasPerSm;
     const long long cap = plan.flatGrid ? 0x7fffffffLL : (long long)plan.smCount * per;
@@ -749,7 +758,7 @@ cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream
     if (e != cudaSuccess) return e;
     count++;
   }
-  const long long first = tiles * tg;
+  const long long first = bulkDone + tiles * tg;
   if (first < a.n) {
     const long long rest = a.n - first;
     const long long blocks = (rest + 127) / 128;

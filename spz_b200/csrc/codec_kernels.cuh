@@ -73,6 +73,7 @@ struct LaunchPlan {
   int ctasPerSm;       // persistent grid only: smCount * ctasPerSm CTAs (1..4); 0 = default (4)
   bool flatGrid;       // one CTA per tile (default) instead of persistent grid-stride CTAs
   bool decodeBulk;     // decode the SH plane through bulk async copies (TMA) instead of registers
+  bool encodeBulk;     // planar encoder through the one-thread-per-gaussian bulk-copy kernel instead of the register-path tiles (default off: slower)
   bool plyMapped;      // test hook: PLY rows always through the column-map kernels, never the canonical-layout ones
 };
 
@@ -85,8 +86,9 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
 cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, int *launches);
 cudaError_t launchDecodePly(const PlyDecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, int *launches);
 int plyTileGaussians();
-// canonical property order only (ply_canonical_kernels.cu); *done = leading gaussians handled
+// canonical property order only (pergaussian_kernels.cu); *done = leading gaussians handled
 cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done);
+cudaError_t launchEncodePerGaussianPlanar(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done);
 cudaError_t launchDecodePlyCanonical(const PlyDecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done);
 
 // Gaussians per tile of the vector kernels for a given shDim (the sharding granule).

@@ -45,11 +45,35 @@ __device__ __forceinline__ void mbarInit(unsigned long long *bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(bar)));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, uint32_t bytes, unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+// SPZ_BULK_HINT (development knob): bit 0 = bulk stores carry an L2 evict-first policy, bit 1 = bulk
+// loads do (every byte is touched once).  scripts/ build and time the alternatives.
+#ifndef SPZ_BULK_HINT
+#define SPZ_BULK_HINT 0
+#endif
+__device__ __forceinline__ uint64_t policyEvictFirst() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// the copy alone, counted on a barrier whose expected byte count the caller has set (mbarExpect)
+__device__ __forceinline__ void bulkLoadOn(void *dstSmem, const void *srcGlobal, uint32_t bytes, unsigned long long *bar) {
+#if SPZ_BULK_HINT & 2
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smemAddr(dstSmem)),
+               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)), "l"(policyEvictFirst())
+               : "memory");
+#else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
                "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
                : "memory");
+#endif
+}
+__device__ __forceinline__ void mbarExpect(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, uint32_t bytes, unsigned long long *bar) {
+  mbarExpect(bar, bytes);
+  bulkLoadOn(dstSmem, srcGlobal, bytes, bar);
 }
 __device__ __forceinline__ void mbarWait(unsigned long long *bar, uint32_t parity) {
   uint32_t done = 0;
@@ -63,8 +87,14 @@ __device__ __forceinline__ void mbarWait(unsigned long long *bar, uint32_t parit
   }
 }
 __device__ __forceinline__ void bulkStore(void *dstGlobal, const void *srcSmem, uint32_t bytes) {
+#if SPZ_BULK_HINT & 1
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dstGlobal), "r"(smemAddr(srcSmem)),
+               "r"(bytes), "l"(policyEvictFirst())
+               : "memory");
+#else
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGlobal), "r"(smemAddr(srcSmem)), "r"(bytes)
                : "memory");
+#endif
 }
 
 }  // namespace spzb200

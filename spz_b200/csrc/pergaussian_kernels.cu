@@ -1,16 +1,23 @@
-// Fused PLY-rows kernels for the CANONICAL record layout -- the property order the reference's
-// saveSplatToPly writes (load-spz.cc:892-916) and the 3DGS trainers emit:
+// One-thread-per-gaussian kernels: the fused PLY-rows encoder and decoder for the CANONICAL record
+// layout, and (same kernel, other source) the planar encoder of packGaussians.  The canonical
+// layout is the property order the reference's saveSplatToPly writes (load-spz.cc:892-916) and the
+// 3DGS trainers emit:
 //
 //     x y z  nx ny nz  f_dc_0..2  f_rest_0..3D-1 (channel-major)  opacity  scale_0..2  rot_0..3 (w x y z)
 //
 // so every column index is a compile-time constant and the column maps of ply_kernels.cu (which
 // stay for any other property order) disappear.  One thread per gaussian, 128 gaussians per CTA:
 //
-//   rows -> packed (encodePlyCanonKernel): the tile's records (31.7 KB at SH degree 3) arrive with
+//   rows -> packed (encodePerGaussianKernel<RowsSource>): the tile's records (31.7 KB at SH degree 3) arrive with
 //     one bulk async copy; thread g reads record g from shared memory (64-bit loads, conflict
 //     free at the even widths, 32-bit at the odd ones), quantises its 59 values with immediate
 //     constants and deposits its bytes into a shared-memory image of the six packed planes, which
 //     leaves with six bulk async stores.
+//   planes -> packed (encodePerGaussianKernel<PlanarSource>): as above, but the tile's six float
+//     planes arrive with six bulk copies and thread g picks its 56 + 12D bytes out of them (odd
+//     word strides, conflict free).  Opt-in (SPZB200_ENCODE=bulk): six copies of 0.5 - 23 KB per tile
+//     sustain less than the register-path tiles of codec_kernels.cu (6357 vs 6853 GB/s at degree 3),
+//     unlike the single 31.7 KB copy of the rows source (7145 GB/s); profiles/r1_tuning_notes.txt.
 //   packed -> rows (decodePlyCanonKernel): the mirror image; six bulk loads bring the tile's packed
 //     planes in, thread g expands gaussian g into record g of the shared-memory tile, one bulk
 //     async store writes the records.
@@ -31,17 +38,26 @@ namespace {
 #ifndef SPZ_PLYC_CTAS
 #define SPZ_PLYC_CTAS 4
 #endif
-constexpr int kG = 128;  // gaussians per tile = threads per CTA
+#ifndef SPZ_PLYC_G_SMALL
+#define SPZ_PLYC_G_SMALL 128
+#endif
+#ifndef SPZ_PLYC_TAB_SMEM
+#define SPZ_PLYC_TAB_SMEM 0
+#endif
+#ifndef SPZ_PLYC_WARP_STORE
+#define SPZ_PLYC_WARP_STORE 0
+#endif
 
 template <int D>
 struct Canon {
   static constexpr int W = 17 + 3 * D;  // floats per record
+  static constexpr int G = D <= 3 ? SPZ_PLYC_G_SMALL : 128;  // gaussians per tile = threads per CTA
   static constexpr int kColor = 6, kRest = 9, kAlpha = 9 + 3 * D, kScale = 10 + 3 * D, kRot = 13 + 3 * D;
-  static constexpr int kRowBytes = kG * W * 4;
+  static constexpr int kRowBytes = G * W * 4;
   // the tile's packed planes in shared memory, in the container's order (load-spz.cc:533-546);
   // every offset and size is a multiple of 16 bytes, as the bulk copies require
-  static constexpr int oPos = 0, oAlpha = 9 * kG, oColor = 10 * kG, oScale = 13 * kG, oRot = 16 * kG, oSh = 20 * kG;
-  static constexpr int kPackedBytes = (20 + 3 * D) * kG + 16;  // + one granule: loadRecord<3> of the last lane reads a word ahead
+  static constexpr int oPos = 0, oAlpha = 9 * G, oColor = 10 * G, oScale = 13 * G, oRot = 16 * G, oSh = 20 * G;
+  static constexpr int kPackedBytes = (20 + 3 * D) * G + 16;  // + one granule: loadRecord<3> of the last lane reads a word ahead
   static constexpr int kSmemBytes = kRowBytes + kPackedBytes;
 };
 
@@ -108,28 +124,86 @@ __device__ __forceinline__ float magicByte(const uint32_t *v, int k) {
   return __uint_as_float(prmt(v[k >> 2], 0x4b000000u, 0x7650u + (uint32_t)(k & 3)));
 }
 
-__device__ __forceinline__ void mbarExpect(unsigned long long *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulkLoadOn(void *dstSmem, const void *srcGlobal, uint32_t bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
-               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
-               : "memory");
-}
+// =================================================================================================
+// encode.  Two sources of the same per-gaussian record r[0..W) (canonical column order):
+//   RowsSource   -- .ply vertex records: packGaussians(loadSplatFromPly(rows, to = X), from = X),
+//                   load-spz.cc:808-838 + :257-331
+//   PlanarSource -- the six GaussianCloud planes (splat-types.h:90-115): packGaussians itself
+// Everything after the record is in registers is shared.
+// =================================================================================================
+template <int D>
+struct RowsSource {
+  using Args = PlyEncodeArgs;
+  static constexpr int kBytes = Canon<D>::kRowBytes;
+  static __device__ __forceinline__ void request(const Args &a, long long tile, unsigned char *buf, unsigned long long *bar) {
+    bulkLoad(buf, a.rows + tile * (long long)(Canon<D>::G * Canon<D>::W), kBytes, bar);
+  }
+  static __device__ __forceinline__ void read(const unsigned char *buf, int t, float (&r)[Canon<D>::W]) {
+    constexpr int W = Canon<D>::W;
+    const float *row = reinterpret_cast<const float *>(buf) + t * W;
+    if constexpr (W % 2 == 0) {
+#pragma unroll
+      for (int j = 0; j < W / 2; j++) {
+        const float2 p = reinterpret_cast<const float2 *>(row)[j];
+        r[2 * j] = p.x;
+        r[2 * j + 1] = p.y;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < W; c++) r[c] = row[c];
+    }
+  }
+};
 
-// =================================================================================================
-// rows -> packed:  packGaussians(loadSplatFromPly(rows, to = X), from = X), load-spz.cc:808-838 + :257-331
-// =================================================================================================
-template <int D, int MODE>
-__global__ void __launch_bounds__(kG, SPZ_PLYC_CTAS)
-encodePlyCanonKernel(const PlyEncodeArgs a, const long long numTiles) {
+template <int D>
+struct PlanarSource {
+  using Args = EncodeArgs;
   using C = Canon<D>;
-  constexpr int W = C::W;
+  static constexpr int G = C::G;
+  // float planes of one tile in shared memory; sizes and offsets are multiples of 16 bytes
+  static constexpr int oPos = 0, oScale = 12 * G, oRot = 24 * G, oAlpha = 40 * G, oColor = 44 * G, oSh = 56 * G;
+  static constexpr int kBytes = (56 + 12 * D) * G;
+  static __device__ __forceinline__ void request(const Args &a, long long tile, unsigned char *buf, unsigned long long *bar) {
+    const long long g0 = tile * G;
+    mbarExpect(bar, kBytes);
+    bulkLoadOn(buf + oPos, a.positions + g0 * 3, 12 * G, bar);
+    bulkLoadOn(buf + oScale, a.scales + g0 * 3, 12 * G, bar);
+    bulkLoadOn(buf + oRot, a.rotations + g0 * 4, 16 * G, bar);
+    bulkLoadOn(buf + oAlpha, a.alphas + g0, 4 * G, bar);
+    bulkLoadOn(buf + oColor, a.colors + g0 * 3, 12 * G, bar);
+    if constexpr (D > 0) bulkLoadOn(buf + oSh, a.sh + g0 * (3 * D), 12 * D * G, bar);
+  }
+  // lane strides of 3 and 3*D words are odd (D = 0, 3, 15; D = 8 keeps the register-path kernel), so the
+  // 32-bit loads are bank-conflict free
+  static __device__ __forceinline__ void read(const unsigned char *buf, int t, float (&r)[C::W]) {
+    const float *f = reinterpret_cast<const float *>(buf);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      r[i] = f[oPos / 4 + 3 * t + i];
+      r[C::kScale + i] = f[oScale / 4 + 3 * t + i];
+      r[C::kColor + i] = f[oColor / 4 + 3 * t + i];
+    }
+    r[3] = r[4] = r[5] = 0.0f;
+    const float4 q = reinterpret_cast<const float4 *>(buf + oRot)[t];  // x, y, z, w
+    r[C::kRot] = q.w;
+    r[C::kRot + 1] = q.x;
+    r[C::kRot + 2] = q.y;
+    r[C::kRot + 3] = q.z;
+    r[C::kAlpha] = f[oAlpha / 4 + t];
+#pragma unroll
+    for (int k = 0; k < 3 * D; k++) r[C::kRest + (k % 3) * D + k / 3] = f[oSh / 4 + 3 * D * t + k];
+  }
+};
+
+template <int D, int MODE, class Src>
+__global__ void __launch_bounds__(Canon<D>::G, SPZ_PLYC_CTAS)
+encodePerGaussianKernel(const typename Src::Args a, const long long numTiles) {
+  using C = Canon<D>;
+  constexpr int W = C::W, kG = C::G;
   extern __shared__ __align__(128) unsigned char dynSmem[];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ float sThr[256];
-  float *rows = reinterpret_cast<float *>(dynSmem);
-  unsigned char *stage = dynSmem + C::kRowBytes;
+  unsigned char *stage = dynSmem + Src::kBytes;
   const int t = threadIdx.x;
   if (t == 0) mbarInit(&bar);
   __syncthreads();
@@ -139,29 +213,15 @@ encodePlyCanonKernel(const PlyEncodeArgs a, const long long numTiles) {
       if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncthreads();
     }
-    if (t == 0) bulkLoad(rows, a.rows + tile * (long long)(kG * W), C::kRowBytes, &bar);
-    if (tile == blockIdx.x) {  // the threshold table arrives while the records are in flight
-      sThr[t] = __ldg(a.alphaThresholds + t);
-      sThr[t + kG] = __ldg(a.alphaThresholds + t + kG);
+    if (t == 0) Src::request(a, tile, dynSmem, &bar);
+    if (tile == blockIdx.x) {  // the threshold table arrives while the tile is in flight
+      for (int i = t; i < 256; i += kG) sThr[i] = __ldg(a.alphaThresholds + i);
       __syncthreads();
     }
     mbarWait(&bar, parity);
 
     float r[W];
-    {
-      const float *row = rows + t * W;
-      if constexpr (W % 2 == 0) {
-#pragma unroll
-        for (int j = 0; j < W / 2; j++) {
-          const float2 p = reinterpret_cast<const float2 *>(row)[j];
-          r[2 * j] = p.x;
-          r[2 * j + 1] = p.y;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < W; c++) r[c] = row[c];
-      }
-    }
+    Src::read(dynSmem, t, r);
     // positions: 3 x 24 bit
     uint32_t pv[3];
     {
@@ -177,7 +237,7 @@ encodePlyCanonKernel(const PlyEncodeArgs a, const long long numTiles) {
     const uint32_t sv[1] = {packSat4<MODE>(m::quant_scale_raw(r[C::kScale]), m::quant_scale_raw(r[C::kScale + 1]),
                                            m::quant_scale_raw(r[C::kScale + 2]), 0)};
     const uint32_t av = m::quant_alpha(r[C::kAlpha], sThr);
-    // the file stores w first (load-spz.cc:826-829)
+    // canonical order has w first (load-spz.cc:826-829)
     const uint32_t rv = m::quant_rotation_smallest3(r[C::kRot + 1], r[C::kRot + 2], r[C::kRot + 3], r[C::kRot], a.flipQ);
     uint32_t hv[D > 0 ? Rec<3 * D>::NV : 1];
     if constexpr (D > 0) {
@@ -225,10 +285,10 @@ encodePlyCanonKernel(const PlyEncodeArgs a, const long long numTiles) {
 // packed -> rows:  saveSplatToPly(unpackGaussians(in, to = X), from = X)'s vertex records, load-spz.cc:467-531 + :858-890
 // =================================================================================================
 template <int D>
-__global__ void __launch_bounds__(kG, SPZ_PLYC_CTAS)
+__global__ void __launch_bounds__(Canon<D>::G, SPZ_PLYC_CTAS)
 decodePlyCanonKernel(const PlyDecodeArgs a, const long long numTiles) {
   using C = Canon<D>;
-  constexpr int W = C::W;
+  constexpr int W = C::W, kG = C::G;
   extern __shared__ __align__(128) unsigned char dynSmem[];
   __shared__ __align__(8) unsigned long long bar;
   float *rows = reinterpret_cast<float *>(dynSmem);
@@ -237,13 +297,18 @@ decodePlyCanonKernel(const PlyDecodeArgs a, const long long numTiles) {
   const bool half = a.version == 1 || a.version == 4;
   const bool s3 = a.version >= 3;
   const uint32_t posBytes = half ? 6 * kG : 9 * kG, rotBytes = s3 ? 4 * kG : 3 * kG;
+#if SPZ_PLYC_TAB_SMEM
+  __shared__ __align__(16) float tab[kDecodeTableFloats];
+  for (int i = t; i < kDecodeTableFloats / 4; i += kG) reinterpret_cast<float4 *>(tab)[i] = __ldg(reinterpret_cast<const float4 *>(a.tables) + i);
+#else
   const float *tab = a.tables;  // 4 KB, read through L1 (the bulk copies do not pass through it)
+#endif
   if (t == 0) mbarInit(&bar);
   __syncthreads();
   uint32_t parity = 0;
   for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
     if (tile != blockIdx.x) {  // multi-tile CTAs only: the previous tile's store is done reading the records
-      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if ((t & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncthreads();
     }
     if (t == 0) {
@@ -295,11 +360,11 @@ decodePlyCanonKernel(const PlyDecodeArgs a, const long long numTiles) {
     rec[3] = rec[4] = rec[5] = 0.0f;  // normals (load-spz.cc:866)
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      rec[C::kColor + i] = __ldg(tab + 256 + byteOf(cv, i));
+      rec[C::kColor + i] = tab[256 + byteOf(cv, i)];
       // (2^23 + s) / 16 - (2^19 + 10) = s/16 - 10, both steps exact (load-spz.cc:506)
       rec[C::kScale + i] = __fmaf_rn(magicByte(sv, i), 0.0625f, -524298.0f);
     }
-    rec[C::kAlpha] = __ldg(tab + av);
+    rec[C::kAlpha] = tab[av];
     {
       float q[4];
       if (s3) m::dequant_rotation_smallest3(rv[0], tab + 512, a.flipQ, q);
@@ -329,13 +394,22 @@ decodePlyCanonKernel(const PlyDecodeArgs a, const long long numTiles) {
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#if SPZ_PLYC_WARP_STORE
+    // a warp's 32 records are written by that warp alone: each warp sends its own as soon as it is done
+    __syncwarp();
+    if ((t & 31) == 0) {
+      bulkStore(a.rows + (tile * kG + t) * (long long)W, rows + t * W, 32 * W * 4);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+#else
     __syncthreads();
     if (t == 0) {
       bulkStore(a.rows + tile * (long long)(kG * W), rows, C::kRowBytes);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+#endif
   }
-  if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if ((t & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -358,21 +432,31 @@ unsigned gridFor(long long tiles, const LaunchPlan &plan) {
   return (unsigned)(tiles < 0x7fffffffLL ? tiles : 0x7fffffffLL);
 }
 
-template <int D, int MODE>
-cudaError_t launchEncodeCanon(const PlyEncodeArgs &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
-  constexpr int smem = Canon<D>::kSmemBytes;
-  cudaError_t e = cudaFuncSetAttribute(encodePlyCanonKernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  encodePlyCanonKernel<D, MODE><<<gridFor(tiles, plan), kG, smem, s>>>(a, tiles);
+template <int D, int MODE, class Src>
+cudaError_t launchEncodePerGaussian(const typename Src::Args &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+  constexpr int smem = Src::kBytes + Canon<D>::kPackedBytes;
+  static_assert(smem <= 48 * 1024, "above 48 KB the kernel would need cudaFuncAttributeMaxDynamicSharedMemorySize on every device");
+  encodePerGaussianKernel<D, MODE, Src><<<gridFor(tiles, plan), Canon<D>::G, smem, s>>>(a, tiles);
   return cudaGetLastError();
+}
+
+template <template <int> class Src, class Args>
+cudaError_t dispatchEncodePerGaussian(const Args &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+  const bool cvt = plan.packMode == kPackCvt;
+  switch (a.shDim) {
+    case 0: return cvt ? launchEncodePerGaussian<0, kPackCvt, Src<0>>(a, tiles, plan, s) : launchEncodePerGaussian<0, kPackAlu, Src<0>>(a, tiles, plan, s);
+    case 3: return cvt ? launchEncodePerGaussian<3, kPackCvt, Src<3>>(a, tiles, plan, s) : launchEncodePerGaussian<3, kPackAlu, Src<3>>(a, tiles, plan, s);
+    case 8: return cvt ? launchEncodePerGaussian<8, kPackCvt, Src<8>>(a, tiles, plan, s) : launchEncodePerGaussian<8, kPackAlu, Src<8>>(a, tiles, plan, s);
+    case 15: return cvt ? launchEncodePerGaussian<15, kPackCvt, Src<15>>(a, tiles, plan, s) : launchEncodePerGaussian<15, kPackAlu, Src<15>>(a, tiles, plan, s);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 template <int D>
 cudaError_t launchDecodeCanon(const PlyDecodeArgs &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
   constexpr int smem = Canon<D>::kSmemBytes;
-  cudaError_t e = cudaFuncSetAttribute(decodePlyCanonKernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  decodePlyCanonKernel<D><<<gridFor(tiles, plan), kG, smem, s>>>(a, tiles);
+  static_assert(smem <= 48 * 1024, "above 48 KB the kernel would need cudaFuncAttributeMaxDynamicSharedMemorySize on every device");
+  decodePlyCanonKernel<D><<<gridFor(tiles, plan), Canon<D>::G, smem, s>>>(a, tiles);
   return cudaGetLastError();
 }
 
@@ -387,18 +471,27 @@ cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &p
   if (!(aligned16(a.rows) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) && aligned16(a.oAlphas) &&
         aligned16(a.oColors) && (a.shDim == 0 || aligned16(a.oSh))))
     return cudaSuccess;
-  const long long tiles = a.n / kG;
+  const int G = a.shDim <= 3 ? Canon<0>::G : Canon<15>::G;
+  const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
-  cudaError_t e;
-  const bool cvt = plan.packMode == kPackCvt;
-  switch (a.shDim) {
-    case 0: e = cvt ? launchEncodeCanon<0, kPackCvt>(a, tiles, plan, stream) : launchEncodeCanon<0, kPackAlu>(a, tiles, plan, stream); break;
-    case 3: e = cvt ? launchEncodeCanon<3, kPackCvt>(a, tiles, plan, stream) : launchEncodeCanon<3, kPackAlu>(a, tiles, plan, stream); break;
-    case 8: e = cvt ? launchEncodeCanon<8, kPackCvt>(a, tiles, plan, stream) : launchEncodeCanon<8, kPackAlu>(a, tiles, plan, stream); break;
-    case 15: e = cvt ? launchEncodeCanon<15, kPackCvt>(a, tiles, plan, stream) : launchEncodeCanon<15, kPackAlu>(a, tiles, plan, stream); break;
-    default: return cudaErrorInvalidValue;
-  }
-  if (e == cudaSuccess) *done = tiles * kG;
+  const cudaError_t e = dispatchEncodePerGaussian<RowsSource>(a, tiles, plan, stream);
+  if (e == cudaSuccess) *done = tiles * G;
+  return e;
+}
+
+// packGaussians on planar float planes through the same kernel (SH degrees 0, 1, 3); *done as above
+cudaError_t launchEncodePerGaussianPlanar(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done) {
+  *done = 0;
+  if (plan.forceGeneric || a.shDim == 8) return cudaSuccess;
+  if (!(aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) && aligned16(a.colors) &&
+        (a.shDim == 0 || aligned16(a.sh)) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) &&
+        aligned16(a.oAlphas) && aligned16(a.oColors) && (a.shDim == 0 || aligned16(a.oSh))))
+    return cudaSuccess;
+  const int G = a.shDim <= 3 ? Canon<0>::G : Canon<15>::G;
+  const long long tiles = a.n / G;
+  if (tiles == 0) return cudaSuccess;
+  const cudaError_t e = dispatchEncodePerGaussian<PlanarSource>(a, tiles, plan, stream);
+  if (e == cudaSuccess) *done = tiles * G;
   return e;
 }
 
@@ -408,7 +501,8 @@ cudaError_t launchDecodePlyCanonical(const PlyDecodeArgs &a, const LaunchPlan &p
   if (!(aligned16(a.rows) && aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) &&
         aligned16(a.colors) && (a.shDim == 0 || aligned16(a.sh))))
     return cudaSuccess;
-  const long long tiles = a.n / kG;
+  const int G = a.shDim <= 3 ? Canon<0>::G : Canon<15>::G;
+  const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
   cudaError_t e;
   switch (a.shDim) {
@@ -418,7 +512,7 @@ cudaError_t launchDecodePlyCanonical(const PlyDecodeArgs &a, const LaunchPlan &p
     case 15: e = launchDecodeCanon<15>(a, tiles, plan, stream); break;
     default: return cudaErrorInvalidValue;
   }
-  if (e == cudaSuccess) *done = tiles * kG;
+  if (e == cudaSuccess) *done = tiles * G;
   return e;
 }
 

@@ -379,7 +379,7 @@ cudaError_t launchEncodePly(const PlyEncodeArgs &a, const LaunchPlan &plan, cuda
                    (a.shDim == 0 || alignedTo(a.oSh, 4));
   const int tileG = a.shDim == 15 ? kPlyTileFor<15> : a.shDim == 8 ? kPlyTileFor<8> : a.shDim == 3 ? kPlyTileFor<3> : kPlyTileFor<0>;
   // 200 KB of shared memory bound the record width the staged kernel accepts (wider: scalar kernel)
-  // the property order the reference writes: compile-time columns (ply_canonical_kernels.cu)
+  // the property order the reference writes: compile-time columns (pergaussian_kernels.cu)
   long long canon = 0;
   if (cudaError_t e = launchEncodePlyCanonical(a, plan, stream, &canon); e != cudaSuccess) return e;
   if (canon > 0) count++;
