@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ply", action="store_true", help="skip the fused PLY-rows kernel timings (N=1 only)")
     ap.add_argument("--cpu-sample-points", type=int, default=0, help="0 = auto")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from an ncu --set full capture")
@@ -183,6 +184,37 @@ def traffic_for(kernel, gaussians, override):
         return t["dram_bytes"] / t["gaussians"] * gaussians
     except Exception:  # noqa: BLE001
         return None
+
+
+def ply_rows_kernels(ctx, codec, dev, deg, n=40_000_000, steps=8):
+    """the fused kernels on the other side of the codec, .ply vertex records <-> packed
+    planes (canonical property order), device-resident, CUDA events, median of `steps`."""
+    import torch
+    names = codec.ply_property_names(deg)
+    w = len(names)
+    rows = torch.empty(n * w, dtype=torch.float32, device=dev).uniform_(-1, 1)
+    out = codec.alloc_packed(n, deg, 3, device=dev)
+    back = torch.empty_like(rows)
+    per = 4 * w + codec.packed_bytes_per_gaussian(deg)
+    res = {"points": n, "sh_degree": deg, "bytes_per_gaussian": per,
+           "note": "packGaussians(loadSplatFromPly(...)) / saveSplatToPly(unpackGaussians(...)) row layout in one kernel each; "
+                   "not part of `value`"}
+    for key, fn in (("rows_to_packed", lambda: ctx.encode_ply_device(rows, n, names, deg, 6, out=out)),
+                    ("packed_to_rows", lambda: ctx.decode_ply_device(out, names, 6, out=back))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(steps):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            e[0].record()
+            fn()
+            e[1].record()
+            torch.cuda.synchronize()
+            ts.append(e[0].elapsed_time(e[1]))
+        ms = statistics.median(ts)
+        res[key] = {"ms": ms, "hbm_gbs": per * n / ms / 1e6, "mgaussians_s": n / ms / 1e3}
+    return res
 
 
 def small_cloud_latency(ctx, codec, torch_cloud, dev, n, deg, args):
@@ -479,6 +511,10 @@ def run_b200_arm(args):
     if rank == 0:
         latency = small_cloud_latency(ctx, codec, torch_cloud, dev, 60_000, deg, args)
 
+    ply_rows = None
+    if rank == 0 and world == 1 and not args.no_ply:
+        ply_rows = ply_rows_kernels(ctx, codec, dev, deg, n=min(n, 40_000_000))
+
     host_zlib = None
     if rank == 0 and not args.no_cpu_baseline:
         host_zlib = time_host_zlib(packed, deg, min(n, 400_000))
@@ -540,6 +576,8 @@ def run_b200_arm(args):
             line["host_zlib"] = host_zlib
         if latency:
             line["latency_60k"] = latency
+        if ply_rows:
+            line["ply_rows"] = ply_rows
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist is not None:

@@ -21,6 +21,10 @@
 #include <string>
 #include <vector>
 
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
+
 #include "spz_internal.hpp"
 
 namespace spz {
@@ -33,9 +37,36 @@ void logLine(const char *fmt, ...) {
   printf("\n");
   fflush(stdout);
 }
+
+void adviseHugePages(void *p, size_t bytes) {
+#if defined(__linux__)
+  constexpr uintptr_t kHuge = (uintptr_t)2 << 20;
+  const uintptr_t a = ((uintptr_t)p + kHuge - 1) & ~(kHuge - 1), e = ((uintptr_t)p + bytes) & ~(kHuge - 1);
+  if (e > a) (void)madvise(reinterpret_cast<void *>(a), e - a, MADV_HUGEPAGE);  // advisory: failure changes nothing
+#else
+  (void)p;
+  (void)bytes;
+#endif
+}
+
+// true when std::vector<T> is {begin, end, end-of-storage} in that order (libstdc++, libc++)
+bool vectorLayoutIsThreePointers() {
+  if (const char *env = std::getenv("SPZ_B200_ZEROFILL")) {
+    if (env[0] == '1') return false;  // plain resize() everywhere (A/B timing, or a safety valve)
+  }
+  std::vector<uint32_t> v;
+  v.reserve(8);
+  v.push_back(1);
+  v.push_back(2);
+  uint32_t *raw[3];
+  if (sizeof v != sizeof raw) return false;
+  std::memcpy(raw, &v, sizeof raw);
+  return raw[0] == v.data() && raw[1] == v.data() + v.size() && raw[2] == v.data() + v.capacity();
+}
 }  // namespace detail
 namespace {
 using detail::logLine;
+using detail::resizeUninitialized;
 
 // The reference prints "[SPZ: ERROR] Check failed: file:line: expr" (load-spz.cc:94-100).
 #define SPZ_REQUIRE(cond)                                                                \
@@ -274,7 +305,8 @@ bool readFile(const std::string &filename, std::vector<uint8_t> *out) {
   if (!in.good()) return false;
   const std::streamoff len = in.tellg();
   if (len < 0) return false;
-  out->resize((size_t)len);
+  out->clear();
+  resizeUninitialized(*out, (size_t)len);
   in.seekg(0, std::ios::beg);
   if (len > 0) in.read(reinterpret_cast<char *>(out->data()), len);
   return in.good();
@@ -308,12 +340,13 @@ PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussian
   packed.fractionalBits = 12;  // load-spz.cc:270
   packed.antialiased = g.antialiased;
   packed.usesQuaternionSmallestThree = true;
-  packed.positions.resize(n * 9);
-  packed.scales.resize(n * 3);
-  packed.rotations.resize(n * 4);
-  packed.alphas.resize(n);
-  packed.colors.resize(n * 3);
-  packed.sh.resize(n * shDim * 3);
+  // every byte is written by the encoder (or the struct is discarded on failure)
+  resizeUninitialized(packed.positions, n * 9);
+  resizeUninitialized(packed.scales, n * 3);
+  resizeUninitialized(packed.rotations, n * 4);
+  resizeUninitialized(packed.alphas, n);
+  resizeUninitialized(packed.colors, n * 3);
+  resizeUninitialized(packed.sh, n * shDim * 3);
   if (n == 0) return PackStatus::Ok;  // nothing to encode; no device needed (load_spz_test.py:753)
 
   const SpzB200Cloud in = viewOf(g);
@@ -350,12 +383,13 @@ GaussianCloud unpackGaussians(const PackedGaussians &packed, const UnpackOptions
   result.numPoints = packed.numPoints;
   result.shDegree = packed.shDegree;
   result.antialiased = packed.antialiased;
-  result.positions.resize((size_t)n * 3);
-  result.scales.resize((size_t)n * 3);
-  result.rotations.resize((size_t)n * 4);
-  result.alphas.resize((size_t)n);
-  result.colors.resize((size_t)n * 3);
-  result.sh.resize((size_t)n * shDim * 3);
+  // every float is written by the decoder (or the struct is discarded on failure)
+  resizeUninitialized(result.positions, (size_t)n * 3);
+  resizeUninitialized(result.scales, (size_t)n * 3);
+  resizeUninitialized(result.rotations, (size_t)n * 4);
+  resizeUninitialized(result.alphas, (size_t)n);
+  resizeUninitialized(result.colors, (size_t)n * 3);
+  resizeUninitialized(result.sh, (size_t)n * shDim * 3);
   if (n == 0) return result;
 
   const SpzB200Packed in = viewOf(packed, streamFlavour(usesFloat16, packed.usesQuaternionSmallestThree));

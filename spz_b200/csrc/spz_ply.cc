@@ -130,7 +130,8 @@ bool readPlyRows(const std::string &filename, PlyLayout *layout, std::vector<flo
   L.width = (int)column.size();
   L.numPoints = count;
 
-  rows->resize((size_t)count * (size_t)L.width);
+  rows->clear();
+  detail::resizeUninitialized(*rows, (size_t)count * (size_t)L.width);  // filled by the read below
   in.read(reinterpret_cast<char *>(rows->data()), (std::streamsize)(rows->size() * sizeof(float)));
   if (!in.good()) {
     say("[SPZ ERROR] Unable to load data from: %s", name);
@@ -150,12 +151,13 @@ GaussianCloud loadSplatFromPly(const std::string &filename, const UnpackOptions 
   GaussianCloud g;
   g.numPoints = (int32_t)numPoints;
   g.shDegree = degreeForShDim((int)shDim);
-  g.positions.resize(numPoints * 3);
-  g.scales.resize(numPoints * 3);
-  g.rotations.resize(numPoints * 4);
-  g.alphas.resize(numPoints);
-  g.colors.resize(numPoints * 3);
-  g.sh.resize(numPoints * shDim * 3);
+  // every element is assigned in the loop below
+  detail::resizeUninitialized(g.positions, numPoints * 3);
+  detail::resizeUninitialized(g.scales, numPoints * 3);
+  detail::resizeUninitialized(g.rotations, numPoints * 4);
+  detail::resizeUninitialized(g.alphas, numPoints);
+  detail::resizeUninitialized(g.colors, numPoints * 3);
+  detail::resizeUninitialized(g.sh, numPoints * shDim * 3);
   for (size_t p = 0; p < numPoints; p++) {
     const float *row = rows.data() + p * width;
     for (int a = 0; a < 3; a++) {
@@ -197,12 +199,12 @@ bool plyToSpz(const std::string &plyFilename, const PackOptions &options, std::v
   packed.fractionalBits = 12;
   packed.antialiased = false;
   packed.usesQuaternionSmallestThree = true;
-  packed.positions.resize(n * 9);
-  packed.scales.resize(n * 3);
-  packed.rotations.resize(n * 4);
-  packed.alphas.resize(n);
-  packed.colors.resize(n * 3);
-  packed.sh.resize(n * (size_t)usedDim * 3);
+  detail::resizeUninitialized(packed.positions, n * 9);
+  detail::resizeUninitialized(packed.scales, n * 3);
+  detail::resizeUninitialized(packed.rotations, n * 4);
+  detail::resizeUninitialized(packed.alphas, n);
+  detail::resizeUninitialized(packed.colors, n * 3);
+  detail::resizeUninitialized(packed.sh, n * (size_t)usedDim * 3);
 
   SpzB200PlyRows in;
   std::memset(&in, 0, sizeof in);
@@ -241,7 +243,8 @@ bool spzToPly(const std::vector<uint8_t> &spzBytes, const UnpackOptions &options
   const int degree = packed.shDegree;
   const size_t shDim = degree == 0 ? 0 : degree == 1 ? 3 : degree == 2 ? 8 : 15;
   const size_t width = 17 + 3 * shDim;
-  std::vector<float> rows(n * width);
+  std::vector<float> rows;
+  detail::resizeUninitialized(rows, n * width);  // the decoder writes every float, unmapped columns as 0
   if (n > 0) {
     SpzB200Packed in;
     std::memset(&in, 0, sizeof in);
