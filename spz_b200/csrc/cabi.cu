@@ -217,7 +217,7 @@ struct SpzB200Context {
   bool forceGeneric = false;
   int ctasPerSm = 0;
   int bounceMode = 1;     // pageable planes: 0 never bounce, 1 bounce large calls (see bounceMinBytes), 2 always
-  size_t bounceMinBytes = (size_t)1 << 30;
+  size_t bounceMinBytes = (size_t)256 << 20;  // steady state the bounce path is 2-4x faster at every size; below this the one-time pinned allocation is not worth it for a one-shot call
   bool encodeBulk = false;  // SPZB200_ENCODE=bulk: planar encoder through the bulk-copy per-gaussian kernel (measured slower, kept as evidence)
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
   bool decodeBulk = true;  // SH plane of the decoder staged with bulk async copies (SPZB200_DECODE=direct: registers)
