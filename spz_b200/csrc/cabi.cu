@@ -122,7 +122,10 @@ void buildAlphaLut(float lut[256]) {
   }
 }
 
-constexpr int kStages = 3;
+#ifndef SPZ_STAGES
+#define SPZ_STAGES 3
+#endif
+constexpr int kStages = SPZ_STAGES;
 
 struct Stage {
   cudaStream_t stream = nullptr;

@@ -31,6 +31,7 @@
 
 #include "codec_math.cuh"
 #include "kernel_utils.cuh"
+#include "record_align.cuh"
 
 namespace spzb200 {
 namespace {
@@ -61,61 +62,13 @@ struct Canon {
   static constexpr int kSmemBytes = kRowBytes + kPackedBytes;
 };
 
-template <int B>
-struct Rec {
-  static constexpr int kMaxShift = (B % 4 == 0) ? 0 : (B % 2 == 0) ? 2 : 3;
-  static constexpr int NL = (B + kMaxShift + 3) / 4;  // words a lane reads to cover its B bytes at any alignment
-  static constexpr int NV = (B + 3) / 4;              // words holding one record, byte 0 first
-};
-
-// v <- the B bytes of gaussian g of a packed plane (record byte k = byte k & 3 of v[k >> 2])
-template <int B>
-__device__ __forceinline__ void loadRecord(const uint32_t *plane, int g, uint32_t (&v)[Rec<B>::NL]) {
-  constexpr int NL = Rec<B>::NL;
-  const uint32_t *p = plane + ((B * g) >> 2);
-  uint32_t w[NL];
-#pragma unroll
-  for (int i = 0; i < NL; i++) w[i] = p[i];
-  if constexpr (B % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < NL; i++) v[i] = w[i];
-  } else {
-    const uint32_t sh = ((uint32_t)(B * g) & 3u) * 8u;
-#pragma unroll
-    for (int i = 0; i + 1 < NL; i++) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
-    v[NL - 1] = w[NL - 1] >> sh;
-  }
-}
-
-// the B bytes in v -> gaussian g's place in a packed plane.  Lane g stores the words that END inside
-// its byte range [B*g, B*(g+1)); bytes at or above B in v's last word are never stored.  Must be
-// called by all 32 lanes of a warp, g = consecutive per lane, lane 0's g a multiple of 32.
+// Must be called by all 32 lanes of a warp, g consecutive per lane, lane 0's g a multiple of 32
+// (record_align.cuh has the word arithmetic).
 template <int B>
 __device__ __forceinline__ void emitRecord(uint32_t *plane, int g, const uint32_t (&v)[Rec<B>::NV]) {
-  constexpr int NV = Rec<B>::NV;
-  uint32_t *p = plane + ((B * g) >> 2);
-  if constexpr (B % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; i++) p[i] = v[i];
-  } else {
-    uint32_t tail;  // record bytes B-4 .. B-1
-    if constexpr (B >= 4) {
-      constexpr int j = (B - 4) >> 2;
-      constexpr uint32_t s = ((B - 4) & 3) * 8;
-      tail = __funnelshift_r(v[j], v[j + 1 < NV ? j + 1 : j], s);
-    } else {
-      tail = v[0] << (8 * (4 - B));
-    }
-    const uint32_t prev = __shfl_up_sync(0xffffffffu, tail, 1);
-    const uint32_t sh = ((uint32_t)(B * g) & 3u) * 8u;
-    uint32_t w[NV];
-    w[0] = __funnelshift_l(prev, v[0], sh);
-#pragma unroll
-    for (int i = 1; i < NV; i++) w[i] = __funnelshift_l(v[i - 1], v[i], sh);
-#pragma unroll
-    for (int i = 0; i + 1 < NV; i++) p[i] = w[i];
-    if (((B * (g + 1)) >> 2) - ((B * g) >> 2) == NV) p[NV - 1] = w[NV - 1];
-  }
+  uint32_t prev = 0;
+  if constexpr (B % 4 != 0) prev = __shfl_up_sync(0xffffffffu, recordTail<B>(v), 1);
+  emitRecordWords<B>(plane, g, v, prev);
 }
 
 __device__ __forceinline__ uint32_t byteOf(const uint32_t *v, int k) { return (v[k >> 2] >> (8 * (k & 3))) & 0xffu; }

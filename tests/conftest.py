@@ -44,8 +44,8 @@ def emul():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libquant_host.so")
     src = os.path.join(here, "quant_host.cc")
-    hdr = os.path.join(ROOT, "spz_b200", "csrc", "codec_math.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "spz_b200", "csrc", h) for h in ("codec_math.cuh", "record_align.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in [src] + hdrs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-frounding-math",
                         "-Wno-unknown-pragmas", "-shared", "-fPIC", src, "-o", so], check=True)
     return ctypes.CDLL(so)

@@ -73,3 +73,57 @@ void emul_flip_bits(int32_t from, int32_t to, uint32_t *p, uint32_t *q, uint32_t
 }
 
 }  // extern "C"
+
+// ---- record realignment (spz_b200/csrc/record_align.cuh), one "lane" after the other --------------
+#include "../../spz_b200/csrc/record_align.cuh"
+
+namespace {
+template <int B>
+void emitAll(int64_t n, const uint8_t *records, uint32_t *plane, uint8_t garbage) {
+  using R = spzb200::Rec<B>;
+  uint32_t prevTail = 0x5a5a5a5au;  // what lane 0's shuffle hands back is its own tail: must not matter
+  for (int64_t g = 0; g < n; g++) {
+    uint8_t bytes[4 * R::NV];
+    for (int i = 0; i < 4 * R::NV; i++) bytes[i] = i < B ? records[g * B + i] : garbage;
+    uint32_t v[R::NV];
+    std::memcpy(v, bytes, sizeof v);
+    const uint32_t mine = spzb200::recordTail<B>(v);
+    spzb200::emitRecordWords<B>(plane, (int)g, v, (g % 32) ? prevTail : mine);
+    prevTail = mine;
+  }
+}
+template <int B>
+void loadAll(int64_t n, const uint32_t *plane, uint8_t *records) {
+  using R = spzb200::Rec<B>;
+  for (int64_t g = 0; g < n; g++) {
+    uint32_t v[R::NL];
+    spzb200::loadRecord<B>(plane, (int)g, v);
+    uint8_t bytes[4 * R::NL];
+    std::memcpy(bytes, v, sizeof v);
+    std::memcpy(records + g * B, bytes, B);
+  }
+}
+}  // namespace
+
+extern "C" {
+// records: n x B bytes -> plane words (caller sizes plane to n * B / 4 + slack and pre-fills it)
+int emul_emit_records(int B, int64_t n, const uint8_t *records, uint32_t *plane, uint8_t garbage) {
+  switch (B) {
+    case 3: emitAll<3>(n, records, plane, garbage); return 0;
+    case 9: emitAll<9>(n, records, plane, garbage); return 0;
+    case 24: emitAll<24>(n, records, plane, garbage); return 0;
+    case 45: emitAll<45>(n, records, plane, garbage); return 0;
+    default: return -1;
+  }
+}
+int emul_load_records(int B, int64_t n, const uint32_t *plane, uint8_t *records) {
+  switch (B) {
+    case 3: loadAll<3>(n, plane, records); return 0;
+    case 6: loadAll<6>(n, plane, records); return 0;
+    case 9: loadAll<9>(n, plane, records); return 0;
+    case 24: loadAll<24>(n, plane, records); return 0;
+    case 45: loadAll<45>(n, plane, records); return 0;
+    default: return -1;
+  }
+}
+}

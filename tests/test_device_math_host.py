@@ -227,3 +227,26 @@ def test_flip_bits_all_pairs(emul, oracle):
             assert [(p.value >> i) & 1 for i in range(3)] == [int(v < 0) for v in fp]
             assert [(q.value >> i) & 1 for i in range(3)] == [int(v < 0) for v in fq]
             assert [(s.value >> i) & 1 for i in range(15)] == [int(v < 0) for v in fsh]
+
+
+@pytest.mark.parametrize("nbytes", [3, 6, 9, 24, 45])
+def test_record_realignment(emul, nbytes):
+    """record_align.cuh: per-gaussian records of 3 / 6 / 9 / 24 / 45 bytes in and out of a packed plane
+    with whole-word accesses (funnel shifts + the predecessor's tail), lane after lane on the host.
+    128 gaussians = one tile = four warps; the plane must come out byte-identical to the plain
+    concatenation of the records, nothing may be written past it, and the don't-care bytes of a
+    record's last register word must never reach memory."""
+    rng = np.random.default_rng(77 + nbytes)
+    n = 128
+    records = rng.integers(0, 256, n * nbytes, dtype=np.uint8)
+    if nbytes != 6:  # the kernels only ever read half-float positions
+        for garbage in (0x00, 0xEE):
+            plane = np.full(n * nbytes // 4 + 8, 0xDEADBEEF, np.uint32)
+            assert emul.emul_emit_records(C.c_int(nbytes), C.c_int64(n), records.ctypes.data_as(_u8p), plane.ctypes.data_as(_u32p),
+                                          C.c_uint8(garbage)) == 0
+            assert np.array_equal(plane[:n * nbytes // 4].view(np.uint8), records), (nbytes, garbage)
+            assert (plane[n * nbytes // 4:] == 0xDEADBEEF).all(), "wrote past the plane"
+    plane = np.concatenate([records, rng.integers(0, 256, 32, dtype=np.uint8)]).view(np.uint32)
+    back = np.zeros(n * nbytes, np.uint8)
+    assert emul.emul_load_records(C.c_int(nbytes), C.c_int64(n), plane.ctypes.data_as(_u32p), back.ctypes.data_as(_u8p)) == 0
+    assert np.array_equal(back, records), nbytes
