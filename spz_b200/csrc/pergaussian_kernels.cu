@@ -36,6 +36,10 @@
 namespace spzb200 {
 namespace {
 
+// Build-time knobs kept so scripts/ can time the alternatives; all were measured and lost
+// (profiles/r1_tuning_notes.txt): other __launch_bounds__ CTA counts (no change: shared memory sets 5
+// CTAs/SM), 256-gaussian tiles at SH degree 0/1 (-2 %), decode tables copied to shared memory instead of
+// read through L1 (-4 %), one bulk store per warp instead of per CTA (-2 %).
 #ifndef SPZ_PLYC_CTAS
 #define SPZ_PLYC_CTAS 4
 #endif
