@@ -33,7 +33,10 @@ def run(ctx, n, deg):
     ms = statistics.median(ts)
     print(json.dumps({"op": "packed->rows", "points": n, "sh_degree": deg, "ms": round(ms, 3), "gbs": round(b / ms / 1e6), "mgs": round(n / ms / 1e3)}), flush=True)
 
-with codec.Context(0) as ctx:
-    for deg in (3, 0):
-        for n in (10_000_000, 40_000_000):
-            run(ctx, n, deg)
+if __name__ == "__main__":
+    sizes = [int(float(x)) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["1e7", "4e7"])]
+    degs = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["3", "0"])]
+    with codec.Context(0) as ctx:
+        for deg in degs:
+            for n in sizes:
+                run(ctx, n, deg)

@@ -6,7 +6,7 @@
 //     x y z  nx ny nz  f_dc_0..2  f_rest_0..3D-1 (channel-major)  opacity  scale_0..2  rot_0..3 (w x y z)
 //
 // so every column index is a compile-time constant and the column maps of ply_kernels.cu (which
-// stay for any other property order) disappear.  One thread per gaussian, 128 gaussians per CTA:
+// stay for any other property order) disappear.  One thread per gaussian, 64 - 256 gaussians per CTA:
 //
 //   rows -> packed (encodePerGaussianKernel<RowsSource>): the tile's records (31.7 KB at SH degree 3) arrive with
 //     one bulk async copy; thread g reads record g from shared memory (64-bit loads, conflict
@@ -36,16 +36,9 @@
 namespace spzb200 {
 namespace {
 
-// Build-time knobs kept so scripts/ can time the alternatives; all were measured and lost
-// (profiles/r1_tuning_notes.txt): other __launch_bounds__ CTA counts (no change: shared memory sets 5
-// CTAs/SM), 256-gaussian tiles at SH degree 0/1 (-2 %), decode tables copied to shared memory instead of
-// read through L1 (-4 %), one bulk store per warp instead of per CTA (-2 %).
-#ifndef SPZ_PLYC_CTAS
-#define SPZ_PLYC_CTAS 4
-#endif
-#ifndef SPZ_PLYC_G_SMALL
-#define SPZ_PLYC_G_SMALL 128
-#endif
+// Build-time knobs kept so scripts/ can time the alternatives; both were measured and lost
+// (profiles/r1_tuning_notes.txt): decode tables copied to shared memory instead of read through L1
+// (-4 %), one bulk store per warp instead of per CTA (-2 %).
 #ifndef SPZ_PLYC_TAB_SMEM
 #define SPZ_PLYC_TAB_SMEM 0
 #endif
@@ -53,10 +46,10 @@ namespace {
 #define SPZ_PLYC_WARP_STORE 0
 #endif
 
-template <int D>
+template <int D, int G_>
 struct Canon {
   static constexpr int W = 17 + 3 * D;  // floats per record
-  static constexpr int G = D <= 3 ? SPZ_PLYC_G_SMALL : 128;  // gaussians per tile = threads per CTA
+  static constexpr int G = G_;          // gaussians per tile = threads per CTA
   static constexpr int kColor = 6, kRest = 9, kAlpha = 9 + 3 * D, kScale = 10 + 3 * D, kRot = 13 + 3 * D;
   static constexpr int kRowBytes = G * W * 4;
   // the tile's packed planes in shared memory, in the container's order (load-spz.cc:533-546);
@@ -65,6 +58,27 @@ struct Canon {
   static constexpr int kPackedBytes = (20 + 3 * D) * G + 16;  // + one granule: loadRecord<3> of the last lane reads a word ahead
   static constexpr int kSmemBytes = kRowBytes + kPackedBytes;
 };
+
+// Gaussians per tile (= threads per CTA) and the __launch_bounds__ CTA count, per direction and SH
+// dimension, from device-timed sweeps at 40M points (profiles/r1_tuning_notes.txt).  The decoder
+// wants small tiles -- each CTA holds its shared memory through load wait, expansion and store
+// drain, and more, smaller CTAs per SM overlap those phases better (64 instead of 128 gaussians:
+// 6166 -> 6675 GB/s at degree 3) -- while the SH-less encoder is issue-bound and wants every thread
+// slot of the SM filled (256 x 8).
+template <int D>
+struct EncGeo {
+  static constexpr int G = D == 0 ? 256 : 128;
+  static constexpr int CTAS = D <= 3 ? 8 : 4;
+  using C = Canon<D, G>;
+};
+template <int D>
+struct DecGeo {
+  static constexpr int G = D <= 3 ? 128 : 64;
+  static constexpr int CTAS = 8;
+  using C = Canon<D, G>;
+};
+constexpr int encTileGaussians(int shDim) { return shDim == 0 ? EncGeo<0>::G : shDim == 3 ? EncGeo<3>::G : shDim == 8 ? EncGeo<8>::G : EncGeo<15>::G; }
+constexpr int decTileGaussians(int shDim) { return shDim == 0 ? DecGeo<0>::G : shDim == 3 ? DecGeo<3>::G : shDim == 8 ? DecGeo<8>::G : DecGeo<15>::G; }
 
 // Must be called by all 32 lanes of a warp, g consecutive per lane, lane 0's g a multiple of 32
 // (record_align.cuh has the word arithmetic).
@@ -91,12 +105,13 @@ __device__ __forceinline__ float magicByte(const uint32_t *v, int k) {
 template <int D>
 struct RowsSource {
   using Args = PlyEncodeArgs;
-  static constexpr int kBytes = Canon<D>::kRowBytes;
+  using C = typename EncGeo<D>::C;
+  static constexpr int kBytes = C::kRowBytes;
   static __device__ __forceinline__ void request(const Args &a, long long tile, unsigned char *buf, unsigned long long *bar) {
-    bulkLoad(buf, a.rows + tile * (long long)(Canon<D>::G * Canon<D>::W), kBytes, bar);
+    bulkLoad(buf, a.rows + tile * (long long)(C::G * C::W), kBytes, bar);
   }
-  static __device__ __forceinline__ void read(const unsigned char *buf, int t, float (&r)[Canon<D>::W]) {
-    constexpr int W = Canon<D>::W;
+  static __device__ __forceinline__ void read(const unsigned char *buf, int t, float (&r)[C::W]) {
+    constexpr int W = C::W;
     const float *row = reinterpret_cast<const float *>(buf) + t * W;
     if constexpr (W % 2 == 0) {
 #pragma unroll
@@ -115,7 +130,7 @@ struct RowsSource {
 template <int D>
 struct PlanarSource {
   using Args = EncodeArgs;
-  using C = Canon<D>;
+  using C = typename EncGeo<D>::C;
   static constexpr int G = C::G;
   // float planes of one tile in shared memory; sizes and offsets are multiples of 16 bytes
   static constexpr int oPos = 0, oScale = 12 * G, oRot = 24 * G, oAlpha = 40 * G, oColor = 44 * G, oSh = 56 * G;
@@ -153,9 +168,9 @@ struct PlanarSource {
 };
 
 template <int D, int MODE, class Src>
-__global__ void __launch_bounds__(Canon<D>::G, SPZ_PLYC_CTAS)
+__global__ void __launch_bounds__(EncGeo<D>::G, EncGeo<D>::CTAS)
 encodePerGaussianKernel(const typename Src::Args a, const long long numTiles) {
-  using C = Canon<D>;
+  using C = typename EncGeo<D>::C;
   constexpr int W = C::W, kG = C::G;
   extern __shared__ __align__(128) unsigned char dynSmem[];
   __shared__ __align__(8) unsigned long long bar;
@@ -242,9 +257,9 @@ encodePerGaussianKernel(const typename Src::Args a, const long long numTiles) {
 // packed -> rows:  saveSplatToPly(unpackGaussians(in, to = X), from = X)'s vertex records, load-spz.cc:467-531 + :858-890
 // =================================================================================================
 template <int D>
-__global__ void __launch_bounds__(Canon<D>::G, SPZ_PLYC_CTAS)
+__global__ void __launch_bounds__(DecGeo<D>::G, DecGeo<D>::CTAS)
 decodePlyCanonKernel(const PlyDecodeArgs a, const long long numTiles) {
-  using C = Canon<D>;
+  using C = typename DecGeo<D>::C;
   constexpr int W = C::W, kG = C::G;
   extern __shared__ __align__(128) unsigned char dynSmem[];
   __shared__ __align__(8) unsigned long long bar;
@@ -381,9 +396,9 @@ bool canonicalColumns(const Args &a) {
   return ok;
 }
 
-unsigned gridFor(long long tiles, const LaunchPlan &plan) {
+unsigned gridFor(long long tiles, const LaunchPlan &plan, int ctasPerSm) {
   if (!plan.flatGrid) {
-    const long long g = (long long)plan.smCount * SPZ_PLYC_CTAS;
+    const long long g = (long long)plan.smCount * ctasPerSm;
     return (unsigned)(tiles < g ? tiles : g);
   }
   return (unsigned)(tiles < 0x7fffffffLL ? tiles : 0x7fffffffLL);
@@ -391,9 +406,9 @@ unsigned gridFor(long long tiles, const LaunchPlan &plan) {
 
 template <int D, int MODE, class Src>
 cudaError_t launchEncodePerGaussian(const typename Src::Args &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
-  constexpr int smem = Src::kBytes + Canon<D>::kPackedBytes;
+  constexpr int smem = Src::kBytes + EncGeo<D>::C::kPackedBytes;
   static_assert(smem <= 48 * 1024, "above 48 KB the kernel would need cudaFuncAttributeMaxDynamicSharedMemorySize on every device");
-  encodePerGaussianKernel<D, MODE, Src><<<gridFor(tiles, plan), Canon<D>::G, smem, s>>>(a, tiles);
+  encodePerGaussianKernel<D, MODE, Src><<<gridFor(tiles, plan, EncGeo<D>::CTAS), EncGeo<D>::G, smem, s>>>(a, tiles);
   return cudaGetLastError();
 }
 
@@ -411,9 +426,9 @@ cudaError_t dispatchEncodePerGaussian(const Args &a, long long tiles, const Laun
 
 template <int D>
 cudaError_t launchDecodeCanon(const PlyDecodeArgs &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
-  constexpr int smem = Canon<D>::kSmemBytes;
+  constexpr int smem = DecGeo<D>::C::kSmemBytes;
   static_assert(smem <= 48 * 1024, "above 48 KB the kernel would need cudaFuncAttributeMaxDynamicSharedMemorySize on every device");
-  decodePlyCanonKernel<D><<<gridFor(tiles, plan), Canon<D>::G, smem, s>>>(a, tiles);
+  decodePlyCanonKernel<D><<<gridFor(tiles, plan, DecGeo<D>::CTAS), DecGeo<D>::G, smem, s>>>(a, tiles);
   return cudaGetLastError();
 }
 
@@ -428,7 +443,7 @@ cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &p
   if (!(aligned16(a.rows) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) && aligned16(a.oAlphas) &&
         aligned16(a.oColors) && (a.shDim == 0 || aligned16(a.oSh))))
     return cudaSuccess;
-  const int G = a.shDim <= 3 ? Canon<0>::G : Canon<15>::G;
+  const int G = encTileGaussians(a.shDim);
   const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
   const cudaError_t e = dispatchEncodePerGaussian<RowsSource>(a, tiles, plan, stream);
@@ -444,7 +459,7 @@ cudaError_t launchEncodePerGaussianPlanar(const EncodeArgs &a, const LaunchPlan 
         (a.shDim == 0 || aligned16(a.sh)) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) &&
         aligned16(a.oAlphas) && aligned16(a.oColors) && (a.shDim == 0 || aligned16(a.oSh))))
     return cudaSuccess;
-  const int G = a.shDim <= 3 ? Canon<0>::G : Canon<15>::G;
+  const int G = encTileGaussians(a.shDim);
   const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
   const cudaError_t e = dispatchEncodePerGaussian<PlanarSource>(a, tiles, plan, stream);
@@ -458,7 +473,7 @@ cudaError_t launchDecodePlyCanonical(const PlyDecodeArgs &a, const LaunchPlan &p
   if (!(aligned16(a.rows) && aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) &&
         aligned16(a.colors) && (a.shDim == 0 || aligned16(a.sh))))
     return cudaSuccess;
-  const int G = a.shDim <= 3 ? Canon<0>::G : Canon<15>::G;
+  const int G = decTileGaussians(a.shDim);
   const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
   cudaError_t e;
