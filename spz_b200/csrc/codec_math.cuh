@@ -19,8 +19,17 @@
 
 #if defined(__CUDACC__)
 #define SPZ_HD __host__ __device__ __forceinline__
+// rarely-taken general forms.  Inlined by default (the tile encoder is 6 % faster at SH degree 0 with
+// them inline: a call under its 48-register cap spills); a translation unit that defines
+// SPZ_COLD_NOINLINE before including this header gets one called copy instead.
+#if defined(SPZ_COLD_NOINLINE)
+#define SPZ_HD_COLD static __host__ __device__ __noinline__
+#else
+#define SPZ_HD_COLD __host__ __device__ __forceinline__
+#endif
 #else
 #define SPZ_HD inline
+#define SPZ_HD_COLD inline
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -42,6 +51,8 @@ SPZ_HD float add(float a, float b) { return __fadd_rn(a, b); }
 SPZ_HD float sub(float a, float b) { return __fsub_rn(a, b); }
 SPZ_HD float div(float a, float b) { return __fdiv_rn(a, b); }
 SPZ_HD float sqrt_rn(float a) { return __fsqrt_rn(a); }
+SPZ_HD float rcp_rn(float a) { return __frcp_rn(a); }
+SPZ_HD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }  // one rounding: used only where the reference has none to match
 SPZ_HD float add_rz(float a, float b) { return __fadd_rz(a, b); }
 SPZ_HD int32_t f2i_rz(float a) { return __float2int_rz(a); }        // saturating, NaN -> 0
 SPZ_HD uint32_t f2u_rz(float a) { return __float2uint_rz(a); }      // saturating, NaN -> 0
@@ -56,6 +67,8 @@ inline float add(float a, float b) { volatile float r = a + b; return r; }
 inline float sub(float a, float b) { volatile float r = a - b; return r; }
 inline float div(float a, float b) { volatile float r = a / b; return r; }
 inline float sqrt_rn(float a) { return std::sqrt(a); }
+inline float rcp_rn(float a) { volatile float r = 1.0f / a; return r; }
+inline float fma_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float add_rz(float a, float b) {
   const int old = std::fegetround();
   std::fesetround(FE_TOWARDZERO);
@@ -174,8 +187,10 @@ SPZ_HD uint32_t cast_u32_like_x86(float v) {
 
 // rotations, load-spz.cc:216-255 (packQuaternionSmallestThree) + splat-types.cc:71-74
 // (normalized).  rot = x,y,z,w; flipBits bit i set = negate component i (i < 3) after the
-// normalisation.  Same operations in the same order as the reference.
-SPZ_HD uint32_t quant_rotation_smallest3(float x, float y, float z, float w, uint32_t flipBits) {
+// normalisation.  Same operations in the same order as the reference; valid for every input
+// (NaN, Inf, zero and denormal norms included).  The kernels reach it only through the guard of
+// quant_rotation_smallest3 below.
+SPZ_HD_COLD uint32_t quant_rotation_smallest3_general(float x, float y, float z, float w, uint32_t flipBits) {
   const float kInvSqrt2 = 0.70710678118654752440f;
   const float n2 = add(add(add(mul(x, x), mul(y, y)), mul(z, z)), mul(w, w));
   const float nrm = sqrt_rn(n2);
@@ -205,6 +220,74 @@ SPZ_HD uint32_t quant_rotation_smallest3(float x, float y, float z, float w, uin
     }
   }
   return comp;
+}
+
+// The IEEE quotient x / b from rb = RN(1 / b), the correctly rounded reciprocal (Markstein 1990; Muller
+// et al., Handbook of Floating-Point Arithmetic, "division with an FMA"): q0 = RN(x * rb) is within 2 ulp
+// of x / b; one residual correction leaves an error of 2^-46 relative before rounding, i.e. a
+// faithful q1; for a faithful q1 the residual x - b * q1 is exact and RN(q1 + residual * rb) is the
+// correctly rounded quotient.  Preconditions, established by the caller: x, b, the quotient and the
+// residuals are in the normal range (or x == 0), and b's significand is not all ones.  Five
+// branch-free instructions instead of the ~14 of a guarded division, and the reciprocal is shared by
+// the four components.  tests/test_device_math_host.py checks it against the plain division on random
+// operand pairs from that domain (2^33 pairs once, profiles/r1_tuning_notes.txt; 2^27 per test run).
+SPZ_HD float div_by_rcp(float x, float b, float rb) {
+  float q = mul(x, rb);
+  q = fma_rn(fma_rn(-b, q, x), rb, q);
+  return fma_rn(fma_rn(-b, q, x), rb, q);
+}
+
+// a / sqrt1_2 for a in {0} U [2^-81, 1.01]: one correction is enough for this divisor -- checked
+// against the plain division for every float of that range (tests/test_device_math_host.py).
+SPZ_HD float div_by_sqrt1_2(float a) {
+  const float c = 0.70710678118654752440f;            // 0x3f3504f3, the reference's sqrt1_2 (load-spz.cc:218)
+  const float rc = 1.41421353816986083984375f;        // RN(1 / c) = 0x3fb504f3
+  const float q = mul(a, rc);
+  return fma_rn(fma_rn(-c, q, a), rc, q);
+}
+
+// packQuaternionSmallestThree for the inputs real clouds hold -- squared norm in [2^-40, 2^40], every
+// component zero or at least 2^-60 in magnitude -- with the seven divisions done by div_by_rcp;
+// anything else (NaN, Inf, vanishing or huge norms, denormal components) takes the general form
+// above.  Inside the guard every normalised component is within [2^-81, 1 + 2^-21] or zero, so the
+// magnitude 511 * (a / sqrt1_2) + 0.5 stays below 724 and the plain truncating conversion is what the
+// x86 cast computes; no NaN can occur, so the strict-> argmax and the < 0 tests are plain compares.
+SPZ_HD uint32_t quant_rotation_smallest3(float x, float y, float z, float w, uint32_t flipBits) {
+  const float n2 = add(add(add(mul(x, x), mul(y, y)), mul(z, z)), mul(w, w));
+  const float nrm = sqrt_rn(n2);
+  // (u - 1) >= 2^-60 - 1 as unsigned: true for u == 0 (wraps) and for u >= bits(2^-60)
+  const uint32_t lowest = 0x21800000u - 1u;
+  const bool componentsOk = ((fbits(x) & 0x7fffffffu) - 1u) >= lowest && ((fbits(y) & 0x7fffffffu) - 1u) >= lowest &&
+                            ((fbits(z) & 0x7fffffffu) - 1u) >= lowest && ((fbits(w) & 0x7fffffffu) - 1u) >= lowest;
+  const bool normOk = n2 >= 9.094947017729282e-13f && n2 <= 1099511627776.0f && (fbits(nrm) & 0x007fffffu) != 0x007fffffu;
+  if (!(componentsOk && normOk)) return quant_rotation_smallest3_general(x, y, z, w, flipBits);
+
+  const float rn = rcp_rn(nrm);
+  float q[4];
+  q[0] = bitsf(fbits(div_by_rcp(x, nrm, rn)) ^ ((flipBits & 1u) << 31));
+  q[1] = bitsf(fbits(div_by_rcp(y, nrm, rn)) ^ ((flipBits & 2u) << 30));
+  q[2] = bitsf(fbits(div_by_rcp(z, nrm, rn)) ^ ((flipBits & 4u) << 29));
+  q[3] = div_by_rcp(w, nrm, rn);
+  float a[4];
+  uint32_t sgn[4], field[4];  // q < 0 as bit 9, and that bit over the 9-bit magnitude
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    a[i] = bitsf(fbits(q[i]) & 0x7fffffffu);
+    sgn[i] = q[i] < 0.0f ? 512u : 0u;
+    // <= 511 for every component but the largest (a <= sqrt1_2 * (1 + 2^-21)), whose field is not stored
+    field[i] = f2u_rz(add(mul(511.0f, div_by_sqrt1_2(a[i])), 0.5f)) | sgn[i];
+  }
+  uint32_t big = 0;
+  float best = a[0];
+#pragma unroll
+  for (uint32_t i = 1; i < 4; i++) {
+    if (a[i] > best) { best = a[i]; big = i; }  // strict >: first index of the maximum (ref :227)
+  }
+  const uint32_t negate = big == 0 ? sgn[0] : big == 1 ? sgn[1] : big == 2 ? sgn[2] : sgn[3];  // q[big] < 0: kept signs are relative to it
+  const uint32_t first = big == 0 ? field[1] : field[0];
+  const uint32_t second = big <= 1 ? field[2] : field[1];
+  const uint32_t third = big == 3 ? field[2] : field[3];
+  return (big << 30) | ((first ^ negate) << 20) | ((second ^ negate) << 10) | (third ^ negate);
 }
 
 // ---- decode-side dequantizers ---------------------------------------------------------------

@@ -46,8 +46,10 @@ def emul():
     src = os.path.join(here, "quant_host.cc")
     hdrs = [os.path.join(ROOT, "spz_b200", "csrc", h) for h in ("codec_math.cuh", "record_align.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in [src] + hdrs):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-frounding-math",
-                        "-Wno-unknown-pragmas", "-shared", "-fPIC", src, "-o", so], check=True)
+        # -mfma only turns std::fmaf into the hardware instruction (exact either way, 20x faster); contraction stays off
+        fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read().split("flags", 1)[-1].split("\n", 1)[0].split() else []
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-frounding-math"] + fma +
+                       ["-Wno-unknown-pragmas", "-shared", "-fPIC", src, "-o", so], check=True)
     return ctypes.CDLL(so)
 
 

@@ -127,3 +127,64 @@ int emul_load_records(int B, int64_t n, const uint32_t *plane, uint8_t *records)
   }
 }
 }
+
+// ---- div_by_rcp (codec_math.cuh) against the plain IEEE division ---------------------------------------
+namespace {
+inline uint64_t splitmix(uint64_t &s) {
+  uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+}  // namespace
+
+extern "C" {
+// Pseudo-random operand pairs from the domain quant_rotation_smallest3's guard admits: divisor b (the
+// norm) in [2^-20, 2^20] with a significand that is not all ones, dividend x = 0 or 2^-60 <= |x| <=
+// b * (1 + 2^-21).  Returns the number of quotients that differ from x / b; the first offender's bits
+// go to bad[0..1].
+int64_t emul_check_div_by_rcp_random(uint64_t seed, int64_t count, uint32_t *bad) {
+  int64_t wrong = 0;
+  uint64_t s = seed;
+  for (int64_t i = 0; i < count; i++) {
+    const uint64_t r = splitmix(s), r2 = splitmix(s);
+    uint32_t mant = (uint32_t)r & 0x7fffffu;
+    if (mant == 0x7fffffu) mant = 0x7ffffeu;
+    const uint32_t be = 107u + (uint32_t)((r >> 23) % 41u);  // exponent of 2^-20 .. 2^20
+    const float b = bitsf((be << 23) | mant);
+    // dividend: random significand, exponent anywhere from 2^-60 up to b's; some exactly at the top
+    uint32_t xe = 67u + (uint32_t)((r2 >> 23) % (be - 67u + 1u));
+    if (((r2 >> 40) & 3u) == 0) xe = be;  // a quarter of the pairs near |x| ~ b, where the quotient is near 1
+    float x = bitsf((xe << 23) | ((uint32_t)r2 & 0x7fffffu) | ((uint32_t)(r2 >> 63) << 31));
+    if (std::fabs(x) > b * 1.0000005f) x = bitsf((fbits(x) & 0x80000000u) | fbits(b));
+    if (((r2 >> 44) & 1023u) == 0) x = bitsf((uint32_t)(r2 >> 63) << 31);  // +-0
+    volatile float want = x / b;
+    const float got = div_by_rcp(x, b, rcp_rn(b));
+    const float w = want;
+    const bool same = fbits(got) == fbits(w) || (got == 0.0f && w == 0.0f);  // the sign of a zero quotient is not used
+    if (!same) {
+      if (wrong == 0 && bad) { bad[0] = fbits(x); bad[1] = fbits(b); }
+      wrong++;
+    }
+  }
+  return wrong;
+}
+
+// Every float a with bits in [lo, hi] divided by the constant sqrt1_2 through its precomputed
+// reciprocal, against a / sqrt1_2.
+int64_t emul_check_div_by_sqrt1_2(uint32_t lo, uint32_t hi, uint32_t *bad) {
+  const float c = 0.70710678118654752440f;
+  int64_t wrong = 0;
+  for (uint64_t u = lo; u <= hi; u++) {
+    const float a = bitsf((uint32_t)u);
+    volatile float want = a / c;
+    const float got = div_by_sqrt1_2(a);
+    const float w = want;
+    if (fbits(got) != fbits(w)) {
+      if (wrong == 0 && bad) bad[0] = (uint32_t)u;
+      wrong++;
+    }
+  }
+  return wrong;
+}
+}

@@ -250,3 +250,18 @@ def test_record_realignment(emul, nbytes):
     back = np.zeros(n * nbytes, np.uint8)
     assert emul.emul_load_records(C.c_int(nbytes), C.c_int64(n), plane.ctypes.data_as(_u32p), back.ctypes.data_as(_u8p)) == 0
     assert np.array_equal(back, records), nbytes
+
+
+def test_division_through_the_reciprocal_is_the_ieee_quotient(emul):
+    """codec_math.cuh: div_by_rcp (two FMA residual corrections on x * RN(1/b)) against x / b: every
+    float in [2^-81, 1.01] and 0 for the constant divisor sqrt1_2 (the magnitudes of the smallest-three
+    packer), and 2^27 random pairs from the domain the rotation quantizer's guard admits."""
+    bad = np.zeros(2, np.uint32)
+    emul.emul_check_div_by_sqrt1_2.restype = C.c_int64
+    emul.emul_check_div_by_rcp_random.restype = C.c_int64
+    lo, hi = int(np.float32(2.0 ** -81).view(np.uint32)), int(np.float32(1.01).view(np.uint32))
+    assert emul.emul_check_div_by_sqrt1_2(C.c_uint32(lo), C.c_uint32(hi), bad.ctypes.data_as(_u32p)) == 0, hex(bad[0])
+    assert emul.emul_check_div_by_sqrt1_2(C.c_uint32(0), C.c_uint32(0), bad.ctypes.data_as(_u32p)) == 0
+    for seed in (1, 2):
+        wrong = emul.emul_check_div_by_rcp_random(C.c_uint64(seed), C.c_int64(1 << 26), bad.ctypes.data_as(_u32p))
+        assert wrong == 0, (wrong, hex(bad[0]), hex(bad[1]))
