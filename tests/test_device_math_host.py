@@ -149,6 +149,23 @@ def test_rotations_encode(emul, oracle):
         assert bad.size == 0, (frm, bad[:5], rot.reshape(-1, 4)[bad[:5]])
 
 
+def test_rotations_encode_guard_boundaries(emul, oracle):
+    """The fast path of quant_rotation_smallest3 and its fallback meet exactly at the guard: quaternions on
+    and around every boundary of it, against the oracle."""
+    from spz_b200.codec import flip_bits
+    from util import rotation_guard_stress
+    rng = np.random.default_rng(12)
+    n = 400000
+    rot = rotation_guard_stress(rng, n)
+    for frm in (0, 7):
+        _, fq, _ = flip_bits(frm, 4)
+        got = np.zeros(n, np.uint32)
+        emul.emul_rotations(C.c_int64(n), rot.ctypes.data_as(_f32p), C.c_uint32(fq), got.ctypes.data_as(_u32p))
+        want = oracle.pack(_rot_cloud(rot), frm).rotations.view("<u4")
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, (frm, bad[:5], rot.reshape(-1, 4)[bad[:5]])
+
+
 def test_rotations_decode_all_streams(emul, oracle):
     """Every 30-bit payload class: all 2^20 combos of two fields with the third random, x 4 index."""
     rng = np.random.default_rng(13)

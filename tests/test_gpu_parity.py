@@ -420,6 +420,22 @@ def test_rotation_decode_first_three_exhaustive(gpu_ctx, oracle):
     assert np.array_equal(bits(got.rotations), bits(want.rotations))
 
 
+def test_rotation_encode_guard_boundaries(gpu_ctx, oracle):
+    """As tests/test_device_math_host.py::test_rotations_encode_guard_boundaries, on the device: the
+    Markstein-quotient fast path of the smallest-three packer and the general form behind its guard."""
+    from util import rotation_guard_stress
+    rng = np.random.default_rng(78)
+    n = 2_000_000
+    rot = rotation_guard_stress(rng, n)
+    z3, z1 = np.zeros(3 * n, np.float32), np.zeros(n, np.float32)
+    c = Cloud(n, 0, z3, z3, rot, z1, z3, np.zeros(0, np.float32))
+    for frm in (0, 5, 8):
+        got = gpu_pack(gpu_ctx, c, frm)
+        want = oracle.pack(c, frm)
+        bad = np.flatnonzero(got.rotations.view("<u4") != want.rotations.view("<u4"))
+        assert bad.size == 0, (frm, bad[:5], rot.reshape(-1, 4)[bad[:5]])
+
+
 def test_rotation_encode_decode_large_random(gpu_ctx, oracle):
     rng = np.random.default_rng(77)
     n = 4_000_000 // 1260 * 1260

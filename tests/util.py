@@ -76,3 +76,35 @@ def cloud_to_ply_rows(c, names):
             cols[f"f_rest_{ch * d + s}"] = sh[:, s, ch]
     zero = np.zeros(n, np.float32)
     return np.ascontiguousarray(np.stack([cols.get(k, zero) for k in names], axis=1), np.float32)
+
+
+def rotation_guard_stress(rng, n):
+    """4n floats of quaternions that sit on and around the boundaries of quant_rotation_smallest3's fast-path
+    guard (codec_math.cuh): squared norms near 2^-40 and 2^40, components near 2^-60 and denormal, exact
+    and negative zeros, norms whose significand is all ones, near-ties between components, components at
+    sqrt(1/2) where the 9-bit magnitude saturates, plus plain random ones at assorted scales."""
+    q = rng.normal(size=(n, 4)).astype(np.float32)
+    k = n // 10
+    scale = np.ones(n, np.float32)
+    scale[0 * k:1 * k] = np.float32(2.0) ** rng.uniform(-21, -19, k).astype(np.float32)      # n2 around 2^-40
+    scale[1 * k:2 * k] = np.float32(2.0) ** rng.uniform(19, 21, k).astype(np.float32)        # n2 around 2^40
+    scale[2 * k:3 * k] = np.float32(2.0) ** rng.integers(-70, 60, k).astype(np.float32)
+    q *= scale[:, None]
+    tiny = np.float32(2.0) ** rng.uniform(-62, -58, k).astype(np.float32)                     # components around 2^-60
+    q[3 * k:4 * k, rng.integers(0, 4, k)] = 0
+    q[3 * k:4 * k, 0] = tiny * np.where(rng.random(k) < 0.5, -1, 1).astype(np.float32)
+    q[4 * k:5 * k, 1] = np.float32(1e-42) * rng.integers(-5, 6, k).astype(np.float32)         # denormal component
+    z = rng.integers(0, 4, k)
+    q[np.arange(5 * k, 6 * k), z] = np.where(rng.random(k) < 0.5, -0.0, 0.0).astype(np.float32)
+    # norm with an all-ones significand: a single non-zero component of that value
+    ones = ((rng.integers(100, 150, k).astype(np.uint32) << 23) | np.uint32(0x7fffff)).view(np.float32)
+    q[6 * k:7 * k] = 0
+    q[np.arange(6 * k, 7 * k), rng.integers(0, 4, k)] = ones * np.where(rng.random(k) < 0.5, -1, 1).astype(np.float32)
+    # near-ties for the largest component and the sqrt(1/2) saturation point
+    base = rng.normal(size=k).astype(np.float32)
+    q[7 * k:8 * k, 0] = base
+    q[7 * k:8 * k, 2] = np.nextafter(base, np.float32(np.inf)) * np.where(rng.random(k) < 0.5, -1, 1).astype(np.float32)
+    q[8 * k:9 * k] = 0
+    q[8 * k:9 * k, 1] = rng.normal(size=k).astype(np.float32)
+    q[8 * k:9 * k, 3] = q[8 * k:9 * k, 1] * np.where(rng.random(k) < 0.5, -1, 1).astype(np.float32)
+    return np.ascontiguousarray(q.reshape(-1))
