@@ -211,6 +211,37 @@ def test_kernels_write_only_their_planes(gpu_ctx, oracle, deg):
             assert np.array_equal(bits(b[pad:pad + n * w].cpu().numpy()), bits(exp)), (n, name)
 
 
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+@pytest.mark.parametrize("extra", [False, True])
+def test_ply_kernels_write_only_their_planes(gpu_ctx, oracle, deg, extra):
+    """Guard bands around every output of the fused PLY-rows kernels -- the bulk-copy kernels of the canonical
+    property order (extra=False) and the column-map kernels (an extra column makes the layout non-canonical) --
+    for sizes on both sides of every tile size in use (64 .. 512 gaussians) and odd remainders."""
+    from spz_b200.codec import PackedPlanes, byte_plane_widths, ply_property_names
+    from util import cloud_to_ply_rows
+    t = _torch()
+    rng = np.random.default_rng(3600 + 2 * deg + extra)
+    names = ply_property_names(deg) + (["extra"] if extra else [])
+    w, pad = len(names), 4096
+    for n in (1, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 3 * 512 + 77):
+        c = random_cloud(rng, n, deg, False)
+        rows = cloud_to_ply_rows(c, names).reshape(-1)
+        want = oracle.pack(c, 6)
+        bufs = [t.full((n * bw + 2 * pad,), 0xA5, dtype=t.uint8, device="cuda") for bw in byte_plane_widths(deg, 3)]
+        out = PackedPlanes(n, deg, *[b[pad:pad + n * bw] for b, bw in zip(bufs, byte_plane_widths(deg, 3))])
+        gpu_ctx.encode_ply_device(t.from_numpy(rows).cuda(), n, names, deg, 6, out=out)
+        t.cuda.synchronize()
+        for name, b, bw, exp in zip(PLANES, bufs, byte_plane_widths(deg, 3), want.planes()):
+            assert bool((b[:pad] == 0xA5).all()) and bool((b[pad + n * bw:] == 0xA5).all()), (n, name, "PLY encode wrote outside its plane")
+            assert np.array_equal(b[pad:pad + n * bw].cpu().numpy(), exp), (n, name)
+        fb = t.full((n * w + 2 * pad,), float("nan"), dtype=t.float32, device="cuda")
+        gpu_ctx.decode_ply_device(to_dev_packed(want), names, 8, out=fb[pad:pad + n * w])
+        t.cuda.synchronize()
+        assert bool(t.isnan(fb[:pad]).all()) and bool(t.isnan(fb[pad + n * w:]).all()), (n, "PLY decode wrote outside its records")
+        exp = cloud_to_ply_rows(oracle.unpack(want, 8), names).reshape(-1)
+        assert np.array_equal(bits(fb[pad:pad + n * w].cpu().numpy()), bits(exp)), n
+
+
 @pytest.mark.parametrize("env", [{"SPZB200_GRID": "persistent"}, {"SPZB200_GRID": "persistent", "SPZB200_CTAS_PER_SM": "1"},
                                  {"SPZB200_DECODE": "direct"}, {"SPZB200_ENCODE": "bulk"}, {"SPZB200_ENCODE": "bulk", "SPZB200_GRID": "persistent"},
                                  {"SPZB200_PACK": "alu"}, {"SPZB200_PLY": "mapped"}])
