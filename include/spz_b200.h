@@ -229,6 +229,15 @@ int spzb200_build_tables(float alpha_thresholds[256], float alpha_lut[256]);
 int spzb200_info(const SpzB200Context *ctx, int32_t *sm_count, int32_t *pack_mode,
                  int64_t *kernel_launches);
 
+/* Self-check on the device of the two division identities the smallest-three packer uses in place of
+ * IEEE divisions (spz_b200/csrc/codec_math.cuh: div_by_sqrt1_2, div_by_rcp).  part 0: a / sqrt1_2 for
+ * every float in {0} U [2^-81, 1.01]; part 1: x / b on pseudo-random operand pairs of the domain the
+ * packer's guard admits, pairs_per_thread of them on each of sm_count * 2048 threads.  *wrong receives
+ * the number of quotients that differ from the device's IEEE division in any bit (0 is the only
+ * acceptable answer), *checked the number compared. */
+int spzb200_selfcheck_division(SpzB200Context *ctx, int32_t part, uint64_t pairs_per_thread, uint64_t seed,
+                               uint64_t *wrong, uint64_t *checked);
+
 /* Test hooks: force the scalar kernels (1) / restore (0); choose the byte packer. */
 void spzb200_set_force_generic(SpzB200Context *ctx, int32_t on);
 void spzb200_set_pack_mode(SpzB200Context *ctx, int32_t mode);

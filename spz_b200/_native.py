@@ -72,6 +72,7 @@ SIGNATURES = {
     "spzb200_flip_bits": (None, [C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "spzb200_get_tables": (C.c_int, [C.c_void_p, _f32p, _f32p]),
     "spzb200_build_tables": (C.c_int, [_f32p, _f32p]),
+    "spzb200_selfcheck_division": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "spzb200_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "spzb200_set_force_generic": (None, [C.c_void_p, C.c_int32]),
     "spzb200_set_pack_mode": (None, [C.c_void_p, C.c_int32]),

@@ -283,6 +283,12 @@ class Context:
     def set_chunk_points(self, points: int):
         N.lib().spzb200_set_chunk_points(self._h, int(points))
 
+    def selfcheck_division(self, part: int, pairs_per_thread: int = 0, seed: int = 1):
+        """(wrong, checked) of spzb200_selfcheck_division: the quotients of the rotation packer against the device's IEEE division."""
+        wrong, checked = C.c_uint64(0), C.c_uint64(0)
+        N.check(N.lib().spzb200_selfcheck_division(self._h, int(part), int(pairs_per_thread), int(seed), C.byref(wrong), C.byref(checked)))
+        return int(wrong.value), int(checked.value)
+
     def set_host_staging(self, bounce: int = 1, copy_threads: int = 0):
         """bounce: 0 never, 1 auto (large calls), 2 always -- see spzb200_set_host_staging."""
         N.lib().spzb200_set_host_staging(self._h, int(bounce), int(copy_threads))

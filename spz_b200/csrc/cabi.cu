@@ -1104,6 +1104,19 @@ int spzb200_info(const SpzB200Context *ctx, int32_t *sm_count, int32_t *pack_mod
   return SPZB200_OK;
 }
 
+int spzb200_selfcheck_division(SpzB200Context *ctx, int32_t part, uint64_t pairs_per_thread, uint64_t seed, uint64_t *wrong,
+                               uint64_t *checked) {
+  if (!ctx || !wrong) return fail(SPZB200_ERR_INVALID, "spzb200_selfcheck_division: null argument");
+  if (part != 0 && part != 1) return fail(SPZB200_ERR_INVALID, "spzb200_selfcheck_division: part %d", (int)part);
+  CU(cudaSetDevice(ctx->device));
+  unsigned long long w = 0, c = 0;
+  CU(spzb200::divisionSelfCheck(part, pairs_per_thread, seed, ctx->smCount, ctx->stage[0].stream, &w, &c));
+  ctx->kernelLaunches += 1;
+  *wrong = w;
+  if (checked) *checked = c;
+  return SPZB200_OK;
+}
+
 void spzb200_set_force_generic(SpzB200Context *ctx, int32_t on) { if (ctx) ctx->forceGeneric = on != 0; }
 void spzb200_set_pack_mode(SpzB200Context *ctx, int32_t mode) {
   if (ctx) ctx->packMode = (mode && ctx->cvtPackOk) ? spzb200::kPackCvt : spzb200::kPackAlu;

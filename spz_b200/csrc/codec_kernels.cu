@@ -822,6 +822,66 @@ cudaError_t buildDecodeTables(float *tables, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// Self-check of the two division identities the rotation quantizer rests on (codec_math.cuh), on the
+// device's own FMA / reciprocal / division units.  part 0: a / sqrt1_2 for every float a in
+// {0} U [2^-81, 1.01] (thread i takes bit patterns i, i + threads, ...); part 1: x / b for
+// `count` pseudo-random pairs of the guard's domain per thread.  Counts quotients that differ in any bit.
+namespace {
+__device__ __forceinline__ uint64_t splitmixStep(uint64_t &s) {
+  uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+__global__ void divisionSelfCheckKernel(int part, uint64_t count, uint64_t seed, unsigned long long *wrong) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, threads = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  if (part == 0) {
+    const uint32_t lo = 0x17000000u /* 2^-81 */, hi = 0x3f8147aeu /* 1.01f */;
+    for (uint64_t u = (uint64_t)lo + tid; u <= hi; u += threads) {
+      const float a = __uint_as_float((uint32_t)u);
+      bad += __float_as_uint(m::div_by_sqrt1_2(a)) != __float_as_uint(__fdiv_rn(a, 0.70710678118654752440f));
+    }
+    if (tid == 0) bad += __float_as_uint(m::div_by_sqrt1_2(0.0f)) != 0u;
+  } else {
+    uint64_t s = seed ^ (tid * 0xd1342543de82ef95ull);
+    for (uint64_t i = 0; i < count; i++) {
+      const uint64_t r = splitmixStep(s), r2 = splitmixStep(s);
+      uint32_t mant = (uint32_t)r & 0x7fffffu;
+      if (mant == 0x7fffffu) mant = 0x7ffffeu;                  // the guard sends all-ones significands to the general form
+      const uint32_t be = 107u + (uint32_t)((r >> 23) % 41u);   // b in [2^-20, 2^21)
+      const float b = __uint_as_float((be << 23) | mant);
+      uint32_t xe = 67u + (uint32_t)((r2 >> 23) % (be - 67u + 1u));  // |x| from 2^-60 up to b's binade
+      if (((r2 >> 40) & 3u) == 0) xe = be;
+      float x = __uint_as_float((xe << 23) | ((uint32_t)r2 & 0x7fffffu) | ((uint32_t)(r2 >> 63) << 31));
+      if (fabsf(x) > __fmul_rn(b, 1.0000005f)) x = __uint_as_float((__float_as_uint(x) & 0x80000000u) | __float_as_uint(b));
+      const float got = m::div_by_rcp(x, b, m::rcp_rn(b)), want = __fdiv_rn(x, b);
+      bad += __float_as_uint(got) != __float_as_uint(want);
+    }
+  }
+  if (bad) atomicAdd(wrong, bad);
+}
+}  // namespace
+
+cudaError_t divisionSelfCheck(int part, unsigned long long pairsPerThread, unsigned long long seed, int smCount, cudaStream_t stream,
+                              unsigned long long *wrong, unsigned long long *checked) {
+  unsigned long long *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof *d);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(d, 0, sizeof *d, stream);
+  const int blocks = smCount * 8, threads = 256;
+  if (e == cudaSuccess) {
+    divisionSelfCheckKernel<<<blocks, threads, 0, stream>>>(part, pairsPerThread, seed, d);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(wrong, d, sizeof *d, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d);
+  if (checked) *checked = part == 0 ? (unsigned long long)(0x3f8147aeu - 0x17000000u) + 2ull : pairsPerThread * (unsigned long long)blocks * threads;
+  return e;
+}
+
 cudaError_t probePackCvt(cudaStream_t stream, int *ok) {
   int *d = nullptr;
   cudaError_t e = cudaMalloc(&d, sizeof(int));

@@ -98,6 +98,10 @@ int tileGaussians(int shDim);
 // load-spz.cc:367); tables[0, 256) is uploaded by the caller.
 cudaError_t buildDecodeTables(float *tables, cudaStream_t stream);
 
+// Device self-check of the division identities of the rotation quantizer (see divisionSelfCheckKernel).
+cudaError_t divisionSelfCheck(int part, unsigned long long pairsPerThread, unsigned long long seed, int smCount, cudaStream_t stream,
+                              unsigned long long *wrong, unsigned long long *checked);
+
 // Runs both byte packers on probe values; *ok = 1 when cvt.pack.sat.u8.s32.b32 orders and
 // saturates bytes the way the kernels assume (decided once per context).
 cudaError_t probePackCvt(cudaStream_t stream, int *ok);

@@ -451,6 +451,17 @@ def test_rotation_decode_first_three_exhaustive(gpu_ctx, oracle):
     assert np.array_equal(bits(got.rotations), bits(want.rotations))
 
 
+def test_division_identities_on_the_device(gpu_ctx):
+    """The quotients the smallest-three packer computes without a division (codec_math.cuh: one shared
+    reciprocal + FMA residual corrections) equal the device's IEEE division bit for bit: exhaustively for
+    the constant divisor sqrt1_2, and on 4e10 pseudo-random operand pairs of the guarded domain."""
+    wrong, checked = gpu_ctx.selfcheck_division(0)
+    assert wrong == 0 and checked == 0x3f8147ae - 0x17000000 + 2, (wrong, checked)  # 6.8e8 floats
+    for seed in (1, 2):
+        wrong, checked = gpu_ctx.selfcheck_division(1, 1 << 16, seed)
+        assert wrong == 0 and checked >= 148 * 2048 * (1 << 16), (wrong, checked)
+
+
 def test_rotation_encode_guard_boundaries(gpu_ctx, oracle):
     """As tests/test_device_math_host.py::test_rotations_encode_guard_boundaries, on the device: the
     Markstein-quotient fast path of the smallest-three packer and the general form behind its guard."""
