@@ -220,7 +220,7 @@ struct SpzB200Context {
   bool forceGeneric = false;
   int ctasPerSm = 0;
   int bounceMode = 1;     // pageable planes: 0 never bounce, 1 bounce large calls (see bounceMinBytes), 2 always
-  size_t bounceMinBytes = (size_t)256 << 20;  // steady state the bounce path is 2-4x faster at every size; below this the one-time pinned allocation is not worth it for a one-shot call
+  size_t bounceMinBytes = (size_t)32 << 20;  // steady state the bounce path is 2-4x faster from ~100K gaussians up; the one-time pinned allocation (tens of ms at these sizes) is small next to CUDA initialisation
   bool encodeBulk = false;  // SPZB200_ENCODE=bulk: planar encoder through the bulk-copy per-gaussian kernel (measured slower, kept as evidence)
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
   bool decodeBulk = true;  // SH plane of the decoder staged with bulk async copies (SPZB200_DECODE=direct: registers)
@@ -413,6 +413,8 @@ int runPipeline(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, lo
                           (ctx->bounceMode == 1 && (callBytes >= ctx->bounceMinBytes || ctx->stage[0].hIn || ctx->stage[0].hOut));
   const bool bounceIn = n > 0 && wantBounce && isPageable(in.ptr[0]);
   const bool bounceOut = n > 0 && wantBounce && isPageable(out.ptr[0]);
+  // (cutting a bounced cloud smaller than a few ranges into ~6 pieces for overlap was tried: the per-range costs --
+  // waking the copy pool, 12 copies, 4 events -- outweigh the overlap: 200K points 7.9 vs 5.1 ms, 1M 12.6 vs 10.2)
   const long long want = (bounceIn || bounceOut) ? ctx->pageableChunkPoints : ctx->chunkPoints;
   long long chunk = std::max<long long>(granule, want / granule * granule);
   if (chunk > n) chunk = std::max<long long>(n, 1);
