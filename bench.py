@@ -538,7 +538,9 @@ def run_b200_arm(args):
         # per-kernel roofline on this rank's shard (rank 0's durations; all shards are equal-sized)
         enc_gbs = alg_bytes * n / (enc_ms * 1e-3) / 1e9
         dec_gbs = alg_bytes * n / (dec_ms * 1e-3) / 1e9
-        dec_kernel = "decodeTilesBulkKernel" if deg > 0 and os.environ.get("SPZB200_DECODE") != "direct" else "decodeTilesKernel"
+        dec_env = os.environ.get("SPZB200_DECODE")
+        dec_kernel = ("decodeTilesKernel" if deg == 0 or dec_env == "direct" else
+                      "decodeTilesBulkKernel" if deg == 2 or dec_env == "bulk" else "decodePerGaussianKernel")
         dom = ("encodeTilesKernel", enc_gbs, enc_ms) if enc_ms >= dec_ms else (dec_kernel, dec_gbs, dec_ms)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -222,6 +222,7 @@ struct SpzB200Context {
   int bounceMode = 1;     // pageable planes: 0 never bounce, 1 bounce large calls (see bounceMinBytes), 2 always
   size_t bounceMinBytes = (size_t)32 << 20;  // steady state the bounce path is 2-4x faster from ~100K gaussians up; the one-time pinned allocation (tens of ms at these sizes) is small next to CUDA initialisation
   bool encodeBulk = false;  // SPZB200_ENCODE=bulk: planar encoder through the bulk-copy per-gaussian kernel (measured slower, kept as evidence)
+  int decodePerGaussian = 1;  // SPZB200_DECODE=pergaussian: 2 (also SH-less clouds); =bulk / =direct: 0 (tile kernels only)
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
   bool decodeBulk = true;  // SH plane of the decoder staged with bulk async copies (SPZB200_DECODE=direct: registers)
   bool flatGrid = true;  // one CTA per tile: the block scheduler keeps the tile frontier compact
@@ -315,6 +316,7 @@ spzb200::LaunchPlan planOf(const SpzB200Context *ctx) {
   p.flatGrid = ctx->flatGrid;
   p.decodeBulk = ctx->decodeBulk;
   p.plyMapped = ctx->plyMapped;
+  p.decodePerGaussian = ctx->decodePerGaussian;
   p.encodeBulk = ctx->encodeBulk;
   return p;
 }
@@ -718,7 +720,10 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   }
   if (const char *env = std::getenv("SPZB200_CTAS_PER_SM")) ctx->ctasPerSm = std::atoi(env);
   if (const char *env = std::getenv("SPZB200_BOUNCE_MIN_MB")) ctx->bounceMinBytes = (size_t)std::atoll(env) << 20;
-  if (const char *env = std::getenv("SPZB200_DECODE")) ctx->decodeBulk = std::strcmp(env, "direct") != 0;
+  if (const char *env = std::getenv("SPZB200_DECODE")) {
+    ctx->decodeBulk = std::strcmp(env, "direct") != 0;
+    ctx->decodePerGaussian = std::strcmp(env, "pergaussian") == 0 ? 2 : (std::strcmp(env, "bulk") == 0 || std::strcmp(env, "direct") == 0) ? 0 : 1;
+  }
   if (const char *env = std::getenv("SPZB200_ENCODE")) ctx->encodeBulk = std::strcmp(env, "bulk") == 0;
   if (const char *env = std::getenv("SPZB200_PLY")) ctx->plyMapped = std::strcmp(env, "mapped") == 0;
   if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = std::strcmp(env, "persistent") != 0;

@@ -74,6 +74,8 @@ struct LaunchPlan {
   bool flatGrid;       // one CTA per tile (default) instead of persistent grid-stride CTAs
   bool decodeBulk;     // decode the SH plane through bulk async copies (TMA) instead of registers
   bool encodeBulk;     // planar encoder through the one-thread-per-gaussian bulk-copy kernel instead of the register-path tiles (default off: slower)
+  int decodePerGaussian;   // planar decoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it
+                           // measured faster (SH degree 1 and 3; default), 2 wherever it exists (all but degree 2)
   bool plyMapped;      // test hook: PLY rows always through the column-map kernels, never the canonical-layout ones
 };
 
@@ -89,6 +91,7 @@ int plyTileGaussians();
 // canonical property order only (pergaussian_kernels.cu); *done = leading gaussians handled
 cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done);
 cudaError_t launchEncodePerGaussianPlanar(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done);
+cudaError_t launchDecodePerGaussianPlanar(const DecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done);
 cudaError_t launchDecodePlyCanonical(const PlyDecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done);
 
 // Gaussians per tile of the vector kernels for a given shDim (the sharding granule).

@@ -18,7 +18,7 @@
 //     word strides, conflict free).  Opt-in (SPZB200_ENCODE=bulk): six copies of 0.5 - 23 KB per tile
 //     sustain less than the register-path tiles of codec_kernels.cu (6357 vs 6853 GB/s at degree 3),
 //     unlike the single 31.7 KB copy of the rows source (7145 GB/s); profiles/r1_tuning_notes.txt.
-//   packed -> rows (decodePlyCanonKernel): the mirror image; six bulk loads bring the tile's packed
+//   packed -> rows (decodePerGaussianKernel<RowsSink>): the mirror image; six bulk loads bring the tile's packed
 //     planes in, thread g expands gaussian g into record g of the shared-memory tile, one bulk
 //     async store writes the records.
 //
@@ -36,16 +36,6 @@
 
 namespace spzb200 {
 namespace {
-
-// Build-time knobs kept so scripts/ can time the alternatives; both were measured and lost
-// (profiles/r1_tuning_notes.txt): decode tables copied to shared memory instead of read through L1
-// (-4 %), one bulk store per warp instead of per CTA (-2 %).
-#ifndef SPZ_PLYC_TAB_SMEM
-#define SPZ_PLYC_TAB_SMEM 0
-#endif
-#ifndef SPZ_PLYC_WARP_STORE
-#define SPZ_PLYC_WARP_STORE 0
-#endif
 
 template <int D, int G_>
 struct Canon {
@@ -257,31 +247,83 @@ encodePerGaussianKernel(const typename Src::Args a, const long long numTiles) {
 // =================================================================================================
 // packed -> rows:  saveSplatToPly(unpackGaussians(in, to = X), from = X)'s vertex records, load-spz.cc:467-531 + :858-890
 // =================================================================================================
+// Two sinks for the same per-gaussian record rec[0..W) (canonical column order):
+//   RowsSink   -- .ply vertex records, one bulk store per tile
+//   PlanarSink -- the six GaussianCloud planes (unpackGaussians itself), six bulk stores per tile: the default
+//                 decoder at SH degree 1 and 3 (launchDecodePerGaussianPlanar)
 template <int D>
+struct RowsSink {
+  using Args = PlyDecodeArgs;
+  using C = typename DecGeo<D>::C;
+  static constexpr int kBytes = C::kRowBytes;
+  static __device__ __forceinline__ void write(unsigned char *buf, int t, const float (&rec)[C::W]) {
+    constexpr int W = C::W;
+    float *row = reinterpret_cast<float *>(buf) + t * W;
+    if constexpr (W % 2 == 0) {
+#pragma unroll
+      for (int j = 0; j < W / 2; j++) reinterpret_cast<float2 *>(row)[j] = make_float2(rec[2 * j], rec[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < W; c++) row[c] = rec[c];
+    }
+  }
+  static __device__ __forceinline__ void store(const Args &a, long long tile, const unsigned char *buf) {
+    bulkStore(a.rows + tile * (long long)(C::G * C::W), buf, kBytes);
+  }
+};
+
+template <int D>
+struct PlanarSink {
+  using Args = DecodeArgs;
+  using C = typename DecGeo<D>::C;
+  static constexpr int G = C::G;
+  static constexpr int oPos = 0, oScale = 12 * G, oRot = 24 * G, oAlpha = 40 * G, oColor = 44 * G, oSh = 56 * G;
+  static constexpr int kBytes = (56 + 12 * D) * G;
+  static __device__ __forceinline__ void write(unsigned char *buf, int t, const float (&rec)[C::W]) {
+    float *f = reinterpret_cast<float *>(buf);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      f[oPos / 4 + 3 * t + i] = rec[i];
+      f[oScale / 4 + 3 * t + i] = rec[C::kScale + i];
+      f[oColor / 4 + 3 * t + i] = rec[C::kColor + i];
+    }
+    reinterpret_cast<float4 *>(buf + oRot)[t] = make_float4(rec[C::kRot + 1], rec[C::kRot + 2], rec[C::kRot + 3], rec[C::kRot]);  // x, y, z, w
+    f[oAlpha / 4 + t] = rec[C::kAlpha];
+#pragma unroll
+    for (int k = 0; k < 3 * D; k++) f[oSh / 4 + 3 * D * t + k] = rec[C::kRest + (k % 3) * D + k / 3];
+  }
+  static __device__ __forceinline__ void store(const Args &a, long long tile, const unsigned char *buf) {
+    const long long g0 = tile * G;
+    bulkStore(a.oPositions + g0 * 3, buf + oPos, 12 * G);
+    bulkStore(a.oScales + g0 * 3, buf + oScale, 12 * G);
+    bulkStore(a.oRotations + g0 * 4, buf + oRot, 16 * G);
+    bulkStore(a.oAlphas + g0, buf + oAlpha, 4 * G);
+    bulkStore(a.oColors + g0 * 3, buf + oColor, 12 * G);
+    if constexpr (D > 0) bulkStore(a.oSh + g0 * (3 * D), buf + oSh, 12 * D * G);
+  }
+};
+
+template <int D, class Sink>
 __global__ void __launch_bounds__(DecGeo<D>::G, DecGeo<D>::CTAS)
-decodePlyCanonKernel(const PlyDecodeArgs a, const long long numTiles) {
+decodePerGaussianKernel(const typename Sink::Args a, const long long numTiles) {
   using C = typename DecGeo<D>::C;
   constexpr int W = C::W, kG = C::G;
   extern __shared__ __align__(128) unsigned char dynSmem[];
   __shared__ __align__(8) unsigned long long bar;
-  float *rows = reinterpret_cast<float *>(dynSmem);
-  unsigned char *in = dynSmem + C::kRowBytes;
+  unsigned char *in = dynSmem + Sink::kBytes;
   const int t = threadIdx.x;
   const bool half = a.version == 1 || a.version == 4;
   const bool s3 = a.version >= 3;
   const uint32_t posBytes = half ? 6 * kG : 9 * kG, rotBytes = s3 ? 4 * kG : 3 * kG;
-#if SPZ_PLYC_TAB_SMEM
-  __shared__ __align__(16) float tab[kDecodeTableFloats];
-  for (int i = t; i < kDecodeTableFloats / 4; i += kG) reinterpret_cast<float4 *>(tab)[i] = __ldg(reinterpret_cast<const float4 *>(a.tables) + i);
-#else
-  const float *tab = a.tables;  // 4 KB, read through L1 (the bulk copies do not pass through it)
-#endif
+  // 4 KB of tables read through L1 (the bulk copies do not pass through it); copying them to shared
+  // memory per CTA measured 4 % slower
+  const float *tab = a.tables;
   if (t == 0) mbarInit(&bar);
   __syncthreads();
   uint32_t parity = 0;
   for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
     if (tile != blockIdx.x) {  // multi-tile CTAs only: the previous tile's store is done reading the records
-      if ((t & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncthreads();
     }
     if (t == 0) {
@@ -356,33 +398,15 @@ decodePlyCanonKernel(const PlyDecodeArgs a, const long long numTiles) {
             m::mul(m::add(magicByte(hv, k), -8388736.0f), signedConst(0.0078125f, (a.flipSh >> coef) & 1u));
       }
     }
-    {
-      float *row = rows + t * W;
-      if constexpr (W % 2 == 0) {
-#pragma unroll
-        for (int j = 0; j < W / 2; j++) reinterpret_cast<float2 *>(row)[j] = make_float2(rec[2 * j], rec[2 * j + 1]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < W; c++) row[c] = rec[c];
-      }
-    }
+    Sink::write(dynSmem, t, rec);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#if SPZ_PLYC_WARP_STORE
-    // a warp's 32 records are written by that warp alone: each warp sends its own as soon as it is done
-    __syncwarp();
-    if ((t & 31) == 0) {
-      bulkStore(a.rows + (tile * kG + t) * (long long)W, rows + t * W, 32 * W * 4);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-#else
-    __syncthreads();
+    __syncthreads();  // (one bulk store per warp instead, issued after __syncwarp, measured 2 % slower)
     if (t == 0) {
-      bulkStore(a.rows + tile * (long long)(kG * W), rows, C::kRowBytes);
+      Sink::store(a, tile, dynSmem);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-#endif
   }
-  if ((t & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -425,12 +449,23 @@ cudaError_t dispatchEncodePerGaussian(const Args &a, long long tiles, const Laun
   }
 }
 
-template <int D>
-cudaError_t launchDecodeCanon(const PlyDecodeArgs &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
-  constexpr int smem = DecGeo<D>::C::kSmemBytes;
+template <int D, class Sink>
+cudaError_t launchDecodePerGaussian(const typename Sink::Args &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+  constexpr int smem = Sink::kBytes + DecGeo<D>::C::kPackedBytes;
   static_assert(smem <= 48 * 1024, "above 48 KB the kernel would need cudaFuncAttributeMaxDynamicSharedMemorySize on every device");
-  decodePlyCanonKernel<D><<<gridFor(tiles, plan, DecGeo<D>::CTAS), DecGeo<D>::G, smem, s>>>(a, tiles);
+  decodePerGaussianKernel<D, Sink><<<gridFor(tiles, plan, DecGeo<D>::CTAS), DecGeo<D>::G, smem, s>>>(a, tiles);
   return cudaGetLastError();
+}
+
+template <template <int> class Sink, class Args>
+cudaError_t dispatchDecodePerGaussian(const Args &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+  switch (a.shDim) {
+    case 0: return launchDecodePerGaussian<0, Sink<0>>(a, tiles, plan, s);
+    case 3: return launchDecodePerGaussian<3, Sink<3>>(a, tiles, plan, s);
+    case 8: return launchDecodePerGaussian<8, Sink<8>>(a, tiles, plan, s);
+    case 15: return launchDecodePerGaussian<15, Sink<15>>(a, tiles, plan, s);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace
@@ -477,14 +512,25 @@ cudaError_t launchDecodePlyCanonical(const PlyDecodeArgs &a, const LaunchPlan &p
   const int G = decTileGaussians(a.shDim);
   const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
-  cudaError_t e;
-  switch (a.shDim) {
-    case 0: e = launchDecodeCanon<0>(a, tiles, plan, stream); break;
-    case 3: e = launchDecodeCanon<3>(a, tiles, plan, stream); break;
-    case 8: e = launchDecodeCanon<8>(a, tiles, plan, stream); break;
-    case 15: e = launchDecodeCanon<15>(a, tiles, plan, stream); break;
-    default: return cudaErrorInvalidValue;
-  }
+  const cudaError_t e = dispatchDecodePerGaussian<RowsSink>(a, tiles, plan, stream);
+  if (e == cudaSuccess) *done = tiles * G;
+  return e;
+}
+
+// unpackGaussians onto planar float planes through the same kernel (SH degrees 0, 1, 3); *done as above
+cudaError_t launchDecodePerGaussianPlanar(const DecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done) {
+  *done = 0;
+  // degree 2 (24-word lane stride: bank conflicts) has no per-gaussian form; SH-less clouds are faster through the
+  // register-path tiles (6.60 vs 5.90 TB/s), so they come here only when asked to (tests)
+  if (plan.forceGeneric || plan.decodePerGaussian == 0 || a.shDim == 8 || (a.shDim == 0 && plan.decodePerGaussian < 2)) return cudaSuccess;
+  if (!(aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) && aligned16(a.colors) &&
+        (a.shDim == 0 || aligned16(a.sh)) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) &&
+        aligned16(a.oAlphas) && aligned16(a.oColors) && (a.shDim == 0 || aligned16(a.oSh))))
+    return cudaSuccess;
+  const int G = decTileGaussians(a.shDim);
+  const long long tiles = a.n / G;
+  if (tiles == 0) return cudaSuccess;
+  const cudaError_t e = dispatchDecodePerGaussian<PlanarSink>(a, tiles, plan, stream);
   if (e == cudaSuccess) *done = tiles * G;
   return e;
 }
