@@ -540,7 +540,7 @@ def run_b200_arm(args):
         dec_gbs = alg_bytes * n / (dec_ms * 1e-3) / 1e9
         dec_env = os.environ.get("SPZB200_DECODE")
         dec_kernel = ("decodeTilesKernel" if deg == 0 or dec_env == "direct" else
-                      "decodeTilesBulkKernel" if deg == 2 or dec_env == "bulk" else "decodePerGaussianKernel")
+                      "decodeTilesBulkKernel" if dec_env == "bulk" else "decodePerGaussianKernel")
         dom = ("encodeTilesKernel", enc_gbs, enc_ms) if enc_ms >= dec_ms else (dec_kernel, dec_gbs, dec_ms)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

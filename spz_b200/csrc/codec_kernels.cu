@@ -26,11 +26,11 @@
 // keeps the set of pages being touched compact; persistent grid-stride CTAs drift apart over a
 // 100M-point cloud and lost 4-12 % (kept as the SPZB200_GRID=persistent knob).  The encoder works
 // from registers.  The tile decoder stages the SH plane -- three quarters of its bytes -- through
-// shared memory with bulk async copies (decodeTilesBulkKernel below).  At SH degree 1 and 3 (and
+// shared memory with bulk async copies (decodeTilesBulkKernel below).  At SH degree 1 - 3 (and
 // 16-byte aligned planes) launchDecode hands the cloud to the one-thread-per-gaussian bulk-copy
 // decoder of pergaussian_kernels.cu instead: as fast at 100M points, faster below (64 / 128
-// gaussians per CTA shorten a launch's ramp-up and tail); the tile decoders keep SH degree 0 and 2
-// and planes that are only 4-byte aligned.  The remainder (< one tile) and any call with
+// gaussians per CTA shorten a launch's ramp-up and tail); the tile decoders keep SH-less clouds
+// and planes that are only 4-byte aligned (SPZB200_DECODE=bulk / direct force them).  The remainder (< one tile) and any call with
 // under-aligned pointers goes to a scalar one-thread-per-gaussian kernel.
 //
 // HBM traffic is exactly the algorithmic 301 B per gaussian at SH degree 3 (236 B floats + 65 B
@@ -787,10 +787,11 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
                    aligned(a.oPositions, 16) && aligned(a.oScales, 16) &&
                    aligned(a.oRotations, 16) && aligned(a.oAlphas, 16) && aligned(a.oColors, 16) &&
                    (a.shDim == 0 || aligned(a.oSh, 16));
-  // SH degree 1 and 3, 16-byte aligned planes: one thread per gaussian, 64 / 128 gaussians per CTA, planes in and out
+  // SH degree 1 - 3, 16-byte aligned planes: one thread per gaussian, 64 / 128 gaussians per CTA, planes in and out
   // by bulk async copies (pergaussian_kernels.cu).  Equal to the tile kernels below at 100M points (6697 vs 6684 GB/s
   // at degree 3) and ahead of them on smaller clouds, whose launches are dominated by ramp-up and tail (1.25M points
-  // 5168 vs 4760; degree 1, 10M points 6373 vs 5463): profiles/r1_tuning_notes.txt.  Anything else falls through.
+  // 5168 vs 4760; degree 1, 10M points 6373 vs 5463; degree 2, 10M 6447 vs 6268): profiles/r1_tuning_notes.txt.
+  // Anything else falls through.
   long long pgDone = 0;
   if (cudaError_t e = launchDecodePerGaussianPlanar(a, plan, stream, &pgDone); e != cudaSuccess) return e;
   if (pgDone > 0) count++;

@@ -75,7 +75,7 @@ struct LaunchPlan {
   bool decodeBulk;     // decode the SH plane through bulk async copies (TMA) instead of registers
   bool encodeBulk;     // planar encoder through the one-thread-per-gaussian bulk-copy kernel instead of the register-path tiles (default off: slower)
   int decodePerGaussian;   // planar decoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it
-                           // measured faster (SH degree 1 and 3; default), 2 wherever it exists (all but degree 2)
+                           // measured faster (SH degree 1 - 3; default), 2 also for SH-less clouds
   bool plyMapped;      // test hook: PLY rows always through the column-map kernels, never the canonical-layout ones
 };
 

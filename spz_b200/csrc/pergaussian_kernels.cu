@@ -250,7 +250,7 @@ encodePerGaussianKernel(const typename Src::Args a, const long long numTiles) {
 // Two sinks for the same per-gaussian record rec[0..W) (canonical column order):
 //   RowsSink   -- .ply vertex records, one bulk store per tile
 //   PlanarSink -- the six GaussianCloud planes (unpackGaussians itself), six bulk stores per tile: the default
-//                 decoder at SH degree 1 and 3 (launchDecodePerGaussianPlanar)
+//                 decoder at SH degree 1, 2 and 3 (launchDecodePerGaussianPlanar)
 template <int D>
 struct RowsSink {
   using Args = PlyDecodeArgs;
@@ -289,8 +289,18 @@ struct PlanarSink {
     }
     reinterpret_cast<float4 *>(buf + oRot)[t] = make_float4(rec[C::kRot + 1], rec[C::kRot + 2], rec[C::kRot + 3], rec[C::kRot]);  // x, y, z, w
     f[oAlpha / 4 + t] = rec[C::kAlpha];
+    if constexpr ((3 * D) % 4 == 0) {
+      // degree 2: a lane stride of 24 words would be an 8-way bank conflict for 32-bit stores; 128-bit ones are 2-way
 #pragma unroll
-    for (int k = 0; k < 3 * D; k++) f[oSh / 4 + 3 * D * t + k] = rec[C::kRest + (k % 3) * D + k / 3];
+      for (int k = 0; k < 3 * D; k += 4) {
+        reinterpret_cast<float4 *>(buf + oSh)[(3 * D * t + k) / 4] =
+            make_float4(rec[C::kRest + (k % 3) * D + k / 3], rec[C::kRest + ((k + 1) % 3) * D + (k + 1) / 3],
+                        rec[C::kRest + ((k + 2) % 3) * D + (k + 2) / 3], rec[C::kRest + ((k + 3) % 3) * D + (k + 3) / 3]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3 * D; k++) f[oSh / 4 + 3 * D * t + k] = rec[C::kRest + (k % 3) * D + k / 3];
+    }
   }
   static __device__ __forceinline__ void store(const Args &a, long long tile, const unsigned char *buf) {
     const long long g0 = tile * G;
@@ -517,12 +527,11 @@ cudaError_t launchDecodePlyCanonical(const PlyDecodeArgs &a, const LaunchPlan &p
   return e;
 }
 
-// unpackGaussians onto planar float planes through the same kernel (SH degrees 0, 1, 3); *done as above
+// unpackGaussians onto planar float planes through the same kernel; *done as above
 cudaError_t launchDecodePerGaussianPlanar(const DecodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done) {
   *done = 0;
-  // degree 2 (24-word lane stride: bank conflicts) has no per-gaussian form; SH-less clouds are faster through the
-  // register-path tiles (6.60 vs 5.90 TB/s), so they come here only when asked to (tests)
-  if (plan.forceGeneric || plan.decodePerGaussian == 0 || a.shDim == 8 || (a.shDim == 0 && plan.decodePerGaussian < 2)) return cudaSuccess;
+  // SH-less clouds are faster through the register-path tiles (6.60 vs 5.90 TB/s), so they come here only when asked to (tests)
+  if (plan.forceGeneric || plan.decodePerGaussian == 0 || (a.shDim == 0 && plan.decodePerGaussian < 2)) return cudaSuccess;
   if (!(aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) && aligned16(a.colors) &&
         (a.shDim == 0 || aligned16(a.sh)) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) &&
         aligned16(a.oAlphas) && aligned16(a.oColors) && (a.shDim == 0 || aligned16(a.oSh))))
