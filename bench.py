@@ -541,7 +541,10 @@ def run_b200_arm(args):
         dec_env = os.environ.get("SPZB200_DECODE")
         dec_kernel = ("decodeTilesKernel" if deg == 0 or dec_env == "direct" else
                       "decodeTilesBulkKernel" if dec_env == "bulk" else "decodePerGaussianKernel")
-        dom = ("encodeTilesKernel", enc_gbs, enc_ms) if enc_ms >= dec_ms else (dec_kernel, dec_gbs, dec_ms)
+        enc_env = os.environ.get("SPZB200_ENCODE")
+        enc_kernel = ("encodePerGaussianKernel" if enc_env == "bulk" or (enc_env != "tiles" and deg == 3 and n <= 24_000_000)
+                      else "encodeTilesKernel")
+        dom = (enc_kernel, enc_gbs, enc_ms) if enc_ms >= dec_ms else (dec_kernel, dec_gbs, dec_ms)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -221,7 +221,7 @@ struct SpzB200Context {
   int ctasPerSm = 0;
   int bounceMode = 1;     // pageable planes: 0 never bounce, 1 bounce large calls (see bounceMinBytes), 2 always
   size_t bounceMinBytes = (size_t)32 << 20;  // steady state the bounce path is 2-4x faster from ~100K gaussians up; the one-time pinned allocation (tens of ms at these sizes) is small next to CUDA initialisation
-  bool encodeBulk = false;  // SPZB200_ENCODE=bulk: planar encoder through the bulk-copy per-gaussian kernel (measured slower, kept as evidence)
+  int encodeBulk = 1;  // planar encoder through the bulk-copy per-gaussian kernel: 1 = where faster (default); SPZB200_ENCODE=bulk: 2, =tiles: 0
   int decodePerGaussian = 1;  // SPZB200_DECODE=pergaussian: 2 (also SH-less clouds); =bulk / =direct: 0 (tile kernels only)
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
   bool decodeBulk = true;  // SH plane of the decoder staged with bulk async copies (SPZB200_DECODE=direct: registers)
@@ -724,7 +724,7 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
     ctx->decodeBulk = std::strcmp(env, "direct") != 0;
     ctx->decodePerGaussian = std::strcmp(env, "pergaussian") == 0 ? 2 : (std::strcmp(env, "bulk") == 0 || std::strcmp(env, "direct") == 0) ? 0 : 1;
   }
-  if (const char *env = std::getenv("SPZB200_ENCODE")) ctx->encodeBulk = std::strcmp(env, "bulk") == 0;
+  if (const char *env = std::getenv("SPZB200_ENCODE")) ctx->encodeBulk = std::strcmp(env, "bulk") == 0 ? 2 : std::strcmp(env, "tiles") == 0 ? 0 : 1;
   if (const char *env = std::getenv("SPZB200_PLY")) ctx->plyMapped = std::strcmp(env, "mapped") == 0;
   if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = std::strcmp(env, "persistent") != 0;
   *out = ctx;

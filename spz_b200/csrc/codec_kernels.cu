@@ -736,14 +736,12 @@ cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream
                    (a.shDim == 0 || aligned(a.sh, 16)) && aligned(a.oPositions, 4) &&
                    aligned(a.oScales, 4) && aligned(a.oRotations, 4) && aligned(a.oAlphas, 4) &&
                    aligned(a.oColors, 4) && (a.shDim == 0 || aligned(a.oSh, 4));
-  // opt-in (SPZB200_ENCODE=bulk): one thread per gaussian, planes in and out by bulk async copies
-  // (pergaussian_kernels.cu).  Measured 6357 vs 6853 GB/s at SH degree 3 and 4837 vs 6530 at degree 0
-  // against the register-path tiles below, so those stay the default.
+  // SH degree 3 and at most 24M gaussians: one thread per gaussian, planes in and out by bulk async copies
+  // (pergaussian_kernels.cu: 7045 vs 6414 GB/s at 10M points); larger launches and the other degrees use the
+  // register-path tiles below, which lead from ~40M points up.  SPZB200_ENCODE=tiles / =bulk force either.
   long long bulkDone = 0;
-  if (plan.encodeBulk) {
-    if (cudaError_t e = launchEncodePerGaussianPlanar(a, plan, stream, &bulkDone); e != cudaSuccess) return e;
-    if (bulkDone > 0) count++;
-  }
+  if (cudaError_t e = launchEncodePerGaussianPlanar(a, plan, stream, &bulkDone); e != cudaSuccess) return e;
+  if (bulkDone > 0) count++;
   const long long tg = tileGaussians(a.shDim);
   const long long tiles = vec && bulkDone == 0 ? a.n / tg : 0;
   if (tiles > 0) {

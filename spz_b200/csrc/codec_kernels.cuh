@@ -73,7 +73,8 @@ struct LaunchPlan {
   int ctasPerSm;       // persistent grid only: smCount * ctasPerSm CTAs (1..4); 0 = default (4)
   bool flatGrid;       // one CTA per tile (default) instead of persistent grid-stride CTAs
   bool decodeBulk;     // decode the SH plane through bulk async copies (TMA) instead of registers
-  bool encodeBulk;     // planar encoder through the one-thread-per-gaussian bulk-copy kernel instead of the register-path tiles (default off: slower)
+  int encodeBulk;      // planar encoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it measured
+                       // faster (SH degree 3, at most 24M gaussians per launch; default), 2 wherever it exists
   int decodePerGaussian;   // planar decoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it
                            // measured faster (SH degree 1 - 3; default), 2 also for SH-less clouds
   bool plyMapped;      // test hook: PLY rows always through the column-map kernels, never the canonical-layout ones

@@ -15,9 +15,10 @@
 //     leaves with six bulk async stores.
 //   planes -> packed (encodePerGaussianKernel<PlanarSource>): as above, but the tile's six float
 //     planes arrive with six bulk copies and thread g picks its 56 + 12D bytes out of them (odd
-//     word strides, conflict free).  Opt-in (SPZB200_ENCODE=bulk): six copies of 0.5 - 23 KB per tile
-//     sustain less than the register-path tiles of codec_kernels.cu (6357 vs 6853 GB/s at degree 3),
-//     unlike the single 31.7 KB copy of the rows source (7145 GB/s); profiles/r1_tuning_notes.txt.
+//     word strides, conflict free).  The default encoder for SH degree 3 clouds of up to 24M gaussians
+//     (7045 vs 6414 GB/s at 10M points); above that the register-path tiles of codec_kernels.cu lead by
+//     about 1 %, and the single 31.7 KB copy of the rows source stays ahead of both (7145 GB/s);
+//     profiles/r1_tuning_notes.txt.
 //   packed -> rows (decodePerGaussianKernel<RowsSink>): the mirror image; six bulk loads bring the tile's packed
 //     planes in, thread g expands gaussian g into record g of the shared-memory tile, one bulk
 //     async store writes the records.
@@ -59,7 +60,7 @@ struct Canon {
 template <int D>
 struct EncGeo {
   static constexpr int G = D == 0 ? 256 : 128;
-  static constexpr int CTAS = D <= 3 ? 8 : 4;
+  static constexpr int CTAS = D <= 3 ? 8 : 6;  // degree 2/3: 80 registers instead of 115 under a bound of 4: planar source +6 %, rows source unchanged
   using C = Canon<D, G>;
 };
 template <int D>
@@ -497,10 +498,16 @@ cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &p
   return e;
 }
 
-// packGaussians on planar float planes through the same kernel (SH degrees 0, 1, 3); *done as above
+// packGaussians on planar float planes through the same kernel; *done as above.  By default only where it measured
+// faster than the register-path tile encoder: SH degree 3 clouds (or shards, or pipeline ranges) of at most 24M
+// gaussians -- 10M points 7045 vs 6414 GB/s, 2.5M 5616 vs 5215, 20M 6902 vs 6793; from 40M up the tile encoder
+// leads by about 1 % (6761 vs 6671 at 100M), and at degree 1 by more.  Degree 2 has no planar form here (24-word
+// lane stride on the 32-bit shared-memory reads).
+constexpr long long kEncodePerGaussianMaxPoints = 24000000;
 cudaError_t launchEncodePerGaussianPlanar(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done) {
   *done = 0;
-  if (plan.forceGeneric || a.shDim == 8) return cudaSuccess;
+  if (plan.forceGeneric || plan.encodeBulk == 0 || a.shDim == 8) return cudaSuccess;
+  if (plan.encodeBulk < 2 && !(a.shDim == 15 && a.n <= kEncodePerGaussianMaxPoints)) return cudaSuccess;
   if (!(aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) && aligned16(a.colors) &&
         (a.shDim == 0 || aligned16(a.sh)) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) &&
         aligned16(a.oAlphas) && aligned16(a.oColors) && (a.shDim == 0 || aligned16(a.oSh))))

@@ -245,7 +245,8 @@ def test_ply_kernels_write_only_their_planes(gpu_ctx, oracle, deg, extra):
 @pytest.mark.parametrize("env", [{"SPZB200_GRID": "persistent"}, {"SPZB200_GRID": "persistent", "SPZB200_CTAS_PER_SM": "1"},
                                  {"SPZB200_DECODE": "direct"}, {"SPZB200_DECODE": "bulk"}, {"SPZB200_DECODE": "bulk", "SPZB200_GRID": "persistent"},
                                  {"SPZB200_DECODE": "pergaussian"}, {"SPZB200_DECODE": "pergaussian", "SPZB200_GRID": "persistent"},
-                                 {"SPZB200_ENCODE": "bulk"}, {"SPZB200_ENCODE": "bulk", "SPZB200_GRID": "persistent"},
+                                 {"SPZB200_ENCODE": "bulk"}, {"SPZB200_ENCODE": "bulk", "SPZB200_GRID": "persistent"}, {"SPZB200_ENCODE": "tiles"},
+                                 {"SPZB200_ENCODE": "tiles", "SPZB200_GRID": "persistent"},
                                  {"SPZB200_PACK": "alu"}, {"SPZB200_PLY": "mapped"}])
 def test_alternate_launch_shapes(env):
     """The development knobs select other code paths of the same kernels (persistent multi-tile CTAs,
