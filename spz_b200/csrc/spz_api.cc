@@ -595,7 +595,8 @@ bool compressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out
 
 namespace detail {
 bool finishSpz(const PackedGaussians &packed, std::vector<uint8_t> *out) {
-  std::vector<uint8_t> stream(serializedBytes(packed));
+  std::vector<uint8_t> stream;
+  resizeUninitialized(stream, serializedBytes(packed));  // serializeInto writes every byte
   serializeInto(packed, stream.data());
   const int threads = gzipThreads();
   if (threads > 1) return compressGzippedParallel(stream.data(), stream.size(), threads, out);
@@ -612,7 +613,7 @@ bool saveSpz(const GaussianCloud &g, const PackOptions &o, std::vector<uint8_t> 
     // A cloud the size checks reject yields the empty struct, which the reference goes on to
     // serialize as a 0-point file (load-spz.cc:598-607); same here.
     if (st == PackStatus::Rejected) packed = PackedGaussians{};
-    stream.resize(serializedBytes(packed));
+    resizeUninitialized(stream, serializedBytes(packed));  // serializeInto writes every byte
     serializeInto(packed, stream.data());
   }
   const int threads = gzipThreads();
