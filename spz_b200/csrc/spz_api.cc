@@ -516,13 +516,16 @@ bool decompressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *o
   z_stream zs;
   std::memset(&zs, 0, sizeof zs);
   if (inflateInit2(&zs, 16 | MAX_WBITS) != Z_OK) return false;
+  // The member's ISIZE trailer sizes the buffer in one go -- but only as a hint: in a truncated or damaged blob
+  // those four bytes are arbitrary, so the hint is capped at 8x the compressed size (the loop below grows the buffer
+  // if a stream really expands more) instead of zero-filling up to 4 GiB for a file that then fails to inflate.
   size_t capacity = 1 << 16;
   if (size >= 18) {
     uint32_t isize;
     std::memcpy(&isize, data + size - 4, 4);
-    capacity = std::max<size_t>(capacity, isize);
+    capacity = std::max<size_t>(capacity, std::min<size_t>(isize, size * 8));
   }
-  out->resize(capacity);
+  resizeUninitialized(*out, capacity);  // inflate fills it; trimmed to what was produced below
   constexpr size_t kChunk = (size_t)1 << 30;  // zlib counts in 32 bits
   size_t fed = 0, produced = 0;
   bool ok = false;

@@ -15,6 +15,8 @@ import struct
 import subprocess
 import zlib
 
+import time
+
 import numpy as np
 import pytest
 
@@ -304,6 +306,54 @@ def test_load_packed_rejects_what_the_reference_rejects(mine, theirs, tmp_path):
     assert mine.load_packed(path.encode(), 2)[0] == empty
     open(path, "wb").write(gzip.compress(good))
     assert mine.load_packed(path.encode(), 2)[0] == theirs.load_packed(path.encode(), 2)[0] == ma
+
+
+def test_load_packed_fuzz_against_the_reference(mine, theirs):
+    """Seeded corruption fuzz of the container reader (load-spz.cc:548-596): header bytes overwritten, the stream
+    truncated or extended at random, gzip payloads cut short.  Whatever the reference makes of a blob -- the
+    empty struct or some set of planes -- the drop-in reader makes the same of it.  Point counts stay far
+    below the reference's 10M cap, the one documented divergence of this reader."""
+    rng = np.random.default_rng(21)
+    agree_empty = agree_data = 0
+    spent = [0.0, 0.0]
+    for trial in range(400):
+        ver = int(rng.integers(1, 4))
+        deg = int(rng.integers(0, 4))
+        n = int(rng.integers(1, 40))
+        p = random_stream(rng, n, deg, ver, int(rng.integers(0, 25)))
+        raw = bytearray(container(p))
+        kind = trial % 5
+        if kind == 0:    # one to three header bytes replaced
+            for _ in range(int(rng.integers(1, 4))):  # (not the count's high bytes: the reference would zero-fill up to 650 MB per trial)
+                raw[int(rng.choice([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 14, 15]))] = int(rng.integers(0, 256))
+        elif kind == 1:  # point count nudged (kept small: the cap is a documented divergence)
+            raw[8:12] = int(rng.integers(0, 80)).to_bytes(4, "little")
+        elif kind == 2:  # truncated or padded
+            cut = int(rng.integers(0, len(raw) + 20))
+            raw = raw[:cut] if cut <= len(raw) else raw + bytes(rng.integers(0, 256, cut - len(raw), dtype=np.uint8))
+        elif kind == 3:  # sh degree / version / flags fields swept
+            raw[4:8] = int(rng.integers(0, 6)).to_bytes(4, "little")
+            raw[12] = int(rng.integers(0, 6))
+            raw[14] = int(rng.integers(0, 256))
+        blob = gzip.compress(bytes(raw), 1)
+        if kind == 4:    # the gzip stream itself damaged
+            blob = blob[:int(rng.integers(0, len(blob)))] if trial % 2 else blob[:10] + bytes(rng.integers(0, 256, 8, dtype=np.uint8)) + blob[18:]
+        t0 = time.perf_counter()
+        ma, pa = mine.load_packed(blob, trial % 2)
+        t1 = time.perf_counter()
+        mb, pb = theirs.load_packed(blob, trial % 2)
+        spent[0] += t1 - t0
+        spent[1] += time.perf_counter() - t1
+        assert ma == mb, (trial, kind, ma, mb)
+        for x, y in zip(pa, pb):
+            assert np.array_equal(x, y), (trial, kind)
+        if ma["n"] == 0:
+            agree_empty += 1
+        else:
+            agree_data += 1
+    assert agree_empty > 30 and agree_data > 30, (agree_empty, agree_data)  # the fuzz reaches both outcomes
+    # a damaged blob must not cost more than a sound one (a truncated member's last four bytes once sized a 4 GiB buffer)
+    assert spent[0] < 10 * spent[1] + 1.0, spent
 
 
 def test_point_cap_is_lifted_and_restorable(mine, theirs):
