@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/spz_b200/spz.hpp"
+#include "spz_internal.hpp"
 
 namespace spz {
 namespace {
@@ -182,7 +183,8 @@ bool decompressGzippedParallel(const uint8_t *data, size_t size, int threads, st
   const uint32_t wantCrc = get32(data + offset[blocks]), isize = get32(data + offset[blocks] + 4);
   const size_t total = (size_t)t.totalSize, lastLen = total - (blocks - 1) * t.blockSize;
   if ((uint32_t)(total & 0xffffffffu) != isize) return decompressGzipped(data, size, out);
-  out->resize(total);
+  out->clear();
+  detail::resizeUninitialized(*out, total);  // every block inflates into its own slice; no zero-fill pass on one thread first
   std::vector<uint32_t> crcs(blocks);
   std::atomic<bool> ok{true};
   parallelFor(blocks, threads, [&](size_t i) {
