@@ -500,6 +500,37 @@ def test_parallel_gzip_is_a_standard_member_with_identical_content(mine, theirs)
     assert mine.gunzip(b"", 4) is None and mine.gunzip(b"\x1f\x8b", 4) is None
 
 
+def test_parallel_gunzip_fuzz(mine):
+    """Seeded damage to block-parallel gzip members (the block table in FEXTRA, block bodies, the trailer,
+    truncation): the inflater never crashes, and gives Python's gzip module's verdict -- the same bytes
+    when that accepts the member, failure when it rejects it."""
+    rng = np.random.default_rng(22)
+    accepted = rejected = 0
+    for trial in range(120):
+        n = int(rng.integers(1, 6)) << 20
+        data = (rng.integers(0, 40, n, dtype=np.uint8) * 3).tobytes() if trial % 3 else rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        blob = bytearray(mine.gzip_parallel(data, 4))
+        kind = trial % 4
+        if kind == 0:    # a byte of the header / block table
+            blob[int(rng.integers(0, 64))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:  # a byte somewhere in the bodies
+            blob[int(rng.integers(64, len(blob) - 8))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 2:  # the CRC / ISIZE trailer
+            blob[len(blob) - 1 - int(rng.integers(0, 8))] ^= 1 << int(rng.integers(0, 8))
+        else:            # truncated (or, one time in four, left intact)
+            blob = blob if trial % 16 == 3 else blob[:int(rng.integers(1, len(blob)))]
+        try:
+            want = gzip.decompress(bytes(blob))
+        except Exception:  # noqa: BLE001  (BadGzipFile, EOFError, zlib.error)
+            want = None
+        for threads in (1, 4):
+            got = mine.gunzip(bytes(blob), threads)
+            assert got == want, (trial, kind, threads, None if got is None else len(got), None if want is None else len(want))
+        accepted += want is not None
+        rejected += want is None
+    assert accepted >= 5 and rejected >= 60, (accepted, rejected)
+
+
 def test_save_load_use_parallel_gzip_when_asked(mine, theirs, tmp_path):
     """SPZ_B200_GZIP_THREADS switches loadSpzPacked to the parallel inflater (the save side needs the
     GPU for its planes and is covered by the gpu test below)."""
