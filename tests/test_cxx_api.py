@@ -356,6 +356,27 @@ def test_load_packed_fuzz_against_the_reference(mine, theirs):
     assert spent[0] < 10 * spent[1] + 1.0, spent
 
 
+def test_zero_fill_free_vectors_and_their_fallback(tmp_path):
+    """spz_internal.hpp: resizeUninitialized (reserve + end pointer, no value-initialisation) and its
+    SPZ_B200_ZEROFILL=1 fallback to resize() read the same file to the same planes (file API -> readFile,
+    gunzip buffer, deserialize), each in a fresh process because the switch is read once."""
+    import sys
+    rng = np.random.default_rng(23)
+    p = random_stream(rng, 5000, 3, 3, 12)
+    path = str(tmp_path / "z.spz")
+    open(path, "wb").write(gzip.compress(container(p), 1))
+    code = ("import sys, hashlib; sys.path[:0] = [%r, %r]; import test_cxx_api as T; m, planes = T.Shim('b200').load_packed(%r.encode(), 2); "
+            "print(m['n'], hashlib.sha256(b''.join(a.tobytes() for a in planes)).hexdigest())") % (os.path.dirname(__file__), ROOT, path)
+    outs = []
+    for env in ({}, {"SPZ_B200_ZEROFILL": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **env), timeout=300)
+        assert r.returncode == 0, r.stderr[-800:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    import hashlib
+    want = "5000 " + hashlib.sha256(b"".join(a.tobytes() for a in p.planes())).hexdigest()
+    assert outs[0] == outs[1] == want, outs
+
+
 def test_point_cap_is_lifted_and_restorable(mine, theirs):
     """Documented divergence: the reference refuses > 10,000,000 points (load-spz.cc:549)."""
     n = 10_000_001
