@@ -109,13 +109,23 @@ typedef struct {
   int32_t reserved;
 } SpzB200Timings;
 
-/* One context per (thread, device): immutable codec tables resident on the device, three worker
- * streams and the staging buffers of the host-pointer pipeline.  A context is not thread-safe;
- * create one per host thread.  Creation fails (no CPU fallback) without an sm_100 device. */
+/* A context: immutable codec tables resident on one device, three worker streams and the staging
+ * buffers of the host-pointer pipeline.  A context is not thread-safe: one caller at a time (own one
+ * per host thread with spzb200_create, or lease one per call with spzb200_acquire).  Creation fails
+ * (no CPU fallback) without an sm_100 device. */
 typedef struct SpzB200Context SpzB200Context;
 
 int spzb200_create(int32_t device, SpzB200Context **out);
 void spzb200_destroy(SpzB200Context *ctx);
+
+/* Process-wide pool: lease a context of `device` for one call (or a batch of calls) and hand it back.
+ * Contexts are created on demand, at most SPZ_B200_MAX_CONTEXTS (default 4) per device -- further
+ * callers block until one is released -- and live until the process exits, so threads that come and go
+ * do not pay for streams, tables, staging and pinned bounce buffers again.  A lease is exclusive.  This
+ * is what the C++ API (spz::packGaussians, ...) and the *_multi entry points use.  spzb200_release
+ * of a context that came from spzb200_create destroys it. */
+int spzb200_acquire(int32_t device, SpzB200Context **out);
+void spzb200_release(SpzB200Context *ctx);
 
 /* ---- device-resident codec: what the benchmark's `value` times ------------------------------
  *
@@ -186,6 +196,33 @@ int spzb200_encode_ply_host(SpzB200Context *ctx, const SpzB200PlyRows *in, int32
 int spzb200_decode_ply_device(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to, SpzB200PlyRows *out, void *stream);
 int spzb200_decode_ply_host(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to, SpzB200PlyRows *out,
                             SpzB200Timings *timings);
+
+/* ---- batched per-gaussian access ----------------------------------------------
+ *
+ * PackedGaussians::at(i) followed by PackedGaussian::unpack (load-spz.cc:383-463) for many gaussians
+ * in one call.  The unit structs are the reference's own, so arrays of them pass through unchanged:
+ *   record  = PackedGaussian   (load-spz.h:28-37), 65 bytes: position[9] rotation[4] scale[3] color[3]
+ *             alpha shR[15] shG[15] shB[15]
+ *   output  = UnpackedGaussian (load-spz.h:13-24), 59 floats: position[3] rotation[4] (x,y,z,w) scale[3]
+ *             color[3] alpha shR[15] shG[15] shB[15]
+ *   converter = CoordinateConverter (splat-types.h:36-41), 21 floats: flipP[3] flipQ[3] flipSh[15];
+ *             NULL = identity.  Applied by multiplication in the reference's order, so any values work.
+ * `version` is the stream flavour (SPZB200_STREAM_*): which position / rotation encoding the records hold. */
+#define SPZB200_RECORD_BYTES 65
+#define SPZB200_UNPACKED_FLOATS 59
+
+/* records (HOST, n x 65 bytes) -> out (HOST, n x 59 floats).  Synchronous. */
+int spzb200_unpack_records_host(SpzB200Context *ctx, const uint8_t *records, int64_t n, int32_t version,
+                                int32_t fractional_bits, const float *converter, float *out);
+/* at(indices[k]) for k < n on HOST planes, then as above.  indices == NULL means 0..n-1 (then n must
+ * not exceed packed->num_points).  An index outside [0, num_points) fails with SPZB200_ERR_INVALID
+ * (the reference reads out of bounds). */
+int spzb200_unpack_gather_host(SpzB200Context *ctx, const SpzB200Packed *packed, const int64_t *indices, int64_t n,
+                               const float *converter, float *out);
+/* The same with DEVICE planes, DEVICE indices (or NULL) and a DEVICE output, asynchronous on `stream`:
+ * the kernel does the gather itself.  Indices are not range-checked. */
+int spzb200_unpack_gather_device(SpzB200Context *ctx, const SpzB200Packed *packed, const int64_t *indices, int64_t n,
+                                 const float *converter, float *out, void *stream);
 
 /* Page-locked host buffers for the *_host entry points (cudaHostAlloc, portable across devices).
  * Pageable memory works too but its copies neither overlap nor reach PCIe bandwidth. */

@@ -51,6 +51,16 @@ typedef struct {
 
 namespace spz {
 
+// Deep copy of a float plane into a new[]-allocated buffer the caller frees (reference: splat-types.h:14-22).
+inline SpzFloatBuffer copyFloatBuffer(const std::vector<float> &vector) {
+  SpzFloatBuffer buffer = {0, nullptr};
+  if (vector.empty()) return buffer;
+  buffer.count = vector.size();
+  buffer.data = new float[buffer.count];
+  std::copy(vector.begin(), vector.end(), buffer.data);
+  return buffer;
+}
+
 // ---- coordinate systems (reference: splat-types.h:24-81) ----------------------------------------
 
 // Axis directions are encoded in the value: bits 0,1,2 of (value - 1) say Right, Up, Front.
@@ -105,25 +115,16 @@ struct GaussianCloud {
 
   // Deep copy into new[]-allocated buffers the caller frees.
   GaussianCloudData data() const {
-    auto dup = [](const std::vector<float> &v) {
-      SpzFloatBuffer b = {0, nullptr};
-      if (!v.empty()) {
-        b.count = v.size();
-        b.data = new float[b.count];
-        std::memcpy(b.data, v.data(), b.count * sizeof(float));
-      }
-      return b;
-    };
     GaussianCloudData d;
     d.numPoints = numPoints;
     d.shDegree = shDegree;
     d.antialiased = antialiased;
-    d.positions = dup(positions);
-    d.scales = dup(scales);
-    d.rotations = dup(rotations);
-    d.alphas = dup(alphas);
-    d.colors = dup(colors);
-    d.sh = dup(sh);
+    d.positions = copyFloatBuffer(positions);
+    d.scales = copyFloatBuffer(scales);
+    d.rotations = copyFloatBuffer(rotations);
+    d.alphas = copyFloatBuffer(alphas);
+    d.colors = copyFloatBuffer(colors);
+    d.sh = copyFloatBuffer(sh);
     return d;
   }
 
@@ -280,6 +281,11 @@ void serializePackedGaussians(const PackedGaussians &packed, std::ostream *out);
 bool compressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out);
 
 // ---- extensions (not in the reference's headers) --------------------------------------------------
+// packed.unpack(i, c) for every i of `indices` in ONE kernel launch (a loop over unpack(i, c) pays a
+// launch per gaussian).  Empty result, after a logged line, when an index is out of range or no device
+// is usable.
+std::vector<UnpackedGaussian> unpackGaussiansAt(const PackedGaussians &packed, const std::vector<int32_t> &indices,
+                                                const CoordinateConverter &c);
 // The inverse of compressGzipped (the reference keeps it file-local, load-spz.cc:169-182).
 bool decompressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out);
 // zlib on several host threads: one standard gzip member made of independently deflated blocks,

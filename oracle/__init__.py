@@ -195,6 +195,24 @@ class Oracle(_Codec):
             f = getattr(L, name)
             f.restype, f.argtypes = rt, [at]
 
+    def unpack_at(self, p: Packed, indices, conv21) -> np.ndarray:
+        """[len(indices), 59] float32: PackedGaussians::unpack(i, c) per index (load-spz.cc:383-463)."""
+        idx = np.ascontiguousarray(indices, np.int64)
+        conv = np.ascontiguousarray(conv21, np.float32)
+        assert conv.size == 21
+        out = np.zeros((idx.size, 59), np.float32)
+        ins = [_u8(a) for a in p.planes()]
+        fn = self.lib.oracle_unpack_at
+        fn.restype = C.c_int
+        rc = fn(C.c_int64(p.n), C.c_int32(p.sh_degree), C.c_int32(p.fractional_bits), C.c_int32(p.version),
+                *[_bp(a) for a in ins], idx.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(idx.size), _fp(conv), _fp(out))
+        if rc != 0:
+            raise ValueError(f"oracle_unpack_at rejected the input (rc={rc})")
+        return out
+
+    def converter(self, frm: int, to: int) -> np.ndarray:
+        return np.concatenate(self.flips(frm, to)).astype(np.float32)
+
     def flips(self, frm: int, to: int):
         p, q, s = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(15, np.float32)
         self.lib.oracle_flips(frm, to, _fp(p), _fp(q), _fp(s))
@@ -228,6 +246,20 @@ class Ref(_Codec):
         L.ref_serialize.restype = C.c_void_p
         L.ref_load_spz.restype = C.c_void_p
         L.ref_gzip_size.restype = C.c_uint64
+
+    def unpack_at(self, p: Packed, indices, conv21) -> np.ndarray:
+        """[len(indices), 59] float32 from the reference's own PackedGaussians::unpack(i, c)."""
+        idx = np.ascontiguousarray(indices, np.int64)
+        conv = np.ascontiguousarray(conv21, np.float32)
+        out = np.zeros((idx.size, 59), np.float32)
+        ins = [_u8(a) for a in p.planes()]
+        fn = self.lib.ref_unpack_at
+        fn.restype = C.c_int
+        rc = fn(C.c_int32(p.n), C.c_int32(p.sh_degree), C.c_int32(p.fractional_bits), C.c_int32(p.version),
+                *[_bp(a) for a in ins], idx.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(idx.size), _fp(conv), _fp(out))
+        if rc != 0:
+            raise ValueError(f"ref_unpack_at rejected the input (rc={rc})")
+        return out
 
     @staticmethod
     def available() -> bool:

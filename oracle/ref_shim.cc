@@ -122,6 +122,38 @@ int ref_unpack(int32_t n, int32_t shDegree, int32_t fractionalBits, int32_t vers
   return 0;
 }
 
+// PackedGaussians::unpack(i, c) (load-spz.cc:461-463) for a list of indices; conv = 21 floats of a
+// CoordinateConverter; 59 floats out per gaussian in UnpackedGaussian's member order.
+int ref_unpack_at(int32_t n, int32_t shDegree, int32_t fractionalBits, int32_t version,
+                  const uint8_t *positions, const uint8_t *scales, const uint8_t *rotations,
+                  const uint8_t *alphas, const uint8_t *colors, const uint8_t *sh,
+                  const int64_t *indices, int64_t count, const float *conv, float *out) {
+  const size_t N = static_cast<size_t>(n);
+  const size_t D = static_cast<size_t>(dimForDegree(shDegree));
+  spz::PackedGaussians p;
+  p.numPoints = n;
+  p.shDegree = shDegree;
+  p.fractionalBits = fractionalBits;
+  p.usesQuaternionSmallestThree = version >= 3;
+  p.positions.assign(positions, positions + N * 3 * ((version == 1 || version == 4) ? 2 : 3));
+  p.scales.assign(scales, scales + N * 3);
+  p.rotations.assign(rotations, rotations + N * (version >= 3 ? 4 : 3));
+  p.alphas.assign(alphas, alphas + N);
+  p.colors.assign(colors, colors + N * 3);
+  p.sh.assign(sh, sh + N * D * 3);
+  spz::CoordinateConverter c;
+  std::copy(conv, conv + 3, c.flipP.begin());
+  std::copy(conv + 3, conv + 6, c.flipQ.begin());
+  std::copy(conv + 6, conv + 21, c.flipSh.begin());
+  static_assert(sizeof(spz::UnpackedGaussian) == 59 * sizeof(float), "UnpackedGaussian is 59 packed floats");
+  for (int64_t k = 0; k < count; k++) {
+    if (indices[k] < 0 || indices[k] >= n) return 2;
+    const spz::UnpackedGaussian u = p.unpack(static_cast<int32_t>(indices[k]), c);
+    std::memcpy(out + 59 * k, &u, sizeof u);
+  }
+  return 0;
+}
+
 // saveSpz(cloud, opts, vector*) (load-spz.cc:598).  Returns a malloc'd gzip buffer (caller frees
 // with ref_free) or NULL.
 uint8_t *ref_save_spz(int32_t n, int32_t shDegree, int32_t antialiased, int32_t from,

@@ -52,6 +52,11 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 SIGNATURES = {
     "spzb200_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "spzb200_destroy": (None, [C.c_void_p]),
+    "spzb200_acquire": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "spzb200_release": (None, [C.c_void_p]),
+    "spzb200_unpack_records_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
+    "spzb200_unpack_gather_host": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_void_p, C.c_int64, _f32p, C.c_void_p]),
+    "spzb200_unpack_gather_device": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_void_p, C.c_int64, _f32p, C.c_void_p, C.c_void_p]),
     "spzb200_encode_device": (C.c_int, [C.c_void_p, C.POINTER(Cloud), C.c_int32, C.POINTER(Packed), C.c_void_p]),
     "spzb200_decode_device": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_int32, C.POINTER(Cloud), C.c_void_p]),
     "spzb200_encode_host": (C.c_int, [C.c_void_p, C.POINTER(Cloud), C.c_int32, C.POINTER(Packed), C.POINTER(Timings)]),

@@ -245,14 +245,17 @@ class Context:
     """One per (thread, device).  Raises CodecError(ERR_NO_DEVICE) when there is no B200: the codec
     has no CPU path."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, pooled: bool = False):
+        """pooled=True leases a context from the process-wide pool (spzb200_acquire) instead of
+        creating one; close() hands it back."""
         self._h = C.c_void_p(None)
         self.device = device
-        N.check(N.lib().spzb200_create(device, C.byref(self._h)))
+        self.pooled = pooled
+        N.check((N.lib().spzb200_acquire if pooled else N.lib().spzb200_create)(device, C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            N.lib().spzb200_destroy(self._h)
+            (N.lib().spzb200_release if self.pooled else N.lib().spzb200_destroy)(self._h)
             self._h = C.c_void_p(None)
 
     __del__ = close
@@ -368,6 +371,76 @@ class Context:
         ps, cs, tm = _packed_struct(packed, False), _cloud_struct(out, False), N.Timings()
         N.check(N.lib().spzb200_decode_host(self._h, C.byref(ps), int(to), C.byref(cs), C.byref(tm)))
         return out, tm.as_dict()
+
+
+    # ---- batched per-gaussian access: PackedGaussians::unpack(i, c), load-spz.cc:383-463 --------
+    @staticmethod
+    def _conv(converter):
+        if converter is None:
+            return None, None
+        conv = np.ascontiguousarray(converter, np.float32).reshape(-1)
+        if conv.size != 21:
+            raise ValueError("converter must hold 21 floats: flipP[3], flipQ[3], flipSh[15]")
+        return conv, conv.ctypes.data_as(N._f32p)
+
+    def unpack_gather_host(self, packed: PackedPlanes, indices=None, converter=None, n: Optional[int] = None) -> np.ndarray:
+        """[n, 59] float32 (UnpackedGaussian rows) of the gaussians `indices` (None: the first n) of HOST planes."""
+        idx = None if indices is None else np.ascontiguousarray(indices, np.int64).reshape(-1)
+        count = idx.size if idx is not None else (packed.n if n is None else int(n))
+        out = np.empty((count, UNPACKED_FLOATS), np.float32)
+        keep, cp = self._conv(converter)
+        ps = _packed_struct(packed, False)
+        N.check(N.lib().spzb200_unpack_gather_host(self._h, C.byref(ps), None if idx is None else C.c_void_p(idx.ctypes.data), count, cp,
+                                                   C.c_void_p(out.ctypes.data)))
+        return out
+
+    def unpack_records_host(self, records, version: int, fractional_bits: int, converter=None) -> np.ndarray:
+        """[n, 59] float32 from n 65-byte PackedGaussian records (what at() returns)."""
+        rec = np.ascontiguousarray(records, np.uint8).reshape(-1, RECORD_BYTES)
+        out = np.empty((rec.shape[0], UNPACKED_FLOATS), np.float32)
+        keep, cp = self._conv(converter)
+        N.check(N.lib().spzb200_unpack_records_host(self._h, C.c_void_p(rec.ctypes.data), rec.shape[0], int(version), int(fractional_bits), cp,
+                                                    C.c_void_p(out.ctypes.data)))
+        return out
+
+    def unpack_gather_device(self, packed: PackedPlanes, indices=None, converter=None, n: Optional[int] = None, out=None, stream=None):
+        """The same on DEVICE planes with a device index tensor (int64) or None; returns a [n, 59] float32 tensor."""
+        import torch
+        count = indices.numel() if indices is not None else (packed.n if n is None else int(n))
+        if out is None:
+            out = torch.empty((count, UNPACKED_FLOATS), dtype=torch.float32, device=packed.positions.device)
+        if indices is not None and (indices.dtype != torch.int64 or not indices.is_contiguous()):
+            raise TypeError("indices must be a contiguous int64 tensor")
+        keep, cp = self._conv(converter)
+        ps = _packed_struct(packed, True)
+        N.check(N.lib().spzb200_unpack_gather_device(self._h, C.byref(ps), None if indices is None else C.c_void_p(indices.data_ptr()), count, cp,
+                                                     C.c_void_p(out.data_ptr()), C.c_void_p(self._stream_handle(stream))))
+        return out
+
+
+RECORD_BYTES = 65      # sizeof(PackedGaussian), load-spz.h:28-37
+UNPACKED_FLOATS = 59   # UnpackedGaussian, load-spz.h:13-24
+
+
+def gather_records(packed: PackedPlanes, indices) -> np.ndarray:
+    """PackedGaussians::at(i) (load-spz.cc:431-459) for a list of indices on host numpy planes: [n, 65] uint8.
+    A pure byte gather (SH de-interleaved per channel, padded with 128); no codec arithmetic."""
+    idx = np.asarray(indices, np.int64)
+    d = SH_DIM[packed.sh_degree]
+    half = packed.version in (1, 4)
+    pb, rb = (6 if half else 9), (4 if packed.version >= 3 else 3)
+    rec = np.zeros((idx.size, RECORD_BYTES), np.uint8)
+    rec[:, 0:pb] = np.asarray(packed.positions).reshape(-1, pb)[idx]
+    rec[:, 9:9 + rb] = np.asarray(packed.rotations).reshape(-1, rb)[idx]
+    rec[:, 13:16] = np.asarray(packed.scales).reshape(-1, 3)[idx]
+    rec[:, 16:19] = np.asarray(packed.colors).reshape(-1, 3)[idx]
+    rec[:, 19] = np.asarray(packed.alphas)[idx]
+    rec[:, 20:65] = 128
+    if d:
+        sh = np.asarray(packed.sh).reshape(-1, d, 3)[idx]
+        for ch in range(3):
+            rec[:, 20 + 15 * ch:20 + 15 * ch + d] = sh[:, :, ch]
+    return rec
 
 
 def encode_host_multi(devices, cloud: CloudPlanes, frm: int = 0, out: Optional[PackedPlanes] = None):

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <condition_variable>
 #include <cstring>
+#include <exception>
 #include <limits>
 #include <mutex>
 #include <string>
@@ -79,7 +80,9 @@ float floatOf(uint32_t k) {
 
 // thr[L-1] = the smallest float whose alpha byte is >= L, L = 1..255; thr[255] = +Inf.
 // Exact because the byte is monotone in a (checked below on a 2^16-point grid plus both
-// neighbours of every threshold; exhaustively in tests/test_tables.py).
+// neighbours of every threshold; over every float of [-8, 8] against the oracle's expression in
+// tests/test_oracle.py::test_alpha_quantizer_is_a_monotone_step_function and against the reference's
+// golden thresholds in tests/test_cabi.py::test_host_built_tables_match_reference).
 bool buildAlphaThresholds(float thr[256], std::string *why) {
   const uint32_t kLo = keyOf(-std::numeric_limits<float>::infinity());
   const uint32_t kHi = keyOf(std::numeric_limits<float>::infinity());
@@ -120,6 +123,24 @@ void buildAlphaLut(float lut[256]) {
     const float x = (float)i / 255.0f;        // load-spz.cc:518
     lut[i] = std::log(x / (1.0f - x));        // load-spz.cc:87
   }
+}
+
+// Both tables depend only on the host's libm, so they are built once per process (the threshold
+// search + its self-check is ~10 ms of host time that every later context skips).
+struct HostTables {
+  float thr[256];
+  float lut[256];
+  bool ok = false;
+  std::string why;
+};
+const HostTables &hostTables() {
+  static const HostTables *t = [] {
+    HostTables *h = new HostTables;
+    h->ok = buildAlphaThresholds(h->thr, &h->why);
+    buildAlphaLut(h->lut);
+    return h;
+  }();
+  return *t;
 }
 
 #ifndef SPZ_STAGES
@@ -218,6 +239,7 @@ struct SpzB200Context {
   int packMode = spzb200::kPackAlu;
   bool cvtPackOk = false;  // the init-time probe of cvt.pack.sat.u8.s32 agreed with the ALU packer
   bool forceGeneric = false;
+  bool pooled = false;  // owned by the process-wide pool (spzb200_acquire): released, never destroyed by callers
   int ctasPerSm = 0;
   int bounceMode = 1;     // pageable planes: 0 never bounce, 1 bounce large calls (see bounceMinBytes), 2 always
   size_t bounceMinBytes = (size_t)32 << 20;  // steady state the bounce path is 2-4x faster from ~100K gaussians up; the one-time pinned allocation (tens of ms at these sizes) is small next to CUDA initialisation
@@ -236,6 +258,15 @@ struct SpzB200Context {
   float *dThr = nullptr;
   float *dLut = nullptr;
   Stage stage[kStages];
+  // batched per-gaussian access (spzb200_unpack_*_host): two slots of pinned + device staging
+  struct GatherSlot {
+    uint8_t *hIn = nullptr;   // pinned, cap * 65 bytes
+    float *hOut = nullptr;    // pinned, cap * 59 floats
+    uint8_t *dIn = nullptr;
+    float *dOut = nullptr;
+    size_t cap = 0;           // records
+    cudaEvent_t done = nullptr;
+  } gather[2];
 };
 
 namespace {
@@ -404,8 +435,8 @@ size_t carveSet(uint8_t *base, const PlaneSet &set, long long points, uint8_t *o
 // threads while the GPU works on the neighbouring ranges.
 // launch(dIn, dOut, points, stream, &launches) queues the kernel(s) for one range.
 template <class Launch>
-int runPipeline(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, long long n, long long granule,
-                Launch &&launch, SpzB200Timings *timings) {
+int runPipelineStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, long long n, long long granule,
+                      Launch &&launch, SpzB200Timings *timings) {
   const double w0 = nowMs();
   CU(cudaSetDevice(ctx->device));
   // Bouncing costs a one-time pinned allocation per context (~1 GB/s on a VM), so small one-shot
@@ -517,6 +548,23 @@ int runPipeline(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, lo
   return SPZB200_OK;
 }
 
+// On failure copies of earlier ranges may still be in flight on the stage streams, reading or writing
+// the caller's planes and the bounce buffers; the caller is about to free or reuse both, so the
+// streams are drained first (secondary errors of that drain are dropped, the first message is kept).
+template <class Launch>
+int runPipeline(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, long long n, long long granule,
+                Launch &&launch, SpzB200Timings *timings) {
+  const int rc = runPipelineStages(ctx, in, out, n, granule, launch, timings);
+  if (rc != SPZB200_OK) {
+    const std::string first = tlsError;
+    for (int s = 0; s < kStages; s++)
+      if (ctx->stage[s].stream) (void)cudaStreamSynchronize(ctx->stage[s].stream);
+    (void)cudaGetLastError();
+    tlsError = first;
+  }
+  return rc;
+}
+
 PlaneSet cloudPlaneSet(const SpzB200Cloud &c) {
   PlaneSet s;
   s.count = 6;
@@ -572,28 +620,69 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
                      }, timings);
 }
 
-// Contexts of the multi-GPU entry points: created on first use, kept for the life of the process
-// (a context owns device staging buffers, pinned bounce buffers and a copy pool -- re-creating them
-// per call costs more than a small cloud's whole encode).  A lease hands one out exclusively, so
-// concurrent *_host_multi calls that name the same device slot in behind each other on it.
-struct SharedContexts {
-  struct Slot {
-    std::mutex busy;
-    SpzB200Context *ctx = nullptr;
+// Process-wide pool of contexts, one free list per device (spzb200_acquire / spzb200_release).
+// A context owns device staging buffers, pinned bounce buffers, streams and a copy pool -- building
+// them costs more than a small cloud's whole encode -- so the C++ API and the multi-GPU entry points
+// lease one per call instead of keeping one per host thread: a server that packs from short-lived
+// threads pays the set-up once per process, not once per request.  A lease is exclusive.  At most
+// `maxLive` contexts exist per device (SPZ_B200_MAX_CONTEXTS, default 4: the PCIe link serialises
+// concurrent calls anyway); further callers wait for a release.  Never destroyed: no CUDA calls at exit.
+struct ContextPool {
+  struct PerDevice {
+    std::vector<SpzB200Context *> idle;
+    int live = 0;
   };
   std::mutex m;
-  std::vector<std::pair<int32_t, Slot *>> slots;  // a device may be listed twice in one call: one slot per (device, ordinal)
-  Slot *slot(int32_t device, int ordinal) {
-    std::lock_guard<std::mutex> g(m);
-    int seen = 0;
-    for (auto &s : slots)
-      if (s.first == device && seen++ == ordinal) return s.second;
-    slots.emplace_back(device, new Slot);
-    return slots.back().second;
+  std::condition_variable cv;
+  std::vector<std::pair<int32_t, PerDevice>> devs;
+  int maxLive = 4;
+  ContextPool() {
+    if (const char *env = std::getenv("SPZ_B200_MAX_CONTEXTS")) maxLive = std::max(1, std::atoi(env));
+  }
+  PerDevice &of(int32_t device) {
+    for (auto &d : devs)
+      if (d.first == device) return d.second;
+    devs.emplace_back(device, PerDevice());
+    return devs.back().second;
+  }
+  int acquire(int32_t device, SpzB200Context **out) {
+    *out = nullptr;
+    {
+      std::unique_lock<std::mutex> g(m);
+      while (true) {
+        PerDevice &d = of(device);
+        if (!d.idle.empty()) {
+          *out = d.idle.back();
+          d.idle.pop_back();
+          return SPZB200_OK;
+        }
+        if (d.live < maxLive) {
+          d.live++;
+          break;
+        }
+        cv.wait(g);
+      }
+    }
+    const int rc = spzb200_create(device, out);  // outside the lock: other devices' callers do not wait for it
+    if (rc != SPZB200_OK) {
+      std::lock_guard<std::mutex> g(m);
+      of(device).live--;
+      cv.notify_all();
+    } else {
+      (*out)->pooled = true;
+    }
+    return rc;
+  }
+  void release(SpzB200Context *ctx) {
+    {
+      std::lock_guard<std::mutex> g(m);
+      of(ctx->device).idle.push_back(ctx);
+    }
+    cv.notify_all();
   }
 };
-SharedContexts &sharedContexts() {
-  static SharedContexts *pool = new SharedContexts;  // intentionally never destroyed: no CUDA calls at exit
+ContextPool &contextPool() {
+  static ContextPool *pool = new ContextPool;
   return *pool;
 }
 
@@ -612,14 +701,15 @@ int runSharded(const int32_t *devices, int32_t numDevices, int64_t n, int32_t sh
       int64_t a = 0, b = 0;
       rc[i] = spzb200_shard_range(n, shDegree, numDevices, i, &a, &b);
       if (rc[i] == SPZB200_OK && b > a) {
-        int ordinal = 0;
-        for (int32_t k = 0; k < i; k++) ordinal += devices[k] == devices[i];
-        SharedContexts::Slot *slot = sharedContexts().slot(devices[i], ordinal);
-        std::lock_guard<std::mutex> lease(slot->busy);
-        if (!slot->ctx) rc[i] = spzb200_create(devices[i], &slot->ctx);
-        if (rc[i] == SPZB200_OK) rc[i] = perShard(slot->ctx, a, b, &tms[i]);
+        SpzB200Context *ctx = nullptr;
+        rc[i] = contextPool().acquire(devices[i], &ctx);
+        if (rc[i] == SPZB200_OK) {
+          rc[i] = perShard(ctx, a, b, &tms[i]);
+          if (rc[i] != SPZB200_OK) msg[i] = spzb200_last_error();
+          contextPool().release(ctx);
+        }
       }
-      if (rc[i] != SPZB200_OK) msg[i] = spzb200_last_error();
+      if (rc[i] != SPZB200_OK && msg[i].empty()) msg[i] = spzb200_last_error();
     });
   }
   for (auto &t : threads) t.join();
@@ -674,6 +764,15 @@ int32_t spzb200_version(void) { return SPZB200_VERSION; }
 int spzb200_create(int32_t device, SpzB200Context **out) {
   if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_create: null out");
   *out = nullptr;
+  // SPZB200_TRACE_INIT=1: one stderr line with where a context's creation time went (profiles/r2_cold_start.txt)
+  const bool trace = std::getenv("SPZB200_TRACE_INIT") != nullptr;
+  double tMark = nowMs();
+  double tQuery = 0, tTables = 0, tAlloc = 0, tStreams = 0, tKernels = 0;
+  auto lap = [&](double &slot) {
+    const double now = nowMs();
+    slot = now - tMark;
+    tMark = now;
+  };
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0)
@@ -681,37 +780,53 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
   if (device < 0 || device >= count)
     return fail(SPZB200_ERR_NO_DEVICE, "spzb200_create: device %d out of range (0..%d)", device, count - 1);
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
+  // (cudaGetDeviceProperties costs ~1 ms per call: it queries every property; the two attributes do not)
+  int major = 0, sms = 0;
+  CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (major != 10) {
+    int minor = 0;
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
     return fail(SPZB200_ERR_NO_DEVICE, "spzb200_create: device %d is sm_%d%d; kernels are built for sm_100a only",
-                device, prop.major, prop.minor);
+                device, major, minor);
+  }
   CU(cudaSetDevice(device));
+  CU(cudaFree(nullptr));  // forces the primary context, so the trace separates CUDA initialisation from ours
+  lap(tQuery);
+  const HostTables &tables = hostTables();
+  if (!tables.ok) return fail(SPZB200_ERR_INVALID, "spzb200_create: %s", tables.why.c_str());
   SpzB200Context *ctx = new SpzB200Context;
   ctx->device = device;
-  ctx->smCount = prop.multiProcessorCount;
-  std::string why;
-  if (!buildAlphaThresholds(ctx->hThr, &why)) {
-    delete ctx;
-    return fail(SPZB200_ERR_INVALID, "spzb200_create: %s", why.c_str());
-  }
-  buildAlphaLut(ctx->hLut);
+  ctx->smCount = sms;
+  std::memcpy(ctx->hThr, tables.thr, sizeof ctx->hThr);
+  std::memcpy(ctx->hLut, tables.lut, sizeof ctx->hLut);
+  lap(tTables);
   auto bail = [&](cudaError_t err, const char *what) {
     spzb200_destroy(ctx);
     return cudaFail(err, what);
   };
-  if ((e = cudaMalloc(&ctx->dThr, 256 * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc tables");
-  if ((e = cudaMalloc(&ctx->dLut, spzb200::kDecodeTableFloats * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc tables");
-  if ((e = cudaMemcpy(ctx->dThr, ctx->hThr, sizeof ctx->hThr, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "table upload");
-  if ((e = cudaMemcpy(ctx->dLut, ctx->hLut, sizeof ctx->hLut, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "table upload");
+  // one allocation: [0, 256) thresholds, the decode tables, one scratch word for the probe
+  if ((e = cudaMalloc(&ctx->dThr, (256 + spzb200::kDecodeTableFloats + 4) * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc tables");
+  ctx->dLut = ctx->dThr + 256;
+  int *dScratch = reinterpret_cast<int *>(ctx->dLut + spzb200::kDecodeTableFloats);
+  lap(tAlloc);
   for (int s = 0; s < kStages; s++) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stage[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (int k = 0; k < 4; k++)
       if ((e = cudaEventCreate(&ctx->stage[s].ev[k])) != cudaSuccess) return bail(e, "cudaEventCreate");
   }
-  if ((e = spzb200::buildDecodeTables(ctx->dLut, ctx->stage[0].stream)) != cudaSuccess) return bail(e, "decode tables");
+  lap(tStreams);
+  // The uploads ride on the stream the table kernels and the probe run on, and the probe ends with a
+  // synchronize of that stream: everything is resident before spzb200_create returns.  (A blocking
+  // cudaMemcpy on the legacy stream would not order against these non-blocking streams.)
+  cudaStream_t s0 = ctx->stage[0].stream;
+  if ((e = cudaMemcpyAsync(ctx->dThr, ctx->hThr, sizeof ctx->hThr, cudaMemcpyHostToDevice, s0)) != cudaSuccess) return bail(e, "table upload");
+  if ((e = cudaMemcpyAsync(ctx->dLut, ctx->hLut, sizeof ctx->hLut, cudaMemcpyHostToDevice, s0)) != cudaSuccess) return bail(e, "table upload");
+  if ((e = spzb200::buildDecodeTables(ctx->dLut, s0)) != cudaSuccess) return bail(e, "decode tables");
   int ok = 0;
-  if ((e = spzb200::probePackCvt(ctx->stage[0].stream, &ok)) != cudaSuccess) return bail(e, "pack probe");
+  if ((e = spzb200::probePackCvt(s0, dScratch, &ok)) != cudaSuccess) return bail(e, "pack probe");
+  if ((e = cudaStreamSynchronize(s0)) != cudaSuccess) return bail(e, "table upload");
+  lap(tKernels);
   ctx->cvtPackOk = ok != 0;
   ctx->packMode = ok ? spzb200::kPackCvt : spzb200::kPackAlu;
   // development knobs (profiles/ records which settings the shipped defaults came from)
@@ -727,12 +842,38 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   if (const char *env = std::getenv("SPZB200_ENCODE")) ctx->encodeBulk = std::strcmp(env, "bulk") == 0 ? 2 : std::strcmp(env, "tiles") == 0 ? 0 : 1;
   if (const char *env = std::getenv("SPZB200_PLY")) ctx->plyMapped = std::strcmp(env, "mapped") == 0;
   if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = std::strcmp(env, "persistent") != 0;
+  if (const char *env = std::getenv("SPZB200_CHUNK_POINTS")) {
+    const long long v = std::atoll(env);
+    if (v > 0) ctx->chunkPoints = v;
+  }
+  if (trace)
+    fprintf(stderr, "[spz_b200 init] device %d: cuda init + device query %.2f ms, host tables %.2f ms, cudaMalloc %.2f ms, "
+            "streams + events %.2f ms, table kernels + probe (first launch loads the module) %.2f ms\n",
+            device, tQuery, tTables, tAlloc, tStreams, tKernels);
   *out = ctx;
   return SPZB200_OK;
 }
 
+int spzb200_acquire(int32_t device, SpzB200Context **out) {
+  if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_acquire: null out");
+  return contextPool().acquire(device, out);
+}
+
+void spzb200_release(SpzB200Context *ctx) {
+  if (!ctx) return;
+  if (!ctx->pooled) {  // a context of spzb200_create: the caller owns it
+    spzb200_destroy(ctx);
+    return;
+  }
+  contextPool().release(ctx);
+}
+
 void spzb200_destroy(SpzB200Context *ctx) {
   if (!ctx) return;
+  if (ctx->pooled) {  // leased contexts go back to the pool, whoever lets go of them
+    contextPool().release(ctx);
+    return;
+  }
   cudaSetDevice(ctx->device);
   delete ctx->pool;
   for (int s = 0; s < kStages; s++) {
@@ -745,8 +886,14 @@ void spzb200_destroy(SpzB200Context *ctx) {
     if (st.dOut) cudaFree(st.dOut);
     if (st.stream) cudaStreamDestroy(st.stream);
   }
-  if (ctx->dThr) cudaFree(ctx->dThr);
-  if (ctx->dLut) cudaFree(ctx->dLut);
+  for (auto &g : ctx->gather) {
+    if (g.hIn) cudaFreeHost(g.hIn);
+    if (g.hOut) cudaFreeHost(g.hOut);
+    if (g.dIn) cudaFree(g.dIn);
+    if (g.dOut) cudaFree(g.dOut);
+    if (g.done) cudaEventDestroy(g.done);
+  }
+  if (ctx->dThr) cudaFree(ctx->dThr);  // dLut lives in the same allocation
   delete ctx;
 }
 
@@ -1049,16 +1196,29 @@ static int handOverBytes(bool ok, const char *who, std::vector<uint8_t> &bytes, 
   return SPZB200_OK;
 }
 
+// No exception may cross the extern "C" boundary: an allocation failure becomes SPZB200_ERR_NOMEM.
 int spzb200_gzip(const uint8_t *data, size_t size, int32_t threads, uint8_t **out, size_t *out_size) {
-  std::vector<uint8_t> bytes;
-  const bool ok = (data || size == 0) && spz::compressGzippedParallel(data, size, threads, &bytes);
-  return handOverBytes(ok, "spzb200_gzip", bytes, out, out_size);
+  try {
+    std::vector<uint8_t> bytes;
+    const bool ok = (data || size == 0) && spz::compressGzippedParallel(data, size, threads, &bytes);
+    return handOverBytes(ok, "spzb200_gzip", bytes, out, out_size);
+  } catch (const std::exception &e) {
+    if (out) *out = nullptr;
+    if (out_size) *out_size = 0;
+    return fail(SPZB200_ERR_NOMEM, "spzb200_gzip: %s", e.what());
+  }
 }
 
 int spzb200_gunzip(const uint8_t *data, size_t size, int32_t threads, uint8_t **out, size_t *out_size) {
-  std::vector<uint8_t> bytes;
-  const bool ok = data && spz::decompressGzippedParallel(data, size, threads, &bytes);
-  return handOverBytes(ok, "spzb200_gunzip", bytes, out, out_size);
+  try {
+    std::vector<uint8_t> bytes;
+    const bool ok = data && spz::decompressGzippedParallel(data, size, threads, &bytes);
+    return handOverBytes(ok, "spzb200_gunzip", bytes, out, out_size);
+  } catch (const std::exception &e) {
+    if (out) *out = nullptr;
+    if (out_size) *out_size = 0;
+    return fail(SPZB200_ERR_NOMEM, "spzb200_gunzip: %s", e.what());
+  }
 }
 
 void spzb200_free(void *ptr) { std::free(ptr); }
@@ -1145,6 +1305,202 @@ void spzb200_set_host_staging(SpzB200Context *ctx, int32_t bounce, int32_t copy_
     delete ctx->pool;
     ctx->pool = nullptr;
   }
+}
+
+}  // extern "C"
+
+// ---- batched per-gaussian access -----------------------------------------------------------------
+namespace {
+
+constexpr long long kGatherChunk = 1 << 16;  // records per staged chunk (4.2 MB in, 15.5 MB out)
+constexpr long long kGatherZeroCopy = 2048;  // up to here the kernel reads and writes the pinned host buffers itself
+
+int ensureGatherSlot(SpzB200Context::GatherSlot &g, size_t records, bool device) {
+  if (!g.done) CU(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+  if (g.cap < records || (device && !g.dIn)) {
+    size_t cap = 256;
+    while (cap < records) cap <<= 1;
+    cap = std::max(cap, g.cap);
+    if (g.cap < cap) {
+      if (g.hIn) cudaFreeHost(g.hIn);
+      if (g.hOut) cudaFreeHost(g.hOut);
+      g.hIn = nullptr; g.hOut = nullptr;
+      if (g.dIn) cudaFree(g.dIn);
+      if (g.dOut) cudaFree(g.dOut);
+      g.dIn = nullptr; g.dOut = nullptr;
+      g.cap = 0;
+      CU(cudaHostAlloc(&g.hIn, cap * SPZB200_RECORD_BYTES, cudaHostAllocMapped));
+      CU(cudaHostAlloc(&g.hOut, cap * SPZB200_UNPACKED_FLOATS * sizeof(float), cudaHostAllocMapped));
+      g.cap = cap;
+    }
+    if (device && !g.dIn) {
+      CU(cudaMalloc(&g.dIn, g.cap * SPZB200_RECORD_BYTES));
+      CU(cudaMalloc(&g.dOut, g.cap * SPZB200_UNPACKED_FLOATS * sizeof(float)));
+    }
+  }
+  return SPZB200_OK;
+}
+
+void fillConverter(spzb200::GatherArgs &a, const float *converter) {
+  for (int i = 0; i < 3; i++) { a.flipP[i] = converter ? converter[i] : 1.0f; a.flipQ[i] = converter ? converter[3 + i] : 1.0f; }
+  for (int i = 0; i < 15; i++) a.flipSh[i] = converter ? converter[6 + i] : 1.0f;
+}
+
+// at(i), load-spz.cc:431-459: pure byte gather of one gaussian into the 65-byte record layout
+void gatherRecord(const SpzB200Packed &p, int shDim, int64_t i, uint8_t *r) {
+  const bool half = p.version == 1 || p.version == 4;
+  const size_t posBytes = half ? 6 : 9, rotBytes = p.version >= 3 ? 4 : 3;
+  std::memset(r, 0, 13);
+  std::memcpy(r, p.positions + (size_t)i * posBytes, posBytes);
+  std::memcpy(r + 9, p.rotations + (size_t)i * rotBytes, rotBytes);
+  std::memcpy(r + 13, p.scales + (size_t)i * 3, 3);
+  std::memcpy(r + 16, p.colors + (size_t)i * 3, 3);
+  r[19] = p.alphas[i];
+  const uint8_t *s = shDim ? p.sh + (size_t)i * shDim * 3 : nullptr;
+  for (int j = 0; j < 15; j++) {
+    const bool have = j < shDim;
+    r[20 + j] = have ? s[3 * j] : 128;
+    r[35 + j] = have ? s[3 * j + 1] : 128;
+    r[50 + j] = have ? s[3 * j + 2] : 128;
+  }
+}
+
+// fill(dst, first, count) writes records [first, first + count) into dst
+template <class Fill>
+int runGatherHost(SpzB200Context *ctx, long long n, int32_t version, int32_t fractionalBits, const float *converter, float *out,
+                  Fill &&fill) {
+  if (n == 0) return SPZB200_OK;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t stream = ctx->stage[0].stream;
+  spzb200::GatherArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.version = version;
+  a.positionScale = positionScaleFor(fractionalBits);
+  a.tables = ctx->dLut;
+  fillConverter(a, converter);
+  const bool zeroCopy = n <= kGatherZeroCopy;
+  const long long chunk = std::min<long long>(n, kGatherChunk);
+  const long long chunks = (n + chunk - 1) / chunk;
+  const int slots = (int)std::min<long long>(2, chunks);
+  for (int s = 0; s < slots; s++) {
+    const int rc = ensureGatherSlot(ctx->gather[s], (size_t)chunk, !zeroCopy);
+    if (rc != SPZB200_OK) return rc;
+  }
+  auto drain = [&](long long c) -> int {
+    SpzB200Context::GatherSlot &g = ctx->gather[c & 1];
+    const long long first = c * chunk, count = std::min(n, first + chunk) - first;
+    CU(cudaEventSynchronize(g.done));
+    std::memcpy(out + first * SPZB200_UNPACKED_FLOATS, g.hOut, (size_t)count * SPZB200_UNPACKED_FLOATS * sizeof(float));
+    return SPZB200_OK;
+  };
+  for (long long c = 0; c < chunks; c++) {
+    SpzB200Context::GatherSlot &g = ctx->gather[c & 1];
+    if (c >= 2) {
+      const int rc = drain(c - 2);
+      if (rc != SPZB200_OK) return rc;
+    }
+    const long long first = c * chunk, count = std::min(n, first + chunk) - first;
+    fill(g.hIn, first, count);
+    int launches = 0;
+    a.n = count;
+    if (zeroCopy) {
+      // a handful of gaussians: the kernel reads the pinned records and writes the pinned result over
+      // PCIe itself -- one launch and one synchronize instead of copy, launch, copy
+      a.records = g.hIn;
+      a.out = g.hOut;
+    } else {
+      CU(cudaMemcpyAsync(g.dIn, g.hIn, (size_t)count * SPZB200_RECORD_BYTES, cudaMemcpyHostToDevice, stream));
+      a.records = g.dIn;
+      a.out = g.dOut;
+    }
+    CU(spzb200::launchUnpackRecords(a, stream, &launches));
+    ctx->kernelLaunches += launches;
+    if (!zeroCopy)
+      CU(cudaMemcpyAsync(g.hOut, g.dOut, (size_t)count * SPZB200_UNPACKED_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CU(cudaEventRecord(g.done, stream));
+  }
+  for (long long c = std::max<long long>(0, chunks - 2); c < chunks; c++) {
+    const int rc = drain(c);
+    if (rc != SPZB200_OK) return rc;
+  }
+  return SPZB200_OK;
+}
+
+int gatherFailed(SpzB200Context *ctx, int rc) {
+  if (rc != SPZB200_OK) {  // nothing of this call may still be reading or writing the staging buffers
+    const std::string first = tlsError;
+    (void)cudaStreamSynchronize(ctx->stage[0].stream);
+    (void)cudaGetLastError();
+    tlsError = first;
+  }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spzb200_unpack_records_host(SpzB200Context *ctx, const uint8_t *records, int64_t n, int32_t version,
+                                int32_t fractional_bits, const float *converter, float *out) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_unpack_records_host: null context");
+  if (n < 0) return fail(SPZB200_ERR_INVALID, "spzb200_unpack_records_host: n < 0");
+  if (version < 1 || version > SPZB200_STREAM_HALF_POSITIONS_SMALLEST_THREE)
+    return fail(SPZB200_ERR_INVALID, "spzb200_unpack_records_host: version %d not in 1..4", version);
+  if (n > 0 && (!records || !out)) return fail(SPZB200_ERR_INVALID, "spzb200_unpack_records_host: null pointer");
+  return gatherFailed(ctx, runGatherHost(ctx, n, version, fractional_bits, converter, out, [&](uint8_t *dst, long long first, long long count) {
+    std::memcpy(dst, records + (size_t)first * SPZB200_RECORD_BYTES, (size_t)count * SPZB200_RECORD_BYTES);
+  }));
+}
+
+int spzb200_unpack_gather_host(SpzB200Context *ctx, const SpzB200Packed *packed, const int64_t *indices, int64_t n,
+                               const float *converter, float *out) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_unpack_gather_host: null context");
+  int rc = checkPacked(packed, "spzb200_unpack_gather_host", true);
+  if (rc) return rc;
+  if (n < 0) return fail(SPZB200_ERR_INVALID, "spzb200_unpack_gather_host: n < 0");
+  if (n > 0 && !out) return fail(SPZB200_ERR_INVALID, "spzb200_unpack_gather_host: null out");
+  if (!indices && n > packed->num_points)
+    return fail(SPZB200_ERR_INVALID, "spzb200_unpack_gather_host: n exceeds num_points and no indices were given");
+  if (indices)
+    for (int64_t k = 0; k < n; k++)
+      if (indices[k] < 0 || indices[k] >= packed->num_points)
+        return fail(SPZB200_ERR_INVALID, "spzb200_unpack_gather_host: index %lld at position %lld is outside [0, %lld)",
+                    (long long)indices[k], (long long)k, (long long)packed->num_points);
+  const int shDim = shDimOf(packed->sh_degree);
+  const SpzB200Packed p = *packed;
+  return gatherFailed(ctx, runGatherHost(ctx, n, p.version, p.fractional_bits, converter, out, [&](uint8_t *dst, long long first, long long count) {
+    for (long long k = 0; k < count; k++)
+      gatherRecord(p, shDim, indices ? indices[first + k] : first + k, dst + (size_t)k * SPZB200_RECORD_BYTES);
+  }));
+}
+
+int spzb200_unpack_gather_device(SpzB200Context *ctx, const SpzB200Packed *packed, const int64_t *indices, int64_t n,
+                                 const float *converter, float *out, void *stream) {
+  if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_unpack_gather_device: null context");
+  int rc = checkPacked(packed, "spzb200_unpack_gather_device", true);
+  if (rc) return rc;
+  if (n < 0) return fail(SPZB200_ERR_INVALID, "spzb200_unpack_gather_device: n < 0");
+  if (n > 0 && !out) return fail(SPZB200_ERR_INVALID, "spzb200_unpack_gather_device: null out");
+  if (!indices && n > packed->num_points)
+    return fail(SPZB200_ERR_INVALID, "spzb200_unpack_gather_device: n exceeds num_points and no indices were given");
+  if (n == 0) return SPZB200_OK;
+  CU(cudaSetDevice(ctx->device));
+  spzb200::GatherArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.positions = packed->positions; a.scales = packed->scales; a.rotations = packed->rotations;
+  a.alphas = packed->alphas; a.colors = packed->colors; a.sh = packed->sh;
+  a.indices = reinterpret_cast<const long long *>(indices);
+  a.out = out;
+  a.n = n;
+  a.shDim = shDimOf(packed->sh_degree);
+  a.version = packed->version;
+  a.positionScale = positionScaleFor(packed->fractional_bits);
+  a.tables = ctx->dLut;
+  fillConverter(a, converter);
+  int launches = 0;
+  CU(spzb200::launchUnpackRecords(a, (cudaStream_t)stream, &launches));
+  ctx->kernelLaunches += launches;
+  return SPZB200_OK;
 }
 
 }  // extern "C"

@@ -892,15 +892,11 @@ cudaError_t divisionSelfCheck(int part, unsigned long long pairsPerThread, unsig
   return e;
 }
 
-cudaError_t probePackCvt(cudaStream_t stream, int *ok) {
-  int *d = nullptr;
-  cudaError_t e = cudaMalloc(&d, sizeof(int));
-  if (e != cudaSuccess) return e;
-  probePackKernel<<<1, 1, 0, stream>>>(d);
-  e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(ok, d, sizeof(int), cudaMemcpyDeviceToHost, stream);
+cudaError_t probePackCvt(cudaStream_t stream, int *scratch, int *ok) {
+  probePackKernel<<<1, 1, 0, stream>>>(scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ok, scratch, sizeof(int), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  cudaFree(d);
   return e;
 }
 

@@ -64,6 +64,23 @@ struct PlyDecodeArgs {
   const float *tables;
 };
 
+// Batched PackedGaussians::at(i) + PackedGaussian::unpack (load-spz.cc:383-463), gather_kernels.cu.
+// Either `records` (n x 65-byte PackedGaussian) or the six packed planes (+ optional index list) is
+// the source; `out` receives n x 59 floats (UnpackedGaussian).  All pointers are device-accessible.
+struct GatherArgs {
+  const uint8_t *records;  // non-null: array of PackedGaussian; null: gather from the planes below
+  const uint8_t *positions, *scales, *rotations, *alphas, *colors, *sh;
+  const long long *indices;  // null = gaussians 0..n-1 of the planes
+  float *out;
+  long long n;
+  int shDim;
+  int version;             // stream flavour 1..4 (include/spz_b200.h)
+  float positionScale;     // (float)(1.0 / (1 << fractionalBits))
+  float flipP[3], flipQ[3], flipSh[15];  // the caller's CoordinateConverter, applied by multiplication
+  const float *tables;
+};
+cudaError_t launchUnpackRecords(const GatherArgs &a, cudaStream_t stream, int *launches);
+
 enum PackMode { kPackAlu = 0, kPackCvt = 1 };
 
 struct LaunchPlan {
@@ -107,7 +124,7 @@ cudaError_t divisionSelfCheck(int part, unsigned long long pairsPerThread, unsig
                               unsigned long long *wrong, unsigned long long *checked);
 
 // Runs both byte packers on probe values; *ok = 1 when cvt.pack.sat.u8.s32.b32 orders and
-// saturates bytes the way the kernels assume (decided once per context).
-cudaError_t probePackCvt(cudaStream_t stream, int *ok);
+// saturates bytes the way the kernels assume (decided once per context).  `scratch` = one device int.
+cudaError_t probePackCvt(cudaStream_t stream, int *scratch, int *ok);
 
 }  // namespace spzb200

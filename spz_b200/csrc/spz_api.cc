@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <limits>
 #include <mutex>
@@ -85,8 +86,9 @@ constexpr size_t kHeaderBytes = 16;
 
 // ---- devices and contexts -----------------------------------------------------------------------
 // SPZ_B200_DEVICES="0,1,2,3" shards every call by point range over those GPUs (no collective);
-// default is device 0 (or SPZ_B200_DEVICE).  One context per host thread and device, created on
-// first use and kept until the thread exits.
+// default is device 0 (or SPZ_B200_DEVICE).  Every call leases a context from the process-wide pool
+// (spzb200_acquire) and hands it back on return, so short-lived host threads do not rebuild streams,
+// tables, staging and pinned bounce buffers per thread.
 
 }  // namespace
 
@@ -110,35 +112,18 @@ std::vector<int32_t> configuredDevices() {
   return devs;
 }
 
-struct ThreadContext {
-  SpzB200Context *ctx = nullptr;
-  int32_t device = -1;
-  ~ThreadContext() {
-    if (ctx) spzb200_destroy(ctx);
-  }
-};
-
-SpzB200Context *contextFor(int32_t device) {
-  thread_local ThreadContext tc;
-  if (tc.ctx && tc.device == device) return tc.ctx;
-  if (tc.ctx) {
-    spzb200_destroy(tc.ctx);
-    tc.ctx = nullptr;
-  }
-  if (spzb200_create(device, &tc.ctx) != SPZB200_OK) {
+ContextLease::ContextLease(int32_t device) {
+  if (spzb200_acquire(device, &ctx_) != SPZB200_OK) {
     logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
-    tc.ctx = nullptr;
-    return nullptr;
+    ctx_ = nullptr;
   }
-  tc.device = device;
-  return tc.ctx;
 }
 
 }  // namespace detail
 
 namespace {
 using detail::configuredDevices;
-using detail::contextFor;
+using detail::ContextLease;
 
 bool checkCloudSizes(const GaussianCloud &g) {
   // the reference's checks (load-spz.cc:106-117) with the products taken in 64 bits
@@ -356,9 +341,9 @@ PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussian
   if (devs.size() > 1) {
     rc = spzb200_encode_host_multi(devs.data(), (int32_t)devs.size(), &in, (int32_t)o.from, &out, nullptr);
   } else {
-    SpzB200Context *ctx = contextFor(devs[0]);
-    if (!ctx) return PackStatus::DeviceError;
-    rc = spzb200_encode_host(ctx, &in, (int32_t)o.from, &out, nullptr);
+    ContextLease lease(devs[0]);
+    if (!lease.get()) return PackStatus::DeviceError;
+    rc = spzb200_encode_host(lease.get(), &in, (int32_t)o.from, &out, nullptr);
   }
   if (rc != SPZB200_OK) {
     logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
@@ -399,9 +384,9 @@ GaussianCloud unpackGaussians(const PackedGaussians &packed, const UnpackOptions
   if (devs.size() > 1) {
     rc = spzb200_decode_host_multi(devs.data(), (int32_t)devs.size(), &in, (int32_t)o.to, &out, nullptr);
   } else {
-    SpzB200Context *ctx = contextFor(devs[0]);
-    if (!ctx) return {};
-    rc = spzb200_decode_host(ctx, &in, (int32_t)o.to, &out, nullptr);
+    ContextLease lease(devs[0]);
+    if (!lease.get()) return {};
+    rc = spzb200_decode_host(lease.get(), &in, (int32_t)o.to, &out, nullptr);
   }
   if (rc != SPZB200_OK) {
     logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
@@ -438,56 +423,56 @@ PackedGaussian PackedGaussians::at(int32_t i) const {
   return r;
 }
 
-// One gaussian through the same decode kernel as the bulk path (a 1-point degree-3 stream, no
-// flips), then the caller's converter applied as plain multiplications, which is where the
-// reference applies it too (load-spz.cc:391,401,426-428; :377-379 for the quaternion).
+// One gaussian through the batched gather kernel (gather_kernels.cu): the struct IS the kernel's
+// 65-byte record and the result IS its 59-float output, so there is no marshalling; for a handful of
+// records the kernel reads and writes pinned host memory itself (one launch, one synchronize, ~10 us).
+// A caller that wants many should use unpackGaussiansAt below: one launch for the whole list.
+// Without a usable device there is no CPU path: the failure is logged and every field is NaN, which no
+// valid stream decodes to -- never a plausible-looking all-zero gaussian.
+static_assert(sizeof(PackedGaussian) == SPZB200_RECORD_BYTES, "PackedGaussian must be the 65-byte record");
+static_assert(sizeof(UnpackedGaussian) == SPZB200_UNPACKED_FLOATS * sizeof(float), "UnpackedGaussian must be 59 floats");
+static_assert(sizeof(CoordinateConverter) == 21 * sizeof(float), "CoordinateConverter must be 21 floats");
+
+namespace {
+void poison(UnpackedGaussian *u, size_t count) {
+  float *f = reinterpret_cast<float *>(u);
+  for (size_t i = 0; i < count * SPZB200_UNPACKED_FLOATS; i++) f[i] = std::numeric_limits<float>::quiet_NaN();
+}
+}  // namespace
+
 UnpackedGaussian PackedGaussian::unpack(bool usesFloat16, bool usesQuaternionSmallestThree,
                                         int32_t fractionalBits, const CoordinateConverter &c) const {
   UnpackedGaussian u;
-  std::memset(&u, 0, sizeof u);
-  uint8_t shBytes[45];
-  for (int j = 0; j < 15; j++) {
-    shBytes[3 * j] = shR[j];
-    shBytes[3 * j + 1] = shG[j];
-    shBytes[3 * j + 2] = shB[j];
-  }
-  float shOut[45], pos[3], rot[4], scl[3], col[3], alp[1];
-  SpzB200Packed in;
-  std::memset(&in, 0, sizeof in);
-  in.num_points = 1;
-  in.sh_degree = 3;
-  in.fractional_bits = fractionalBits;
-  in.version = streamFlavour(usesFloat16, usesQuaternionSmallestThree);
-  in.positions = const_cast<uint8_t *>(position.data());
-  in.scales = const_cast<uint8_t *>(scale.data());
-  in.rotations = const_cast<uint8_t *>(rotation.data());
-  in.alphas = const_cast<uint8_t *>(&alpha);
-  in.colors = const_cast<uint8_t *>(color.data());
-  in.sh = shBytes;
-  SpzB200Cloud out;
-  std::memset(&out, 0, sizeof out);
-  out.num_points = 1;
-  out.sh_degree = 3;
-  out.positions = pos; out.scales = scl; out.rotations = rot; out.alphas = alp; out.colors = col; out.sh = shOut;
-  SpzB200Context *ctx = contextFor(configuredDevices()[0]);
-  if (!ctx || spzb200_decode_host(ctx, &in, SPZB200_COORD_UNSPECIFIED, &out, nullptr) != SPZB200_OK) {
-    if (ctx) logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
-    return u;
-  }
-  for (int a = 0; a < 3; a++) {
-    u.position[a] = c.flipP[a] * pos[a];
-    u.scale[a] = scl[a];
-    u.color[a] = col[a];
-    u.rotation[a] = rot[a] * c.flipQ[a];
-  }
-  u.rotation[3] = rot[3];
-  u.alpha = alp[0];
-  for (int j = 0; j < 15; j++) {
-    u.shR[j] = c.flipSh[j] * shOut[3 * j];
-    u.shG[j] = c.flipSh[j] * shOut[3 * j + 1];
-    u.shB[j] = c.flipSh[j] * shOut[3 * j + 2];
+  ContextLease lease(configuredDevices()[0]);
+  if (!lease.get() ||
+      spzb200_unpack_records_host(lease.get(), reinterpret_cast<const uint8_t *>(this), 1, streamFlavour(usesFloat16, usesQuaternionSmallestThree),
+                                  fractionalBits, c.flipP.data(), reinterpret_cast<float *>(&u)) != SPZB200_OK) {
+    if (lease.get()) logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
+    poison(&u, 1);
   }
   return u;
+}
+
+// Extension: PackedGaussians::unpack(i, c) for a list of indices in one launch.
+// Returns an empty vector (after a logged line) when an index is out of range or no device is usable.
+std::vector<UnpackedGaussian> unpackGaussiansAt(const PackedGaussians &packed, const std::vector<int32_t> &indices,
+                                                const CoordinateConverter &c) {
+  std::vector<UnpackedGaussian> out;
+  if (indices.empty()) return out;
+  const bool usesFloat16 = packed.usesFloat16();
+  if (packed.numPoints < 0 || packed.shDegree < 0 || packed.shDegree > 3 ||
+      !checkPackedSizes(packed, packed.numPoints, shDimOf(packed.shDegree), usesFloat16))
+    return out;
+  std::vector<int64_t> idx(indices.begin(), indices.end());
+  const SpzB200Packed in = viewOf(packed, streamFlavour(usesFloat16, packed.usesQuaternionSmallestThree));
+  out.resize(indices.size());
+  ContextLease lease(configuredDevices()[0]);
+  if (!lease.get() || spzb200_unpack_gather_host(lease.get(), &in, idx.data(), (int64_t)idx.size(), c.flipP.data(),
+                                                 reinterpret_cast<float *>(out.data())) != SPZB200_OK) {
+    if (lease.get()) logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
+    out.clear();
+  }
+  return out;
 }
 
 UnpackedGaussian PackedGaussians::unpack(int32_t i, const CoordinateConverter &c) const {
@@ -634,9 +619,14 @@ bool saveSpz(const GaussianCloud &g, const PackOptions &o, const std::string &fi
 }
 
 PackedGaussians loadSpzPacked(const uint8_t *data, int32_t size) {
-  std::vector<uint8_t> stream;
-  if (size < 0 || !decompressGzippedParallel(data, (size_t)size, gzipThreads(), &stream)) return {};
-  return deserialize(stream.data(), stream.size());
+  try {
+    std::vector<uint8_t> stream;
+    if (size < 0 || !decompressGzippedParallel(data, (size_t)size, gzipThreads(), &stream)) return {};
+    return deserialize(stream.data(), stream.size());
+  } catch (const std::exception &e) {  // out of memory on a hostile or huge file: a failed load, not a throw
+    logLine("[SPZ ERROR] loadSpzPacked: %s", e.what());
+    return {};
+  }
 }
 
 PackedGaussians loadSpzPacked(const std::vector<uint8_t> &data) {

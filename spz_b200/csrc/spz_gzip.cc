@@ -21,6 +21,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -183,8 +184,23 @@ bool decompressGzippedParallel(const uint8_t *data, size_t size, int threads, st
   const uint32_t wantCrc = get32(data + offset[blocks]), isize = get32(data + offset[blocks] + 4);
   const size_t total = (size_t)t.totalSize, lastLen = total - (blocks - 1) * t.blockSize;
   if ((uint32_t)(total & 0xffffffffu) != isize) return decompressGzipped(data, size, out);
+  // The table is untrusted input and sizes the allocation below before a byte has been inflated.
+  // Deflate cannot expand by more than 1032 : 1 (a 258-byte match costs at least 2 bits), so a block
+  // that claims more than that for its compressed length -- and with it any absurd total -- is not
+  // ours: the serial inflater, whose buffer only grows with what zlib really produces, gives the verdict.
+  constexpr uint64_t kMaxExpansion = 1032;
+  if (t.blockSize >= ((size_t)1 << 31)) return decompressGzipped(data, size, out);  // zlib counts a block in 32 bits
+  for (size_t i = 0; i < blocks; i++) {
+    const uint64_t len = i + 1 == blocks ? lastLen : t.blockSize;
+    if (len > kMaxExpansion * ((uint64_t)t.compressed[i] + 1)) return decompressGzipped(data, size, out);
+  }
   out->clear();
-  detail::resizeUninitialized(*out, total);  // every block inflates into its own slice; no zero-fill pass on one thread first
+  try {
+    detail::resizeUninitialized(*out, total);  // every block inflates into its own slice; no zero-fill pass on one thread first
+  } catch (const std::exception &) {  // the API never throws (load-spz.cc:94-100): an allocation failure is a failed load
+    out->clear();
+    return false;
+  }
   std::vector<uint32_t> crcs(blocks);
   std::atomic<bool> ok{true};
   parallelFor(blocks, threads, [&](size_t i) {
@@ -197,12 +213,14 @@ bool decompressGzippedParallel(const uint8_t *data, size_t size, int threads, st
     zs.next_out = out->data() + i * t.blockSize;
     zs.avail_out = (uInt)len;
     const int rc = inflate(&zs, Z_SYNC_FLUSH);
-    if (!((rc == Z_OK || rc == Z_STREAM_END) && zs.avail_out == 0)) ok = false;  // content is vouched for by the CRC below
+    const bool filled = (rc == Z_OK || rc == Z_STREAM_END) && zs.avail_out == 0;  // content is vouched for by the CRC below
     inflateEnd(&zs);
+    if (!filled) { ok = false; return; }  // the slice is only partly written: nothing to checksum
     crcs[i] = (uint32_t)crc32(crc32(0L, Z_NULL, 0), out->data() + i * t.blockSize, (uInt)len);
   });
   uLong crc = crc32(0L, Z_NULL, 0);
-  for (size_t i = 0; i < blocks; i++) crc = crc32_combine(crc, crcs[i], (z_off_t)(i + 1 == blocks ? lastLen : t.blockSize));
+  if (ok)
+    for (size_t i = 0; i < blocks; i++) crc = crc32_combine(crc, crcs[i], (z_off_t)(i + 1 == blocks ? lastLen : t.blockSize));
   if (!ok || (uint32_t)crc != wantCrc) {
     // a damaged table or block: let the serial inflater give the verdict the reference would
     return decompressGzipped(data, size, out);

@@ -224,9 +224,9 @@ bool plyToSpz(const std::string &plyFilename, const PackOptions &options, std::v
   out.sh_degree = degree;
   out.positions = packed.positions.data(); out.scales = packed.scales.data(); out.rotations = packed.rotations.data();
   out.alphas = packed.alphas.data(); out.colors = packed.colors.data(); out.sh = packed.sh.data();
-  SpzB200Context *ctx = detail::contextFor(detail::configuredDevices()[0]);
-  if (!ctx) return false;
-  if (spzb200_encode_ply_host(ctx, &in, (int32_t)options.from, &out, nullptr) != SPZB200_OK) {
+  detail::ContextLease lease(detail::configuredDevices()[0]);
+  if (!lease.get()) return false;
+  if (spzb200_encode_ply_host(lease.get(), &in, (int32_t)options.from, &out, nullptr) != SPZB200_OK) {
     detail::logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
     return false;
   }
@@ -270,9 +270,9 @@ bool spzToPly(const std::vector<uint8_t> &spzBytes, const UnpackOptions &options
     const int32_t rot0 = (int32_t)(13 + 3 * shDim);
     out.col_rot[3] = rot0;  // w
     for (int a = 0; a < 3; a++) out.col_rot[a] = rot0 + 1 + a;
-    SpzB200Context *ctx = detail::contextFor(detail::configuredDevices()[0]);
-    if (!ctx) return false;
-    if (spzb200_decode_ply_host(ctx, &in, (int32_t)options.to, &out, nullptr) != SPZB200_OK) {
+    detail::ContextLease lease(detail::configuredDevices()[0]);
+    if (!lease.get()) return false;
+    if (spzb200_decode_ply_host(lease.get(), &in, (int32_t)options.to, &out, nullptr) != SPZB200_OK) {
       detail::logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
       return false;
     }

@@ -4,6 +4,7 @@
 // The two builds expose the same flat C functions so tests can feed both the same inputs and
 // compare outputs byte for byte.  That the file compiles unchanged against either header set is
 // itself the drop-in check.
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -285,6 +286,65 @@ void SHIM(packed_unpack_one)(int32_t n, int32_t deg, int32_t fb, int32_t version
   std::memcpy(o, u.shR.data(), 60); o += 15;
   std::memcpy(o, u.shG.data(), 60); o += 15;
   std::memcpy(o, u.shB.data(), 60);
+}
+
+// PackedGaussians::unpack(idx[k], c) for a list of indices and ANY converter (21 floats: flipP, flipQ,
+// flipSh), 59 floats out each.  use_batch != 0 takes this repo's one-launch extension
+// (spz::unpackGaussiansAt) where the headers have it; otherwise, and always for the reference, a
+// loop over unpack(i, c).  Returns the number of gaussians written.
+int32_t SHIM(packed_unpack_many)(int32_t n, int32_t deg, int32_t fb, int32_t version, const uint8_t *const planes[6],
+                                 const int32_t *idx, int32_t count, const float *conv21, int32_t use_batch, float *out) {
+  const spz::PackedGaussians p = makePacked(n, deg, fb, version, 0, planes);
+  spz::CoordinateConverter c;
+  std::memcpy(c.flipP.data(), conv21, 12);
+  std::memcpy(c.flipQ.data(), conv21 + 3, 12);
+  std::memcpy(c.flipSh.data(), conv21 + 6, 60);
+  static_assert(sizeof(spz::UnpackedGaussian) == 59 * sizeof(float), "UnpackedGaussian is 59 packed floats");
+#ifdef SHIM_HAS_EXTENSIONS
+  if (use_batch) {
+    const std::vector<spz::UnpackedGaussian> got = spz::unpackGaussiansAt(p, std::vector<int32_t>(idx, idx + count), c);
+    if (!got.empty()) std::memcpy(out, got.data(), got.size() * sizeof(spz::UnpackedGaussian));
+    return (int32_t)got.size();
+  }
+#endif
+  (void)use_batch;
+  for (int32_t k = 0; k < count; k++) {
+    const spz::UnpackedGaussian u = p.unpack(idx[k], c);
+    std::memcpy(out + (size_t)k * 59, &u, sizeof u);
+  }
+  return count;
+}
+
+// `threads` short-lived host threads, each packing the cloud ONCE and exiting (a request-per-thread
+// server).  run_concurrently = 0 starts them one after the other, 2 = one thread does all the packs.  Returns the wall time in
+// milliseconds, or -1 if any result differs from the first thread's.
+double SHIM(short_lived_threads)(int32_t n, int32_t deg, int32_t from, const float *const planes[6], int32_t threads,
+                                 int32_t run_concurrently) {
+  const spz::GaussianCloud g = makeCloud(n, deg, 0, planes);
+  spz::PackOptions po; po.from = (spz::CoordinateSystem)from;
+  std::vector<spz::PackedGaussians> packed((size_t)threads);
+  const auto t0 = std::chrono::steady_clock::now();
+  if (run_concurrently == 2) {  // the yardstick: the same number of packs from ONE thread
+    std::thread th([&] {
+      for (int t = 0; t < threads; t++) packed[t] = spz::packGaussians(g, po);
+    });
+    th.join();
+  } else if (run_concurrently) {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back([&, t] { packed[t] = spz::packGaussians(g, po); });
+    for (auto &t : pool) t.join();
+  } else {
+    for (int t = 0; t < threads; t++) {
+      std::thread th([&, t] { packed[t] = spz::packGaussians(g, po); });
+      th.join();
+    }
+  }
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  for (int t = 0; t < threads; t++)
+    if (packed[t].numPoints != n || packed[t].sh != packed[0].sh || packed[t].rotations != packed[0].rotations ||
+        packed[t].positions != packed[0].positions)
+      return -1.0;
+  return ms;
 }
 
 void SHIM(converter)(int32_t from, int32_t to, float *out21) {

@@ -190,6 +190,22 @@ class Shim:
                                      C.c_int32(i), C.c_int32(frm), C.c_int32(to), out.ctypes.data_as(_f32p))
         return out
 
+    def unpack_many(self, p: Packed, idx, conv21, batch: bool) -> np.ndarray:
+        _, ip = self._bplanes(p.planes())
+        idx = np.ascontiguousarray(idx, np.int32)
+        conv = np.ascontiguousarray(conv21, np.float32)
+        out = np.zeros((idx.size, 59), np.float32)
+        got = self.fn("packed_unpack_many")(C.c_int32(p.n), C.c_int32(p.sh_degree), C.c_int32(p.fractional_bits), C.c_int32(p.version), ip,
+                                            idx.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(idx.size), conv.ctypes.data_as(_f32p),
+                                            C.c_int32(int(batch)), out.ctypes.data_as(_f32p))
+        return out[:got]
+
+    def short_lived_threads(self, c: Cloud, frm: int, threads: int, concurrently) -> float:
+        _, ip = self._fplanes(c.planes())
+        f = self.fn("short_lived_threads")
+        f.restype = C.c_double
+        return f(C.c_int32(c.n), C.c_int32(c.sh_degree), C.c_int32(frm), ip, C.c_int32(threads), C.c_int32(int(concurrently)))
+
     def converter(self, frm, to) -> np.ndarray:
         out = np.zeros(21, np.float32)
         self.fn("converter")(C.c_int32(frm), C.c_int32(to), out.ctypes.data_as(_f32p))
@@ -521,6 +537,43 @@ def test_parallel_gzip_is_a_standard_member_with_identical_content(mine, theirs)
     assert mine.gunzip(b"", 4) is None and mine.gunzip(b"\x1f\x8b", 4) is None
 
 
+def test_parallel_gunzip_rejects_a_hostile_block_table(mine):
+    """the 'SZ' FEXTRA table is untrusted and used to size the output before a byte is inflated.  A
+    table that claims terabytes (or just more than deflate's 1032:1 ceiling for a block's compressed length) must
+    neither allocate that nor throw across the API: the serial inflater -- whose buffer grows only with what zlib
+    really produces -- gives the verdict, through the C++ API, the loader and the extern "C" entry point."""
+    import resource
+    from spz_b200 import codec
+    data = bytes(3 << 20)  # zeros: three 1 MiB blocks of ~1 KB each
+    z = bytearray(mine.gzip_parallel(data, 4))
+    assert z[3] == 4 and z[12:14] == b"SZ"
+    blocks = struct.unpack_from("<I", z, 20)[0]
+    assert blocks == 3 and struct.unpack_from("<I", z, 16)[0] == 1 << 20
+
+    def forged(block_size, total):
+        f = bytearray(z)
+        struct.pack_into("<IIII", f, 16, block_size, blocks, total & 0xffffffff, total >> 32)
+        struct.pack_into("<I", f, len(f) - 4, total & 0xffffffff)  # ISIZE agrees with the table
+        return bytes(f)
+
+    before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    for block_size, total in ((1 << 30, (2 << 30) + 5), (0xffff0000, 2 * 0xffff0000 + 1), (1 << 31, (2 << 31) + 1),
+                              ((1 << 20) + 4096, 2 * ((1 << 20) + 4096) + 1)):
+        blob = forged(block_size, total)
+        for call in (lambda b: mine.gunzip(b, 4), lambda b: codec.gunzip_bytes(b, 4)):
+            try:
+                got = call(blob)
+            except Exception as e:  # noqa: BLE001 -- a clean refusal (CodecError) is fine too
+                assert "zlib" in str(e) or "memory" in str(e)
+                got = None
+            assert got is None  # the serial inflater sees ISIZE disagree with what the stream really holds
+        meta, _ = mine.load_packed(blob)
+        assert meta["n"] == 0
+    after = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    assert after - before < 512 * 1024  # KiB: nothing near the forged gigabytes was ever touched
+    assert mine.gunzip(bytes(z), 4) == data
+
+
 def test_parallel_gunzip_fuzz(mine):
     """Seeded damage to block-parallel gzip members (the block table in FEXTRA, block bodies, the trailer,
     truncation): the inflater never crashes, and gives Python's gzip module's verdict -- the same bytes
@@ -781,6 +834,61 @@ def test_unpack_one_matches_reference(mine, theirs):
                 for frm, to in ((0, 0), (4, 6), (4, 7)):
                     a, b = mine.unpack_one(s, i, frm, to), theirs.unpack_one(s, i, frm, to)
                     assert np.array_equal(bits(a), bits(b)), (ver, deg, i, frm, to)
+
+
+@pytest.mark.gpu
+def test_unpack_many_matches_a_loop_over_the_reference(mine, theirs, relinked):
+    """batched at()/unpack(i) -- one launch for a list of indices -- against the reference's
+    PackedGaussians::unpack (load-spz.cc:383-463) called in a loop, every stream flavour and SH degree, the
+    nine coordinate converters and a hand-built converter with arbitrary factors (applied by multiplication,
+    in the reference's order)."""
+    rng = np.random.default_rng(410)
+    odd = (rng.normal(size=21) * 3).astype(np.float32)
+    odd[[2, 9]] = [0.0, -0.0]
+    convs = [mine.converter(frm, to) for frm, to in ((0, 0), (4, 6), (4, 7), (1, 8), (6, 3))] + [odd]
+    for ver in (1, 2, 3, 4):
+        for deg in range(4):
+            n = 700
+            s = random_stream(rng, n, deg, ver, int(rng.choice([0, 5, 12, 20])))
+            if ver >= 3:
+                s.rotations.view("<u4")[::2] &= np.uint32(0xEFFBFEFF)  # half of them valid unit quaternions, half NaN roots
+            idx = np.concatenate([[0, n - 1, n - 1, 3], rng.integers(0, n, 300)]).astype(np.int32)
+            for conv in convs:
+                want = theirs.unpack_many(s, idx, conv, False)
+                got = mine.unpack_many(s, idx, conv, True)
+                assert got.shape == want.shape
+                assert np.array_equal(bits(got), bits(want)), (ver, deg, conv[:3])
+            # the one-at-a-time accessor, through this library and through a consumer built against the reference's headers
+            few = idx[:6]
+            want = theirs.unpack_many(s, few, odd, False)
+            assert np.array_equal(bits(mine.unpack_many(s, few, odd, False)), bits(want))
+            assert np.array_equal(bits(relinked.unpack_many(s, few, odd, False)), bits(want))
+    # an index outside the cloud is refused (empty result), not read out of bounds
+    assert mine.unpack_many(s, np.array([0, n], np.int32), convs[0], True).shape[0] == 0
+    # a list longer than one staged chunk (65536 records) exercises the double-buffered path
+    big = random_stream(rng, 5000, 3, 3)
+    big.rotations.view("<u4")[:] &= np.uint32(0xEFFBFEFF)
+    idx = rng.integers(0, 5000, 150_000).astype(np.int32)
+    got = mine.unpack_many(big, idx, convs[1], True)
+    uniq = theirs.unpack_many(big, np.arange(5000, dtype=np.int32), convs[1], False)
+    assert np.array_equal(bits(got), bits(uniq[idx]))
+
+
+@pytest.mark.gpu
+def test_short_lived_threads_share_pooled_contexts(mine):
+    """a server that packs from threads that come and go must not rebuild the GPU context
+    (streams, tables, staging, pinned bounce buffers) per thread.  64 threads that each pack once and exit take
+    less than twice as long as 64 packs from one thread; results identical."""
+    rng = np.random.default_rng(420)
+    c = random_cloud(rng, 60_000, 3, False)
+    assert mine.short_lived_threads(c, 6, 4, False) >= 0          # warm: the pool now holds a context
+    steady_ms = min(mine.short_lived_threads(c, 6, 64, 2) for _ in range(2))
+    serial_ms = mine.short_lived_threads(c, 6, 64, False)
+    burst_ms = mine.short_lived_threads(c, 6, 64, True)
+    assert serial_ms >= 0 and burst_ms >= 0, "results differ between threads"
+    print(f"64 packs of 60k SH3: one thread {steady_ms:.1f} ms, 64 one-shot threads in turn {serial_ms:.1f} ms, at once {burst_ms:.1f} ms")
+    assert serial_ms < 2 * steady_ms + 20
+    assert burst_ms < 2 * steady_ms + 20
 
 
 @pytest.mark.gpu

@@ -628,3 +628,72 @@ def test_full_size_10m_sh3_properties(gpu_ctx, oracle):
     t.cuda.synchronize()
     for name, a, b in zip(PLANES, p.planes(), out.planes()):
         assert t.equal(a, b), name
+
+
+# ---- batched per-gaussian access (load-spz.cc:383-463) ---------------------------
+
+def test_unpack_gather_golden(gpu_ctx):
+    """spzb200_unpack_gather_host / _device / _records_host against vectors made by the reference's own
+    PackedGaussians::unpack(i, c): every stream flavour x SH degree x {identity, RUB->RDF, arbitrary factors}."""
+    import os
+    from spz_b200 import codec
+    t = _torch()
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_unpack_at.npz"))
+    convs = G["converters"]
+    for ver in (1, 2, 3, 4):
+        for deg in range(4):
+            key = f"v{ver}d{deg}"
+            s = Packed(64, deg, int(G[f"{key}_fb"]), ver, *[G[f"{key}_{p}"] for p in PLANES])
+            hp = codec.PackedPlanes(64, deg, *[np.ascontiguousarray(a) for a in s.planes()], fractional_bits=s.fractional_bits, version=ver)
+            dp = to_dev_packed(s)
+            idx = G[f"{key}_idx"]
+            for k, conv in enumerate(convs):
+                want = G[f"{key}_out{k}"]
+                assert np.array_equal(bits(gpu_ctx.unpack_gather_host(hp, idx, conv)), want), (key, k, "host")
+                got = gpu_ctx.unpack_gather_device(dp, t.from_numpy(idx).cuda(), conv)
+                t.cuda.synchronize()
+                assert np.array_equal(bits(got.cpu().numpy()), want), (key, k, "device")
+                rec = codec.gather_records(hp, idx)
+                assert np.array_equal(bits(gpu_ctx.unpack_records_host(rec, ver, s.fractional_bits, conv)), want), (key, k, "records")
+
+
+def test_unpack_gather_against_the_oracle(gpu_ctx, oracle):
+    """Larger random streams: all three entry points against oracle_unpack_at; a list longer than one staged chunk;
+    indices == None; the small zero-copy path (n <= 2048) and the staged path give the same floats; and with a
+    +-1 converter the gather equals the bulk decoder on the same gaussians."""
+    from spz_b200 import codec
+    from spz_b200._native import CodecError
+    t = _torch()
+    rng = np.random.default_rng(811)
+    for ver, deg, n in ((3, 3, 70_001), (2, 1, 5_000), (1, 2, 3_001), (4, 0, 777), (3, 0, 129)):
+        s = random_stream(rng, n, deg, ver, int(rng.choice([0, 7, 12, 31, 35])))
+        if ver >= 3:
+            s.rotations.view("<u4")[::3] &= np.uint32(0xEFFBFEFF)
+        hp = codec.PackedPlanes(n, deg, *[np.ascontiguousarray(a) for a in s.planes()], fractional_bits=s.fractional_bits, version=ver)
+        dp = to_dev_packed(s)
+        conv = (rng.normal(size=21) * 2).astype(np.float32)
+        for count in (1, 5, 2048, 2049, min(n, 40_000), 140_000):
+            idx = rng.integers(0, n, count).astype(np.int64)
+            want = bits(oracle.unpack_at(s, idx, conv))
+            assert np.array_equal(bits(gpu_ctx.unpack_gather_host(hp, idx, conv)), want), (ver, deg, count, "host")
+            got = gpu_ctx.unpack_gather_device(dp, t.from_numpy(idx).cuda(), conv)
+            t.cuda.synchronize()
+            assert np.array_equal(bits(got.cpu().numpy()), want), (ver, deg, count, "device")
+        # no index list: gaussians 0..n-1 in order, no converter: identity
+        want = bits(oracle.unpack_at(s, np.arange(n), oracle.converter(0, 0)))
+        assert np.array_equal(bits(gpu_ctx.unpack_gather_host(hp)), want)
+        got = gpu_ctx.unpack_gather_device(dp)
+        t.cuda.synchronize()
+        assert np.array_equal(bits(got.cpu().numpy()), want)
+        # the bulk decoder with the same flips
+        full = gpu_unpack(gpu_ctx, s, 6)
+        rows = gpu_ctx.unpack_gather_host(hp, None, oracle.converter(4, 6))
+        assert np.array_equal(bits(rows[:, 0:3].reshape(-1)), bits(full.positions))
+        assert np.array_equal(bits(rows[:, 3:7].reshape(-1)), bits(full.rotations))
+        assert np.array_equal(bits(rows[:, 7:10].reshape(-1)), bits(full.scales))
+        assert np.array_equal(bits(rows[:, 13]), bits(full.alphas))
+        with pytest.raises(CodecError):
+            gpu_ctx.unpack_gather_host(hp, [0, n])
+        with pytest.raises(CodecError):
+            gpu_ctx.unpack_gather_host(hp, [-1])
+    assert gpu_ctx.unpack_gather_host(hp, np.zeros(0, np.int64)).shape == (0, 59)

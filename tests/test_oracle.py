@@ -214,3 +214,37 @@ def test_alpha_quantizer_is_a_monotone_step_function(oracle):
     assert oracle.lib.oracle_quant_alpha(8.0) == 255 and oracle.lib.oracle_quant_alpha(-8.0) == 0
     assert oracle.lib.oracle_quant_alpha(float("inf")) == 255 and oracle.lib.oracle_quant_alpha(float("-inf")) == 0
     assert oracle.lib.oracle_quant_alpha(3e38) == 255 and oracle.lib.oracle_quant_alpha(-3e38) == 0
+
+
+def test_unpack_at_restatement_matches_golden_and_live_reference(oracle, ref):
+    """oracle_unpack_at (PackedGaussians::at + unpack, load-spz.cc:383-463) against vectors the reference made
+    (tests/golden/make_golden_unpack_at.py) and against the reference library itself on fresh streams."""
+    import os
+    from util import PLANES, random_stream
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_unpack_at.npz"))
+    convs = G["converters"]
+    assert np.array_equal(convs[1], oracle.converter(4, 6))
+    for ver in (1, 2, 3, 4):
+        for deg in range(4):
+            key = f"v{ver}d{deg}"
+            s = Packed(64, deg, int(G[f"{key}_fb"]), ver, *[G[f"{key}_{p}"] for p in PLANES])
+            for k, conv in enumerate(convs):
+                assert np.array_equal(bits(oracle.unpack_at(s, G[f"{key}_idx"], conv)), G[f"{key}_out{k}"]), (key, k)
+    rng = np.random.default_rng(77)
+    for ver in (1, 2, 3, 4):
+        for deg in (0, 1, 3):
+            s = random_stream(rng, 300, deg, ver, int(rng.integers(0, 40)))
+            idx = rng.integers(0, 300, 500)
+            conv = (rng.normal(size=21) * 2).astype(np.float32)
+            assert np.array_equal(bits(oracle.unpack_at(s, idx, conv)), bits(ref.unpack_at(s, idx, conv))), (ver, deg)
+    # with +-1 converters the gather equals the bulk decoder (unpackGaussians) on the same gaussians
+    s = random_stream(rng, 100, 2, 3)
+    s.rotations.view("<u4")[:] &= np.uint32(0xEFFBFEFF)
+    full = oracle.unpack(s, 6)  # RUB -> RDF
+    rows = oracle.unpack_at(s, np.arange(100), oracle.converter(4, 6))
+    assert np.array_equal(bits(rows[:, 0:3].reshape(-1)), bits(full.positions))
+    assert np.array_equal(bits(rows[:, 3:7].reshape(-1)), bits(full.rotations))
+    assert np.array_equal(bits(rows[:, 14:22]), bits(full.sh.reshape(100, 8, 3)[:, :, 0]))
+    assert np.all(rows[:, 22:29] == 0)  # coefficients the stream does not carry decode from the pad byte 128
+    with pytest.raises(ValueError):
+        oracle.unpack_at(s, [100], convs[0])
