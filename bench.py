@@ -114,7 +114,7 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # the reference's CPU implementation, timed (cpu_baseline and --impl reference)
 # -------------------------------------------------------------------------------------------------
-def cpu_reference_run(points_total, deg, frm, to, steps, warmup, threads, sample_points):
+def cpu_reference_run(points_total, deg, frm, to, steps, warmup, threads, sample_points, best=False):
     """Times encode+decode of a bounded sample of the workload with the reference's own code
     (oracle/_ref/libspz_ref.so = the unmodified C++ compiled in place) or, if that build is not
     present, the C restatement (oracle/_build/libspz_oracle.so).  `threads` independent point
@@ -157,10 +157,13 @@ def cpu_reference_run(points_total, deg, frm, to, steps, warmup, threads, sample
                 times.append(dt)
                 inner.append(res)
     n_step = per_thread * threads
+    if best:  # best of `steps`, judged on the time inside the two functions
+        k = min(range(len(times)), key=lambda i: sum(max(r[j] for r in inner[i]) for j in (0, 1)) if inner[i][0][0] is not None else times[i])
+        times, inner = [times[k]], [inner[k]]
     mean = sum(times) / len(times)
     out = {"value": n_step / mean / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
            "sample": f"{n_step} gaussians per step ({threads} x {per_thread}-point ranges of the synthetic SH{deg} "
-                     f"workload), {steps} steps; wall time of pack+unpack calls incl. marshalling copies",
+                     f"workload), {'best of ' if best else ''}{steps} steps; wall time of pack+unpack calls incl. marshalling copies",
            "ms_per_step": mean * 1e3}
     if kind == "reference" and inner and inner[0][0][0] is not None:
         # time inside packGaussians / unpackGaussians alone (marshalling excluded), slowest thread
@@ -175,15 +178,16 @@ def cpu_reference_run(points_total, deg, frm, to, steps, warmup, threads, sample
 
 
 def traffic_for(kernel, gaussians, override):
-    """DRAM bytes per launch of `kernel`: the ncu --set full capture recorded in profiles/traffic.json
-    (taken at a different launch size), scaled per gaussian to this launch."""
+    """(DRAM bytes per launch of `kernel`, how that figure was obtained).  Not a measurement of this run: the
+    ncu --set full capture recorded in profiles/traffic.json was taken at another launch size and is scaled
+    per gaussian to this launch; --traffic-bytes passes a capture of this very configuration instead."""
     if override is not None:
-        return override
+        return override, "ncu_capture_passed_on_the_command_line"
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
-        return t["dram_bytes"] / t["gaussians"] * gaussians
+        return t["dram_bytes"] / t["gaussians"] * gaussians, f"scaled_from_ncu_{t['gaussians'] // 1000000}M"
     except Exception:  # noqa: BLE001
-        return None
+        return None, None
 
 
 def ply_rows_kernels(ctx, codec, dev, deg, n=40_000_000, steps=8):
@@ -316,7 +320,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32->u8", "data": "synthetic",
-            "config": {"workload": workload_name(args.points, args.sh_degree), "from": args.from_coord, "to": args.to_coord},
+            "config": bench_config(args, max(1, args.gpus)),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -340,6 +344,16 @@ def reduce_scalar(dist, x, op, device):
     return t.item()
 
 
+def allsum_u64(dist, x, device):
+    """sum mod 2^64 of one unsigned 64-bit value per rank (the shard hashes); identity when not distributed."""
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x - (1 << 64) if x >= (1 << 63) else x], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item()) & 0xFFFFFFFFFFFFFFFF
+
+
 def rank_shard(points_total, sh_degree, world, rank):
     """[a, b) of this rank: contiguous point range with tile-aligned boundaries (spzb200_shard_range)."""
     from spz_b200 import codec
@@ -347,13 +361,142 @@ def rank_shard(points_total, sh_degree, world, rank):
 
 
 # -------------------------------------------------------------------------------------------------
+# parity inside the bench (outside every timed region): sampled blocks against the oracle, and
+# order-sensitive 64-bit hashes of whole planes that add up across shards
+# -------------------------------------------------------------------------------------------------
+_HASH_C1 = -7046029254386353131   # 0x9E3779B97F4A7C15 as int64
+_HASH_C2 = -4658895280553007687   # 0xBF58476D1CE4E5B9 as int64
+
+
+def plane_hash(t, global_byte_offset, salt, dev):
+    """sum over 8-byte words w_i (global word index i) of mix(w_i, i) mod 2^64.  Additive over contiguous
+    shards (every shard boundary is a multiple of 8 bytes in every plane), sensitive to any changed or
+    moved word.  `t`: device tensor or host numpy array; hashed on `dev` in bounded slices."""
+    import numpy as np
+    import torch
+    assert global_byte_offset % 8 == 0
+    flat = t.view(np.uint8).reshape(-1) if isinstance(t, np.ndarray) else t.view(torch.uint8).reshape(-1)
+    n = flat.shape[0]
+    total = 0
+    step = 1 << 29  # bytes per slice
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        chunk = flat[s:e]
+        if isinstance(chunk, np.ndarray):
+            chunk = torch.from_numpy(chunk).to(dev, non_blocking=False)
+        if (e - s) % 8:
+            chunk = torch.cat([chunk, torch.zeros(8 - (e - s) % 8, dtype=torch.uint8, device=dev)])
+        w = chunk.view(torch.int64)
+        i = torch.arange(w.numel(), dtype=torch.int64, device=dev) + ((global_byte_offset + s) // 8 + salt * 0x100000001B3)
+        x = (w ^ (i * _HASH_C1)) * _HASH_C2
+        x = x ^ (x >> 29)
+        total = (total + int(x.sum().item())) & 0xFFFFFFFFFFFFFFFF
+        del w, i, x, chunk
+    return total
+
+
+def planes_hash(planes, widths_bytes, a, dev):
+    """hash of a set of planes holding gaussians [a, a + n) of the whole cloud"""
+    h = 0
+    for k, (t, wb) in enumerate(zip(planes, widths_bytes)):
+        size = t.size if hasattr(t, "size") and not callable(t.size) else t.numel()
+        if size:
+            h = (h + plane_hash(t, a * wb, k + 1, dev)) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def oracle_block_parity(cloud, packed, decoded, n, deg, frm, to, rank, blocks=6, block_points=65536):
+    """Sampled blocks of this rank's shard: the device-resident encoder / decoder outputs against the CPU
+    checker (the unmodified reference compiled in place where its build is present, else the C restatement),
+    byte for byte and float bit for float bit.  Returns (blocks checked, blocks equal, checker kind)."""
+    import numpy as np
+
+    import oracle as O
+    from spz_b200 import codec
+    try:
+        checker, kind = O.Ref(), "reference"
+    except Exception:  # noqa: BLE001
+        checker, kind = O.Oracle(), "port"
+    tg = codec.tile_gaussians(deg)
+    bp = min(block_points, n)
+    rng = np.random.default_rng(1234 + rank)
+    starts = {0, max(0, n - bp)}  # the first block and the last one (which holds the sub-tile remainder)
+    while len(starts) < min(blocks, max(1, n // max(bp, 1))):
+        starts.add(int(rng.integers(0, max(1, (n - bp) // tg + 1))) * tg)
+    fw, bw = codec.float_plane_widths(deg), codec.byte_plane_widths(deg, 3)
+    ok = 0
+    for s0 in sorted(starts):
+        src = [t[s0 * w:(s0 + bp) * w].cpu().numpy() for t, w in zip(cloud.planes(), fw)]
+        want = checker.pack(O.Cloud(bp, deg, *src), frm)
+        same = all(np.array_equal(t[s0 * w:(s0 + bp) * w].cpu().numpy(), e) for t, w, e in zip(packed.planes(), bw, want.planes()))
+        back = checker.unpack(want, to)
+        same = same and all(np.array_equal(O.bits(t[s0 * w:(s0 + bp) * w].cpu().numpy()), O.bits(e))
+                            for t, w, e in zip(decoded.planes(), fw, back.planes()))
+        ok += int(same)
+    return len(starts), ok, kind
+
+
+def link_ceiling(dev, barrier, seconds=1.0, mb=1024, chunk_mb=256):
+    """Bare host<->device link of this rank while every other rank does the same: plain pinned
+    cudaMemcpyAsync (torch copy_ on pinned tensors), nothing of the codec.  H2D alone, D2H alone, both at
+    once on two streams; GB/s of this rank per phase and direction (scripts/link_probe.py is the standalone form)."""
+    import torch
+    nbytes = mb << 20
+    host_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host_in.fill_(1)
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    chunk = chunk_mb << 20
+
+    def loop(secs, h2d, d2h):
+        torch.cuda.synchronize(dev)
+        moved = 0
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < secs:
+            for a in range(0, nbytes, chunk):
+                if h2d:
+                    with torch.cuda.stream(s_in):
+                        d_in[a:a + chunk].copy_(host_in[a:a + chunk], non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(s_out):
+                        host_out[a:a + chunk].copy_(d_out[a:a + chunk], non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+            moved += nbytes
+        return moved / (time.perf_counter() - t0) / 1e9
+
+    loop(0.2, True, True)
+    out = {}
+    for name, h2d, d2h in (("h2d_alone", True, False), ("d2h_alone", False, True), ("duplex", True, True)):
+        barrier()
+        out[name] = loop(seconds, h2d, d2h)  # each direction moves `moved` bytes: GB/s per direction
+    barrier()
+    del host_in, host_out, d_in, d_out
+    return out
+
+
+def bench_config(args, world):
+    """The `config` object of the JSON line; identical for the B200 arm and the reference arm."""
+    from spz_b200 import codec
+    n_total, deg = args.points, args.sh_degree
+    a0, b0 = codec.shard_range(n_total, deg, world, 0)
+    return {"workload": workload_name(n_total, deg), "points_total": n_total, "points_per_gpu": b0 - a0,
+            "sh_degree": deg, "stream_version": 3, "from": args.from_coord, "to": args.to_coord,
+            "l2": "working set per step >> 126 MB L2, no flush needed", "sharding": f"point-range x{world}, no collective",
+            "data": "one counter-seeded cloud (seed 1); rank r holds slice [a_r, b_r) of it"}
+
+
+# -------------------------------------------------------------------------------------------------
 # the B200 arm
 # -------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
+    import numpy as np
     import torch
 
     from spz_b200 import codec
-    from spz_b200.synth import torch_cloud
+    from spz_b200.synth import counter_cloud_torch
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the codec has no CPU path (use --impl reference for the CPU arm)")
@@ -366,9 +509,11 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        import datetime
+
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=20))
 
     def barrier():
         if dist is not None:
@@ -380,10 +525,13 @@ def run_b200_arm(args):
     n = b - a
     ctx = codec.Context(local)
     dev = torch.device("cuda", local)
-    cloud = torch_cloud(n, deg, dev, seed=1 + rank)
+    # ONE cloud for every N: rank r generates gaussians [a_r, b_r) of it (counter-based)
+    cloud = counter_cloud_torch(n_total, deg, dev, a, b, seed=1)
     packed = codec.alloc_packed(n, deg, 3, device=dev)
     decoded = codec.alloc_cloud(n, deg, device=dev)
     alg_bytes = codec.algorithmic_bytes_per_gaussian(deg, 3)
+    fwb = [4 * w for w in codec.float_plane_widths(deg)]
+    bwb = list(codec.byte_plane_widths(deg, 3))
 
     def step(evs=None):
         if evs:
@@ -414,6 +562,21 @@ def run_b200_arm(args):
     launches = ctx.info()["kernel_launches"] - launches0
     enc_ms = statistics.mean(ev[0].elapsed_time(ev[1]) for ev in evs)
     dec_ms = statistics.mean(ev[1].elapsed_time(ev[2]) for ev in evs)
+
+    # ---- parity of what was just timed (outside the timed region) ---------------------------------
+    # (1) sampled 64k-point blocks of this rank's shard against the CPU checker; (2) order-sensitive
+    # hashes of every output plane, which add up over the shards: the all-reduced value is a function
+    # of the cloud alone, so the lines of N = 1, 2, 4, 8 must print the same two numbers.
+    par_blocks, par_ok, par_kind = oracle_block_parity(cloud, packed, decoded, n, deg, args.from_coord, args.to_coord, rank)
+    enc_hash_local = planes_hash(packed.planes(), bwb, a, dev)
+    dec_hash_local = planes_hash(decoded.planes(), fwb, a, dev)
+
+    enc_hash, dec_hash = allsum_u64(dist, enc_hash_local, dev), allsum_u64(dist, dec_hash_local, dev)
+
+    # ---- the bare link, every rank at once: the ceiling e2e is measured against ---------------------
+    link = None
+    if not args.no_e2e:
+        link = link_ceiling(dev, barrier)
 
     # ---- e2e: the same step through the host-pointer C-ABI with pinned host planes ---------------
     e2e = None
@@ -451,11 +614,6 @@ def run_b200_arm(args):
         e2e = {"s": e2e_s, "h2d": h2d, "d2h": d2h,
                "enc": {k: statistics.mean(p[0][k] for p in phases) for k in ("h2d_ms", "kernel_ms", "d2h_ms", "wall_ms")},
                "dec": {k: statistics.mean(p[1][k] for p in phases) for k in ("h2d_ms", "kernel_ms", "d2h_ms", "wall_ms")}}
-        # the e2e path is the same kernels: spot-check its bytes against the device-resident result
-        for name, hp, dp in zip(codec.PLANES, h_packed.planes(), packed.planes()):
-            k = min(hp.size, 1 << 22)
-            if k and not torch.equal(torch.from_numpy(hp[:k]), dp[:k].cpu()):
-                raise SystemExit(f"bench.py: e2e plane {name} differs from the device-resident encode")
 
         # Full-duplex form of the same step: a second host thread (own context) decodes the stream
         # the previous step produced while this step's cloud is being encoded, so both directions of
@@ -482,12 +640,24 @@ def run_b200_arm(args):
         e2e["duplex_dec_wall_ms"] = statistics.mean(p[1]["wall_ms"] for p in dphases)
         pool.shutdown()
         ctx2.close()
-        hb, db = torch.from_numpy(h_back.sh[:1 << 20] if deg else h_back.alphas[:1 << 20]), None
-        ref_back = ctx.decode_device(packed, args.to_coord)
-        db = (ref_back.sh if deg else ref_back.alphas)[:hb.numel()].cpu()
-        if not torch.equal(hb.view(torch.int32), db.view(torch.int32)):
-            raise SystemExit("bench.py: duplex e2e decode differs from the device-resident decode")
-        del ref_back
+        # what the e2e path produced, whole planes, against what the device-resident path produced
+        e2e["hash_ok"] = (planes_hash(h_packed.planes(), bwb, a, dev) == enc_hash_local and
+                          planes_hash(h_packed2.planes(), bwb, a, dev) == enc_hash_local and
+                          planes_hash(h_back.planes(), fwb, a, dev) == dec_hash_local)
+        if not e2e["hash_ok"]:
+            raise SystemExit("bench.py: the host-pointer (e2e) path produced different planes than the device-resident path")
+        del h_cloud, h_packed, h_packed2, h_back, streams
+
+    # ---- e2e_multi: the library's own multi-GPU entry point, one process driving all N GPUs -------
+    # rank 0 holds the WHOLE cloud in pinned host memory and calls spzb200_encode_host_multi /
+    # spzb200_decode_host_multi over devices 0..N-1 (what spz::packGaussians does under
+    # SPZ_B200_DEVICES); the other ranks idle at the barrier.  Its planes must hash to the same values.
+    e2e_multi = None
+    if not args.no_e2e and world > 1:
+        barrier()
+        if rank == 0:
+            e2e_multi = run_e2e_multi(args, codec, dev, world, n_total, deg, fwb, bwb, enc_hash, dec_hash)
+        barrier()
 
     # ---- reduce over ranks (max time; sums of bytes and launches) -----------------------------------
     def allmax(x):
@@ -499,16 +669,20 @@ def run_b200_arm(args):
     total_ms = allmax(total_ms)
     enc_ms_max, dec_ms_max = allmax(enc_ms), allmax(dec_ms)
     launches = int(allsum(launches))
+    par_blocks, par_ok = int(allsum(par_blocks)), int(allsum(par_ok))
     if e2e:
         e2e["s"] = allmax(e2e["s"])
         e2e["duplex_s"] = allmax(e2e["duplex_s"])
         e2e["h2d"] = int(allsum(e2e["h2d"]))
         e2e["d2h"] = int(allsum(e2e["d2h"]))
+    if link:
+        link = {k: {"sum": allsum(v), "min_rank": -allmax(-v)} for k, v in link.items()}
 
     # ---- config 1 of BASELINE.json is a 60k-gaussian file: far too small to be bandwidth-bound, so
     # what matters there is latency.  Device-resident launch pair and the host-pointer call, median of 50.
     latency = None
     if rank == 0:
+        from spz_b200.synth import torch_cloud
         latency = small_cloud_latency(ctx, codec, torch_cloud, dev, 60_000, deg, args)
 
     ply_rows = None
@@ -521,8 +695,9 @@ def run_b200_arm(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample_points or 2_000_000
-        cpu = cpu_reference_run(n_total, deg, args.from_coord, args.to_coord, steps=2, warmup=1, threads=1, sample_points=sample)
+        # BASELINE.md section 4 / SURVEY.md 8d: the reference's pack + unpack, ONE thread, best of 3 on 10M points
+        sample = args.cpu_sample_points or min(n_total, 10_000_000)
+        cpu = cpu_reference_run(n_total, deg, args.from_coord, args.to_coord, steps=3, warmup=0, threads=1, sample_points=sample, best=True)
         cpu = {k: cpu[k] for k in cpu if k != "ms_per_step"}
 
     if rank == 0:
@@ -545,36 +720,51 @@ def run_b200_arm(args):
         enc_kernel = ("encodePerGaussianKernel" if enc_env == "bulk" or (enc_env != "tiles" and deg == 3 and n <= 24_000_000)
                       else "encodeTilesKernel")
         dom = (enc_kernel, enc_gbs, enc_ms) if enc_ms >= dec_ms else (dec_kernel, dec_gbs, dec_ms)
+        traffic, traffic_kind = traffic_for(dom[0], n, args.traffic_bytes)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32->u8", "data": "synthetic",
-            "config": {"workload": workload_name(n_total, deg), "points_total": n_total, "points_per_gpu": n,
-                       "sh_degree": deg, "stream_version": 3, "from": args.from_coord, "to": args.to_coord,
-                       "l2": "working set per step >> 126 MB L2, no flush needed", "sharding": f"point-range x{world}, no collective"},
+            "config": bench_config(args, world),
             "encode_mgs": n_total / (enc_ms_max * 1e-3) / 1e6, "decode_mgs": n_total / (dec_ms_max * 1e-3) / 1e6,
             "encode_ms": enc_ms_max, "decode_ms": dec_ms_max,
             "hbm_gbs_per_gpu": {"encode": enc_gbs, "decode": dec_gbs},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom[1], "peak": peak, "unit": "GB/s",
                          "frac": dom[1] / peak, "frac_of_nominal_8TBs": dom[1] / 8000.0, "peak_source": peak_src,
                          "algorithmic_bytes_per_gaussian": alg_bytes, "gaussians_per_launch": n,
-                         "avg_launch_ms": dom[2], "traffic": traffic_for(dom[0], n, args.traffic_bytes),
-                         "traffic_source": "profiles/traffic.json (ncu --set full dram bytes per gaussian x gaussians per launch)",
+                         "avg_launch_ms": dom[2], "traffic": traffic, "traffic_kind": traffic_kind,
                          "encode": {"achieved": enc_gbs, "frac": enc_gbs / peak, "avg_launch_ms": enc_ms},
                          "decode": {"achieved": dec_gbs, "frac": dec_gbs / peak, "avg_launch_ms": dec_ms}},
             "gpu_launches": launches, "clocks": clocks,
+            "parity": {"ok": par_ok == par_blocks, "blocks": par_blocks, "blocks_equal": par_ok, "block_points": min(65536, n),
+                       "checker": par_kind, "what": "sampled blocks of every rank's device-resident encode and decode output vs the CPU checker, "
+                                                   "bytes and float bits; outside the timed region",
+                       "encode_hash": f"{enc_hash:016x}", "decode_hash": f"{dec_hash:016x}",
+                       "hash": "order-sensitive 64-bit sum over all output planes of all ranks; a function of the cloud alone, so equal for every N"},
         }
         if e2e:
-            line["e2e"] = {"value": n_total / e2e["duplex_s"] / 1e6, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
-                           "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["duplex_s"] * 1e3, "steps": args.e2e_steps,
+            step_s = e2e["duplex_s"]
+            line["e2e"] = {"value": n_total / step_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                           "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": step_s * 1e3, "steps": args.e2e_steps,
                            "api": "spzb200_encode_host + spzb200_decode_host (pinned host planes)",
                            "mode": "full duplex: step i's encode_host and the decode_host of step i-1's stream are issued concurrently "
                                    "from two host threads (one context each), so H2D and D2H of a step's planes overlap on the PCIe link",
                            "encode_call_ms": e2e["duplex_enc_wall_ms"], "decode_call_ms": e2e["duplex_dec_wall_ms"],
+                           "planes_equal_device_path": True,
                            "sequential": {"value": n_total / e2e["s"] / 1e6, "ms_per_step": e2e["s"] * 1e3,
                                           "mode": "one host thread: encode_host, then decode_host of its result",
                                           "phases_note": "h2d/kernel/d2h_ms are sums over point ranges of per-range stream time; ranges run on 3 streams and overlap, wall_ms is the call",
                                           "encode_phases_ms": e2e["enc"], "decode_phases_ms": e2e["dec"]}}
+            if link:
+                ach_h2d, ach_d2h = e2e["h2d"] / step_s / 1e9, e2e["d2h"] / step_s / 1e9
+                line["e2e"]["link_ceiling_gbs"] = {
+                    "how": "bare pinned cudaMemcpyAsync (torch copy_), 1 GiB per direction per rank in 256 MiB pieces, all ranks at once, 1 s per phase; "
+                           "GB/s per direction, summed over ranks (and the slowest rank)",
+                    "h2d_alone": link["h2d_alone"], "d2h_alone": link["d2h_alone"], "duplex_each_direction": link["duplex"]}
+                line["e2e"]["achieved_gbs"] = {"h2d": ach_h2d, "d2h": ach_d2h}
+                line["e2e"]["frac_of_link"] = min(ach_h2d, ach_d2h) / link["duplex"]["sum"]
+        if e2e_multi:
+            line["e2e_multi"] = e2e_multi
         if cpu:
             line["cpu_baseline"] = cpu
         if host_zlib:
@@ -589,6 +779,48 @@ def run_b200_arm(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_e2e_multi(args, codec, dev, world, n_total, deg, fwb, bwb, enc_hash, dec_hash):
+    """spzb200_encode_host_multi + spzb200_decode_host_multi over all `world` GPUs from this one process, on the
+    whole cloud in pinned host memory."""
+    import torch
+
+    from spz_b200.synth import counter_cloud_torch
+    devices = list(range(world))
+    h_cloud = codec.alloc_cloud(n_total, deg, pinned=True, numpy_arrays=True)
+    h_packed = codec.alloc_packed(n_total, deg, 3, pinned=True, numpy_arrays=True)
+    h_back = codec.alloc_cloud(n_total, deg, pinned=True, numpy_arrays=True)
+    fw = codec.float_plane_widths(deg)
+    piece = 5_000_000 // 1280 * 1280
+    for a in range(0, n_total, piece):  # the same counter-seeded cloud, generated piecewise on this GPU
+        b = min(n_total, a + piece)
+        part = counter_cloud_torch(n_total, deg, dev, a, b, seed=1)
+        for src, dst, w in zip(part.planes(), h_cloud.planes(), fw):
+            if w:
+                torch.from_numpy(dst[a * w:b * w]).copy_(src)
+        del part
+    torch.cuda.synchronize()
+
+    def one():
+        _, te = codec.encode_host_multi(devices, h_cloud, args.from_coord, out=h_packed)
+        _, td = codec.decode_host_multi(devices, h_packed, args.to_coord, out=h_back)
+        return te, td
+
+    one()  # warm: creates the pooled contexts of every device
+    t0 = time.perf_counter()
+    tms = [one() for _ in range(args.e2e_steps)]
+    step_s = (time.perf_counter() - t0) / args.e2e_steps
+    ok = planes_hash(h_packed.planes(), bwb, 0, dev) == enc_hash and planes_hash(h_back.planes(), fwb, 0, dev) == dec_hash
+    if not ok:
+        raise SystemExit("bench.py: spzb200_*_host_multi produced different planes than the per-rank device-resident path")
+    return {"value": n_total / step_s / 1e6, "unit": UNIT, "ms_per_step": step_s * 1e3, "steps": args.e2e_steps, "devices": devices,
+            "api": "spzb200_encode_host_multi + spzb200_decode_host_multi: ONE process, the whole cloud in pinned host memory, "
+                   "sharded by point range over the devices; sequential (encode, then decode its result)",
+            "encode_call_ms": statistics.mean(t[0]["wall_ms"] for t in tms), "decode_call_ms": statistics.mean(t[1]["wall_ms"] for t in tms),
+            "h2d_bytes_per_step": tms[-1][0]["h2d_bytes"] + tms[-1][1]["h2d_bytes"],
+            "d2h_bytes_per_step": tms[-1][0]["d2h_bytes"] + tms[-1][1]["d2h_bytes"],
+            "planes_hash_equals_parity_hash": True}
 
 
 def main():

@@ -1,0 +1,28 @@
+#!/bin/bash
+# One runner for everything that goes to the GPU box:   gpurun -- 'bash scripts/gpu.sh <task> [args]'
+# Every task writes under gpurun_out/ (merged back by gpurun) and prints a short tail.
+set -u
+mkdir -p gpurun_out
+export SPZB200_NO_REBUILD=1
+task=${1:-tests}; shift || true
+case "$task" in
+  box)      { nproc; free -g; cat /sys/fs/cgroup/memory.max 2>/dev/null; nvidia-smi -L; nvidia-smi topo -m; lscpu | head -24; numactl -H 2>/dev/null; } > gpurun_out/box.txt 2>&1; cat gpurun_out/box.txt ;;
+  smoke)    timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log ;;
+  tests)    timeout 2400 python -m pytest tests -m gpu -x -q "$@" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log ;;
+  bench)    # bench [name] [bench.py args...]
+            name=${1:-bench}; shift || true
+            timeout 1500 python bench.py "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err; echo "bench rc=$?"; cat gpurun_out/$name.json; tail -3 gpurun_out/$name.err ;;
+  benchn)   # benchn N [name] [bench.py args...]: N ranks under torchrun
+            n=$1; name=${2:-bench_n$1}; shift 2 || true
+            timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n "$@" \
+              > gpurun_out/$name.json 2> gpurun_out/$name.err; echo "bench x$n rc=$?"; grep '^{' gpurun_out/$name.json | tail -1; tail -3 gpurun_out/$name.err ;;
+  refarm)   timeout 900 python bench.py --impl reference "$@" > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json ;;
+  coldstart) timeout 300 python scripts/cold_start.py > gpurun_out/cold_start.txt 2>&1; echo "rc=$?"; cat gpurun_out/cold_start.txt ;;
+  link)     # link [args to scripts/link_probe.py]
+            timeout 900 python scripts/link_probe.py "$@" > gpurun_out/link_probe.jsonl 2> gpurun_out/link_probe.err; echo "rc=$?"; cat gpurun_out/link_probe.jsonl; tail -3 gpurun_out/link_probe.err ;;
+  launches) # launch list of one short bench run (after the same command ran clean without ncu)
+            timeout 900 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/launch_pre.json 2> gpurun_out/launch_pre.err || { echo "plain run failed"; exit 1; }
+            timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+              python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/ncu_list.log 2>&1; echo "ncu rc=$?"; tail -5 gpurun_out/launches.csv ;;
+  *)        echo "unknown task $task"; exit 2 ;;
+esac

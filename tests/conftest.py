@@ -9,6 +9,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# tests/golden/ holds fixtures -- including a byte-identical copy of the reference's own pytest file, which
+# tests/test_reference_suite.py runs in a subprocess against this repo's `spz` module -- not tests of this tree
+collect_ignore_glob = ["golden/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 

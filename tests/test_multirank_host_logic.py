@@ -23,9 +23,22 @@ edges = [None] * world
 dist.all_gather_object(edges, (a, b))
 mx = bench.reduce_scalar(dist, 10.0 + rank, "max", "cpu")
 sm = bench.reduce_scalar(dist, 40 + rank, "sum", "cpu")
+# every rank generates ITS slice of the one counter-seeded cloud; the shard hashes add up to the hash of the whole
+from spz_b200 import codec
+from spz_b200.synth import counter_cloud_torch
+m, d2 = 7 * 1280 + 77, 2
+a2, b2 = bench.rank_shard(m, d2, world, rank)
+part = counter_cloud_torch(m, d2, "cpu", a2, b2, seed=1)
+fwb = [4 * w for w in codec.float_plane_widths(d2)]
+h = bench.allsum_u64(dist, bench.planes_hash(part.planes(), fwb, a2, "cpu"), "cpu")
+whole = counter_cloud_torch(m, d2, "cpu", seed=1)
+h_whole = bench.planes_hash(whole.planes(), fwb, 0, "cpu")
+swapped = [p.clone() for p in whole.planes()]
+swapped[5][8:16], swapped[5][16:24] = whole.planes()[5][16:24].clone(), whole.planes()[5][8:16].clone()
+h_swapped = bench.planes_hash(swapped, fwb, 0, "cpu")
 dist.barrier()
 if rank == 0:
-    print(json.dumps({"edges": edges, "max": mx, "sum": sm}))
+    print(json.dumps({"edges": edges, "max": mx, "sum": sm, "hash": h, "hash_whole": h_whole, "hash_swapped": h_swapped}))
 dist.destroy_process_group()
 """
 
@@ -44,6 +57,8 @@ def test_two_gloo_ranks_partition_and_reduce(tmp_path):
     assert a0 == 0 and b0 == a1 and b1 == 100_000_000
     assert b0 % 1280 == 0 and abs((b0 - a0) - (b1 - a1)) <= 2 * 1280
     assert out["max"] == 11.0 and out["sum"] == 81.0
+    # shard hashes are additive over the partition, and sensitive to two words trading places
+    assert out["hash"] == out["hash_whole"] != out["hash_swapped"]
 
 
 def test_reference_arm_runs_on_rank0_only():
