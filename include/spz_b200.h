@@ -119,7 +119,7 @@ int spzb200_create(int32_t device, SpzB200Context **out);
 void spzb200_destroy(SpzB200Context *ctx);
 
 /* Process-wide pool: lease a context of `device` for one call (or a batch of calls) and hand it back.
- * Contexts are created on demand, at most SPZ_B200_MAX_CONTEXTS (default 4) per device -- further
+ * Contexts are created on demand, at most SPZ_B200_MAX_CONTEXTS (default 2) per device -- further
  * callers block until one is released -- and live until the process exits, so threads that come and go
  * do not pay for streams, tables, staging and pinned bounce buffers again.  A lease is exclusive.  This
  * is what the C++ API (spz::packGaussians, ...) and the *_multi entry points use.  spzb200_release

@@ -20,6 +20,10 @@ case "$task" in
   coldstart) timeout 300 python scripts/cold_start.py > gpurun_out/cold_start.txt 2>&1; echo "rc=$?"; cat gpurun_out/cold_start.txt ;;
   link)     # link [args to scripts/link_probe.py]
             timeout 900 python scripts/link_probe.py "$@" > gpurun_out/link_probe.jsonl 2> gpurun_out/link_probe.err; echo "rc=$?"; cat gpurun_out/link_probe.jsonl; tail -3 gpurun_out/link_probe.err ;;
+  pool)     timeout 900 python scripts/pool_sweep.py > gpurun_out/pool_sweep.jsonl 2>&1; echo "rc=$?"; cat gpurun_out/pool_sweep.jsonl ;;
+  sweep)    # sweep <name> <script> [args]: any scripts/*.py measurement, output kept under gpurun_out/<name>
+            name=$1; script=$2; shift 2 || true
+            timeout 1500 python scripts/$script "$@" > gpurun_out/$name 2> gpurun_out/$name.err; echo "rc=$?"; cat gpurun_out/$name; tail -3 gpurun_out/$name.err ;;
   launches) # launch list of one short bench run (after the same command ran clean without ncu)
             timeout 900 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/launch_pre.json 2> gpurun_out/launch_pre.err || { echo "plain run failed"; exit 1; }
             timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \

@@ -247,6 +247,8 @@ struct SpzB200Context {
   int decodePerGaussian = 1;  // SPZB200_DECODE=pergaussian: 2 (also SH-less clouds); =bulk / =direct: 0 (tile kernels only)
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
   bool decodeBulk = true;  // SH plane of the decoder staged with bulk async copies (SPZB200_DECODE=direct: registers)
+  bool pdl = true;       // SPZB200_PDL=0: plain stream-ordered launches (A/B timing)
+  bool foldRest = true;  // SPZB200_REST=separate: the sub-tile remainder as a launch of its own (A/B timing)
   bool flatGrid = true;  // one CTA per tile: the block scheduler keeps the tile frontier compact
   long long chunkPoints = 1 << 21;        // pinned / registered host planes: copied straight from the caller
   long long pageableChunkPoints = 1 << 18;  // pageable planes: bounced through pinned buffers of this many points
@@ -347,6 +349,8 @@ spzb200::LaunchPlan planOf(const SpzB200Context *ctx) {
   p.flatGrid = ctx->flatGrid;
   p.decodeBulk = ctx->decodeBulk;
   p.plyMapped = ctx->plyMapped;
+  p.foldRest = ctx->foldRest;
+  p.pdl = ctx->pdl;
   p.decodePerGaussian = ctx->decodePerGaussian;
   p.encodeBulk = ctx->encodeBulk;
   return p;
@@ -625,8 +629,10 @@ int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &clou
 // them costs more than a small cloud's whole encode -- so the C++ API and the multi-GPU entry points
 // lease one per call instead of keeping one per host thread: a server that packs from short-lived
 // threads pays the set-up once per process, not once per request.  A lease is exclusive.  At most
-// `maxLive` contexts exist per device (SPZ_B200_MAX_CONTEXTS, default 4: the PCIe link serialises
-// concurrent calls anyway); further callers wait for a release.  Never destroyed: no CUDA calls at exit.
+// `maxLive` contexts exist per device (SPZ_B200_MAX_CONTEXTS, default 2: one H2D-heavy encode and one
+// D2H-heavy decode keep both directions of the PCIe link busy; more callers only queue on the link, and on
+// the driver's staging of pageable copies); further callers wait for a release.  Never destroyed: no CUDA
+// calls at exit.
 struct ContextPool {
   struct PerDevice {
     std::vector<SpzB200Context *> idle;
@@ -635,7 +641,7 @@ struct ContextPool {
   std::mutex m;
   std::condition_variable cv;
   std::vector<std::pair<int32_t, PerDevice>> devs;
-  int maxLive = 4;
+  int maxLive = 2;
   ContextPool() {
     if (const char *env = std::getenv("SPZ_B200_MAX_CONTEXTS")) maxLive = std::max(1, std::atoi(env));
   }
@@ -841,6 +847,8 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   }
   if (const char *env = std::getenv("SPZB200_ENCODE")) ctx->encodeBulk = std::strcmp(env, "bulk") == 0 ? 2 : std::strcmp(env, "tiles") == 0 ? 0 : 1;
   if (const char *env = std::getenv("SPZB200_PLY")) ctx->plyMapped = std::strcmp(env, "mapped") == 0;
+  if (const char *env = std::getenv("SPZB200_PDL")) ctx->pdl = std::strcmp(env, "0") != 0;
+  if (const char *env = std::getenv("SPZB200_REST")) ctx->foldRest = std::strcmp(env, "separate") != 0;
   if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = std::strcmp(env, "persistent") != 0;
   if (const char *env = std::getenv("SPZB200_CHUNK_POINTS")) {
     const long long v = std::atoll(env);

@@ -39,6 +39,7 @@
 
 #include "codec_math.cuh"
 #include "kernel_utils.cuh"
+#include "scalar_path.cuh"
 
 namespace spzb200 {
 namespace {
@@ -132,11 +133,18 @@ struct ShPhase {
 // =================================================================================================
 template <int D, int MODE>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-encodeTilesKernel(const EncodeArgs a, const long long numTiles) {
+encodeTilesKernel(const EncodeArgs a, const long long numTiles, const int restCtas) {
   constexpr int S = kThreads;
   constexpr int M = Geo<D>::M;
   __shared__ float sThr[256];
   __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
+  pdlTrigger();
+  if ((int)blockIdx.x < restCtas) {  // the sub-tile remainder rides in the first CTA(s): scalar_path.cuh
+    const long long g = numTiles * Geo<D>::TG + (long long)blockIdx.x * kThreads + threadIdx.x;
+    pdlWait();
+    if (g < a.n) encodeOneGaussian(a, g);
+    return;
+  }
   for (int i = threadIdx.x; i < 256; i += kThreads) sThr[i] = a.alphaThresholds[i];
   __syncthreads();
   const int t = threadIdx.x;
@@ -148,8 +156,9 @@ encodeTilesKernel(const EncodeArgs a, const long long numTiles) {
   float posScale3[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) posScale3[k] = signedConst(4096.0f, (a.flipP >> ((t + k) % 3)) & 1u);
+  pdlWait();  // tables and constants are in place; the planes may only be touched from here on
 
-  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+  for (long long tile = (int)blockIdx.x - restCtas; tile < numTiles; tile += (int)gridDim.x - restCtas) {
 #pragma unroll 1
     for (int mm = 0; mm < M; mm++) {
       const long long q = tile * M + mm;  // sub-tile: gaussians [q*1280, (q+1)*1280)
@@ -255,29 +264,9 @@ encodeTilesKernel(const EncodeArgs a, const long long numTiles) {
 __global__ void __launch_bounds__(128)
 encodeGenericKernel(const EncodeArgs a, const long long first) {
   const long long g = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.n) return;
-#pragma unroll
-  for (int ax = 0; ax < 3; ax++) {
-    const uint32_t n = m::quant_position24(a.positions[g * 3 + ax],
-                                           signedConst(4096.0f, (a.flipP >> ax) & 1u));
-    uint8_t *o = a.oPositions + (g * 3 + ax) * 3;
-    o[0] = (uint8_t)n; o[1] = (uint8_t)(n >> 8); o[2] = (uint8_t)(n >> 16);
-    a.oScales[g * 3 + ax] = (uint8_t)m::quant_scale(a.scales[g * 3 + ax]);
-    a.oColors[g * 3 + ax] = (uint8_t)m::quant_color(a.colors[g * 3 + ax]);
-  }
-  a.oAlphas[g] = (uint8_t)m::quant_alpha(a.alphas[g], a.alphaThresholds);
-  const float *r = a.rotations + g * 4;
-  const uint32_t comp = m::quant_rotation_smallest3(r[0], r[1], r[2], r[3], a.flipQ);
-  uint8_t *ro = a.oRotations + g * 4;
-  ro[0] = (uint8_t)comp; ro[1] = (uint8_t)(comp >> 8); ro[2] = (uint8_t)(comp >> 16); ro[3] = (uint8_t)(comp >> 24);
-  const int per = a.shDim * 3;
-  const float *s = a.sh + g * per;
-  uint8_t *so = a.oSh + g * per;
-  for (int j = 0; j < per; j++) {
-    const uint32_t bucket = j < 9 ? 8u : 16u;
-    so[j] = (uint8_t)m::quant_sh(s[j], signedConst(128.0f, (a.flipSh >> (j / 3)) & 1u),
-                                 128u + bucket / 2u, ~(bucket - 1u));
-  }
+  pdlTrigger();
+  pdlWait();
+  if (g < a.n) encodeOneGaussian(a, g);
 }
 
 // =================================================================================================
@@ -459,12 +448,19 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
 
 template <int D, int VER>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
+decodeTilesKernel(const DecodeArgs a, const long long numTiles, const int restCtas) {
   constexpr int S = kThreads;
   constexpr int M = Geo<D>::M;
   constexpr bool kS3 = (VER >= 3);
   __shared__ float sTab[kS3 ? kDecodeTableFloats : 512];
   __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
+  pdlTrigger();
+  if ((int)blockIdx.x < restCtas) {  // the sub-tile remainder rides in the first CTA(s): scalar_path.cuh
+    const long long g = numTiles * Geo<D>::TG + (long long)blockIdx.x * kThreads + threadIdx.x;
+    pdlWait();
+    if (g < a.n) decodeOneGaussian(a, g);
+    return;
+  }
   for (int i = threadIdx.x; i < (kS3 ? kDecodeTableFloats : 512); i += kThreads) sTab[i] = __ldg(a.tables + i);
   const float *sAlpha = sTab, *sColor = sTab + 256, *sMag = sTab + 512;
   __syncthreads();
@@ -472,8 +468,9 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles) {
   uint32_t *stage = sStage[t >> 5];
   DecodePosConsts pc;
   pc.init(a, t);
+  pdlWait();  // tables and constants are in place; the planes may only be touched from here on
 
-  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+  for (long long tile = (int)blockIdx.x - restCtas; tile < numTiles; tile += (int)gridDim.x - restCtas) {
 #pragma unroll 1
     for (int mm = 0; mm < M; mm++) decodeSmallPlanes<VER, false>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc);
     // ---- spherical harmonics: word -> float4 -------------------------------------------------
@@ -544,8 +541,15 @@ struct BulkGeo {
 
 template <int D, int VER>
 __global__ void __launch_bounds__(kThreads, 2)
-decodeTilesBulkKernel(const DecodeArgs a, const long long numTiles) {
+decodeTilesBulkKernel(const DecodeArgs a, const long long numTiles, const int restCtas) {
   static_assert(D > 0, "SH-less clouds use decodeTilesKernel");
+  pdlTrigger();
+  if ((int)blockIdx.x < restCtas) {  // the sub-tile remainder rides in the first CTA(s): scalar_path.cuh
+    const long long g = numTiles * Geo<D>::TG + (long long)blockIdx.x * kThreads + threadIdx.x;
+    pdlWait();
+    if (g < a.n) decodeOneGaussian(a, g);
+    return;
+  }
   constexpr int S = kThreads;
   constexpr int M = Geo<D>::M;
   constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS, SB = BulkGeo<D>::SB;
@@ -562,9 +566,10 @@ decodeTilesBulkKernel(const DecodeArgs a, const long long numTiles) {
   uint32_t *stage = reinterpret_cast<uint32_t *>(obuf) + (t >> 5) * (3 * 96);
   DecodePosConsts pc;
   pc.init(a, t);
+  pdlWait();  // tables and constants are in place; the planes may only be touched from here on
 
   uint32_t parity = 0;
-  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
+  for (long long tile = (int)blockIdx.x - restCtas; tile < numTiles; tile += (int)gridDim.x - restCtas, parity ^= 1u) {
     // the SH words of the whole tile: one bulk copy, in flight while the small planes are decoded
     if (t == 0)
       bulkLoad(win, reinterpret_cast<const uint32_t *>(a.sh) + tile * ((long long)ROWS * S), BulkGeo<D>::kWordBytes, &bar);
@@ -625,50 +630,9 @@ decodeTilesBulkKernel(const DecodeArgs a, const long long numTiles) {
 __global__ void __launch_bounds__(128)
 decodeGenericKernel(const DecodeArgs a, const long long first) {
   const long long g = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.n) return;
-#pragma unroll
-  for (int ax = 0; ax < 3; ax++) {
-    const uint32_t flip = ((a.flipP >> ax) & 1u) << 31;
-    float p;
-    if (a.version == 1 || a.version == 4) {
-      const uint8_t *h = a.positions + (g * 3 + ax) * 2;
-      p = __uint_as_float(__float_as_uint(m::half_bits_to_float((uint32_t)h[0] | ((uint32_t)h[1] << 8))) ^ flip);
-    } else {
-      const uint8_t *b = a.positions + (g * 3 + ax) * 3;
-      const uint32_t lo24 = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16);
-      p = m::dequant_position24(lo24, __uint_as_float(__float_as_uint(a.positionScale) ^ flip));
-    }
-    a.oPositions[g * 3 + ax] = p;
-    a.oScales[g * 3 + ax] = m::dequant_scale(a.scales[g * 3 + ax]);
-    a.oColors[g * 3 + ax] = m::dequant_color(a.colors[g * 3 + ax]);
-  }
-  a.oAlphas[g] = a.tables[a.alphas[g]];
-  float r[4];
-  if (a.version >= 3) {
-    const uint8_t *b = a.rotations + g * 4;
-    uint32_t comp = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
-    // no table here: compute the three magnitudes directly (same expression as the table fill)
-    const uint32_t big = comp >> 30;
-    float sum = 0.0f;
-    for (int i = 3; i >= 0; --i) {
-      if ((uint32_t)i == big) continue;
-      const float v = __uint_as_float(__float_as_uint(m::dequant_s3_magnitude(comp & 511u)) | ((comp & 512u) << 22));
-      comp >>= 10;
-      r[i] = v;
-      sum = m::add(sum, m::mul(v, v));
-    }
-    r[big] = m::sqrt_rn(m::sub(1.0f, sum));
-    for (int i = 0; i < 3; i++) r[i] = __uint_as_float(__float_as_uint(r[i]) ^ (((a.flipQ >> i) & 1u) << 31));
-  } else {
-    const uint8_t *b = a.rotations + g * 3;
-    m::dequant_rotation_first3(b[0], b[1], b[2], a.flipQ, r);
-  }
-  for (int i = 0; i < 4; i++) a.oRotations[g * 4 + i] = r[i];
-  const int per = a.shDim * 3;
-  const uint8_t *s = a.sh + g * per;
-  float *so = a.oSh + g * per;
-  for (int j = 0; j < per; j++)
-    so[j] = m::dequant_sh(s[j], signedConst(0.0078125f, (a.flipSh >> (j / 3)) & 1u));
+  pdlTrigger();
+  pdlWait();
+  if (g < a.n) decodeOneGaussian(a, g);
 }
 
 __global__ void buildDecodeTablesKernel(float *tables) {
@@ -691,34 +655,31 @@ __global__ void probePackKernel(int *ok) {
 bool aligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 template <int D, int MODE>
-cudaError_t launchEncodeTiles(const EncodeArgs &a, long long tiles, int grid, cudaStream_t s) {
-  encodeTilesKernel<D, MODE><<<grid, kThreads, 0, s>>>(a, tiles);
-  return cudaGetLastError();
+cudaError_t launchEncodeTiles(const EncodeArgs &a, long long tiles, int grid, int restCtas, bool pdl, cudaStream_t s) {
+  return launchKernel(encodeTilesKernel<D, MODE>, grid + restCtas, kThreads, 0, s, pdl, a, tiles, restCtas);
 }
 
 template <int D, int VER>
-cudaError_t launchDecodeTilesVer(const DecodeArgs &a, long long tiles, int grid, bool bulk, cudaStream_t s) {
+cudaError_t launchDecodeTilesVer(const DecodeArgs &a, long long tiles, int grid, int restCtas, bool bulk, bool pdl, cudaStream_t s) {
   if constexpr (D > 0) {
     if (bulk) {
       // per launch, not once: the attribute belongs to the current device, and one process may drive several
       const cudaError_t attr = cudaFuncSetAttribute(decodeTilesBulkKernel<D, VER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     BulkGeo<D>::kSmemBytes);
       if (attr != cudaSuccess) return attr;
-      decodeTilesBulkKernel<D, VER><<<grid, kThreads, BulkGeo<D>::kSmemBytes, s>>>(a, tiles);
-      return cudaGetLastError();
+      return launchKernel(decodeTilesBulkKernel<D, VER>, grid + restCtas, kThreads, BulkGeo<D>::kSmemBytes, s, pdl, a, tiles, restCtas);
     }
   }
-  decodeTilesKernel<D, VER><<<grid, kThreads, 0, s>>>(a, tiles);
-  return cudaGetLastError();
+  return launchKernel(decodeTilesKernel<D, VER>, grid + restCtas, kThreads, 0, s, pdl, a, tiles, restCtas);
 }
 
 template <int D>
-cudaError_t launchDecodeTiles(const DecodeArgs &a, long long tiles, int grid, bool bulk, cudaStream_t s) {
+cudaError_t launchDecodeTiles(const DecodeArgs &a, long long tiles, int grid, int restCtas, bool bulk, bool pdl, cudaStream_t s) {
   switch (a.version) {
-    case 1: return launchDecodeTilesVer<D, 1>(a, tiles, grid, bulk, s);
-    case 2: return launchDecodeTilesVer<D, 2>(a, tiles, grid, bulk, s);
-    case 4: return launchDecodeTilesVer<D, 4>(a, tiles, grid, bulk, s);
-    default: return launchDecodeTilesVer<D, 3>(a, tiles, grid, bulk, s);
+    case 1: return launchDecodeTilesVer<D, 1>(a, tiles, grid, restCtas, bulk, pdl, s);
+    case 2: return launchDecodeTilesVer<D, 2>(a, tiles, grid, restCtas, bulk, pdl, s);
+    case 4: return launchDecodeTilesVer<D, 4>(a, tiles, grid, restCtas, bulk, pdl, s);
+    default: return launchDecodeTilesVer<D, 3>(a, tiles, grid, restCtas, bulk, pdl, s);
   }
 }
 
@@ -744,29 +705,31 @@ cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream
   if (bulkDone > 0) count++;
   const long long tg = tileGaussians(a.shDim);
   const long long tiles = vec && bulkDone == 0 ? a.n / tg : 0;
+  int restCtas = 0;
   if (tiles > 0) {
     const int per = plan.ctasPerSm >= 1 && plan.ctasPerSm <= kCtasPerSm ? plan.ctasPerSm : kCtasPerSm;
     const long long cap = plan.flatGrid ? 0x7fffffffLL : (long long)plan.smCount * per;
     const int grid = (int)(tiles < cap ? tiles : cap);
+    // one CTA per tile: the remainder (< one tile) is folded into the same launch as leading CTAs
+    restCtas = plan.flatGrid && plan.foldRest ? (int)((a.n - tiles * tg + kThreads - 1) / kThreads) : 0;
     cudaError_t e;
     const bool cvt = plan.packMode == kPackCvt;
     switch (a.shDim) {
-      case 0: e = cvt ? launchEncodeTiles<0, kPackCvt>(a, tiles, grid, stream) : launchEncodeTiles<0, kPackAlu>(a, tiles, grid, stream); break;
-      case 3: e = cvt ? launchEncodeTiles<3, kPackCvt>(a, tiles, grid, stream) : launchEncodeTiles<3, kPackAlu>(a, tiles, grid, stream); break;
-      case 8: e = cvt ? launchEncodeTiles<8, kPackCvt>(a, tiles, grid, stream) : launchEncodeTiles<8, kPackAlu>(a, tiles, grid, stream); break;
-      case 15: e = cvt ? launchEncodeTiles<15, kPackCvt>(a, tiles, grid, stream) : launchEncodeTiles<15, kPackAlu>(a, tiles, grid, stream); break;
+      case 0: e = cvt ? launchEncodeTiles<0, kPackCvt>(a, tiles, grid, restCtas, plan.pdl, stream) : launchEncodeTiles<0, kPackAlu>(a, tiles, grid, restCtas, plan.pdl, stream); break;
+      case 3: e = cvt ? launchEncodeTiles<3, kPackCvt>(a, tiles, grid, restCtas, plan.pdl, stream) : launchEncodeTiles<3, kPackAlu>(a, tiles, grid, restCtas, plan.pdl, stream); break;
+      case 8: e = cvt ? launchEncodeTiles<8, kPackCvt>(a, tiles, grid, restCtas, plan.pdl, stream) : launchEncodeTiles<8, kPackAlu>(a, tiles, grid, restCtas, plan.pdl, stream); break;
+      case 15: e = cvt ? launchEncodeTiles<15, kPackCvt>(a, tiles, grid, restCtas, plan.pdl, stream) : launchEncodeTiles<15, kPackAlu>(a, tiles, grid, restCtas, plan.pdl, stream); break;
       default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;
     count++;
   }
-  const long long first = bulkDone + tiles * tg;
+  const long long first = restCtas > 0 ? a.n : bulkDone + tiles * tg;
   if (first < a.n) {
     const long long rest = a.n - first;
     const long long blocks = (rest + 127) / 128;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    encodeGenericKernel<<<(unsigned)blocks, 128, 0, stream>>>(a, first);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launchKernel(encodeGenericKernel, (unsigned)blocks, 128, 0, stream, plan.pdl, a, first);
     if (e != cudaSuccess) return e;
     count++;
   }
@@ -795,6 +758,7 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
   if (pgDone > 0) count++;
   const long long tg = tileGaussians(a.shDim);
   const long long tiles = vec && pgDone == 0 ? a.n / tg : 0;
+  int restCtas = 0;
   if (tiles > 0) {
     const int per = plan.ctasPerSm >= 1 && plan.ctasPerSm <= kCtasPerSm ? plan.ctasPerSm : kCtasPerSm;
     const long long cap = plan.flatGrid ? 0x7fffffffLL : (long long)plan.smCount * per;
@@ -802,24 +766,24 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
     // the bulk-copy kernel needs the packed SH plane 16-byte aligned (cp.async.bulk); 4-byte aligned
     // planes still take the register-path tile kernel
     const bool bulk = plan.decodeBulk && aligned(a.sh, 16);
+    restCtas = plan.flatGrid && plan.foldRest ? (int)((a.n - tiles * tg + kThreads - 1) / kThreads) : 0;
     cudaError_t e;
     switch (a.shDim) {
-      case 0: e = launchDecodeTiles<0>(a, tiles, grid, false, stream); break;
-      case 3: e = launchDecodeTiles<3>(a, tiles, grid, bulk, stream); break;
-      case 8: e = launchDecodeTiles<8>(a, tiles, grid, bulk, stream); break;
-      case 15: e = launchDecodeTiles<15>(a, tiles, grid, bulk, stream); break;
+      case 0: e = launchDecodeTiles<0>(a, tiles, grid, restCtas, false, plan.pdl, stream); break;
+      case 3: e = launchDecodeTiles<3>(a, tiles, grid, restCtas, bulk, plan.pdl, stream); break;
+      case 8: e = launchDecodeTiles<8>(a, tiles, grid, restCtas, bulk, plan.pdl, stream); break;
+      case 15: e = launchDecodeTiles<15>(a, tiles, grid, restCtas, bulk, plan.pdl, stream); break;
       default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;
     count++;
   }
-  const long long first = pgDone + tiles * tg;
+  const long long first = restCtas > 0 ? a.n : pgDone + tiles * tg;
   if (first < a.n) {
     const long long rest = a.n - first;
     const long long blocks = (rest + 127) / 128;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    decodeGenericKernel<<<(unsigned)blocks, 128, 0, stream>>>(a, first);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launchKernel(decodeGenericKernel, (unsigned)blocks, 128, 0, stream, plan.pdl, a, first);
     if (e != cudaSuccess) return e;
     count++;
   }

@@ -94,6 +94,8 @@ struct LaunchPlan {
                        // faster (SH degree 3, at most 24M gaussians per launch; default), 2 wherever it exists
   int decodePerGaussian;   // planar decoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it
                            // measured faster (SH degree 1 - 3; default), 2 also for SH-less clouds
+  bool pdl;            // launch with programmatic stream serialization (kernel_utils.cuh); default on, SPZB200_PDL=0 turns it off
+  bool foldRest;       // the sub-tile remainder rides in the vector kernel's first CTA(s) instead of a launch of its own (default)
   bool plyMapped;      // test hook: PLY rows always through the column-map kernels, never the canonical-layout ones
 };
 

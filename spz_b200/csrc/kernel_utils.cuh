@@ -39,6 +39,32 @@ __device__ __forceinline__ float signedConst(float magnitude, uint32_t negate) {
   return __uint_as_float(__float_as_uint(magnitude) | (negate << 31));
 }
 
+// Programmatic dependent launch (PDL).  Every vector / scalar codec kernel is launched with the
+// programmatic-stream-serialization attribute (launchKernel below): its CTAs may become resident while
+// the previous kernel of the stream is still draining, run their prologue (table staging, barrier
+// init, constants), and then block in pdlWait() until that kernel has completed and its writes are
+// visible.  So: NO global read of a plane and NO global write before pdlWait().  pdlTrigger() lets the
+// NEXT kernel's CTAs in as soon as all of this grid's CTAs have started.  Without the attribute (or
+// behind a kernel that never triggers) both are no-ops and the stream serialises as usual.
+__device__ __forceinline__ void pdlTrigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launchKernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, bool pdl,
+                                Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbarInit(unsigned long long *bar) {

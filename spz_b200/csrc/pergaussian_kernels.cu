@@ -34,6 +34,7 @@
 #include "codec_math.cuh"
 #include "kernel_utils.cuh"
 #include "record_align.cuh"
+#include "scalar_path.cuh"
 
 namespace spzb200 {
 namespace {
@@ -97,6 +98,8 @@ __device__ __forceinline__ float magicByte(const uint32_t *v, int k) {
 template <int D>
 struct RowsSource {
   using Args = PlyEncodeArgs;
+  static constexpr bool kFoldRest = false;  // the remainder of a rows call goes to the column-map kernels
+  static __device__ __forceinline__ void rest(const Args &, long long) {}
   using C = typename EncGeo<D>::C;
   static constexpr int kBytes = C::kRowBytes;
   static __device__ __forceinline__ void request(const Args &a, long long tile, unsigned char *buf, unsigned long long *bar) {
@@ -122,6 +125,8 @@ struct RowsSource {
 template <int D>
 struct PlanarSource {
   using Args = EncodeArgs;
+  static constexpr bool kFoldRest = true;  // the sub-tile remainder rides in CTA 0 (scalar_path.cuh)
+  static __device__ __forceinline__ void rest(const Args &a, long long g) { encodeOneGaussian(a, g); }
   using C = typename EncGeo<D>::C;
   static constexpr int G = C::G;
   // float planes of one tile in shared memory; sizes and offsets are multiples of 16 bytes
@@ -161,7 +166,7 @@ struct PlanarSource {
 
 template <int D, int MODE, class Src>
 __global__ void __launch_bounds__(EncGeo<D>::G, EncGeo<D>::CTAS)
-encodePerGaussianKernel(const typename Src::Args a, const long long numTiles) {
+encodePerGaussianKernel(const typename Src::Args a, const long long numTiles, const int restCtas) {
   using C = typename EncGeo<D>::C;
   constexpr int W = C::W, kG = C::G;
   extern __shared__ __align__(128) unsigned char dynSmem[];
@@ -169,19 +174,27 @@ encodePerGaussianKernel(const typename Src::Args a, const long long numTiles) {
   __shared__ float sThr[256];
   unsigned char *stage = dynSmem + Src::kBytes;
   const int t = threadIdx.x;
+  pdlTrigger();
+  if constexpr (Src::kFoldRest) {
+    if ((int)blockIdx.x < restCtas) {  // fewer than kG gaussians past the last whole tile: one scalar CTA, started first
+      const long long g = numTiles * kG + t;
+      pdlWait();
+      if (g < a.n) Src::rest(a, g);
+      return;
+    }
+  }
   if (t == 0) mbarInit(&bar);
+  for (int i = t; i < 256; i += kG) sThr[i] = __ldg(a.alphaThresholds + i);  // written at context creation, never by a kernel of the stream
   __syncthreads();
+  pdlWait();  // the planes may only be touched from here on
   uint32_t parity = 0;
-  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
-    if (tile != blockIdx.x) {  // multi-tile CTAs only: the previous tile's stores are done reading the stage
+  const long long firstTile = (int)blockIdx.x - restCtas;
+  for (long long tile = firstTile; tile < numTiles; tile += (int)gridDim.x - restCtas, parity ^= 1u) {
+    if (tile != firstTile) {  // multi-tile CTAs only: the previous tile's stores are done reading the stage
       if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncthreads();
     }
     if (t == 0) Src::request(a, tile, dynSmem, &bar);
-    if (tile == blockIdx.x) {  // the threshold table arrives while the tile is in flight
-      for (int i = t; i < 256; i += kG) sThr[i] = __ldg(a.alphaThresholds + i);
-      __syncthreads();
-    }
     mbarWait(&bar, parity);
 
     float r[W];
@@ -255,6 +268,8 @@ encodePerGaussianKernel(const typename Src::Args a, const long long numTiles) {
 template <int D>
 struct RowsSink {
   using Args = PlyDecodeArgs;
+  static constexpr bool kFoldRest = false;
+  static __device__ __forceinline__ void rest(const Args &, long long) {}
   using C = typename DecGeo<D>::C;
   static constexpr int kBytes = C::kRowBytes;
   static __device__ __forceinline__ void write(unsigned char *buf, int t, const float (&rec)[C::W]) {
@@ -276,6 +291,8 @@ struct RowsSink {
 template <int D>
 struct PlanarSink {
   using Args = DecodeArgs;
+  static constexpr bool kFoldRest = true;
+  static __device__ __forceinline__ void rest(const Args &a, long long g) { decodeOneGaussian(a, g); }
   using C = typename DecGeo<D>::C;
   static constexpr int G = C::G;
   static constexpr int oPos = 0, oScale = 12 * G, oRot = 24 * G, oAlpha = 40 * G, oColor = 44 * G, oSh = 56 * G;
@@ -316,13 +333,22 @@ struct PlanarSink {
 
 template <int D, class Sink>
 __global__ void __launch_bounds__(DecGeo<D>::G, DecGeo<D>::CTAS)
-decodePerGaussianKernel(const typename Sink::Args a, const long long numTiles) {
+decodePerGaussianKernel(const typename Sink::Args a, const long long numTiles, const int restCtas) {
   using C = typename DecGeo<D>::C;
   constexpr int W = C::W, kG = C::G;
   extern __shared__ __align__(128) unsigned char dynSmem[];
   __shared__ __align__(8) unsigned long long bar;
   unsigned char *in = dynSmem + Sink::kBytes;
   const int t = threadIdx.x;
+  pdlTrigger();
+  if constexpr (Sink::kFoldRest) {
+    if ((int)blockIdx.x < restCtas) {  // fewer than kG gaussians past the last whole tile: one scalar CTA, started first
+      const long long g = numTiles * kG + t;
+      pdlWait();
+      if (g < a.n) Sink::rest(a, g);
+      return;
+    }
+  }
   const bool half = a.version == 1 || a.version == 4;
   const bool s3 = a.version >= 3;
   const uint32_t posBytes = half ? 6 * kG : 9 * kG, rotBytes = s3 ? 4 * kG : 3 * kG;
@@ -331,9 +357,11 @@ decodePerGaussianKernel(const typename Sink::Args a, const long long numTiles) {
   const float *tab = a.tables;
   if (t == 0) mbarInit(&bar);
   __syncthreads();
+  pdlWait();  // the planes may only be touched from here on
   uint32_t parity = 0;
-  for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x, parity ^= 1u) {
-    if (tile != blockIdx.x) {  // multi-tile CTAs only: the previous tile's store is done reading the records
+  const long long firstTile = (int)blockIdx.x - restCtas;
+  for (long long tile = firstTile; tile < numTiles; tile += (int)gridDim.x - restCtas, parity ^= 1u) {
+    if (tile != firstTile) {  // multi-tile CTAs only: the previous tile's store is done reading the records
       if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncthreads();
     }
@@ -441,40 +469,40 @@ unsigned gridFor(long long tiles, const LaunchPlan &plan, int ctasPerSm) {
 }
 
 template <int D, int MODE, class Src>
-cudaError_t launchEncodePerGaussian(const typename Src::Args &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+cudaError_t launchEncodePerGaussian(const typename Src::Args &a, long long tiles, int restCtas, const LaunchPlan &plan, cudaStream_t s) {
   constexpr int smem = Src::kBytes + EncGeo<D>::C::kPackedBytes;
   static_assert(smem <= 48 * 1024, "above 48 KB the kernel would need cudaFuncAttributeMaxDynamicSharedMemorySize on every device");
-  encodePerGaussianKernel<D, MODE, Src><<<gridFor(tiles, plan, EncGeo<D>::CTAS), EncGeo<D>::G, smem, s>>>(a, tiles);
-  return cudaGetLastError();
+  return launchKernel(encodePerGaussianKernel<D, MODE, Src>, gridFor(tiles, plan, EncGeo<D>::CTAS) + restCtas, EncGeo<D>::G, smem, s, plan.pdl, a, tiles,
+                      restCtas);
 }
 
 template <template <int> class Src, class Args>
-cudaError_t dispatchEncodePerGaussian(const Args &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+cudaError_t dispatchEncodePerGaussian(const Args &a, long long tiles, int restCtas, const LaunchPlan &plan, cudaStream_t s) {
   const bool cvt = plan.packMode == kPackCvt;
   switch (a.shDim) {
-    case 0: return cvt ? launchEncodePerGaussian<0, kPackCvt, Src<0>>(a, tiles, plan, s) : launchEncodePerGaussian<0, kPackAlu, Src<0>>(a, tiles, plan, s);
-    case 3: return cvt ? launchEncodePerGaussian<3, kPackCvt, Src<3>>(a, tiles, plan, s) : launchEncodePerGaussian<3, kPackAlu, Src<3>>(a, tiles, plan, s);
-    case 8: return cvt ? launchEncodePerGaussian<8, kPackCvt, Src<8>>(a, tiles, plan, s) : launchEncodePerGaussian<8, kPackAlu, Src<8>>(a, tiles, plan, s);
-    case 15: return cvt ? launchEncodePerGaussian<15, kPackCvt, Src<15>>(a, tiles, plan, s) : launchEncodePerGaussian<15, kPackAlu, Src<15>>(a, tiles, plan, s);
+    case 0: return cvt ? launchEncodePerGaussian<0, kPackCvt, Src<0>>(a, tiles, restCtas, plan, s) : launchEncodePerGaussian<0, kPackAlu, Src<0>>(a, tiles, restCtas, plan, s);
+    case 3: return cvt ? launchEncodePerGaussian<3, kPackCvt, Src<3>>(a, tiles, restCtas, plan, s) : launchEncodePerGaussian<3, kPackAlu, Src<3>>(a, tiles, restCtas, plan, s);
+    case 8: return cvt ? launchEncodePerGaussian<8, kPackCvt, Src<8>>(a, tiles, restCtas, plan, s) : launchEncodePerGaussian<8, kPackAlu, Src<8>>(a, tiles, restCtas, plan, s);
+    case 15: return cvt ? launchEncodePerGaussian<15, kPackCvt, Src<15>>(a, tiles, restCtas, plan, s) : launchEncodePerGaussian<15, kPackAlu, Src<15>>(a, tiles, restCtas, plan, s);
     default: return cudaErrorInvalidValue;
   }
 }
 
 template <int D, class Sink>
-cudaError_t launchDecodePerGaussian(const typename Sink::Args &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+cudaError_t launchDecodePerGaussian(const typename Sink::Args &a, long long tiles, int restCtas, const LaunchPlan &plan, cudaStream_t s) {
   constexpr int smem = Sink::kBytes + DecGeo<D>::C::kPackedBytes;
   static_assert(smem <= 48 * 1024, "above 48 KB the kernel would need cudaFuncAttributeMaxDynamicSharedMemorySize on every device");
-  decodePerGaussianKernel<D, Sink><<<gridFor(tiles, plan, DecGeo<D>::CTAS), DecGeo<D>::G, smem, s>>>(a, tiles);
-  return cudaGetLastError();
+  return launchKernel(decodePerGaussianKernel<D, Sink>, gridFor(tiles, plan, DecGeo<D>::CTAS) + restCtas, DecGeo<D>::G, smem, s, plan.pdl, a, tiles,
+                      restCtas);
 }
 
 template <template <int> class Sink, class Args>
-cudaError_t dispatchDecodePerGaussian(const Args &a, long long tiles, const LaunchPlan &plan, cudaStream_t s) {
+cudaError_t dispatchDecodePerGaussian(const Args &a, long long tiles, int restCtas, const LaunchPlan &plan, cudaStream_t s) {
   switch (a.shDim) {
-    case 0: return launchDecodePerGaussian<0, Sink<0>>(a, tiles, plan, s);
-    case 3: return launchDecodePerGaussian<3, Sink<3>>(a, tiles, plan, s);
-    case 8: return launchDecodePerGaussian<8, Sink<8>>(a, tiles, plan, s);
-    case 15: return launchDecodePerGaussian<15, Sink<15>>(a, tiles, plan, s);
+    case 0: return launchDecodePerGaussian<0, Sink<0>>(a, tiles, restCtas, plan, s);
+    case 3: return launchDecodePerGaussian<3, Sink<3>>(a, tiles, restCtas, plan, s);
+    case 8: return launchDecodePerGaussian<8, Sink<8>>(a, tiles, restCtas, plan, s);
+    case 15: return launchDecodePerGaussian<15, Sink<15>>(a, tiles, restCtas, plan, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -493,7 +521,7 @@ cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &p
   const int G = encTileGaussians(a.shDim);
   const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
-  const cudaError_t e = dispatchEncodePerGaussian<RowsSource>(a, tiles, plan, stream);
+  const cudaError_t e = dispatchEncodePerGaussian<RowsSource>(a, tiles, 0, plan, stream);
   if (e == cudaSuccess) *done = tiles * G;
   return e;
 }
@@ -515,8 +543,9 @@ cudaError_t launchEncodePerGaussianPlanar(const EncodeArgs &a, const LaunchPlan 
   const int G = encTileGaussians(a.shDim);
   const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
-  const cudaError_t e = dispatchEncodePerGaussian<PlanarSource>(a, tiles, plan, stream);
-  if (e == cudaSuccess) *done = tiles * G;
+  const int restCtas = plan.flatGrid && plan.foldRest && a.n > tiles * G ? 1 : 0;
+  const cudaError_t e = dispatchEncodePerGaussian<PlanarSource>(a, tiles, restCtas, plan, stream);
+  if (e == cudaSuccess) *done = restCtas ? a.n : tiles * G;
   return e;
 }
 
@@ -529,7 +558,7 @@ cudaError_t launchDecodePlyCanonical(const PlyDecodeArgs &a, const LaunchPlan &p
   const int G = decTileGaussians(a.shDim);
   const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
-  const cudaError_t e = dispatchDecodePerGaussian<RowsSink>(a, tiles, plan, stream);
+  const cudaError_t e = dispatchDecodePerGaussian<RowsSink>(a, tiles, 0, plan, stream);
   if (e == cudaSuccess) *done = tiles * G;
   return e;
 }
@@ -546,8 +575,9 @@ cudaError_t launchDecodePerGaussianPlanar(const DecodeArgs &a, const LaunchPlan 
   const int G = decTileGaussians(a.shDim);
   const long long tiles = a.n / G;
   if (tiles == 0) return cudaSuccess;
-  const cudaError_t e = dispatchDecodePerGaussian<PlanarSink>(a, tiles, plan, stream);
-  if (e == cudaSuccess) *done = tiles * G;
+  const int restCtas = plan.flatGrid && plan.foldRest && a.n > tiles * G ? 1 : 0;
+  const cudaError_t e = dispatchDecodePerGaussian<PlanarSink>(a, tiles, restCtas, plan, stream);
+  if (e == cudaSuccess) *done = restCtas ? a.n : tiles * G;
   return e;
 }
 
