@@ -138,6 +138,15 @@ void spzb200_release(SpzB200Context *ctx);
 int spzb200_encode_device(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from,
                           SpzB200Packed *out, void *stream);
 
+/* The same encoder writing another stream flavour.  stream_version = SPZB200_STREAM_V3 is
+ * spzb200_encode_device; SPZB200_STREAM_V2 stores rotations as the first three components in 3 bytes
+ * (out->rotations = 3n bytes), the form unpackQuaternionFirstThree (load-spz.cc:333-345) reads.
+ * PARITY UNPINNED for version 2: the reference tree has only that decoder, no encoder to compare with;
+ * this follows upstream nianticlabs/spz before smallest-three (normalise, make w >= 0, toUint8(xyz * 127.5
+ * + 127.5)).  Every other plane is byte-identical to version 3. */
+int spzb200_encode_device_as(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from, int32_t stream_version,
+                             SpzB200Packed *out, void *stream);
+
 /* Replaces unpackGaussians (load-spz.cc:467-531) including its trailing
  * convertCoordinates(RUB, to) (load-spz.cc:529, splat-types.h:134-164), fused into the kernel.
  * `to` is UnpackOptions::to.  in->version selects the stream flavour: 3 = smallest-three
@@ -155,6 +164,8 @@ int spzb200_decode_device(SpzB200Context *ctx, const SpzB200Packed *in, int32_t 
  * Synchronous: returns when `out` is complete.  timings may be NULL. */
 int spzb200_encode_host(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from,
                         SpzB200Packed *out, SpzB200Timings *timings);
+int spzb200_encode_host_as(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from, int32_t stream_version,
+                           SpzB200Packed *out, SpzB200Timings *timings);
 int spzb200_decode_host(SpzB200Context *ctx, const SpzB200Packed *in, int32_t to,
                         SpzB200Cloud *out, SpzB200Timings *timings);
 

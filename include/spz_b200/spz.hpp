@@ -281,6 +281,11 @@ void serializePackedGaussians(const PackedGaussians &packed, std::ostream *out);
 bool compressGzipped(const uint8_t *data, size_t size, std::vector<uint8_t> *out);
 
 // ---- extensions (not in the reference's headers) --------------------------------------------------
+// The version-2 form of the stream (rotations as the first three components, 3 bytes; the form
+// unpackQuaternionFirstThree reads) and a container whose header says so.  PARITY UNPINNED: the reference
+// has no encoder for it; every other plane equals packGaussians'.
+PackedGaussians packGaussiansV2(const GaussianCloud &g, const PackOptions &o);
+bool saveSpzV2(const GaussianCloud &gaussians, const PackOptions &options, std::vector<uint8_t> *output);
 // packed.unpack(i, c) for every i of `indices` in ONE kernel launch (a loop over unpack(i, c) pays a
 // launch per gaussian).  Empty result, after a logged line, when an index is out of range or no device
 // is usable.

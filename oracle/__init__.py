@@ -195,6 +195,17 @@ class Oracle(_Codec):
             f = getattr(L, name)
             f.restype, f.argtypes = rt, [at]
 
+    def pack_v2(self, c: Cloud, frm: int = 0) -> Packed:
+        """PARITY UNPINNED restatement of upstream's version-2 encoder (see oracle_pack_v2)."""
+        out = _empty_packed(c.n, c.sh_degree, version=2)
+        ins = [_f32(p) for p in c.planes()]
+        fn = self.lib.oracle_pack_v2
+        fn.restype = C.c_int
+        rc = fn(C.c_int64(c.n), C.c_int32(c.sh_degree), C.c_int32(frm), *[_fp(a) for a in ins], *[_bp(a) for a in out.planes()])
+        if rc != 0:
+            raise ValueError(f"oracle_pack_v2 rejected the input (rc={rc})")
+        return out
+
     def unpack_at(self, p: Packed, indices, conv21) -> np.ndarray:
         """[len(indices), 59] float32: PackedGaussians::unpack(i, c) per index (load-spz.cc:383-463)."""
         idx = np.ascontiguousarray(indices, np.int64)

@@ -26,16 +26,19 @@ def timed(fn, reps=20, rounds=5):
         ts.append(e[0].elapsed_time(e[1]) / reps)
     return statistics.median(ts)
 
+LUF, RUF = 7, 8  # splat-types.h:24-34 (round 1 passed 3 and 4 here, which are LUB and RUB -- RUB is "no flip at all")
 dev = torch.device("cuda", 0)
 with codec.Context(0) as ctx:
-    for label, n, deg, ver, frames in (("config 3: 10M SH3 v3", 10_000_000, 3, 3, (6,)), ("config 4: 10M SH0 v3", 10_000_000, 0, 3, (3, 4)),
-                                       ("config 4: 10M SH0 v2 decode", 10_000_000, 0, 2, (3, 4)), ("100M SH0 v3", 100_000_000, 0, 3, (3,)),
-                                       ("100M SH0 v2 decode", 100_000_000, 0, 2, (4,))):
+    for label, n, deg, ver, frames in (("config 3: 10M SH3 v3", 10_000_000, 3, 3, (6,)), ("config 4: 10M SH0 v3", 10_000_000, 0, 3, (LUF, RUF)),
+                                       ("config 4: 10M SH0 v2 decode", 10_000_000, 0, 2, (LUF, RUF)), ("10M SH1 v3", 10_000_000, 1, 3, (6,)),
+                                       ("10M SH2 v3", 10_000_000, 2, 3, (6,)), ("2.5M SH3 v3", 2_500_000, 3, 3, (6,)),
+                                       ("100M SH0 v3", 100_000_000, 0, 3, (LUF,)), ("100M SH0 v2 decode", 100_000_000, 0, 2, (RUF,))):
         cloud = torch_cloud(n, deg, dev, seed=1)
         packed = codec.alloc_packed(n, deg, 3, device=dev)
         out = codec.alloc_cloud(n, deg, device=dev)
-        for frame in frames:  # 3 = LUF, 4 = RUF, 6 = RDF
-            res = {"case": label, "points": n, "sh_degree": deg, "stream_version": ver, "coordinate_system": frame}
+        for frame in frames:  # CoordinateSystem ids (splat-types.h:24-34): 6 = RDF, 7 = LUF, 8 = RUF
+            res = {"case": label, "points": n, "sh_degree": deg, "stream_version": ver, "coordinate_system": frame,
+                   "coordinate_name": {6: "RDF", 7: "LUF", 8: "RUF"}[frame], "flip_bits_encode": codec.flip_bits(frame, 4), "flip_bits_decode": codec.flip_bits(4, frame)}
             if ver == 3:
                 b = codec.algorithmic_bytes_per_gaussian(deg, 3) * n
                 ms = timed(lambda: ctx.encode_device(cloud, frame, out=packed))

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from spz_b200 import codec
 from spz_b200.synth import torch_cloud
-n, deg, dev = 40_000_000, 0, torch.device("cuda", 0)
+n, deg, dev = int(float(sys.argv[1])) if len(sys.argv) > 1 else 40_000_000, 0, torch.device("cuda", 0)
 with codec.Context(0) as ctx:
     cloud = torch_cloud(n, deg, dev, seed=1)
     packed = codec.alloc_packed(n, deg, 3, device=dev)
@@ -14,8 +14,8 @@ with codec.Context(0) as ctx:
     rot = torch.randint(0, 256, (3 * n,), dtype=torch.uint8, device=dev)
     p2 = codec.PackedPlanes(n, deg, packed.positions, packed.scales, rot, packed.alphas, packed.colors, packed.sh, fractional_bits=12, version=2)
     for _ in range(2):
-        ctx.encode_device(cloud, 3, out=packed)
-        ctx.decode_device(packed, 4, out=out)
-        ctx.decode_device(p2, 3, out=out)
+        ctx.encode_device(cloud, 7, out=packed)   # CoordinateSystem ids, splat-types.h:24-34: 7 = LUF, 8 = RUF
+        ctx.decode_device(packed, 8, out=out)
+        ctx.decode_device(p2, 7, out=out)
     torch.cuda.synchronize()
 print("ok")

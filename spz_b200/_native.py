@@ -58,6 +58,8 @@ SIGNATURES = {
     "spzb200_unpack_gather_host": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_void_p, C.c_int64, _f32p, C.c_void_p]),
     "spzb200_unpack_gather_device": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_void_p, C.c_int64, _f32p, C.c_void_p, C.c_void_p]),
     "spzb200_encode_device": (C.c_int, [C.c_void_p, C.POINTER(Cloud), C.c_int32, C.POINTER(Packed), C.c_void_p]),
+    "spzb200_encode_device_as": (C.c_int, [C.c_void_p, C.POINTER(Cloud), C.c_int32, C.c_int32, C.POINTER(Packed), C.c_void_p]),
+    "spzb200_encode_host_as": (C.c_int, [C.c_void_p, C.POINTER(Cloud), C.c_int32, C.c_int32, C.POINTER(Packed), C.POINTER(Timings)]),
     "spzb200_decode_device": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_int32, C.POINTER(Cloud), C.c_void_p]),
     "spzb200_encode_host": (C.c_int, [C.c_void_p, C.POINTER(Cloud), C.c_int32, C.POINTER(Packed), C.POINTER(Timings)]),
     "spzb200_decode_host": (C.c_int, [C.c_void_p, C.POINTER(Packed), C.c_int32, C.POINTER(Cloud), C.POINTER(Timings)]),

@@ -304,12 +304,14 @@ class Context:
             return torch.cuda.current_stream().cuda_stream
         return stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
 
-    def encode_device(self, cloud: CloudPlanes, frm: int = 0, out: Optional[PackedPlanes] = None, stream=None) -> PackedPlanes:
+    def encode_device(self, cloud: CloudPlanes, frm: int = 0, out: Optional[PackedPlanes] = None, stream=None, version: int = 3) -> PackedPlanes:
+        """version=2 writes first-three rotations (3 bytes each; parity unpinned, see spzb200_encode_device_as)."""
         if out is None:
-            out = alloc_packed(cloud.n, cloud.sh_degree, 3, device=cloud.positions.device)
+            out = alloc_packed(cloud.n, cloud.sh_degree, version, device=cloud.positions.device)
         out.antialiased = cloud.antialiased
+        out.version = version
         cs, ps = _cloud_struct(cloud, True), _packed_struct(out, True)
-        N.check(N.lib().spzb200_encode_device(self._h, C.byref(cs), int(frm), C.byref(ps), C.c_void_p(self._stream_handle(stream))))
+        N.check(N.lib().spzb200_encode_device_as(self._h, C.byref(cs), int(frm), int(version), C.byref(ps), C.c_void_p(self._stream_handle(stream))))
         out.fractional_bits, out.version = ps.fractional_bits, ps.version
         return out
 
@@ -355,12 +357,13 @@ class Context:
         return out, tm.as_dict()
 
     # ---- host pointers (numpy arrays or CPU tensors, pinned for overlap) ----------------------
-    def encode_host(self, cloud: CloudPlanes, frm: int = 0, out: Optional[PackedPlanes] = None):
+    def encode_host(self, cloud: CloudPlanes, frm: int = 0, out: Optional[PackedPlanes] = None, version: int = 3):
         if out is None:
-            out = alloc_packed(cloud.n, cloud.sh_degree, 3, numpy_arrays=True)
+            out = alloc_packed(cloud.n, cloud.sh_degree, version, numpy_arrays=True)
         out.antialiased = cloud.antialiased
+        out.version = version
         cs, ps, tm = _cloud_struct(cloud, False), _packed_struct(out, False), N.Timings()
-        N.check(N.lib().spzb200_encode_host(self._h, C.byref(cs), int(frm), C.byref(ps), C.byref(tm)))
+        N.check(N.lib().spzb200_encode_host_as(self._h, C.byref(cs), int(frm), int(version), C.byref(ps), C.byref(tm)))
         out.fractional_bits, out.version = ps.fractional_bits, ps.version
         return out, tm.as_dict()
 

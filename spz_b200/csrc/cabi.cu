@@ -247,6 +247,7 @@ struct SpzB200Context {
   int decodePerGaussian = 1;  // SPZB200_DECODE=pergaussian: 2 (also SH-less clouds); =bulk / =direct: 0 (tile kernels only)
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
   bool decodeBulk = true;  // SH plane of the decoder staged with bulk async copies (SPZB200_DECODE=direct: registers)
+  bool decodeSh0Staged = true;  // SPZB200_DECODE0=tiles: SH-less clouds through decodeTilesKernel<0> (A/B timing)
   bool pdl = true;       // SPZB200_PDL=0: plain stream-ordered launches (A/B timing)
   bool foldRest = true;  // SPZB200_REST=separate: the sub-tile remainder as a launch of its own (A/B timing)
   bool flatGrid = true;  // one CTA per tile: the block scheduler keeps the tile frontier compact
@@ -317,6 +318,7 @@ spzb200::EncodeArgs makeEncodeArgs(const SpzB200Context *ctx, const SpzB200Cloud
   a.oAlphas = out.alphas; a.oColors = out.colors; a.oSh = out.sh;
   a.n = in.num_points;
   a.shDim = shDimOf(in.sh_degree);
+  a.version = out.version == 2 ? 2 : 3;
   const spzb200::m::FlipBits f = spzb200::m::make_flip_bits(from, SPZB200_COORD_RUB);
   a.flipP = f.p; a.flipQ = f.q; a.flipSh = f.sh;
   a.alphaThresholds = ctx->dThr;
@@ -351,6 +353,7 @@ spzb200::LaunchPlan planOf(const SpzB200Context *ctx) {
   p.plyMapped = ctx->plyMapped;
   p.foldRest = ctx->foldRest;
   p.pdl = ctx->pdl;
+  p.decodeSh0Staged = ctx->decodeSh0Staged;
   p.decodePerGaussian = ctx->decodePerGaussian;
   p.encodeBulk = ctx->encodeBulk;
   return p;
@@ -606,7 +609,7 @@ SpzB200Packed packedOn(const SpzB200Packed &like, uint8_t *const d[6], long long
 // encode_host / decode_host: float planes in and byte planes out, or the reverse.
 int runHostPipeline(SpzB200Context *ctx, bool isEncode, const SpzB200Cloud &cloud,
                     const SpzB200Packed &packed, int32_t coord, SpzB200Timings *timings) {
-  const int version = isEncode ? 3 : packed.version;
+  const int version = isEncode ? (packed.version == 2 ? 2 : 3) : packed.version;
   const PlaneSet fl = cloudPlaneSet(cloud), by = packedPlaneSet(packed, version);
   const long long granule = spzb200::tileGaussians(shDimOf(cloud.sh_degree));
   const spzb200::LaunchPlan plan = planOf(ctx);
@@ -843,10 +846,12 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   if (const char *env = std::getenv("SPZB200_BOUNCE_MIN_MB")) ctx->bounceMinBytes = (size_t)std::atoll(env) << 20;
   if (const char *env = std::getenv("SPZB200_DECODE")) {
     ctx->decodeBulk = std::strcmp(env, "direct") != 0;
+    if (!ctx->decodeBulk) ctx->decodeSh0Staged = false;
     ctx->decodePerGaussian = std::strcmp(env, "pergaussian") == 0 ? 2 : (std::strcmp(env, "bulk") == 0 || std::strcmp(env, "direct") == 0) ? 0 : 1;
   }
   if (const char *env = std::getenv("SPZB200_ENCODE")) ctx->encodeBulk = std::strcmp(env, "bulk") == 0 ? 2 : std::strcmp(env, "tiles") == 0 ? 0 : 1;
   if (const char *env = std::getenv("SPZB200_PLY")) ctx->plyMapped = std::strcmp(env, "mapped") == 0;
+  if (const char *env = std::getenv("SPZB200_DECODE0")) ctx->decodeSh0Staged = std::strcmp(env, "tiles") != 0;
   if (const char *env = std::getenv("SPZB200_PDL")) ctx->pdl = std::strcmp(env, "0") != 0;
   if (const char *env = std::getenv("SPZB200_REST")) ctx->foldRest = std::strcmp(env, "separate") != 0;
   if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = std::strcmp(env, "persistent") != 0;
@@ -907,14 +912,21 @@ void spzb200_destroy(SpzB200Context *ctx) {
 
 int spzb200_encode_device(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from,
                           SpzB200Packed *out, void *stream) {
+  return spzb200_encode_device_as(ctx, in, from, SPZB200_STREAM_V3, out, stream);
+}
+
+int spzb200_encode_device_as(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from, int32_t stream_version,
+                             SpzB200Packed *out, void *stream) {
   if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_encode_device: null context");
+  if (stream_version != SPZB200_STREAM_V2 && stream_version != SPZB200_STREAM_V3)
+    return fail(SPZB200_ERR_INVALID, "spzb200_encode_device: the encoder writes stream version 2 or 3, not %d", stream_version);
   int rc = checkCloud(in, "spzb200_encode_device");
   if (rc) return rc;
   if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_encode_device: null out");
   out->num_points = in->num_points;
   out->sh_degree = in->sh_degree;
   out->fractional_bits = 12;  // load-spz.cc:270
-  out->version = 3;           // load-spz.cc:133,272
+  out->version = stream_version;  // 3: load-spz.cc:133,272
   rc = checkPacked(out, "spzb200_encode_device", true);
   if (rc) return rc;
   if (from < 0 || from > 8) return fail(SPZB200_ERR_INVALID, "spzb200_encode_device: coordinate system %d", from);
@@ -945,14 +957,21 @@ int spzb200_decode_device(SpzB200Context *ctx, const SpzB200Packed *in, int32_t 
 
 int spzb200_encode_host(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from,
                         SpzB200Packed *out, SpzB200Timings *timings) {
+  return spzb200_encode_host_as(ctx, in, from, SPZB200_STREAM_V3, out, timings);
+}
+
+int spzb200_encode_host_as(SpzB200Context *ctx, const SpzB200Cloud *in, int32_t from, int32_t stream_version,
+                           SpzB200Packed *out, SpzB200Timings *timings) {
   if (!ctx) return fail(SPZB200_ERR_INVALID, "spzb200_encode_host: null context");
+  if (stream_version != SPZB200_STREAM_V2 && stream_version != SPZB200_STREAM_V3)
+    return fail(SPZB200_ERR_INVALID, "spzb200_encode_host: the encoder writes stream version 2 or 3, not %d", stream_version);
   int rc = checkCloud(in, "spzb200_encode_host");
   if (rc) return rc;
   if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_encode_host: null out");
   out->num_points = in->num_points;
   out->sh_degree = in->sh_degree;
   out->fractional_bits = 12;
-  out->version = 3;
+  out->version = stream_version;
   rc = checkPacked(out, "spzb200_encode_host", true);
   if (rc) return rc;
   if (from < 0 || from > 8) return fail(SPZB200_ERR_INVALID, "spzb200_encode_host: coordinate system %d", from);

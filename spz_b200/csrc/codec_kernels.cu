@@ -131,9 +131,9 @@ struct ShPhase {
 // =================================================================================================
 // encode, vector path
 // =================================================================================================
-template <int D, int MODE>
+template <int D, int MODE, bool V2 = false>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-encodeTilesKernel(const EncodeArgs a, const long long numTiles, const int restCtas) {
+encodeTilesKernel(const __grid_constant__ EncodeArgs a, const long long numTiles, const int restCtas) {
   constexpr int S = kThreads;
   constexpr int M = Geo<D>::M;
   __shared__ float sThr[256];
@@ -208,19 +208,37 @@ encodeTilesKernel(const EncodeArgs a, const long long numTiles, const int restCt
       // ---- alphas (float4 -> word) and rotations (quaternion -> word) -------------------------
       {
         const float4 va = ldStream(reinterpret_cast<const float4 *>(a.alphas) + q * S + t);
-        const float4 *inR = reinterpret_cast<const float4 *>(a.rotations) + q * (4 * S) + t;
-        uint32_t *outR = reinterpret_cast<uint32_t *>(a.oRotations) + q * (4 * S) + t;
+        // version 2 (3 bytes per quaternion): a warp owns 128 consecutive quaternions = 96 packed words; lane L takes
+        // quaternions L, L+32, L+64, L+96 (four contiguous 512-byte warp loads), drops its 3 bytes each into the warp's
+        // stage, and the 96 words leave as three contiguous lines -- the mirror image of the v2 decoder
+        const float4 *inR = reinterpret_cast<const float4 *>(a.rotations) + q * (4 * S) + (V2 ? warp * 128 + lane : t);
         float4 vr[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) vr[i] = ldStream(inR + i * S);
+        for (int i = 0; i < 4; i++) vr[i] = ldStream(inR + i * (V2 ? 32 : S));
         const uint32_t a0 = m::quant_alpha(va.x, sThr), a1 = m::quant_alpha(va.y, sThr);
         const uint32_t a2 = m::quant_alpha(va.z, sThr), a3 = m::quant_alpha(va.w, sThr);
         stStream(reinterpret_cast<uint32_t *>(a.oAlphas) + q * S + t,
                  a0 | (a1 << 8) | (a2 << 16) | (a3 << 24));
+        if constexpr (V2) {
+          uint8_t *sb = reinterpret_cast<uint8_t *>(stage);
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-          stStream(outR + i * S,
-                   m::quant_rotation_smallest3(vr[i].x, vr[i].y, vr[i].z, vr[i].w, a.flipQ));
+          for (int i = 0; i < 4; i++) {
+            const uint32_t b = m::quant_rotation_first3(vr[i].x, vr[i].y, vr[i].z, vr[i].w, a.flipQ);
+            const int qi = 3 * (lane + 32 * i);
+            sb[qi] = (uint8_t)b; sb[qi + 1] = (uint8_t)(b >> 8); sb[qi + 2] = (uint8_t)(b >> 16);
+          }
+          __syncwarp();
+          uint32_t *outR = reinterpret_cast<uint32_t *>(a.oRotations) + q * (3 * S) + warp * 96 + lane;
+#pragma unroll
+          for (int k = 0; k < 3; k++) stStream(outR + k * 32, stage[k * 32 + lane]);
+          __syncwarp();
+        } else {
+          uint32_t *outR = reinterpret_cast<uint32_t *>(a.oRotations) + q * (4 * S) + t;
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            stStream(outR + i * S,
+                     m::quant_rotation_smallest3(vr[i].x, vr[i].y, vr[i].z, vr[i].w, a.flipQ));
+        }
       }
     }
     // ---- spherical harmonics: float4 -> word; rows c, c+CYC, ... share their constants ---------
@@ -262,7 +280,7 @@ encodeTilesKernel(const EncodeArgs a, const long long numTiles, const int restCt
 // encode, scalar path: remainders, tiny clouds, under-aligned pointers.  One thread per gaussian.
 // =================================================================================================
 __global__ void __launch_bounds__(128)
-encodeGenericKernel(const EncodeArgs a, const long long first) {
+encodeGenericKernel(const __grid_constant__ EncodeArgs a, const long long first) {
   const long long g = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   pdlTrigger();
   pdlWait();
@@ -291,11 +309,32 @@ struct DecodePosConsts {
 // positions, scales, colours, alphas and rotations of sub-tile q (gaussians [q*1280, (q+1)*1280)):
 // direct 128-byte-aligned loads and stores, shared by both decode kernels.  `stage` is this warp's
 // 288-word scratch.
-template <int VER, bool HOIST>
+// Where the expanded float4s of a sub-tile go.  Both sinks hold one float4 pointer per plane, already
+// advanced to the sub-tile; `idx` is the float4 index inside that plane's part of the sub-tile.
+struct GlobalSink {  // straight to the output planes with streaming stores
+  float4 *pos, *scale, *rot, *alpha, *color;
+  template <int S>
+  static __device__ __forceinline__ GlobalSink at(const DecodeArgs &a, long long q) {
+    return {reinterpret_cast<float4 *>(a.oPositions) + q * (3 * S), reinterpret_cast<float4 *>(a.oScales) + q * (3 * S),
+            reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S), reinterpret_cast<float4 *>(a.oAlphas) + q * S,
+            reinterpret_cast<float4 *>(a.oColors) + q * (3 * S)};
+  }
+  static __device__ __forceinline__ void put(float4 *plane, int idx, float4 v) { stStream(plane + idx, v); }
+};
+struct SmemSink {  // into a shared-memory image of the sub-tile's five float planes (bulk-stored by the caller)
+  float4 *pos, *scale, *rot, *alpha, *color;
+  template <int S>
+  static __device__ __forceinline__ SmemSink at(float4 *base) {
+    return {base, base + 3 * S, base + 6 * S, base + 10 * S, base + 11 * S};
+  }
+  static __device__ __forceinline__ void put(float4 *plane, int idx, float4 v) { plane[idx] = v; }
+};
+
+template <int VER, bool HOIST, int S = kThreads, class Sink = GlobalSink>
 __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const long long q, const int t, uint32_t *stage,
                                                   const float *sAlpha, const float *sColor, const float *sMag,
-                                                  const DecodePosConsts &pc) {
-  constexpr int S = kThreads;
+                                                  const DecodePosConsts &pc, const Sink &sink) {
+  static_assert((4 * S) % 3 == 2, "the xyz phase of element e in row i is taken as (t + e + 2 i) mod 3");
   constexpr bool kHalf = (VER == 1 || VER == 4);  // float16 positions
   constexpr bool kS3 = (VER >= 3);                // smallest-three rotations
   const int lane = t & 31, warp = t >> 5;
@@ -343,7 +382,6 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
   }
   // ---- positions ------------------------------------------------------------------------
   {
-    float4 *out = reinterpret_cast<float4 *>(a.oPositions) + q * (3 * S) + t;
     if (!HOIST) loadPositions();
     if (kHalf) {
 #pragma unroll
@@ -353,7 +391,7 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
         o.y = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].x >> 16)) ^ posFlip3[(1 + 2 * i) % 3]);
         o.z = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y & 0xffffu)) ^ posFlip3[(2 + 2 * i) % 3]);
         o.w = __uint_as_float(__float_as_uint(m::half_bits_to_float(w[i].y >> 16)) ^ posFlip3[(3 + 2 * i) % 3]);
-        stStream(out + i * S, o);
+        Sink::put(sink.pos, i * S + t, o);
       }
     } else {
       // re-deal through the per-warp stage so each lane gets the three words of its four 24-bit values
@@ -377,15 +415,13 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
         o.y = m::mul(m::i2f(f1), posScale3[(1 + 2 * i) % 3]);
         o.z = m::mul(m::i2f(f2), posScale3[(2 + 2 * i) % 3]);
         o.w = m::mul(m::i2f(f3), posScale3[(3 + 2 * i) % 3]);
-        stStream(out + i * S, o);
+        Sink::put(sink.pos, i * S + t, o);
       }
       __syncwarp();
     }
   }
   // ---- scales (exact FMA on the magic float) and colours (table) ---------------------------
   {
-    float4 *outS = reinterpret_cast<float4 *>(a.oScales) + q * (3 * S) + t;
-    float4 *outC = reinterpret_cast<float4 *>(a.oColors) + q * (3 * S) + t;
     if (!HOIST) loadScalesColors();
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -396,13 +432,13 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
       o.y = __fmaf_rn(byteAsMagicFloat<1>(ws[i]), 0.0625f, -524298.0f);
       o.z = __fmaf_rn(byteAsMagicFloat<2>(ws[i]), 0.0625f, -524298.0f);
       o.w = __fmaf_rn(byteAsMagicFloat<3>(ws[i]), 0.0625f, -524298.0f);
-      stStream(outS + i * S, o);
+      Sink::put(sink.scale, i * S + t, o);
       float4 c;
       c.x = sColor[wc[i] & 0xffu];
       c.y = sColor[(wc[i] >> 8) & 0xffu];
       c.z = sColor[(wc[i] >> 16) & 0xffu];
       c.w = sColor[wc[i] >> 24];
-      stStream(outC + i * S, c);
+      Sink::put(sink.color, i * S + t, c);
     }
   }
   // ---- alphas (table) ---------------------------------------------------------------------
@@ -413,24 +449,22 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
     o.y = sAlpha[(wa >> 8) & 0xffu];
     o.z = sAlpha[(wa >> 16) & 0xffu];
     o.w = sAlpha[wa >> 24];
-    stStream(reinterpret_cast<float4 *>(a.oAlphas) + q * S + t, o);
+    Sink::put(sink.alpha, t, o);
   }
   // ---- rotations ----------------------------------------------------------------------------
   if (kS3) {
-    float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + t;
     if (!HOIST) loadRotations();
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       float r[4];
       m::dequant_rotation_smallest3(wr[i], sMag, a.flipQ, r);
-      stStream(out + i * S, make_float4(r[0], r[1], r[2], r[3]));
+      Sink::put(sink.rot, i * S + t, make_float4(r[0], r[1], r[2], r[3]));
     }
   } else {
     // 3 bytes per quaternion.  A warp owns 128 consecutive quaternions = 96 words, loaded as
     // three contiguous lines into the stage; lane L then decodes quaternions L, L+32, L+64,
     // L+96 so that each of its four float4 stores is a contiguous 512-byte warp store.
     const uint32_t *in = reinterpret_cast<const uint32_t *>(a.rotations) + q * (3 * S) + warp * 96 + lane;
-    float4 *out = reinterpret_cast<float4 *>(a.oRotations) + q * (4 * S) + warp * 128 + lane;
 #pragma unroll
     for (int k = 0; k < 3; k++) stage[k * 32 + lane] = ldStream(in + k * 32);
     __syncwarp();
@@ -440,7 +474,7 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
       const int qi = 3 * (lane + 32 * i);
       float r[4];
       m::dequant_rotation_first3(sb[qi], sb[qi + 1], sb[qi + 2], a.flipQ, r);
-      stStream(out + 32 * i, make_float4(r[0], r[1], r[2], r[3]));
+      Sink::put(sink.rot, warp * 128 + lane + 32 * i, make_float4(r[0], r[1], r[2], r[3]));
     }
     __syncwarp();
   }
@@ -448,7 +482,7 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
 
 template <int D, int VER>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-decodeTilesKernel(const DecodeArgs a, const long long numTiles, const int restCtas) {
+decodeTilesKernel(const __grid_constant__ DecodeArgs a, const long long numTiles, const int restCtas) {
   constexpr int S = kThreads;
   constexpr int M = Geo<D>::M;
   constexpr bool kS3 = (VER >= 3);
@@ -472,7 +506,8 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles, const int restCt
 
   for (long long tile = (int)blockIdx.x - restCtas; tile < numTiles; tile += (int)gridDim.x - restCtas) {
 #pragma unroll 1
-    for (int mm = 0; mm < M; mm++) decodeSmallPlanes<VER, false>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc);
+    for (int mm = 0; mm < M; mm++)
+      decodeSmallPlanes<VER, false>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc, GlobalSink::at<kThreads>(a, tile * M + mm));
     // ---- spherical harmonics: word -> float4 -------------------------------------------------
     if (D > 0) {
       constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS;
@@ -522,6 +557,67 @@ decodeTilesKernel(const DecodeArgs a, const long long numTiles, const int restCt
     }
 }
 
+// ---- SH-less clouds: outputs staged in shared memory, written with bulk async stores ---------------
+// An SH-less decode writes 56 of its 76 bytes per gaussian.  scripts/membench.cu: for that write-heavy
+// mix STG.128 from registers sustains 6.09 TB/s, bulk async stores from shared memory (UBLKCP.G.S) 6.76.
+// Same per-value work as decodeTilesKernel<0, VER> (the packed words arrive with plain 128-byte-aligned
+// loads -- a quarter of the traffic), but every float4 goes into a shared-memory image of the tile's
+// five float planes, which leaves through five bulk stores.  Tiles are small (4 x 128 gaussians, 28 KB
+// of shared memory, 6 CTAs per SM): a CTA holds its image through load wait, expansion and store
+// drain, and many small CTAs overlap those phases and keep a launch's tail short.  The three decode
+// tables are read through L1 instead of being copied into every CTA's shared memory.
+#ifndef SPZ_DEC0_THREADS
+#define SPZ_DEC0_THREADS 128
+#endif
+#ifndef SPZ_DEC0_CTAS
+#define SPZ_DEC0_CTAS 6
+#endif
+#ifndef SPZ_DEC0_HOIST
+#define SPZ_DEC0_HOIST true
+#endif
+constexpr int kDec0Threads = SPZ_DEC0_THREADS;
+constexpr int kDec0Tile = 4 * kDec0Threads;  // gaussians per CTA
+
+template <int VER>
+__global__ void __launch_bounds__(kDec0Threads, SPZ_DEC0_CTAS)
+decodeSh0StagedKernel(const __grid_constant__ DecodeArgs a, const long long numTiles, const int restCtas) {
+  constexpr int S = kDec0Threads;
+  extern __shared__ __align__(128) unsigned char dynSmem[];  // 14 * S float4: positions 3S, scales 3S, rotations 4S, alphas S, colours 3S
+  __shared__ uint32_t sStage[S / 32][3 * 96];
+  const int t = threadIdx.x;
+  pdlTrigger();
+  if ((int)blockIdx.x < restCtas) {  // the sub-tile remainder rides in the first CTA(s): scalar_path.cuh
+    const long long g = numTiles * kDec0Tile + (long long)blockIdx.x * S + t;
+    pdlWait();
+    if (g < a.n) decodeOneGaussian(a, g);
+    return;
+  }
+  float4 *image = reinterpret_cast<float4 *>(dynSmem);
+  const SmemSink sink = SmemSink::at<S>(image);
+  DecodePosConsts pc;
+  pc.init(a, t);
+  pdlWait();  // constants are in place; the planes may only be touched from here on
+  const long long firstTile = (int)blockIdx.x - restCtas;
+  for (long long tile = firstTile; tile < numTiles; tile += (int)gridDim.x - restCtas) {
+    if (tile != firstTile) {  // multi-tile CTAs only: the previous tile's stores are done reading the image
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncthreads();
+    }
+    decodeSmallPlanes<VER, SPZ_DEC0_HOIST, S, SmemSink>(a, tile, t, sStage[t >> 5], a.tables, a.tables + 256, a.tables + 512, pc, sink);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the STS visible to the copy engine
+    __syncthreads();
+    if (t == 0) {
+      bulkStore(reinterpret_cast<float4 *>(a.oPositions) + tile * (3 * S), sink.pos, 3 * S * 16);
+      bulkStore(reinterpret_cast<float4 *>(a.oScales) + tile * (3 * S), sink.scale, 3 * S * 16);
+      bulkStore(reinterpret_cast<float4 *>(a.oRotations) + tile * (4 * S), sink.rot, 4 * S * 16);
+      bulkStore(reinterpret_cast<float4 *>(a.oAlphas) + tile * S, sink.alpha, S * 16);
+      bulkStore(reinterpret_cast<float4 *>(a.oColors) + tile * (3 * S), sink.color, 3 * S * 16);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the stores' reads
+}
+
 // ---- bulk-copy (TMA) staging of the SH plane ---------------------------------------------------------
 // scripts/membench.cu (profiles/r1_membench_patterns.txt): for decode's write-heavy mix, moving the
 // packed words in with ONE bulk async copy per tile (UBLKCP.S.G, completion on an mbarrier) and
@@ -541,7 +637,7 @@ struct BulkGeo {
 
 template <int D, int VER>
 __global__ void __launch_bounds__(kThreads, 2)
-decodeTilesBulkKernel(const DecodeArgs a, const long long numTiles, const int restCtas) {
+decodeTilesBulkKernel(const __grid_constant__ DecodeArgs a, const long long numTiles, const int restCtas) {
   static_assert(D > 0, "SH-less clouds use decodeTilesKernel");
   pdlTrigger();
   if ((int)blockIdx.x < restCtas) {  // the sub-tile remainder rides in the first CTA(s): scalar_path.cuh
@@ -574,7 +670,8 @@ decodeTilesBulkKernel(const DecodeArgs a, const long long numTiles, const int re
     if (t == 0)
       bulkLoad(win, reinterpret_cast<const uint32_t *>(a.sh) + tile * ((long long)ROWS * S), BulkGeo<D>::kWordBytes, &bar);
 #pragma unroll 1
-    for (int mm = 0; mm < M; mm++) decodeSmallPlanes<VER, SPZ_DEC_HOIST>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc);
+    for (int mm = 0; mm < M; mm++)
+      decodeSmallPlanes<VER, SPZ_DEC_HOIST>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc, GlobalSink::at<kThreads>(a, tile * M + mm));
     mbarWait(&bar, parity);
     __syncthreads();  // every warp is done with its word stage, which the out buffers overlay
 
@@ -628,7 +725,7 @@ decodeTilesBulkKernel(const DecodeArgs a, const long long numTiles, const int re
 // decode, scalar path
 // =================================================================================================
 __global__ void __launch_bounds__(128)
-decodeGenericKernel(const DecodeArgs a, const long long first) {
+decodeGenericKernel(const __grid_constant__ DecodeArgs a, const long long first) {
   const long long g = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   pdlTrigger();
   pdlWait();
@@ -656,7 +753,8 @@ bool aligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p
 
 template <int D, int MODE>
 cudaError_t launchEncodeTiles(const EncodeArgs &a, long long tiles, int grid, int restCtas, bool pdl, cudaStream_t s) {
-  return launchKernel(encodeTilesKernel<D, MODE>, grid + restCtas, kThreads, 0, s, pdl, a, tiles, restCtas);
+  if (a.version == 2) return launchKernel(encodeTilesKernel<D, MODE, true>, grid + restCtas, kThreads, 0, s, pdl, a, tiles, restCtas);
+  return launchKernel(encodeTilesKernel<D, MODE, false>, grid + restCtas, kThreads, 0, s, pdl, a, tiles, restCtas);
 }
 
 template <int D, int VER>
@@ -671,6 +769,15 @@ cudaError_t launchDecodeTilesVer(const DecodeArgs &a, long long tiles, int grid,
     }
   }
   return launchKernel(decodeTilesKernel<D, VER>, grid + restCtas, kThreads, 0, s, pdl, a, tiles, restCtas);
+}
+
+template <int VER>
+cudaError_t launchDecodeSh0Staged(const DecodeArgs &a, long long tiles, unsigned grid, int restCtas, size_t smem, bool pdl, cudaStream_t s) {
+  if (smem > 48 * 1024) {  // per launch, not once: the attribute belongs to the current device
+    const cudaError_t attr = cudaFuncSetAttribute(decodeSh0StagedKernel<VER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (attr != cudaSuccess) return attr;
+  }
+  return launchKernel(decodeSh0StagedKernel<VER>, grid + restCtas, kDec0Threads, smem, s, pdl, a, tiles, restCtas);
 }
 
 template <int D>
@@ -756,6 +863,24 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
   long long pgDone = 0;
   if (cudaError_t e = launchDecodePerGaussianPlanar(a, plan, stream, &pgDone); e != cudaSuccess) return e;
   if (pgDone > 0) count++;
+  // SH-less clouds with 16-byte aligned float planes: the staged bulk-store decoder above
+  if (pgDone == 0 && vec && a.shDim == 0 && plan.decodeSh0Staged && a.n >= kDec0Tile) {
+    const long long tiles0 = a.n / kDec0Tile;
+    const long long cap = plan.flatGrid ? 0x7fffffffLL : (long long)plan.smCount * SPZ_DEC0_CTAS;
+    const unsigned grid = (unsigned)(tiles0 < cap ? tiles0 : cap);
+    const int rest0 = plan.flatGrid && plan.foldRest ? (int)((a.n - tiles0 * kDec0Tile + kDec0Threads - 1) / kDec0Threads) : 0;
+    constexpr size_t smem = 14 * kDec0Threads * 16;
+    cudaError_t e;
+    switch (a.version) {
+      case 1: e = launchDecodeSh0Staged<1>(a, tiles0, grid, rest0, smem, plan.pdl, stream); break;
+      case 2: e = launchDecodeSh0Staged<2>(a, tiles0, grid, rest0, smem, plan.pdl, stream); break;
+      case 4: e = launchDecodeSh0Staged<4>(a, tiles0, grid, rest0, smem, plan.pdl, stream); break;
+      default: e = launchDecodeSh0Staged<3>(a, tiles0, grid, rest0, smem, plan.pdl, stream); break;
+    }
+    if (e != cudaSuccess) return e;
+    count++;
+    pgDone = rest0 > 0 ? a.n : tiles0 * kDec0Tile;
+  }
   const long long tg = tileGaussians(a.shDim);
   const long long tiles = vec && pgDone == 0 ? a.n / tg : 0;
   int restCtas = 0;

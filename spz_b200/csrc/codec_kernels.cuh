@@ -13,6 +13,8 @@ struct EncodeArgs {
   uint8_t *oPositions, *oScales, *oRotations, *oAlphas, *oColors, *oSh;
   long long n;
   int shDim;
+  int version;                    // 3: smallest-three rotations, 4 bytes each (what the reference writes); 2: first-three, 3 bytes
+                                  // each (upstream's earlier form: parity unpinned, codec_math.cuh: quant_rotation_first3)
   uint32_t flipP, flipQ, flipSh;  // sign-bit sets of coordinateConverter(from, RUB)
   const float *alphaThresholds;   // device, 256 floats (255 thresholds + +Inf pad)
 };
@@ -94,6 +96,7 @@ struct LaunchPlan {
                        // faster (SH degree 3, at most 24M gaussians per launch; default), 2 wherever it exists
   int decodePerGaussian;   // planar decoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it
                            // measured faster (SH degree 1 - 3; default), 2 also for SH-less clouds
+  bool decodeSh0Staged;  // SH-less decode through the staged bulk-store kernel (default; SPZB200_DECODE=direct / tiles0 keep the register-path tiles)
   bool pdl;            // launch with programmatic stream serialization (kernel_utils.cuh); default on, SPZB200_PDL=0 turns it off
   bool foldRest;       // the sub-tile remainder rides in the vector kernel's first CTA(s) instead of a launch of its own (default)
   bool plyMapped;      // test hook: PLY rows always through the column-map kernels, never the canonical-layout ones

@@ -290,6 +290,21 @@ SPZ_HD uint32_t quant_rotation_smallest3(float x, float y, float z, float w, uin
   return (big << 30) | ((first ^ negate) << 20) | ((second ^ negate) << 10) | (third ^ negate);
 }
 
+// rotations, version-2 streams (first three components as bytes).  PARITY UNPINNED: the reference tree
+// has only the decoder for this form (load-spz.cc:333-345); this is the encoder upstream nianticlabs/spz
+// shipped before the smallest-three change -- normalise, flip, make w non-negative, store
+// toUint8(q.xyz * 127.5 + 127.5) -- written with the reference's own primitives (normalized,
+// splat-types.cc:71-74; toUint8, load-spz.cc:74).  Returns the three bytes in bits 0..23.
+SPZ_HD_COLD uint32_t quant_rotation_first3(float x, float y, float z, float w, uint32_t flipBits) {
+  const float n2 = add(add(add(mul(x, x), mul(y, y)), mul(z, z)), mul(w, w));
+  const float nrm = sqrt_rn(n2);
+  const float qx = bitsf(fbits(div(x, nrm)) ^ ((flipBits & 1u) << 31));
+  const float qy = bitsf(fbits(div(y, nrm)) ^ ((flipBits & 2u) << 30));
+  const float qz = bitsf(fbits(div(z, nrm)) ^ ((flipBits & 4u) << 29));
+  const float s = div(w, nrm) < 0.0f ? -127.5f : 127.5f;
+  return to_u8(add(mul(qx, s), 127.5f)) | (to_u8(add(mul(qy, s), 127.5f)) << 8) | (to_u8(add(mul(qz, s), 127.5f)) << 16);
+}
+
 // ---- decode-side dequantizers ---------------------------------------------------------------
 
 // scales, load-spz.cc:506: s / 16.0f - 10.0f.  s/16 is exact and the difference is a multiple of

@@ -166,7 +166,7 @@ struct PlanarSource {
 
 template <int D, int MODE, class Src>
 __global__ void __launch_bounds__(EncGeo<D>::G, EncGeo<D>::CTAS)
-encodePerGaussianKernel(const typename Src::Args a, const long long numTiles, const int restCtas) {
+encodePerGaussianKernel(const __grid_constant__ typename Src::Args a, const long long numTiles, const int restCtas) {
   using C = typename EncGeo<D>::C;
   constexpr int W = C::W, kG = C::G;
   extern __shared__ __align__(128) unsigned char dynSmem[];
@@ -333,7 +333,7 @@ struct PlanarSink {
 
 template <int D, class Sink>
 __global__ void __launch_bounds__(DecGeo<D>::G, DecGeo<D>::CTAS)
-decodePerGaussianKernel(const typename Sink::Args a, const long long numTiles, const int restCtas) {
+decodePerGaussianKernel(const __grid_constant__ typename Sink::Args a, const long long numTiles, const int restCtas) {
   using C = typename DecGeo<D>::C;
   constexpr int W = C::W, kG = C::G;
   extern __shared__ __align__(128) unsigned char dynSmem[];
@@ -534,7 +534,7 @@ cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &p
 constexpr long long kEncodePerGaussianMaxPoints = 24000000;
 cudaError_t launchEncodePerGaussianPlanar(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done) {
   *done = 0;
-  if (plan.forceGeneric || plan.encodeBulk == 0 || a.shDim == 8) return cudaSuccess;
+  if (plan.forceGeneric || plan.encodeBulk == 0 || a.shDim == 8 || a.version != 3) return cudaSuccess;  // version-2 streams: tile encoder only
   if (plan.encodeBulk < 2 && !(a.shDim == 15 && a.n <= kEncodePerGaussianMaxPoints)) return cudaSuccess;
   if (!(aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) && aligned16(a.colors) &&
         (a.shDim == 0 || aligned16(a.sh)) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) &&

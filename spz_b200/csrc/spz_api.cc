@@ -305,7 +305,7 @@ bool readFile(const std::string &filename, std::vector<uint8_t> *out) {
 
 namespace {
 enum class PackStatus { Ok, Rejected, DeviceError };
-PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussians *result);
+PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussians *result, int32_t streamVersion = SPZB200_STREAM_V3);
 }  // namespace
 
 PackedGaussians packGaussians(const GaussianCloud &g, const PackOptions &o) {
@@ -314,8 +314,32 @@ PackedGaussians packGaussians(const GaussianCloud &g, const PackOptions &o) {
   return packed;
 }
 
+// Extension, PARITY UNPINNED: the version-2 form of the stream -- rotations as the first three
+// components of the normalised, w >= 0 quaternion in 3 bytes, what unpackQuaternionFirstThree (load-spz.cc:333-345)
+// reads.  The reference tree holds no encoder for it; every other plane is what packGaussians writes.
+PackedGaussians packGaussiansV2(const GaussianCloud &g, const PackOptions &o) {
+  PackedGaussians packed;
+  if (packImpl(g, o, &packed, SPZB200_STREAM_V2) != PackStatus::Ok) return {};
+  return packed;
+}
+
+// ... and the container for it: header version 2 (the reference's writer always says 3, load-spz.cc:133), so that
+// the reference's loadSpz takes its first-three path.
+bool saveSpzV2(const GaussianCloud &g, const PackOptions &o, std::vector<uint8_t> *out) {
+  PackedGaussians packed;
+  if (packImpl(g, o, &packed, SPZB200_STREAM_V2) != PackStatus::Ok) return false;
+  std::vector<uint8_t> stream;
+  resizeUninitialized(stream, serializedBytes(packed));
+  serializeInto(packed, stream.data());
+  const uint32_t two = 2;
+  std::memcpy(stream.data() + 4, &two, 4);
+  const int threads = gzipThreads();
+  if (threads > 1) return compressGzippedParallel(stream.data(), stream.size(), threads, out);
+  return compressGzipped(stream.data(), stream.size(), out);
+}
+
 namespace {
-PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussians *result) {
+PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussians *result, int32_t streamVersion) {
   PackedGaussians &packed = *result;
   if (!checkCloudSizes(g)) return PackStatus::Rejected;
   const size_t n = (size_t)g.numPoints;
@@ -324,26 +348,26 @@ PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussian
   packed.shDegree = g.shDegree;
   packed.fractionalBits = 12;  // load-spz.cc:270
   packed.antialiased = g.antialiased;
-  packed.usesQuaternionSmallestThree = true;
+  packed.usesQuaternionSmallestThree = streamVersion != SPZB200_STREAM_V2;
   // every byte is written by the encoder (or the struct is discarded on failure)
   resizeUninitialized(packed.positions, n * 9);
   resizeUninitialized(packed.scales, n * 3);
-  resizeUninitialized(packed.rotations, n * 4);
+  resizeUninitialized(packed.rotations, n * (packed.usesQuaternionSmallestThree ? 4 : 3));
   resizeUninitialized(packed.alphas, n);
   resizeUninitialized(packed.colors, n * 3);
   resizeUninitialized(packed.sh, n * shDim * 3);
   if (n == 0) return PackStatus::Ok;  // nothing to encode; no device needed (load_spz_test.py:753)
 
   const SpzB200Cloud in = viewOf(g);
-  SpzB200Packed out = viewOf(packed, SPZB200_STREAM_V3);
+  SpzB200Packed out = viewOf(packed, streamVersion);
   const std::vector<int32_t> devs = configuredDevices();
   int rc;
-  if (devs.size() > 1) {
+  if (devs.size() > 1 && streamVersion == SPZB200_STREAM_V3) {
     rc = spzb200_encode_host_multi(devs.data(), (int32_t)devs.size(), &in, (int32_t)o.from, &out, nullptr);
   } else {
     ContextLease lease(devs[0]);
     if (!lease.get()) return PackStatus::DeviceError;
-    rc = spzb200_encode_host(lease.get(), &in, (int32_t)o.from, &out, nullptr);
+    rc = spzb200_encode_host_as(lease.get(), &in, (int32_t)o.from, streamVersion, &out, nullptr);
   }
   if (rc != SPZB200_OK) {
     logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());

@@ -110,6 +110,18 @@ uint8_t *SHIM(save_spz)(int32_t n, int32_t deg, int32_t aa, int32_t from, const 
   return dupBytes(bytes.data(), bytes.size(), outSize);
 }
 
+#ifdef SHIM_HAS_EXTENSIONS
+// saveSpzV2 (this repo's extension: first-three rotations under a version-2 header) -> malloc'd gzip bytes
+uint8_t *SHIM(save_spz_v2)(int32_t n, int32_t deg, int32_t aa, int32_t from, const float *const planes[6], uint64_t *outSize) {
+  const spz::GaussianCloud g = makeCloud(n, deg, aa, planes);
+  spz::PackOptions o;
+  o.from = (spz::CoordinateSystem)from;
+  std::vector<uint8_t> bytes;
+  if (!spz::saveSpzV2(g, o, &bytes)) return nullptr;
+  return dupBytes(bytes.data(), bytes.size(), outSize);
+}
+#endif
+
 int SHIM(save_spz_file)(int32_t n, int32_t deg, int32_t aa, int32_t from, const float *const planes[6], const char *path) {
   const spz::GaussianCloud g = makeCloud(n, deg, aa, planes);
   spz::PackOptions o;

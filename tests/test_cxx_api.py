@@ -96,6 +96,14 @@ class Shim:
         ptr = self.fn("save_spz")(C.c_int32(c.n), C.c_int32(c.sh_degree), C.c_int32(int(c.antialiased)), C.c_int32(frm), ip, C.byref(size))
         return None if not ptr else self._take(ptr, size)
 
+    def save_spz_v2(self, c: Cloud, frm=0):
+        _, ip = self._fplanes(c.planes())
+        size = C.c_uint64(0)
+        f = self.fn("save_spz_v2")
+        f.restype = C.c_void_p
+        ptr = f(C.c_int32(c.n), C.c_int32(c.sh_degree), C.c_int32(int(c.antialiased)), C.c_int32(frm), ip, C.byref(size))
+        return None if not ptr else self._take(ptr, size)
+
     def save_spz_file(self, c: Cloud, path: str, frm=0) -> bool:
         _, ip = self._fplanes(c.planes())
         return bool(self.fn("save_spz_file")(C.c_int32(c.n), C.c_int32(c.sh_degree), C.c_int32(int(c.antialiased)), C.c_int32(frm), ip, path.encode()))
@@ -872,6 +880,29 @@ def test_unpack_many_matches_a_loop_over_the_reference(mine, theirs, relinked):
     got = mine.unpack_many(big, idx, convs[1], True)
     uniq = theirs.unpack_many(big, np.arange(5000, dtype=np.int32), convs[1], False)
     assert np.array_equal(bits(got), bits(uniq[idx]))
+
+
+@pytest.mark.gpu
+def test_version2_files_are_read_by_the_reference(mine, theirs):
+    """saveSpzV2 (extension, parity unpinned: the reference has no version-2 encoder): the container says version 2,
+    the UNMODIFIED reference loads it down its first-three path, and this library's loader decodes the same bytes to
+    the same floats; the quaternions come back within the 8-bit step of the normalised, w >= 0 input."""
+    rng = np.random.default_rng(430)
+    for deg in (0, 3):
+        c = random_cloud(rng, 5000, deg, False)
+        blob = mine.save_spz_v2(c, 6)
+        raw = gzip.decompress(blob)
+        assert struct.unpack_from("<III", raw, 0) == (0x5053474e, 2, 5000) and len(raw) == 16 + 5000 * (19 + 3 * SH_DIM[deg])
+        a, b = mine.load_spz(blob, 8), theirs.load_spz(blob, 8)
+        assert_cloud_bits_equal(a, b, f"v2 file deg{deg}")
+        v3 = theirs.load_spz(theirs.save_spz(c, 6), 8)
+        for name in ("positions", "scales", "alphas", "colors", "sh"):
+            assert np.array_equal(bits(getattr(a, name)), bits(getattr(v3, name))), name
+        q = c.rotations.reshape(-1, 4).astype(np.float64)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        q *= np.where(q[:, 3:4] < 0, -1.0, 1.0)
+        want = q * np.concatenate([theirs.converter(6, 8)[3:6], [1.0]])
+        assert np.abs(a.rotations.reshape(-1, 4)[:, :3] - want[:, :3]).max() <= 0.5 / 127.5 + 1e-6
 
 
 @pytest.mark.gpu

@@ -247,7 +247,9 @@ def test_ply_kernels_write_only_their_planes(gpu_ctx, oracle, deg, extra):
                                  {"SPZB200_DECODE": "pergaussian"}, {"SPZB200_DECODE": "pergaussian", "SPZB200_GRID": "persistent"},
                                  {"SPZB200_ENCODE": "bulk"}, {"SPZB200_ENCODE": "bulk", "SPZB200_GRID": "persistent"}, {"SPZB200_ENCODE": "tiles"},
                                  {"SPZB200_ENCODE": "tiles", "SPZB200_GRID": "persistent"},
-                                 {"SPZB200_PACK": "alu"}, {"SPZB200_PLY": "mapped"}])
+                                 {"SPZB200_PACK": "alu"}, {"SPZB200_PLY": "mapped"},
+                                 {"SPZB200_DECODE0": "tiles"}, {"SPZB200_DECODE0": "tiles", "SPZB200_GRID": "persistent"},
+                                 {"SPZB200_REST": "separate"}, {"SPZB200_PDL": "0"}, {"SPZB200_PDL": "0", "SPZB200_REST": "separate"}])
 def test_alternate_launch_shapes(env):
     """The development knobs select other code paths of the same kernels (persistent multi-tile CTAs,
     which exercise the bulk decoder's mbarrier phase flip and buffer hand-over between tiles; the
@@ -697,3 +699,50 @@ def test_unpack_gather_against_the_oracle(gpu_ctx, oracle):
         with pytest.raises(CodecError):
             gpu_ctx.unpack_gather_host(hp, [-1])
     assert gpu_ctx.unpack_gather_host(hp, np.zeros(0, np.int64)).shape == (0, 59)
+
+
+# ---- version-2 encoder: PARITY UNPINNED, the reference has only the decoder -----------
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_v2_encoder_against_its_restatement_and_the_reference_decoder(gpu_ctx, oracle, ref, deg):
+    """spzb200_encode_device_as / _host_as with stream version 2.  What CAN be pinned is pinned: (1) every plane but
+    the rotations is byte-identical to the version-3 encoder's (which is pinned to the reference); (2) the rotation
+    bytes equal oracle_pack_v2, the restatement of upstream's pre-smallest-three encoder; (3) the REFERENCE's own
+    decoder (unpackQuaternionFirstThree, load-spz.cc:333-345) turns them back into the normalised input quaternion
+    (sign-fixed to w >= 0) within the 8-bit step; (4) tile kernel, scalar remainder, scalar-only path and host
+    pipeline agree."""
+    from spz_b200 import codec
+    rng = np.random.default_rng(5200 + deg)
+    n = 3 * codec.tile_gaussians(deg) + 333
+    c = random_cloud(rng, n, deg, False)
+    for frm in (0, 6, 7):
+        v3 = gpu_pack(gpu_ctx, c, frm)
+        got = host_packed(gpu_ctx.encode_device(to_dev_cloud(c), frm, version=2))
+        assert got.version == 2 and got.rotations.size == 3 * n
+        want = oracle.pack_v2(c, frm)
+        for name in ("positions", "scales", "alphas", "colors", "sh"):
+            assert np.array_equal(getattr(got, name), getattr(v3, name)), (frm, name)
+        assert np.array_equal(got.rotations, want.rotations), frm
+        # through the reference's decoder: q / |q|, flipped, sign chosen so that w >= 0
+        back = ref.unpack(Packed(n, deg, 12, 2, *got.planes()), 0)
+        q = c.rotations.reshape(n, 4).astype(np.float64)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        fq = np.concatenate([oracle.flips(frm, 4)[1], [1.0]])
+        q = q * fq * np.where(q[:, 3:4] < 0, -1.0, 1.0)
+        r = back.rotations.reshape(n, 4)
+        assert np.abs(r[:, :3] - q[:, :3]).max() <= 0.5 / 127.5 + 1e-6
+        ok = np.abs(q[:, 3]) > 0.2  # w = sqrt(1 - |xyz|^2) amplifies the byte error as w -> 0
+        assert np.abs(r[ok, 3] - q[ok, 3]).max() < 0.03
+    gpu_ctx.set_force_generic(True)
+    try:
+        assert np.array_equal(host_packed(gpu_ctx.encode_device(to_dev_cloud(c), 6, version=2)).rotations, oracle.pack_v2(c, 6).rotations)
+    finally:
+        gpu_ctx.set_force_generic(False)
+    hp, _ = gpu_ctx.encode_host(codec.CloudPlanes(n, deg, *c.planes()), 6, version=2)
+    assert np.array_equal(hp.rotations, oracle.pack_v2(c, 6).rotations) and np.array_equal(hp.sh, oracle.pack(c, 6).sh)
+    # specials (NaN / Inf / zero quaternions): the restatement's x86 answers, byte for byte
+    s = random_cloud(rng, 2 * codec.tile_gaussians(deg) + 5, deg, True)
+    s.rotations[:8] = 0
+    assert np.array_equal(host_packed(gpu_ctx.encode_device(to_dev_cloud(s), 1, version=2)).rotations, oracle.pack_v2(s, 1).rotations)
+    with pytest.raises(Exception):
+        gpu_ctx.encode_device(to_dev_cloud(c), 0, version=1)
