@@ -24,6 +24,7 @@ case "$task" in
   sweep)    # sweep <name> <script> [args]: any scripts/*.py measurement, output kept under gpurun_out/<name>
             name=$1; script=$2; shift 2 || true
             timeout 1500 python scripts/$script "$@" > gpurun_out/$name 2> gpurun_out/$name.err; echo "rc=$?"; cat gpurun_out/$name; tail -3 gpurun_out/$name.err ;;
+  abr1)     timeout 1500 bash scripts/ab_vs_r1.sh "$@" > gpurun_out/ab_vs_r1.jsonl 2> gpurun_out/ab_vs_r1.err; echo "rc=$?"; cat gpurun_out/ab_vs_r1.jsonl; tail -3 gpurun_out/ab_vs_r1.err ;;
   launches) # launch list of one short bench run (after the same command ran clean without ncu)
             timeout 900 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/launch_pre.json 2> gpurun_out/launch_pre.err || { echo "plain run failed"; exit 1; }
             timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \

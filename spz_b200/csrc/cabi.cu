@@ -247,10 +247,11 @@ struct SpzB200Context {
   int decodePerGaussian = 1;  // SPZB200_DECODE=pergaussian: 2 (also SH-less clouds); =bulk / =direct: 0 (tile kernels only)
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
   bool decodeBulk = true;  // SH plane of the decoder staged with bulk async copies (SPZB200_DECODE=direct: registers)
-  bool decodeSh0Staged = true;  // SPZB200_DECODE0=tiles: SH-less clouds through decodeTilesKernel<0> (A/B timing)
+  bool decodeSh0Staged = false;  // SPZB200_DECODE0=staged: SH-less clouds through decodeSh0StagedKernel (measured slower: 5.63 vs 6.36 TB/s at 10M, 5.57 vs 6.56 at 100M)
   bool pdl = true;       // SPZB200_PDL=0: plain stream-ordered launches (A/B timing)
   bool foldRest = true;  // SPZB200_REST=separate: the sub-tile remainder as a launch of its own (A/B timing)
   bool flatGrid = true;  // one CTA per tile: the block scheduler keeps the tile frontier compact
+  bool adaptiveChunks = true;             // SPZB200_CHUNK_POINTS / spzb200_set_chunk_points pin the range size instead
   long long chunkPoints = 1 << 21;        // pinned / registered host planes: copied straight from the caller
   long long pageableChunkPoints = 1 << 18;  // pageable planes: bounced through pinned buffers of this many points
   int copyThreads = 0;                      // 0 = auto (min(8, hardware threads))
@@ -455,8 +456,13 @@ int runPipelineStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &o
   const bool bounceOut = n > 0 && wantBounce && isPageable(out.ptr[0]);
   // (cutting a bounced cloud smaller than a few ranges into ~6 pieces for overlap was tried: the per-range costs --
   // waking the copy pool, 12 copies, 4 events -- outweigh the overlap: 200K points 7.9 vs 5.1 ms, 1M 12.6 vs 10.2)
-  const long long want = (bounceIn || bounceOut) ? ctx->pageableChunkPoints : ctx->chunkPoints;
-  long long chunk = std::max<long long>(granule, want / granule * granule);
+  long long want = (bounceIn || bounceOut) ? ctx->pageableChunkPoints : ctx->chunkPoints;
+  // Pinned planes: 2M-point ranges keep the copy engines in long transfers, but a cloud of only a few such ranges
+  // spends a visible part of the call filling and draining the three-stage pipeline (10M points = 5 ranges: 0.84 of
+  // the link; in ~12 ranges: profiles/r2_tuning_notes.txt).  So mid-sized clouds are cut into about a dozen ranges,
+  // never below 256K points.
+  if (!(bounceIn || bounceOut) && ctx->adaptiveChunks) want = std::min(want, std::max<long long>(1 << 18, (n + 11) / 12));
+  long long chunk = std::max<long long>(granule, (want + granule - 1) / granule * granule);
   if (chunk > n) chunk = std::max<long long>(n, 1);
   const long long numChunks = n == 0 ? 0 : (n + chunk - 1) / chunk;
   const int stages = (int)std::min<long long>(kStages, numChunks);
@@ -851,13 +857,16 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   }
   if (const char *env = std::getenv("SPZB200_ENCODE")) ctx->encodeBulk = std::strcmp(env, "bulk") == 0 ? 2 : std::strcmp(env, "tiles") == 0 ? 0 : 1;
   if (const char *env = std::getenv("SPZB200_PLY")) ctx->plyMapped = std::strcmp(env, "mapped") == 0;
-  if (const char *env = std::getenv("SPZB200_DECODE0")) ctx->decodeSh0Staged = std::strcmp(env, "tiles") != 0;
+  if (const char *env = std::getenv("SPZB200_DECODE0")) ctx->decodeSh0Staged = std::strcmp(env, "staged") == 0;
   if (const char *env = std::getenv("SPZB200_PDL")) ctx->pdl = std::strcmp(env, "0") != 0;
   if (const char *env = std::getenv("SPZB200_REST")) ctx->foldRest = std::strcmp(env, "separate") != 0;
   if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = std::strcmp(env, "persistent") != 0;
   if (const char *env = std::getenv("SPZB200_CHUNK_POINTS")) {
     const long long v = std::atoll(env);
-    if (v > 0) ctx->chunkPoints = v;
+    if (v > 0) {
+      ctx->chunkPoints = v;
+      ctx->adaptiveChunks = false;
+    }
   }
   if (trace)
     fprintf(stderr, "[spz_b200 init] device %d: cuda init + device query %.2f ms, host tables %.2f ms, cudaMalloc %.2f ms, "
@@ -1319,9 +1328,11 @@ void spzb200_set_chunk_points(SpzB200Context *ctx, int64_t points) {
   if (!ctx) return;
   if (points > 0) {
     ctx->chunkPoints = ctx->pageableChunkPoints = points;
+    ctx->adaptiveChunks = false;
   } else {  // back to the defaults
     ctx->chunkPoints = 1 << 21;
     ctx->pageableChunkPoints = 1 << 18;
+    ctx->adaptiveChunks = true;
   }
 }
 void spzb200_set_host_staging(SpzB200Context *ctx, int32_t bounce, int32_t copy_threads) {

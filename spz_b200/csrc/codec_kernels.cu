@@ -480,13 +480,26 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
   }
 }
 
+// Development knobs of the register-path tile decoder (scripts/ build and time the alternatives):
+//   SPZ_DEC_TAB_L1       1: the three decode tables are read through L1 instead of being copied into every CTA's shared memory
+//   SPZ_DEC_TILES_HOIST  true: all 20 small-plane words of a sub-tile are requested before the first is expanded
+//   SPZ_DEC0_CTAS_PER_SM resident CTAs per SM the SH-less instantiation is register-bounded for (4: 48 registers, 5: 40, 6: 32)
+#ifndef SPZ_DEC_TAB_L1
+#define SPZ_DEC_TAB_L1 0
+#endif
+#ifndef SPZ_DEC_TILES_HOIST
+#define SPZ_DEC_TILES_HOIST false
+#endif
+#ifndef SPZ_DEC0_CTAS_PER_SM
+#define SPZ_DEC0_CTAS_PER_SM SPZ_CTAS_PER_SM
+#endif
 template <int D, int VER>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+__global__ void __launch_bounds__(kThreads, D == 0 ? SPZ_DEC0_CTAS_PER_SM : kCtasPerSm)
 decodeTilesKernel(const __grid_constant__ DecodeArgs a, const long long numTiles, const int restCtas) {
   constexpr int S = kThreads;
   constexpr int M = Geo<D>::M;
   constexpr bool kS3 = (VER >= 3);
-  __shared__ float sTab[kS3 ? kDecodeTableFloats : 512];
+  __shared__ float sTab[SPZ_DEC_TAB_L1 ? 1 : (kS3 ? kDecodeTableFloats : 512)];
   __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
   pdlTrigger();
   if ((int)blockIdx.x < restCtas) {  // the sub-tile remainder rides in the first CTA(s): scalar_path.cuh
@@ -495,9 +508,13 @@ decodeTilesKernel(const __grid_constant__ DecodeArgs a, const long long numTiles
     if (g < a.n) decodeOneGaussian(a, g);
     return;
   }
+#if SPZ_DEC_TAB_L1
+  const float *sAlpha = a.tables, *sColor = a.tables + 256, *sMag = a.tables + 512;
+#else
   for (int i = threadIdx.x; i < (kS3 ? kDecodeTableFloats : 512); i += kThreads) sTab[i] = __ldg(a.tables + i);
   const float *sAlpha = sTab, *sColor = sTab + 256, *sMag = sTab + 512;
   __syncthreads();
+#endif
   const int t = threadIdx.x;
   uint32_t *stage = sStage[t >> 5];
   DecodePosConsts pc;
@@ -507,7 +524,7 @@ decodeTilesKernel(const __grid_constant__ DecodeArgs a, const long long numTiles
   for (long long tile = (int)blockIdx.x - restCtas; tile < numTiles; tile += (int)gridDim.x - restCtas) {
 #pragma unroll 1
     for (int mm = 0; mm < M; mm++)
-      decodeSmallPlanes<VER, false>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc, GlobalSink::at<kThreads>(a, tile * M + mm));
+      decodeSmallPlanes<VER, SPZ_DEC_TILES_HOIST>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc, GlobalSink::at<kThreads>(a, tile * M + mm));
     // ---- spherical harmonics: word -> float4 -------------------------------------------------
     if (D > 0) {
       constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS;
@@ -558,6 +575,11 @@ decodeTilesKernel(const __grid_constant__ DecodeArgs a, const long long numTiles
 }
 
 // ---- SH-less clouds: outputs staged in shared memory, written with bulk async stores ---------------
+// EXPERIMENT, opt-in (SPZB200_DECODE0=staged), kept because the result is instructive: round 2 measured it
+// SLOWER than decodeTilesKernel<0, VER> on the same box -- 5.63 vs 6.36 TB/s at 10M gaussians, 5.57 vs 6.56
+// at 100M, 5.03 vs 5.76 at 2.5M (profiles/r2_tuning_notes.txt).  The premise came from the stripped-down
+// pattern benchmark below; with the real expansion in between, the extra shared-memory round trip and
+// the per-CTA fence / barrier / store-drain of a 28 KB image cost more than the store path gains.
 // An SH-less decode writes 56 of its 76 bytes per gaussian.  scripts/membench.cu: for that write-heavy
 // mix STG.128 from registers sustains 6.09 TB/s, bulk async stores from shared memory (UBLKCP.G.S) 6.76.
 // Same per-value work as decodeTilesKernel<0, VER> (the packed words arrive with plain 128-byte-aligned

@@ -96,7 +96,7 @@ struct LaunchPlan {
                        // faster (SH degree 3, at most 24M gaussians per launch; default), 2 wherever it exists
   int decodePerGaussian;   // planar decoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it
                            // measured faster (SH degree 1 - 3; default), 2 also for SH-less clouds
-  bool decodeSh0Staged;  // SH-less decode through the staged bulk-store kernel (default; SPZB200_DECODE=direct / tiles0 keep the register-path tiles)
+  bool decodeSh0Staged;  // SH-less decode through the staged bulk-store kernel (opt-in, SPZB200_DECODE0=staged: it measured slower than the register-path tiles)
   bool pdl;            // launch with programmatic stream serialization (kernel_utils.cuh); default on, SPZB200_PDL=0 turns it off
   bool foldRest;       // the sub-tile remainder rides in the vector kernel's first CTA(s) instead of a launch of its own (default)
   bool plyMapped;      // test hook: PLY rows always through the column-map kernels, never the canonical-layout ones

@@ -184,7 +184,6 @@ encodePerGaussianKernel(const __grid_constant__ typename Src::Args a, const long
     }
   }
   if (t == 0) mbarInit(&bar);
-  for (int i = t; i < 256; i += kG) sThr[i] = __ldg(a.alphaThresholds + i);  // written at context creation, never by a kernel of the stream
   __syncthreads();
   pdlWait();  // the planes may only be touched from here on
   uint32_t parity = 0;
@@ -195,6 +194,10 @@ encodePerGaussianKernel(const __grid_constant__ typename Src::Args a, const long
       __syncthreads();
     }
     if (t == 0) Src::request(a, tile, dynSmem, &bar);
+    if (tile == firstTile) {  // the threshold table arrives while the tile is in flight (these CTAs live for one tile)
+      for (int i = t; i < 256; i += kG) sThr[i] = __ldg(a.alphaThresholds + i);
+      __syncthreads();
+    }
     mbarWait(&bar, parity);
 
     float r[W];

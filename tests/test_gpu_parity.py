@@ -248,7 +248,7 @@ def test_ply_kernels_write_only_their_planes(gpu_ctx, oracle, deg, extra):
                                  {"SPZB200_ENCODE": "bulk"}, {"SPZB200_ENCODE": "bulk", "SPZB200_GRID": "persistent"}, {"SPZB200_ENCODE": "tiles"},
                                  {"SPZB200_ENCODE": "tiles", "SPZB200_GRID": "persistent"},
                                  {"SPZB200_PACK": "alu"}, {"SPZB200_PLY": "mapped"},
-                                 {"SPZB200_DECODE0": "tiles"}, {"SPZB200_DECODE0": "tiles", "SPZB200_GRID": "persistent"},
+                                 {"SPZB200_DECODE0": "staged"}, {"SPZB200_DECODE0": "staged", "SPZB200_GRID": "persistent"},
                                  {"SPZB200_REST": "separate"}, {"SPZB200_PDL": "0"}, {"SPZB200_PDL": "0", "SPZB200_REST": "separate"}])
 def test_alternate_launch_shapes(env):
     """The development knobs select other code paths of the same kernels (persistent multi-tile CTAs,
@@ -731,8 +731,8 @@ def test_v2_encoder_against_its_restatement_and_the_reference_decoder(gpu_ctx, o
         q = q * fq * np.where(q[:, 3:4] < 0, -1.0, 1.0)
         r = back.rotations.reshape(n, 4)
         assert np.abs(r[:, :3] - q[:, :3]).max() <= 0.5 / 127.5 + 1e-6
-        ok = np.abs(q[:, 3]) > 0.2  # w = sqrt(1 - |xyz|^2) amplifies the byte error as w -> 0
-        assert np.abs(r[ok, 3] - q[ok, 3]).max() < 0.03
+        ok = np.abs(q[:, 3]) > 0.2  # w = sqrt(1 - |xyz|^2) amplifies the byte error by (|x| + |y| + |z|) / w <= sqrt(3) / 0.2
+        assert np.abs(r[ok, 3] - q[ok, 3]).max() < 0.04
     gpu_ctx.set_force_generic(True)
     try:
         assert np.array_equal(host_packed(gpu_ctx.encode_device(to_dev_cloud(c), 6, version=2)).rotations, oracle.pack_v2(c, 6).rotations)
