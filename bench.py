@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--to-coord", type=int, default=6, help="UnpackOptions.to (6 = RDF)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunk-sweep", default="", help="comma-separated pipeline range sizes (points) to re-time the duplex e2e step with")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ply", action="store_true", help="skip the fused PLY-rows kernel timings (N=1 only)")
     ap.add_argument("--cpu-sample-points", type=int, default=0, help="0 = auto")
@@ -630,14 +631,28 @@ def run_b200_arm(args):
             fb = pool.submit(ctx2.decode_host, streams[(i + 1) % 2], args.to_coord, h_back)
             return fa.result()[1], fb.result()[1]
 
-        duplex_step(0)
-        barrier()
-        t0 = time.perf_counter()
-        dphases = [duplex_step(1 + i) for i in range(args.e2e_steps)]
-        barrier()
-        e2e["duplex_s"] = (time.perf_counter() - t0) / args.e2e_steps
+        def measure_duplex(steps):
+            duplex_step(0)
+            barrier()
+            t0 = time.perf_counter()
+            ph = [duplex_step(1 + i) for i in range(steps)]
+            barrier()
+            return (time.perf_counter() - t0) / steps, ph
+
+        e2e["duplex_s"], dphases = measure_duplex(args.e2e_steps)
         e2e["duplex_enc_wall_ms"] = statistics.mean(p[0]["wall_ms"] for p in dphases)
         e2e["duplex_dec_wall_ms"] = statistics.mean(p[1]["wall_ms"] for p in dphases)
+        e2e["chunk_sweep"] = None
+        if args.e2e_chunk_sweep:  # development: the same duplex step with other pipeline range sizes (all ranks together)
+            e2e["chunk_sweep"] = []
+            for pts in [int(x) for x in args.e2e_chunk_sweep.split(",")]:
+                ctx.set_chunk_points(pts)
+                ctx2.set_chunk_points(pts)
+                s_step, _ = measure_duplex(2)
+                e2e["chunk_sweep"].append({"chunk_points": pts, "s": s_step})
+            ctx.set_chunk_points(0)
+            ctx2.set_chunk_points(0)
+            measure_duplex(1)  # the planes hashed below come from the default configuration again
         pool.shutdown()
         ctx2.close()
         # what the e2e path produced, whole planes, against what the device-resident path produced
@@ -656,7 +671,12 @@ def run_b200_arm(args):
     if not args.no_e2e and world > 1:
         barrier()
         if rank == 0:
-            e2e_multi = run_e2e_multi(args, codec, dev, world, n_total, deg, fwb, bwb, enc_hash, dec_hash)
+            need_multi = (2 * codec.float_bytes_per_gaussian(deg) + codec.packed_bytes_per_gaussian(deg)) * n_total
+            avail = host_memory_available()
+            if avail is not None and need_multi > 0.7 * avail:
+                e2e_multi = {"skipped": f"needs {need_multi / 1e9:.1f} GB of pinned host memory for the whole cloud, {avail / 1e9:.1f} GB available"}
+            else:
+                e2e_multi = run_e2e_multi(args, codec, dev, world, n_total, deg, fwb, bwb, enc_hash, dec_hash)
         barrier()
 
     # ---- reduce over ranks (max time; sums of bytes and launches) -----------------------------------
@@ -673,6 +693,8 @@ def run_b200_arm(args):
     if e2e:
         e2e["s"] = allmax(e2e["s"])
         e2e["duplex_s"] = allmax(e2e["duplex_s"])
+        for row in e2e["chunk_sweep"] or []:
+            row["s"] = allmax(row["s"])
         e2e["h2d"] = int(allsum(e2e["h2d"]))
         e2e["d2h"] = int(allsum(e2e["d2h"]))
     if link:
@@ -755,6 +777,8 @@ def run_b200_arm(args):
                                           "mode": "one host thread: encode_host, then decode_host of its result",
                                           "phases_note": "h2d/kernel/d2h_ms are sums over point ranges of per-range stream time; ranges run on 3 streams and overlap, wall_ms is the call",
                                           "encode_phases_ms": e2e["enc"], "decode_phases_ms": e2e["dec"]}}
+            if e2e["chunk_sweep"]:
+                line["e2e"]["chunk_sweep"] = [{"chunk_points": r["chunk_points"], "value": n_total / r["s"] / 1e6} for r in e2e["chunk_sweep"]]
             if link:
                 ach_h2d, ach_d2h = e2e["h2d"] / step_s / 1e9, e2e["d2h"] / step_s / 1e9
                 line["e2e"]["link_ceiling_gbs"] = {
