@@ -29,5 +29,10 @@ case "$task" in
             timeout 900 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/launch_pre.json 2> gpurun_out/launch_pre.err || { echo "plain run failed"; exit 1; }
             timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
               python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/ncu_list.log 2>&1; echo "ncu rc=$?"; tail -5 gpurun_out/launches.csv ;;
+  ncufull)  # ncufull <name> <kernel regex> <skip> <count> <command...>: one ncu --set full capture, after the same command ran clean without ncu
+            name=$1; regex=$2; skip=$3; count=$4; shift 4
+            timeout 900 "$@" > gpurun_out/${name}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${name}_plain.log; exit 1; }
+            timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"$regex" -s $skip -c $count -o gpurun_out/$name -f "$@" > gpurun_out/${name}_ncu.log 2>&1
+            echo "ncu rc=$?"; grep -c "Profiling" gpurun_out/${name}_ncu.log; ls -la gpurun_out/$name.ncu-rep ;;
   *)        echo "unknown task $task"; exit 2 ;;
 esac
