@@ -6,21 +6,33 @@ HBM GB/s vs roofline at 1/2/4/8 B200).
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's own CPU pack/unpack on the host cores
 
-Workload (config 5 of BASELINE.json; it fits one GPU, so it is also the N=1 workload): a synthetic
-100M-gaussian SH-degree-3 cloud, v3 stream, sharded by contiguous point range over the N ranks
-(strong scaling: the cloud is fixed, each rank owns n/N points; no collective on the data path).
-One "step" = encode the rank's shard (float planes -> byte planes), then decode the result back
-(byte planes -> float planes, with a coordinate flip folded in).  `value` = gaussians through that
-encode+decode round trip per second, whole job, inputs resident in HBM, timed with CUDA events on
-the launching stream, max over ranks.  `e2e` = the same step through the host-pointer C-ABI
-(spzb200_encode_host / spzb200_decode_host: pinned host planes in, pinned host planes out, H2D and
-D2H inside the timed region), issued full duplex -- step i's encode and the decode of step i-1's
-stream run concurrently from two host threads so both directions of the PCIe link are busy; the
-one-thread "encode, then decode its result" figure is reported beside it as e2e.sequential.  The working set (30.1 GB per step at N=1) is far larger than the
-126 MB L2, so no explicit flush is needed between iterations.
+Workload (config 5 of BASELINE.json; it fits one GPU, so it is also the N=1 workload): ONE synthetic
+100M-gaussian SH-degree-3 cloud (counter-seeded: every float is a function of the seed and its global
+index), v3 stream, sharded by contiguous point range over the N ranks -- rank r generates and owns
+gaussians [a_r, b_r) of that cloud (strong scaling; no collective on the data path).  One "step" =
+encode the rank's shard (float planes -> byte planes), then decode the result back (byte planes ->
+float planes, with a coordinate flip folded in).
 
-The oracle / reference build under oracle/ is used here ONLY as the timed CPU baseline
-(`cpu_baseline`, `--impl reference`), never on the measured GPU path.
+  value     gaussians through that encode+decode round trip per second, whole job, inputs resident in
+            HBM, timed with CUDA events on the launching stream, max over ranks.
+  parity    outside the timed region: sampled 64k-point blocks of every rank's encode and decode output
+            against the CPU checker (oracle/), and order-sensitive hashes of ALL output planes that add up
+            over the shards -- the same two numbers must come out for every N.
+  e2e       the same step through the host-pointer C-ABI (spzb200_encode_host / spzb200_decode_host:
+            pinned host planes in and out, H2D and D2H inside the timed region), issued full duplex --
+            step i's encode and the decode of step i-1's stream run concurrently from two host threads
+            so both directions of the PCIe link are busy; the one-thread figure is e2e.sequential.
+            e2e.link_ceiling_gbs is the bare link measured in the same run by the same processes (plain
+            pinned cudaMemcpyAsync, all ranks at once); e2e.frac_of_link = achieved / that ceiling.
+  e2e_multi (N > 1) rank 0 alone drives all N GPUs through spzb200_encode_host_multi /
+            spzb200_decode_host_multi on the whole cloud in pinned host memory -- the library's own
+            multi-GPU entry point; its planes must hash to the parity hashes.
+
+The working set (30.1 GB per step at N=1) is far larger than the 126 MB L2, so no explicit flush is
+needed between iterations.
+
+The oracle / reference build under oracle/ is used here ONLY as the checker of `parity` and as the
+timed CPU baseline (`cpu_baseline`, `--impl reference`), never on the measured GPU path.
 """
 from __future__ import annotations
 
