@@ -490,11 +490,21 @@ def link_ceiling(dev, barrier, seconds=1.0, mb=1024, chunk_mb=256):
     return out
 
 
+def shard_range_py(n, sh_degree, num_shards, index):
+    """spzb200_shard_range restated in Python (whole tiles dealt out evenly, the remainder on the last shard), so the
+    reference arm can describe the workload without loading this repo's library; tests/test_multirank_host_logic.py
+    checks it against the C-ABI."""
+    g = 6400 if sh_degree == 1 else 1280
+    tiles = n // g
+    a = tiles * index // num_shards * g
+    b = n if index == num_shards - 1 else tiles * (index + 1) // num_shards * g
+    return a, b
+
+
 def bench_config(args, world):
     """The `config` object of the JSON line; identical for the B200 arm and the reference arm."""
-    from spz_b200 import codec
     n_total, deg = args.points, args.sh_degree
-    a0, b0 = codec.shard_range(n_total, deg, world, 0)
+    a0, b0 = shard_range_py(n_total, deg, world, 0)
     return {"workload": workload_name(n_total, deg), "points_total": n_total, "points_per_gpu": b0 - a0,
             "sh_degree": deg, "stream_version": 3, "from": args.from_coord, "to": args.to_coord,
             "l2": "working set per step >> 126 MB L2, no flush needed", "sharding": f"point-range x{world}, no collective",

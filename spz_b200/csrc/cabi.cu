@@ -7,6 +7,9 @@
 //   * the 255 thresholds of the alpha quantizer  a -> toUint8(sigmoid(a) * 255)   (uses expf)
 //   * the 256 values of the alpha dequantizer    b -> invSigmoid(b / 255.0f)      (uses logf)
 #include <cuda_runtime.h>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -146,6 +149,9 @@ const HostTables &hostTables() {
 #ifndef SPZ_STAGES
 #define SPZ_STAGES 3
 #endif
+#ifndef SPZ_BOUNCE_THP_DEFAULT
+#define SPZ_BOUNCE_THP_DEFAULT false
+#endif
 constexpr int kStages = SPZ_STAGES;
 
 struct Stage {
@@ -156,6 +162,7 @@ struct Stage {
   uint8_t *hIn = nullptr;      // pinned bounce buffers, used only when the caller's planes are pageable
   uint8_t *hOut = nullptr;
   size_t hInCap = 0, hOutCap = 0;
+  bool hInMapped = false, hOutMapped = false;  // mmap + cudaHostRegister (transparent huge pages) instead of cudaHostAlloc
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -386,12 +393,63 @@ int ensureStage(Stage &s, size_t inBytes_, size_t outBytes_) {
   return SPZB200_OK;
 }
 
-int ensureBounce(uint8_t *&buf, size_t &cap, size_t bytes) {
+// Pinned bounce buffers.  cudaHostAlloc pins fresh 4 KiB pages at about 1 GB/s on these VMs (the first bounced call of a
+// process paid ~370 ms for 3 x 79 MB).  The same bytes as an anonymous mapping advised to transparent huge pages,
+// touched, then cudaHostRegister'ed fault 512x fewer pages (profiles/r2_cold_start.txt compares the two;
+// SPZB200_BOUNCE_ALLOC=hostalloc / thp selects).  The copy engines see no difference (profiles/r2_link_probe_*.jsonl).
+struct BounceAlloc {
+  static bool useThp() {
+    static const bool thp = [] {
+      const char *env = std::getenv("SPZB200_BOUNCE_ALLOC");
+      return env ? std::strcmp(env, "thp") == 0 : SPZ_BOUNCE_THP_DEFAULT;
+    }();
+    return thp;
+  }
+};
+
+void freeBounce(uint8_t *&buf, size_t &cap, bool &mapped) {
+  if (!buf) return;
+#if defined(__linux__)
+  if (mapped) {
+    cudaHostUnregister(buf);
+    munmap(buf, cap);
+  } else
+#endif
+    cudaFreeHost(buf);
+  buf = nullptr;
+  cap = 0;
+  mapped = false;
+}
+
+int ensureBounce(uint8_t *&buf, size_t &cap, bool &mapped, size_t bytes) {
   if (cap >= bytes) return SPZB200_OK;
-  if (buf) cudaFreeHost(buf);
-  buf = nullptr; cap = 0;
+  freeBounce(buf, cap, mapped);
+#if defined(__linux__)
+  if (BounceAlloc::useThp()) {
+    constexpr size_t kHuge = (size_t)2 << 20;
+    const size_t len = alignUp(bytes, kHuge);
+    // over-map by one huge page and trim to a 2 MiB-aligned window so every page of it can be a huge page
+    uint8_t *raw = static_cast<uint8_t *>(mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+    if (raw != MAP_FAILED) {
+      uint8_t *base = reinterpret_cast<uint8_t *>(alignUp(reinterpret_cast<size_t>(raw), kHuge));
+      if (base > raw) munmap(raw, (size_t)(base - raw));
+      if (base + len < raw + len + kHuge) munmap(base + len, (size_t)(raw + len + kHuge - (base + len)));
+      (void)madvise(base, len, MADV_HUGEPAGE);
+      for (size_t off = 0; off < len; off += kHuge) base[off] = 0;  // first touch: one fault per huge page
+      if (cudaHostRegister(base, len, cudaHostRegisterDefault) == cudaSuccess) {
+        buf = base;
+        cap = len;
+        mapped = true;
+        return SPZB200_OK;
+      }
+      (void)cudaGetLastError();
+      munmap(base, len);
+    }
+  }
+#endif
   CU(cudaHostAlloc(&buf, bytes, cudaHostAllocDefault));
   cap = bytes;
+  mapped = false;
   return SPZB200_OK;
 }
 
@@ -477,8 +535,8 @@ int runPipelineStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &o
     for (int s = 0; s < stages; s++) {
       Stage &st = ctx->stage[s];
       int rc = ensureStage(st, inBytes, outBytes);
-      if (rc == SPZB200_OK && bounceIn) rc = ensureBounce(st.hIn, st.hInCap, inBytes);
-      if (rc == SPZB200_OK && bounceOut) rc = ensureBounce(st.hOut, st.hOutCap, outBytes);
+      if (rc == SPZB200_OK && bounceIn) rc = ensureBounce(st.hIn, st.hInCap, st.hInMapped, inBytes);
+      if (rc == SPZB200_OK && bounceOut) rc = ensureBounce(st.hOut, st.hOutCap, st.hOutMapped, outBytes);
       if (rc != SPZB200_OK) return rc;
     }
     if ((bounceIn || bounceOut) && !ctx->pool) {
@@ -901,8 +959,8 @@ void spzb200_destroy(SpzB200Context *ctx) {
   for (int s = 0; s < kStages; s++) {
     Stage &st = ctx->stage[s];
     if (st.stream) cudaStreamSynchronize(st.stream);
-    if (st.hIn) cudaFreeHost(st.hIn);
-    if (st.hOut) cudaFreeHost(st.hOut);
+    freeBounce(st.hIn, st.hInCap, st.hInMapped);
+    freeBounce(st.hOut, st.hOutCap, st.hOutMapped);
     for (int k = 0; k < 4; k++) if (st.ev[k]) cudaEventDestroy(st.ev[k]);
     if (st.dIn) cudaFree(st.dIn);
     if (st.dOut) cudaFree(st.dOut);

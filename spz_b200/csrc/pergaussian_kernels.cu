@@ -535,10 +535,15 @@ cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &p
 // leads by about 1 % (6761 vs 6671 at 100M), and at degree 1 by more.  Degree 2 has no planar form here (24-word
 // lane stride on the 32-bit shared-memory reads).
 constexpr long long kEncodePerGaussianMaxPoints = 24000000;
+// Round 2, SH degree 1 (profiles/r2_ab_encode_pergaussian_vs_tiles.jsonl): the tile encoder's 6400-gaussian tiles quantise small launches
+// badly (1.25M points = 195 CTAs on 148 SMs).  Per-gaussian vs tiles, same box, GB/s: 1.25M 5062 vs 2734, 2.5M 5583 vs 4780, 5M 5862 vs 5327,
+// 10M 6056 vs 6267, 20M 6141 vs 6424 -> per-gaussian up to 6M points.
+constexpr long long kEncodePerGaussianMaxPointsSh1 = 6000000;
 cudaError_t launchEncodePerGaussianPlanar(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done) {
   *done = 0;
   if (plan.forceGeneric || plan.encodeBulk == 0 || a.shDim == 8 || a.version != 3) return cudaSuccess;  // version-2 streams: tile encoder only
-  if (plan.encodeBulk < 2 && !(a.shDim == 15 && a.n <= kEncodePerGaussianMaxPoints)) return cudaSuccess;
+  if (plan.encodeBulk < 2 && !((a.shDim == 15 && a.n <= kEncodePerGaussianMaxPoints) || (a.shDim == 3 && a.n <= kEncodePerGaussianMaxPointsSh1)))
+    return cudaSuccess;
   if (!(aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) && aligned16(a.colors) &&
         (a.shDim == 0 || aligned16(a.sh)) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) &&
         aligned16(a.oAlphas) && aligned16(a.oColors) && (a.shDim == 0 || aligned16(a.oSh))))

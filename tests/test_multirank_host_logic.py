@@ -61,6 +61,16 @@ def test_two_gloo_ranks_partition_and_reduce(tmp_path):
     assert out["hash"] == out["hash_whole"] != out["hash_swapped"]
 
 
+def test_python_shard_ranges_equal_the_library():
+    import bench
+    from spz_b200 import codec
+    for deg in range(4):
+        for n in (0, 1, 6399, 6400, 12_499_200, 100_000_000, 3_000_000_007):
+            for shards in (1, 2, 3, 4, 8):
+                for i in range(shards):
+                    assert bench.shard_range_py(n, deg, shards, i) == codec.shard_range(n, deg, shards, i), (deg, n, shards, i)
+
+
 def test_reference_arm_runs_on_rank0_only():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
@@ -73,3 +83,8 @@ def test_reference_arm_runs_on_rank0_only():
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
+    # the same `config` object as the B200 arm prints for the same arguments
+    import argparse
+    import bench
+    want = bench.bench_config(argparse.Namespace(points=100_000_000, sh_degree=3, from_coord=6, to_coord=6), 2)
+    assert line["config"] == want and want["points_per_gpu"] == 49_999_360
