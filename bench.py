@@ -761,7 +761,7 @@ def run_b200_arm(args):
         dec_kernel = ("decodeTilesKernel" if deg == 0 or dec_env == "direct" else
                       "decodeTilesBulkKernel" if dec_env == "bulk" else "decodePerGaussianKernel")
         enc_env = os.environ.get("SPZB200_ENCODE")
-        enc_kernel = ("encodePerGaussianKernel" if enc_env == "bulk" or (enc_env != "tiles" and deg == 3 and n <= 24_000_000)
+        enc_kernel = ("encodePerGaussianKernel" if enc_env == "bulk" or (enc_env != "tiles" and ((deg == 3 and n <= 24_000_000) or (deg == 1 and n <= 6_000_000)))
                       else "encodeTilesKernel")
         dom = (enc_kernel, enc_gbs, enc_ms) if enc_ms >= dec_ms else (dec_kernel, dec_gbs, dec_ms)
         traffic, traffic_kind = traffic_for(dom[0], n, args.traffic_bytes)

@@ -746,3 +746,20 @@ def test_v2_encoder_against_its_restatement_and_the_reference_decoder(gpu_ctx, o
     assert np.array_equal(host_packed(gpu_ctx.encode_device(to_dev_cloud(s), 1, version=2)).rotations, oracle.pack_v2(s, 1).rotations)
     with pytest.raises(Exception):
         gpu_ctx.encode_device(to_dev_cloud(c), 0, version=1)
+
+
+def test_counter_seeded_cloud_is_the_same_on_host_and_device(gpu_ctx):
+    """bench.py's workload (counter-based, so shards generate identical data): the torch generator on the
+    GPU gives, bit for bit, the numpy generator's slice of the same cloud -- whatever the slice and the scratch size."""
+    from spz_b200.synth import counter_cloud_numpy, counter_cloud_torch
+    t = _torch()
+    n_total = 3_000_000
+    for deg, a, b in ((3, 1280 * 700, 1280 * 700 + 40_001), (0, 0, 70_000), (1, n_total - 50_000, n_total)):
+        host = counter_cloud_numpy(n_total, deg, a, b, seed=1)
+        dev = counter_cloud_torch(n_total, deg, t.device("cuda", 0), a, b, seed=1, slice_elems=1 << 16)
+        for name, x, y in zip(PLANES, host.planes(), dev.planes()):
+            assert np.array_equal(x.view(np.uint32), y.cpu().numpy().view(np.uint32)), (deg, name)
+    # and it is a sensible cloud: the encoder's output of a slice equals the oracle's
+    c = counter_cloud_numpy(n_total, 3, 5 * 1280, 5 * 1280 + 3000, seed=1)
+    from oracle import Oracle
+    assert_packed_equal(gpu_pack(gpu_ctx, Cloud(3000, 3, *c.planes()), 6), Oracle().pack(Cloud(3000, 3, *c.planes()), 6), "counter cloud")
