@@ -264,7 +264,7 @@ def small_cloud_latency(ctx, codec, torch_cloud, dev, n, deg, args):
             host_us.append((time.perf_counter() - t0) * 1e6)
     return {"points": n, "sh_degree": deg, "device_encode_plus_decode_us": statistics.median(dev_us),
             "host_api_encode_plus_decode_us": statistics.median(host_us),
-            "note": "median of 50; device = four launches (two tile kernels + two scalar tails) on resident planes, issued from Python through ctypes, so it is launch-bound, not bandwidth-bound (the data moves in ~6 us); host = spzb200_encode_host + spzb200_decode_host with pinned planes, i.e. 18 MB over PCIe each way"}
+            "note": "median of 50; device = two launches (encode, decode; the sub-tile remainder rides in each) on resident planes, issued from Python through ctypes, so it is launch-bound, not bandwidth-bound (the data moves in ~6 us); host = spzb200_encode_host + spzb200_decode_host with pinned planes, i.e. 18 MB over PCIe each way"}
 
 
 def time_host_zlib(packed, deg, sample_points):

@@ -50,15 +50,23 @@ constexpr int kWarps = kThreads / 32;
 #define SPZ_CTAS_PER_SM 4
 #endif
 constexpr int kCtasPerSm = SPZ_CTAS_PER_SM;  // resident CTAs per SM the register budget is set for
+#ifndef SPZ_SMALL_CTAS_PER_SM
+#define SPZ_SMALL_CTAS_PER_SM 10  // 128-thread CTAs: the same 48 registers per thread
+#endif
 
 constexpr int gcdc(int a, int b) { return b == 0 ? a : gcdc(b, a % b); }
 
-template <int D>
+// S = threads per CTA.  320 is the geometry everything was tuned for at 100M points; 128 (round 2) gives tiles 2.5x
+// smaller for launches whose tail is a visible part of their duration (SH degree 0, 1, 2; at degree 3 the phase
+// cycle would be 45 rows long with S = 128, and small degree-3 clouds use the per-gaussian kernels anyway).
+constexpr int kSmallThreads = 128;
+template <int D, int S = kThreads>
 struct Geo {
-  static constexpr int M = (D == 3) ? 5 : 1;          // sub-tiles (4*320 gaussians each) per tile
-  static constexpr int TG = 4 * kThreads * M;         // gaussians per tile
+  static_assert((4 * S) % 3 == 2, "the xyz phase of element e in row i is taken as (t + e + 2 i) mod 3");
+  static constexpr int M = (D == 3) ? 5 : 1;          // sub-tiles (4*S gaussians each) per tile
+  static constexpr int TG = 4 * S * M;                // gaussians per tile
   static constexpr int MOD = 3 * D;                   // floats per SH record
-  static constexpr int STEP = D ? (4 * kThreads) % (D ? MOD : 1) : 0;  // phase advance per row
+  static constexpr int STEP = D ? (4 * S) % (D ? MOD : 1) : 0;  // phase advance per row
   static constexpr int CYC = D ? MOD / gcdc(STEP, MOD) : 1;            // rows until the phase repeats
   static constexpr int ROWS = 3 * D * M;              // SH rows per tile
   static constexpr int U = D ? ROWS / CYC : 1;        // rows sharing one set of constants
@@ -109,18 +117,18 @@ __device__ __forceinline__ void stStream(T *p, T v) {
 
 // Phase bookkeeping of the SH plane: pos[e] = index of the thread's element e inside its
 // 3*D-float SH record for the current row class; advance() moves to the next class.
-template <int D>
+template <int D, int S = kThreads>
 struct ShPhase {
   int pos[4];
   __device__ __forceinline__ void init(int t) {
 #pragma unroll
-    for (int e = 0; e < 4; e++) pos[e] = (4 * t + e) % Geo<D>::MOD;
+    for (int e = 0; e < 4; e++) pos[e] = (4 * t + e) % Geo<D, S>::MOD;
   }
   __device__ __forceinline__ void advance() {
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      pos[e] += Geo<D>::STEP;
-      if (pos[e] >= Geo<D>::MOD) pos[e] -= Geo<D>::MOD;
+      pos[e] += Geo<D, S>::STEP;
+      if (pos[e] >= Geo<D, S>::MOD) pos[e] -= Geo<D, S>::MOD;
     }
   }
   __device__ __forceinline__ uint32_t flip(int e, uint32_t flipSh) const {
@@ -131,21 +139,20 @@ struct ShPhase {
 // =================================================================================================
 // encode, vector path
 // =================================================================================================
-template <int D, int MODE, bool V2 = false>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+template <int D, int MODE, bool V2 = false, int S = kThreads>
+__global__ void __launch_bounds__(S, S == kThreads ? kCtasPerSm : SPZ_SMALL_CTAS_PER_SM)
 encodeTilesKernel(const __grid_constant__ EncodeArgs a, const long long numTiles, const int restCtas) {
-  constexpr int S = kThreads;
-  constexpr int M = Geo<D>::M;
+  constexpr int M = Geo<D, S>::M;
   __shared__ float sThr[256];
-  __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
+  __shared__ uint32_t sStage[S / 32][3 * 96];  // per warp: 3 rows x 96 position words
   pdlTrigger();
   if ((int)blockIdx.x < restCtas) {  // the sub-tile remainder rides in the first CTA(s): scalar_path.cuh
-    const long long g = numTiles * Geo<D>::TG + (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long g = numTiles * Geo<D, S>::TG + (long long)blockIdx.x * S + threadIdx.x;
     pdlWait();
     if (g < a.n) encodeOneGaussian(a, g);
     return;
   }
-  for (int i = threadIdx.x; i < 256; i += kThreads) sThr[i] = a.alphaThresholds[i];
+  for (int i = threadIdx.x; i < 256; i += S) sThr[i] = a.alphaThresholds[i];
   __syncthreads();
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
@@ -243,10 +250,10 @@ encodeTilesKernel(const __grid_constant__ EncodeArgs a, const long long numTiles
     }
     // ---- spherical harmonics: float4 -> word; rows c, c+CYC, ... share their constants ---------
     if (D > 0) {
-      constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS;
+      constexpr int U = Geo<D, S>::U, CYC = Geo<D, S>::CYC, ROWS = Geo<D, S>::ROWS;
       const float4 *in = reinterpret_cast<const float4 *>(a.sh) + tile * ((long long)ROWS * S) + t;
       uint32_t *out = reinterpret_cast<uint32_t *>(a.oSh) + tile * ((long long)ROWS * S) + t;
-      ShPhase<D> ph;
+      ShPhase<D, S> ph;
       ph.init(t);
 #pragma unroll 1
       for (int c = 0; c < CYC; c++) {
@@ -493,17 +500,16 @@ __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const lon
 #ifndef SPZ_DEC0_CTAS_PER_SM
 #define SPZ_DEC0_CTAS_PER_SM SPZ_CTAS_PER_SM
 #endif
-template <int D, int VER>
-__global__ void __launch_bounds__(kThreads, D == 0 ? SPZ_DEC0_CTAS_PER_SM : kCtasPerSm)
+template <int D, int VER, int S = kThreads>
+__global__ void __launch_bounds__(S, S != kThreads ? SPZ_SMALL_CTAS_PER_SM : D == 0 ? SPZ_DEC0_CTAS_PER_SM : kCtasPerSm)
 decodeTilesKernel(const __grid_constant__ DecodeArgs a, const long long numTiles, const int restCtas) {
-  constexpr int S = kThreads;
-  constexpr int M = Geo<D>::M;
+  constexpr int M = Geo<D, S>::M;
   constexpr bool kS3 = (VER >= 3);
   __shared__ float sTab[SPZ_DEC_TAB_L1 ? 1 : (kS3 ? kDecodeTableFloats : 512)];
-  __shared__ uint32_t sStage[kWarps][3 * 96];  // per warp: 3 rows x 96 position words
+  __shared__ uint32_t sStage[S / 32][3 * 96];  // per warp: 3 rows x 96 position words
   pdlTrigger();
   if ((int)blockIdx.x < restCtas) {  // the sub-tile remainder rides in the first CTA(s): scalar_path.cuh
-    const long long g = numTiles * Geo<D>::TG + (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long g = numTiles * Geo<D, S>::TG + (long long)blockIdx.x * S + threadIdx.x;
     pdlWait();
     if (g < a.n) decodeOneGaussian(a, g);
     return;
@@ -511,7 +517,7 @@ decodeTilesKernel(const __grid_constant__ DecodeArgs a, const long long numTiles
 #if SPZ_DEC_TAB_L1
   const float *sAlpha = a.tables, *sColor = a.tables + 256, *sMag = a.tables + 512;
 #else
-  for (int i = threadIdx.x; i < (kS3 ? kDecodeTableFloats : 512); i += kThreads) sTab[i] = __ldg(a.tables + i);
+  for (int i = threadIdx.x; i < (kS3 ? kDecodeTableFloats : 512); i += S) sTab[i] = __ldg(a.tables + i);
   const float *sAlpha = sTab, *sColor = sTab + 256, *sMag = sTab + 512;
   __syncthreads();
 #endif
@@ -524,13 +530,13 @@ decodeTilesKernel(const __grid_constant__ DecodeArgs a, const long long numTiles
   for (long long tile = (int)blockIdx.x - restCtas; tile < numTiles; tile += (int)gridDim.x - restCtas) {
 #pragma unroll 1
     for (int mm = 0; mm < M; mm++)
-      decodeSmallPlanes<VER, SPZ_DEC_TILES_HOIST>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc, GlobalSink::at<kThreads>(a, tile * M + mm));
+      decodeSmallPlanes<VER, SPZ_DEC_TILES_HOIST, S>(a, tile * M + mm, t, stage, sAlpha, sColor, sMag, pc, GlobalSink::at<S>(a, tile * M + mm));
     // ---- spherical harmonics: word -> float4 -------------------------------------------------
     if (D > 0) {
-      constexpr int U = Geo<D>::U, CYC = Geo<D>::CYC, ROWS = Geo<D>::ROWS;
+      constexpr int U = Geo<D, S>::U, CYC = Geo<D, S>::CYC, ROWS = Geo<D, S>::ROWS;
       const uint32_t *in = reinterpret_cast<const uint32_t *>(a.sh) + tile * ((long long)ROWS * S) + t;
       float4 *out = reinterpret_cast<float4 *>(a.oSh) + tile * ((long long)ROWS * S) + t;
-      ShPhase<D> ph;
+      ShPhase<D, S> ph;
       ph.init(t);
 #if SPZ_DEC_PREFETCH
       // software pipeline: the words of class c+1 are requested before class c is expanded
@@ -773,15 +779,24 @@ __global__ void probePackKernel(int *ok) {
 
 bool aligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-template <int D, int MODE>
-cudaError_t launchEncodeTiles(const EncodeArgs &a, long long tiles, int grid, int restCtas, bool pdl, cudaStream_t s) {
-  if (a.version == 2) return launchKernel(encodeTilesKernel<D, MODE, true>, grid + restCtas, kThreads, 0, s, pdl, a, tiles, restCtas);
-  return launchKernel(encodeTilesKernel<D, MODE, false>, grid + restCtas, kThreads, 0, s, pdl, a, tiles, restCtas);
+#ifndef SPZ_SMALL_TILES_MAX_POINTS
+#define SPZ_SMALL_TILES_MAX_POINTS 16000000
+#endif
+constexpr long long kSmallTilesMaxPoints = SPZ_SMALL_TILES_MAX_POINTS;
+bool smallTilesWanted(const LaunchPlan &plan, int shDim, long long n) {
+  if (!plan.flatGrid || shDim == 15 || plan.smallTiles == 0) return false;
+  return plan.smallTiles == 2 || n <= kSmallTilesMaxPoints;
 }
 
-template <int D, int VER>
+template <int D, int MODE, int S = kThreads>
+cudaError_t launchEncodeTiles(const EncodeArgs &a, long long tiles, int grid, int restCtas, bool pdl, cudaStream_t s) {
+  if (a.version == 2) return launchKernel(encodeTilesKernel<D, MODE, true, S>, grid + restCtas, S, 0, s, pdl, a, tiles, restCtas);
+  return launchKernel(encodeTilesKernel<D, MODE, false, S>, grid + restCtas, S, 0, s, pdl, a, tiles, restCtas);
+}
+
+template <int D, int VER, int S = kThreads>
 cudaError_t launchDecodeTilesVer(const DecodeArgs &a, long long tiles, int grid, int restCtas, bool bulk, bool pdl, cudaStream_t s) {
-  if constexpr (D > 0) {
+  if constexpr (D > 0 && S == kThreads) {
     if (bulk) {
       // per launch, not once: the attribute belongs to the current device, and one process may drive several
       const cudaError_t attr = cudaFuncSetAttribute(decodeTilesBulkKernel<D, VER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -790,7 +805,7 @@ cudaError_t launchDecodeTilesVer(const DecodeArgs &a, long long tiles, int grid,
       return launchKernel(decodeTilesBulkKernel<D, VER>, grid + restCtas, kThreads, BulkGeo<D>::kSmemBytes, s, pdl, a, tiles, restCtas);
     }
   }
-  return launchKernel(decodeTilesKernel<D, VER>, grid + restCtas, kThreads, 0, s, pdl, a, tiles, restCtas);
+  return launchKernel(decodeTilesKernel<D, VER, S>, grid + restCtas, S, 0, s, pdl, a, tiles, restCtas);
 }
 
 template <int VER>
@@ -802,13 +817,13 @@ cudaError_t launchDecodeSh0Staged(const DecodeArgs &a, long long tiles, unsigned
   return launchKernel(decodeSh0StagedKernel<VER>, grid + restCtas, kDec0Threads, smem, s, pdl, a, tiles, restCtas);
 }
 
-template <int D>
+template <int D, int S = kThreads>
 cudaError_t launchDecodeTiles(const DecodeArgs &a, long long tiles, int grid, int restCtas, bool bulk, bool pdl, cudaStream_t s) {
   switch (a.version) {
-    case 1: return launchDecodeTilesVer<D, 1>(a, tiles, grid, restCtas, bulk, pdl, s);
-    case 2: return launchDecodeTilesVer<D, 2>(a, tiles, grid, restCtas, bulk, pdl, s);
-    case 4: return launchDecodeTilesVer<D, 4>(a, tiles, grid, restCtas, bulk, pdl, s);
-    default: return launchDecodeTilesVer<D, 3>(a, tiles, grid, restCtas, bulk, pdl, s);
+    case 1: return launchDecodeTilesVer<D, 1, S>(a, tiles, grid, restCtas, bulk, pdl, s);
+    case 2: return launchDecodeTilesVer<D, 2, S>(a, tiles, grid, restCtas, bulk, pdl, s);
+    case 4: return launchDecodeTilesVer<D, 4, S>(a, tiles, grid, restCtas, bulk, pdl, s);
+    default: return launchDecodeTilesVer<D, 3, S>(a, tiles, grid, restCtas, bulk, pdl, s);
   }
 }
 
@@ -832,6 +847,25 @@ cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream
   long long bulkDone = 0;
   if (cudaError_t e = launchEncodePerGaussianPlanar(a, plan, stream, &bulkDone); e != cudaSuccess) return e;
   if (bulkDone > 0) count++;
+  // Launches whose tail is a visible part of their duration take the 128-thread geometry (tiles 2.5x smaller): SH degree 0, 1, 2
+  // up to kSmallTilesMaxPoints gaussians (SPZB200_TILE=128 / 320 force either; one CTA per tile only).
+  if (vec && bulkDone == 0 && smallTilesWanted(plan, a.shDim, a.n)) {
+    const long long tgS = a.shDim == 3 ? Geo<3, kSmallThreads>::TG : Geo<0, kSmallThreads>::TG;
+    const long long tilesS = a.n / tgS;
+    if (tilesS > 0 && tilesS < 0x7fffffffLL) {
+      const int restS = plan.foldRest ? (int)((a.n - tilesS * tgS + kSmallThreads - 1) / kSmallThreads) : 0;
+      const bool cvt = plan.packMode == kPackCvt;
+      cudaError_t e;
+      switch (a.shDim) {
+        case 0: e = cvt ? launchEncodeTiles<0, kPackCvt, kSmallThreads>(a, tilesS, (int)tilesS, restS, plan.pdl, stream) : launchEncodeTiles<0, kPackAlu, kSmallThreads>(a, tilesS, (int)tilesS, restS, plan.pdl, stream); break;
+        case 3: e = cvt ? launchEncodeTiles<3, kPackCvt, kSmallThreads>(a, tilesS, (int)tilesS, restS, plan.pdl, stream) : launchEncodeTiles<3, kPackAlu, kSmallThreads>(a, tilesS, (int)tilesS, restS, plan.pdl, stream); break;
+        default: e = cvt ? launchEncodeTiles<8, kPackCvt, kSmallThreads>(a, tilesS, (int)tilesS, restS, plan.pdl, stream) : launchEncodeTiles<8, kPackAlu, kSmallThreads>(a, tilesS, (int)tilesS, restS, plan.pdl, stream); break;
+      }
+      if (e != cudaSuccess) return e;
+      count++;
+      bulkDone = restS > 0 ? a.n : tilesS * tgS;
+    }
+  }
   const long long tg = tileGaussians(a.shDim);
   const long long tiles = vec && bulkDone == 0 ? a.n / tg : 0;
   int restCtas = 0;
@@ -902,6 +936,22 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
     if (e != cudaSuccess) return e;
     count++;
     pgDone = rest0 > 0 ? a.n : tiles0 * kDec0Tile;
+  }
+  if (vec && pgDone == 0 && smallTilesWanted(plan, a.shDim, a.n)) {  // as in launchEncode
+    const long long tgS = a.shDim == 3 ? Geo<3, kSmallThreads>::TG : Geo<0, kSmallThreads>::TG;
+    const long long tilesS = a.n / tgS;
+    if (tilesS > 0 && tilesS < 0x7fffffffLL) {
+      const int restS = plan.foldRest ? (int)((a.n - tilesS * tgS + kSmallThreads - 1) / kSmallThreads) : 0;
+      cudaError_t e;
+      switch (a.shDim) {
+        case 0: e = launchDecodeTiles<0, kSmallThreads>(a, tilesS, (int)tilesS, restS, false, plan.pdl, stream); break;
+        case 3: e = launchDecodeTiles<3, kSmallThreads>(a, tilesS, (int)tilesS, restS, false, plan.pdl, stream); break;
+        default: e = launchDecodeTiles<8, kSmallThreads>(a, tilesS, (int)tilesS, restS, false, plan.pdl, stream); break;
+      }
+      if (e != cudaSuccess) return e;
+      count++;
+      pgDone = restS > 0 ? a.n : tilesS * tgS;
+    }
   }
   const long long tg = tileGaussians(a.shDim);
   const long long tiles = vec && pgDone == 0 ? a.n / tg : 0;
