@@ -242,8 +242,8 @@ def ply_rows_struct(rows, n: int, names, sh_degree: int, on_device: Optional[boo
 
 
 class Context:
-    """One per (thread, device).  Raises CodecError(ERR_NO_DEVICE) when there is no B200: the codec
-    has no CPU path."""
+    """One caller at a time (own one per host thread, or lease one per call with pooled=True).  Raises
+    CodecError(ERR_NO_DEVICE) when there is no B200: the codec has no CPU path."""
 
     def __init__(self, device: int = 0, pooled: bool = False):
         """pooled=True leases a context from the process-wide pool (spzb200_acquire) instead of

@@ -255,7 +255,7 @@ struct SpzB200Context {
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
   bool decodeBulk = true;  // SH plane of the decoder staged with bulk async copies (SPZB200_DECODE=direct: registers)
   bool decodeSh0Staged = false;  // SPZB200_DECODE0=staged: SH-less clouds through decodeSh0StagedKernel (measured slower: 5.63 vs 6.36 TB/s at 10M, 5.57 vs 6.56 at 100M)
-  int smallTiles = 1;    // SPZB200_TILE=320: never the 128-thread tile geometry; =128: always (SH degree 0 - 2)
+  int smallTilesEncode = 2, smallTilesDecode = 0;  // 128-thread tile geometry (SH degree 0 - 2): encoder always, decoder never; SPZB200_TILE=128 / 320 set both, =auto the size rule
   bool pdl = true;       // SPZB200_PDL=0: plain stream-ordered launches (A/B timing)
   bool foldRest = true;  // SPZB200_REST=separate: the sub-tile remainder as a launch of its own (A/B timing)
   bool flatGrid = true;  // one CTA per tile: the block scheduler keeps the tile frontier compact
@@ -362,7 +362,8 @@ spzb200::LaunchPlan planOf(const SpzB200Context *ctx) {
   p.plyMapped = ctx->plyMapped;
   p.foldRest = ctx->foldRest;
   p.pdl = ctx->pdl;
-  p.smallTiles = ctx->smallTiles;
+  p.smallTilesEncode = ctx->smallTilesEncode;
+  p.smallTilesDecode = ctx->smallTilesDecode;
   p.decodeSh0Staged = ctx->decodeSh0Staged;
   p.decodePerGaussian = ctx->decodePerGaussian;
   p.encodeBulk = ctx->encodeBulk;
@@ -918,7 +919,8 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   if (const char *env = std::getenv("SPZB200_ENCODE")) ctx->encodeBulk = std::strcmp(env, "bulk") == 0 ? 2 : std::strcmp(env, "tiles") == 0 ? 0 : 1;
   if (const char *env = std::getenv("SPZB200_PLY")) ctx->plyMapped = std::strcmp(env, "mapped") == 0;
   if (const char *env = std::getenv("SPZB200_DECODE0")) ctx->decodeSh0Staged = std::strcmp(env, "staged") == 0;
-  if (const char *env = std::getenv("SPZB200_TILE")) ctx->smallTiles = std::strcmp(env, "320") == 0 ? 0 : std::strcmp(env, "128") == 0 ? 2 : 1;
+  if (const char *env = std::getenv("SPZB200_TILE"))
+    ctx->smallTilesEncode = ctx->smallTilesDecode = std::strcmp(env, "320") == 0 ? 0 : std::strcmp(env, "128") == 0 ? 2 : 1;
   if (const char *env = std::getenv("SPZB200_PDL")) ctx->pdl = std::strcmp(env, "0") != 0;
   if (const char *env = std::getenv("SPZB200_REST")) ctx->foldRest = std::strcmp(env, "separate") != 0;
   if (const char *env = std::getenv("SPZB200_GRID")) ctx->flatGrid = std::strcmp(env, "persistent") != 0;

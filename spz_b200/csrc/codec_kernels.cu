@@ -783,9 +783,10 @@ bool aligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p
 #define SPZ_SMALL_TILES_MAX_POINTS 16000000
 #endif
 constexpr long long kSmallTilesMaxPoints = SPZ_SMALL_TILES_MAX_POINTS;
-bool smallTilesWanted(const LaunchPlan &plan, int shDim, long long n) {
-  if (!plan.flatGrid || shDim == 15 || plan.smallTiles == 0) return false;
-  return plan.smallTiles == 2 || n <= kSmallTilesMaxPoints;
+// mode: 0 never, 1 up to kSmallTilesMaxPoints gaussians per launch, 2 always (LaunchPlan::smallTilesEncode / smallTilesDecode)
+bool smallTilesWanted(const LaunchPlan &plan, int mode, int shDim, long long n) {
+  if (!plan.flatGrid || shDim == 15 || mode == 0) return false;
+  return mode == 2 || n <= kSmallTilesMaxPoints;
 }
 
 template <int D, int MODE, int S = kThreads>
@@ -847,9 +848,10 @@ cudaError_t launchEncode(const EncodeArgs &a, const LaunchPlan &plan, cudaStream
   long long bulkDone = 0;
   if (cudaError_t e = launchEncodePerGaussianPlanar(a, plan, stream, &bulkDone); e != cudaSuccess) return e;
   if (bulkDone > 0) count++;
-  // Launches whose tail is a visible part of their duration take the 128-thread geometry (tiles 2.5x smaller): SH degree 0, 1, 2
-  // up to kSmallTilesMaxPoints gaussians (SPZB200_TILE=128 / 320 force either; one CTA per tile only).
-  if (vec && bulkDone == 0 && smallTilesWanted(plan, a.shDim, a.n)) {
+  // The 128-thread geometry (tiles 2.5x smaller, 10 CTAs per SM) for SH degree 0, 1, 2: measured ahead of the 320-thread one for the
+  // encoder from 2.5M gaussians up (SH0 +2 % at 10M, +7 % at 40M; SH2 +1.5 %; SH1 +1-2 %: profiles/r2_tuning_notes.txt section 12) and
+  // 1-2 % behind it for the SH-less decoder, which keeps 320.  SPZB200_TILE=128 / 320 force either for both directions.
+  if (vec && bulkDone == 0 && smallTilesWanted(plan, plan.smallTilesEncode, a.shDim, a.n)) {
     const long long tgS = a.shDim == 3 ? Geo<3, kSmallThreads>::TG : Geo<0, kSmallThreads>::TG;
     const long long tilesS = a.n / tgS;
     if (tilesS > 0 && tilesS < 0x7fffffffLL) {
@@ -937,7 +939,7 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
     count++;
     pgDone = rest0 > 0 ? a.n : tiles0 * kDec0Tile;
   }
-  if (vec && pgDone == 0 && smallTilesWanted(plan, a.shDim, a.n)) {  // as in launchEncode
+  if (vec && pgDone == 0 && smallTilesWanted(plan, plan.smallTilesDecode, a.shDim, a.n)) {  // as in launchEncode; off by default (measured 1-2 % slower)
     const long long tgS = a.shDim == 3 ? Geo<3, kSmallThreads>::TG : Geo<0, kSmallThreads>::TG;
     const long long tilesS = a.n / tgS;
     if (tilesS > 0 && tilesS < 0x7fffffffLL) {

@@ -161,7 +161,7 @@ void SHIM(cloud_copy)(const CloudHandle *h, float *const out[6]) {
 void SHIM(cloud_free)(CloudHandle *h) { delete h; }
 
 // `threads` host threads pack and unpack the same cloud concurrently (the API is re-entrant: the
-// reference has no shared state; this repo keeps one GPU context per host thread).  Returns the
+// reference has no shared state; this repo leases GPU contexts from a process-wide pool).  Returns the
 // number of threads whose result differs from thread 0's, or -1 if any call failed.
 int SHIM(concurrent_roundtrip)(int32_t n, int32_t deg, int32_t from, int32_t to, const float *const planes[6], int32_t threads) {
   const spz::GaussianCloud g = makeCloud(n, deg, 0, planes);
