@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--sh-degree", type=int, default=3)
     ap.add_argument("--from-coord", type=int, default=6, help="PackOptions.from (6 = RDF)")
     ap.add_argument("--to-coord", type=int, default=6, help="UnpackOptions.to (6 = RDF)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunk-sweep", default="", help="comma-separated pipeline range sizes (points) to re-time the duplex e2e step with")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -41,21 +41,4 @@ for n in (60_000, 1_000_000):
     for rep in range(3):
         timed(f"encode_host {n} SH3 pageable, call {rep}", lambda: p2.encode_host(src, 6))
 p2.close()
-# the first bounced call again in fresh contexts, one per way of getting the pinned bounce buffers
-import subprocess
-WORKER = """
-import os, sys, time
-sys.path.insert(0, os.environ['REPO'])
-from spz_b200 import codec
-from spz_b200.synth import numpy_cloud
-src = numpy_cloud(1_000_000, 3, seed=3)
-ctx = codec.Context(0)
-for rep in range(3):
-    t = time.perf_counter(); _, tm = ctx.encode_host(src, 6); print(f"  {os.environ.get('SPZB200_BOUNCE_ALLOC')}: encode_host 1M SH3 pageable, call {rep}: {1e3 * (time.perf_counter() - t):8.2f} ms (staged={tm['staged']})")
-"""
-for mode in ("hostalloc", "thp"):
-    r = subprocess.run([sys.executable, "-c", WORKER], env=dict(os.environ, REPO=ROOT, SPZB200_BOUNCE_ALLOC=mode, SPZB200_TRACE_INIT="", SPZB200_NO_REBUILD="1"),
-                       capture_output=True, text=True)
-    print(r.stdout.rstrip() or r.stderr[-400:])
-c1.close(); c2.close(); c3.close()
 print(f"whole script                            {1e3 * (time.perf_counter() - t_proc):8.2f} ms")

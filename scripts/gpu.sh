@@ -27,7 +27,7 @@ case "$task" in
   abr1)     timeout 1500 bash scripts/ab_vs_r1.sh "$@" > gpurun_out/ab_vs_r1.jsonl 2> gpurun_out/ab_vs_r1.err; echo "rc=$?"; cat gpurun_out/ab_vs_r1.jsonl; tail -3 gpurun_out/ab_vs_r1.err ;;
   launches) # launch list of one short bench run (after the same command ran clean without ncu)
             timeout 900 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/launch_pre.json 2> gpurun_out/launch_pre.err || { echo "plain run failed"; exit 1; }
-            timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Tiles|PerGaussian|Generic|unpackRecords|Ply|Sh0Staged|Tables|probePack' -c 400 --csv --log-file gpurun_out/launches.csv \
+            timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Tiles|PerGaussian|Generic|unpackRecords|Ply|Tables|probePack' -c 400 --csv --log-file gpurun_out/launches.csv \
               python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/ncu_list.log 2>&1; echo "ncu rc=$?"; tail -5 gpurun_out/launches.csv ;;
   ncufull)  # ncufull <name> <kernel regex> <skip> <count> <command...>: one ncu --set full capture, after the same command ran clean without ncu
             name=$1; regex=$2; skip=$3; count=$4; shift 4

@@ -7,9 +7,6 @@
 //   * the 255 thresholds of the alpha quantizer  a -> toUint8(sigmoid(a) * 255)   (uses expf)
 //   * the 256 values of the alpha dequantizer    b -> invSigmoid(b / 255.0f)      (uses logf)
 #include <cuda_runtime.h>
-#if defined(__linux__)
-#include <sys/mman.h>
-#endif
 
 #include <algorithm>
 #include <chrono>
@@ -149,9 +146,6 @@ const HostTables &hostTables() {
 #ifndef SPZ_STAGES
 #define SPZ_STAGES 3
 #endif
-#ifndef SPZ_BOUNCE_THP_DEFAULT
-#define SPZ_BOUNCE_THP_DEFAULT false
-#endif
 constexpr int kStages = SPZ_STAGES;
 
 struct Stage {
@@ -162,7 +156,6 @@ struct Stage {
   uint8_t *hIn = nullptr;      // pinned bounce buffers, used only when the caller's planes are pageable
   uint8_t *hOut = nullptr;
   size_t hInCap = 0, hOutCap = 0;
-  bool hInMapped = false, hOutMapped = false;  // mmap + cudaHostRegister (transparent huge pages) instead of cudaHostAlloc
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -254,7 +247,6 @@ struct SpzB200Context {
   int decodePerGaussian = 1;  // SPZB200_DECODE=pergaussian: 2 (also SH-less clouds); =bulk / =direct: 0 (tile kernels only)
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
   bool decodeBulk = true;  // SH plane of the decoder staged with bulk async copies (SPZB200_DECODE=direct: registers)
-  bool decodeSh0Staged = false;  // SPZB200_DECODE0=staged: SH-less clouds through decodeSh0StagedKernel (measured slower: 5.63 vs 6.36 TB/s at 10M, 5.57 vs 6.56 at 100M)
   int smallTilesEncode = 2, smallTilesDecode = 0;  // 128-thread tile geometry (SH degree 0 - 2): encoder always, decoder never; SPZB200_TILE=128 / 320 set both, =auto the size rule
   bool pdl = true;       // SPZB200_PDL=0: plain stream-ordered launches (A/B timing)
   bool foldRest = true;  // SPZB200_REST=separate: the sub-tile remainder as a launch of its own (A/B timing)
@@ -364,7 +356,6 @@ spzb200::LaunchPlan planOf(const SpzB200Context *ctx) {
   p.pdl = ctx->pdl;
   p.smallTilesEncode = ctx->smallTilesEncode;
   p.smallTilesDecode = ctx->smallTilesDecode;
-  p.decodeSh0Staged = ctx->decodeSh0Staged;
   p.decodePerGaussian = ctx->decodePerGaussian;
   p.encodeBulk = ctx->encodeBulk;
   return p;
@@ -396,63 +387,14 @@ int ensureStage(Stage &s, size_t inBytes_, size_t outBytes_) {
   return SPZB200_OK;
 }
 
-// Pinned bounce buffers.  cudaHostAlloc pins fresh 4 KiB pages at about 1 GB/s on these VMs (the first bounced call of a
-// process paid ~370 ms for 3 x 79 MB).  The same bytes as an anonymous mapping advised to transparent huge pages,
-// touched, then cudaHostRegister'ed fault 512x fewer pages (profiles/r2_cold_start.txt compares the two;
-// SPZB200_BOUNCE_ALLOC=hostalloc / thp selects).  The copy engines see no difference (profiles/r2_link_probe_*.jsonl).
-struct BounceAlloc {
-  static bool useThp() {
-    static const bool thp = [] {
-      const char *env = std::getenv("SPZB200_BOUNCE_ALLOC");
-      return env ? std::strcmp(env, "thp") == 0 : SPZ_BOUNCE_THP_DEFAULT;
-    }();
-    return thp;
-  }
-};
-
-void freeBounce(uint8_t *&buf, size_t &cap, bool &mapped) {
-  if (!buf) return;
-#if defined(__linux__)
-  if (mapped) {
-    cudaHostUnregister(buf);
-    munmap(buf, cap);
-  } else
-#endif
-    cudaFreeHost(buf);
-  buf = nullptr;
-  cap = 0;
-  mapped = false;
-}
-
-int ensureBounce(uint8_t *&buf, size_t &cap, bool &mapped, size_t bytes) {
+// Pinned bounce buffers (cudaHostAlloc: ~1 GB/s on these VMs, i.e. 0.1-0.4 s for the 3 x 79 MB of a first bounced call; an mmap +
+// MADV_HUGEPAGE + cudaHostRegister variant measured no faster -- commit 116c183, profiles/r2_tuning_notes.txt section 9).
+int ensureBounce(uint8_t *&buf, size_t &cap, size_t bytes) {
   if (cap >= bytes) return SPZB200_OK;
-  freeBounce(buf, cap, mapped);
-#if defined(__linux__)
-  if (BounceAlloc::useThp()) {
-    constexpr size_t kHuge = (size_t)2 << 20;
-    const size_t len = alignUp(bytes, kHuge);
-    // over-map by one huge page and trim to a 2 MiB-aligned window so every page of it can be a huge page
-    uint8_t *raw = static_cast<uint8_t *>(mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
-    if (raw != MAP_FAILED) {
-      uint8_t *base = reinterpret_cast<uint8_t *>(alignUp(reinterpret_cast<size_t>(raw), kHuge));
-      if (base > raw) munmap(raw, (size_t)(base - raw));
-      if (base + len < raw + len + kHuge) munmap(base + len, (size_t)(raw + len + kHuge - (base + len)));
-      (void)madvise(base, len, MADV_HUGEPAGE);
-      for (size_t off = 0; off < len; off += kHuge) base[off] = 0;  // first touch: one fault per huge page
-      if (cudaHostRegister(base, len, cudaHostRegisterDefault) == cudaSuccess) {
-        buf = base;
-        cap = len;
-        mapped = true;
-        return SPZB200_OK;
-      }
-      (void)cudaGetLastError();
-      munmap(base, len);
-    }
-  }
-#endif
+  if (buf) cudaFreeHost(buf);
+  buf = nullptr; cap = 0;
   CU(cudaHostAlloc(&buf, bytes, cudaHostAllocDefault));
   cap = bytes;
-  mapped = false;
   return SPZB200_OK;
 }
 
@@ -538,8 +480,8 @@ int runPipelineStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &o
     for (int s = 0; s < stages; s++) {
       Stage &st = ctx->stage[s];
       int rc = ensureStage(st, inBytes, outBytes);
-      if (rc == SPZB200_OK && bounceIn) rc = ensureBounce(st.hIn, st.hInCap, st.hInMapped, inBytes);
-      if (rc == SPZB200_OK && bounceOut) rc = ensureBounce(st.hOut, st.hOutCap, st.hOutMapped, outBytes);
+      if (rc == SPZB200_OK && bounceIn) rc = ensureBounce(st.hIn, st.hInCap, inBytes);
+      if (rc == SPZB200_OK && bounceOut) rc = ensureBounce(st.hOut, st.hOutCap, outBytes);
       if (rc != SPZB200_OK) return rc;
     }
     if ((bounceIn || bounceOut) && !ctx->pool) {
@@ -913,12 +855,10 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   if (const char *env = std::getenv("SPZB200_BOUNCE_MIN_MB")) ctx->bounceMinBytes = (size_t)std::atoll(env) << 20;
   if (const char *env = std::getenv("SPZB200_DECODE")) {
     ctx->decodeBulk = std::strcmp(env, "direct") != 0;
-    if (!ctx->decodeBulk) ctx->decodeSh0Staged = false;
     ctx->decodePerGaussian = std::strcmp(env, "pergaussian") == 0 ? 2 : (std::strcmp(env, "bulk") == 0 || std::strcmp(env, "direct") == 0) ? 0 : 1;
   }
   if (const char *env = std::getenv("SPZB200_ENCODE")) ctx->encodeBulk = std::strcmp(env, "bulk") == 0 ? 2 : std::strcmp(env, "tiles") == 0 ? 0 : 1;
   if (const char *env = std::getenv("SPZB200_PLY")) ctx->plyMapped = std::strcmp(env, "mapped") == 0;
-  if (const char *env = std::getenv("SPZB200_DECODE0")) ctx->decodeSh0Staged = std::strcmp(env, "staged") == 0;
   if (const char *env = std::getenv("SPZB200_TILE"))
     ctx->smallTilesEncode = ctx->smallTilesDecode = std::strcmp(env, "320") == 0 ? 0 : std::strcmp(env, "128") == 0 ? 2 : 1;
   if (const char *env = std::getenv("SPZB200_PDL")) ctx->pdl = std::strcmp(env, "0") != 0;
@@ -964,8 +904,8 @@ void spzb200_destroy(SpzB200Context *ctx) {
   for (int s = 0; s < kStages; s++) {
     Stage &st = ctx->stage[s];
     if (st.stream) cudaStreamSynchronize(st.stream);
-    freeBounce(st.hIn, st.hInCap, st.hInMapped);
-    freeBounce(st.hOut, st.hOutCap, st.hOutMapped);
+    if (st.hIn) cudaFreeHost(st.hIn);
+    if (st.hOut) cudaFreeHost(st.hOut);
     for (int k = 0; k < 4; k++) if (st.ev[k]) cudaEventDestroy(st.ev[k]);
     if (st.dIn) cudaFree(st.dIn);
     if (st.dOut) cudaFree(st.dOut);

@@ -316,8 +316,10 @@ struct DecodePosConsts {
 // positions, scales, colours, alphas and rotations of sub-tile q (gaussians [q*1280, (q+1)*1280)):
 // direct 128-byte-aligned loads and stores, shared by both decode kernels.  `stage` is this warp's
 // 288-word scratch.
-// Where the expanded float4s of a sub-tile go.  Both sinks hold one float4 pointer per plane, already
-// advanced to the sub-tile; `idx` is the float4 index inside that plane's part of the sub-tile.
+// Where the expanded float4s of a sub-tile go: one float4 pointer per plane, already advanced to the
+// sub-tile; `idx` is the float4 index inside that plane's part of the sub-tile.  (Round 2 also tried a
+// shared-memory sink feeding bulk async stores for SH-less clouds -- commit 251cd9c, slower at every
+// size, profiles/r2_tuning_notes.txt section 6 -- which is why the sink is a policy.)
 struct GlobalSink {  // straight to the output planes with streaming stores
   float4 *pos, *scale, *rot, *alpha, *color;
   template <int S>
@@ -328,15 +330,6 @@ struct GlobalSink {  // straight to the output planes with streaming stores
   }
   static __device__ __forceinline__ void put(float4 *plane, int idx, float4 v) { stStream(plane + idx, v); }
 };
-struct SmemSink {  // into a shared-memory image of the sub-tile's five float planes (bulk-stored by the caller)
-  float4 *pos, *scale, *rot, *alpha, *color;
-  template <int S>
-  static __device__ __forceinline__ SmemSink at(float4 *base) {
-    return {base, base + 3 * S, base + 6 * S, base + 10 * S, base + 11 * S};
-  }
-  static __device__ __forceinline__ void put(float4 *plane, int idx, float4 v) { plane[idx] = v; }
-};
-
 template <int VER, bool HOIST, int S = kThreads, class Sink = GlobalSink>
 __device__ __forceinline__ void decodeSmallPlanes(const DecodeArgs &a, const long long q, const int t, uint32_t *stage,
                                                   const float *sAlpha, const float *sColor, const float *sMag,
@@ -580,72 +573,6 @@ decodeTilesKernel(const __grid_constant__ DecodeArgs a, const long long numTiles
     }
 }
 
-// ---- SH-less clouds: outputs staged in shared memory, written with bulk async stores ---------------
-// EXPERIMENT, opt-in (SPZB200_DECODE0=staged), kept because the result is instructive: round 2 measured it
-// SLOWER than decodeTilesKernel<0, VER> on the same box -- 5.63 vs 6.36 TB/s at 10M gaussians, 5.57 vs 6.56
-// at 100M, 5.03 vs 5.76 at 2.5M (profiles/r2_tuning_notes.txt).  The premise came from the stripped-down
-// pattern benchmark below; with the real expansion in between, the extra shared-memory round trip and
-// the per-CTA fence / barrier / store-drain of a 28 KB image cost more than the store path gains.
-// An SH-less decode writes 56 of its 76 bytes per gaussian.  scripts/membench.cu: for that write-heavy
-// mix STG.128 from registers sustains 6.09 TB/s, bulk async stores from shared memory (UBLKCP.G.S) 6.76.
-// Same per-value work as decodeTilesKernel<0, VER> (the packed words arrive with plain 128-byte-aligned
-// loads -- a quarter of the traffic), but every float4 goes into a shared-memory image of the tile's
-// five float planes, which leaves through five bulk stores.  Tiles are small (4 x 128 gaussians, 28 KB
-// of shared memory, 6 CTAs per SM): a CTA holds its image through load wait, expansion and store
-// drain, and many small CTAs overlap those phases and keep a launch's tail short.  The three decode
-// tables are read through L1 instead of being copied into every CTA's shared memory.
-#ifndef SPZ_DEC0_THREADS
-#define SPZ_DEC0_THREADS 128
-#endif
-#ifndef SPZ_DEC0_CTAS
-#define SPZ_DEC0_CTAS 6
-#endif
-#ifndef SPZ_DEC0_HOIST
-#define SPZ_DEC0_HOIST true
-#endif
-constexpr int kDec0Threads = SPZ_DEC0_THREADS;
-constexpr int kDec0Tile = 4 * kDec0Threads;  // gaussians per CTA
-
-template <int VER>
-__global__ void __launch_bounds__(kDec0Threads, SPZ_DEC0_CTAS)
-decodeSh0StagedKernel(const __grid_constant__ DecodeArgs a, const long long numTiles, const int restCtas) {
-  constexpr int S = kDec0Threads;
-  extern __shared__ __align__(128) unsigned char dynSmem[];  // 14 * S float4: positions 3S, scales 3S, rotations 4S, alphas S, colours 3S
-  __shared__ uint32_t sStage[S / 32][3 * 96];
-  const int t = threadIdx.x;
-  pdlTrigger();
-  if ((int)blockIdx.x < restCtas) {  // the sub-tile remainder rides in the first CTA(s): scalar_path.cuh
-    const long long g = numTiles * kDec0Tile + (long long)blockIdx.x * S + t;
-    pdlWait();
-    if (g < a.n) decodeOneGaussian(a, g);
-    return;
-  }
-  float4 *image = reinterpret_cast<float4 *>(dynSmem);
-  const SmemSink sink = SmemSink::at<S>(image);
-  DecodePosConsts pc;
-  pc.init(a, t);
-  pdlWait();  // constants are in place; the planes may only be touched from here on
-  const long long firstTile = (int)blockIdx.x - restCtas;
-  for (long long tile = firstTile; tile < numTiles; tile += (int)gridDim.x - restCtas) {
-    if (tile != firstTile) {  // multi-tile CTAs only: the previous tile's stores are done reading the image
-      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncthreads();
-    }
-    decodeSmallPlanes<VER, SPZ_DEC0_HOIST, S, SmemSink>(a, tile, t, sStage[t >> 5], a.tables, a.tables + 256, a.tables + 512, pc, sink);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the STS visible to the copy engine
-    __syncthreads();
-    if (t == 0) {
-      bulkStore(reinterpret_cast<float4 *>(a.oPositions) + tile * (3 * S), sink.pos, 3 * S * 16);
-      bulkStore(reinterpret_cast<float4 *>(a.oScales) + tile * (3 * S), sink.scale, 3 * S * 16);
-      bulkStore(reinterpret_cast<float4 *>(a.oRotations) + tile * (4 * S), sink.rot, 4 * S * 16);
-      bulkStore(reinterpret_cast<float4 *>(a.oAlphas) + tile * S, sink.alpha, S * 16);
-      bulkStore(reinterpret_cast<float4 *>(a.oColors) + tile * (3 * S), sink.color, 3 * S * 16);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-  }
-  if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the stores' reads
-}
-
 // ---- bulk-copy (TMA) staging of the SH plane ---------------------------------------------------------
 // scripts/membench.cu (profiles/r1_membench_patterns.txt): for decode's write-heavy mix, moving the
 // packed words in with ONE bulk async copy per tile (UBLKCP.S.G, completion on an mbarrier) and
@@ -809,15 +736,6 @@ cudaError_t launchDecodeTilesVer(const DecodeArgs &a, long long tiles, int grid,
   return launchKernel(decodeTilesKernel<D, VER, S>, grid + restCtas, S, 0, s, pdl, a, tiles, restCtas);
 }
 
-template <int VER>
-cudaError_t launchDecodeSh0Staged(const DecodeArgs &a, long long tiles, unsigned grid, int restCtas, size_t smem, bool pdl, cudaStream_t s) {
-  if (smem > 48 * 1024) {  // per launch, not once: the attribute belongs to the current device
-    const cudaError_t attr = cudaFuncSetAttribute(decodeSh0StagedKernel<VER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (attr != cudaSuccess) return attr;
-  }
-  return launchKernel(decodeSh0StagedKernel<VER>, grid + restCtas, kDec0Threads, smem, s, pdl, a, tiles, restCtas);
-}
-
 template <int D, int S = kThreads>
 cudaError_t launchDecodeTiles(const DecodeArgs &a, long long tiles, int grid, int restCtas, bool bulk, bool pdl, cudaStream_t s) {
   switch (a.version) {
@@ -921,24 +839,6 @@ cudaError_t launchDecode(const DecodeArgs &a, const LaunchPlan &plan, cudaStream
   long long pgDone = 0;
   if (cudaError_t e = launchDecodePerGaussianPlanar(a, plan, stream, &pgDone); e != cudaSuccess) return e;
   if (pgDone > 0) count++;
-  // SH-less clouds with 16-byte aligned float planes: the staged bulk-store decoder above
-  if (pgDone == 0 && vec && a.shDim == 0 && plan.decodeSh0Staged && a.n >= kDec0Tile) {
-    const long long tiles0 = a.n / kDec0Tile;
-    const long long cap = plan.flatGrid ? 0x7fffffffLL : (long long)plan.smCount * SPZ_DEC0_CTAS;
-    const unsigned grid = (unsigned)(tiles0 < cap ? tiles0 : cap);
-    const int rest0 = plan.flatGrid && plan.foldRest ? (int)((a.n - tiles0 * kDec0Tile + kDec0Threads - 1) / kDec0Threads) : 0;
-    constexpr size_t smem = 14 * kDec0Threads * 16;
-    cudaError_t e;
-    switch (a.version) {
-      case 1: e = launchDecodeSh0Staged<1>(a, tiles0, grid, rest0, smem, plan.pdl, stream); break;
-      case 2: e = launchDecodeSh0Staged<2>(a, tiles0, grid, rest0, smem, plan.pdl, stream); break;
-      case 4: e = launchDecodeSh0Staged<4>(a, tiles0, grid, rest0, smem, plan.pdl, stream); break;
-      default: e = launchDecodeSh0Staged<3>(a, tiles0, grid, rest0, smem, plan.pdl, stream); break;
-    }
-    if (e != cudaSuccess) return e;
-    count++;
-    pgDone = rest0 > 0 ? a.n : tiles0 * kDec0Tile;
-  }
   if (vec && pgDone == 0 && smallTilesWanted(plan, plan.smallTilesDecode, a.shDim, a.n)) {  // as in launchEncode; off by default (measured 1-2 % slower)
     const long long tgS = a.shDim == 3 ? Geo<3, kSmallThreads>::TG : Geo<0, kSmallThreads>::TG;
     const long long tilesS = a.n / tgS;

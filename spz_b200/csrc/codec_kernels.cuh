@@ -96,7 +96,6 @@ struct LaunchPlan {
                        // faster (SH degree 3, at most 24M gaussians per launch; default), 2 wherever it exists
   int decodePerGaussian;   // planar decoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it
                            // measured faster (SH degree 1 - 3; default), 2 also for SH-less clouds
-  bool decodeSh0Staged;  // SH-less decode through the staged bulk-store kernel (opt-in, SPZB200_DECODE0=staged: it measured slower than the register-path tiles)
   int smallTilesEncode, smallTilesDecode;  // 128-thread tile geometry for SH degree 0 - 2: 0 never, 1 up to 16M gaussians per launch, 2 always.
                                             // Defaults: encoder always, decoder never (measured); SPZB200_TILE=128 / 320 set both
   bool pdl;            // launch with programmatic stream serialization (kernel_utils.cuh); default on, SPZB200_PDL=0 turns it off

@@ -248,7 +248,6 @@ def test_ply_kernels_write_only_their_planes(gpu_ctx, oracle, deg, extra):
                                  {"SPZB200_ENCODE": "bulk"}, {"SPZB200_ENCODE": "bulk", "SPZB200_GRID": "persistent"}, {"SPZB200_ENCODE": "tiles"},
                                  {"SPZB200_ENCODE": "tiles", "SPZB200_GRID": "persistent"},
                                  {"SPZB200_PACK": "alu"}, {"SPZB200_PLY": "mapped"},
-                                 {"SPZB200_DECODE0": "staged"}, {"SPZB200_DECODE0": "staged", "SPZB200_GRID": "persistent"},
                                  {"SPZB200_TILE": "128"}, {"SPZB200_TILE": "320"}, {"SPZB200_TILE": "128", "SPZB200_REST": "separate"},
                                  {"SPZB200_REST": "separate"}, {"SPZB200_PDL": "0"}, {"SPZB200_PDL": "0", "SPZB200_REST": "separate"}])
 def test_alternate_launch_shapes(env):
