@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SPZB200_VERSION 100 /* 0.1.0 */
+#define SPZB200_VERSION 200 /* 0.2.0: context pool, batched per-gaussian access, stream-version-2 encoder */
 
 /* Status codes.  0 = success; negative = failure, message via spzb200_last_error(). */
 enum {

@@ -37,7 +37,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(N.Cloud) == 8 + 4 + 4 + 6 * 8
     assert C.sizeof(N.Packed) == 8 + 4 * 4 + 6 * 8
     assert C.sizeof(N.Timings) == 4 * 8 + 2 * 8 + 2 * 4 + 8 + 2 * 4
-    assert N.lib().spzb200_version() == 100
+    assert N.lib().spzb200_version() == 200
 
 
 def test_product_does_not_touch_the_oracle():
@@ -108,6 +108,11 @@ def test_no_device_fails_loudly():
     with pytest.raises(N.CodecError) as e:
         codec.encode_host_multi([0], c)
     assert e.value.code == N.ERR_NO_DEVICE
+    # a pooled lease fails the same way (and leaves the pool able to try again)
+    for _ in range(2):
+        with pytest.raises(N.CodecError) as e:
+            codec.Context(0, pooled=True)
+        assert e.value.code == N.ERR_NO_DEVICE
 
 
 def test_argument_validation_needs_no_device():
@@ -116,6 +121,12 @@ def test_argument_validation_needs_no_device():
     assert L.spzb200_encode_device(None, None, 0, None, None) == N.ERR_INVALID
     assert L.spzb200_decode_host(None, None, 0, None, None) == N.ERR_INVALID
     assert b"null context" in L.spzb200_last_error()
+    assert L.spzb200_unpack_records_host(None, None, 1, 3, 12, None, None) == N.ERR_INVALID
+    assert L.spzb200_unpack_gather_host(None, None, None, 1, None, None) == N.ERR_INVALID
+    assert L.spzb200_unpack_gather_device(None, None, None, 1, None, None, None) == N.ERR_INVALID
+    assert L.spzb200_encode_host_as(None, None, 0, 2, None, None) == N.ERR_INVALID
+    assert L.spzb200_acquire(0, None) == N.ERR_INVALID
+    L.spzb200_release(None)  # a no-op, like free(NULL)
     with pytest.raises(TypeError):
         codec._cloud_struct(codec.CloudPlanes(1, 0, *[np.zeros(3, np.float64)] * 6), False)
     with pytest.raises(ValueError):
