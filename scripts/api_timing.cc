@@ -1,6 +1,7 @@
 // Development tool: wall time of the drop-in C++ API (spz::packGaussians / spz::unpackGaussians on
 // std::vector planes) for a synthetic cloud.  Built by scripts/gpu_api.sh against include/spz and
 // libspz_b200.so; not part of the product or the tests.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -52,6 +53,27 @@ int main(int argc, char **argv) {
     printf("{\"api\": \"spz::packGaussians/unpackGaussians\", \"points\": %zu, \"rep\": %d, \"pack_ms\": %.1f, \"unpack_ms\": %.1f, \"check\": %.6f}\n", n, r,
            (t1 - t0) * 1e3, (t2 - t1) * 1e3, (double)back.sh[n * 45 - 1] + back.positions[0]);
     fflush(stdout);
+  }
+  // per-gaussian access: a loop over packed.unpack(i, c) against one unpackGaussiansAt call
+  {
+    const spz::PackedGaussians p = spz::packGaussians(g, {spz::CoordinateSystem::RUB});
+    const spz::CoordinateConverter c = spz::coordinateConverter(spz::CoordinateSystem::RUB, spz::CoordinateSystem::RDF);
+    const int loopN = 2000;
+    double acc = 0;
+    p.unpack(0, c);
+    const double t0 = now();
+    for (int i = 0; i < loopN; i++) acc += p.unpack((int32_t)((size_t)i * 7919u % n), c).position[0];
+    const double t1 = now();
+    std::vector<int32_t> idx(std::min<size_t>(n, 1000000));
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int32_t)(i * 7919u % n);
+    spz::unpackGaussiansAt(p, idx, c);
+    const double t2 = now();
+    const std::vector<spz::UnpackedGaussian> many = spz::unpackGaussiansAt(p, idx, c);
+    const double t3 = now();
+    for (int i = 0; i < loopN; i++) acc -= many[(size_t)i].position[0];
+    printf("{\"api\": \"PackedGaussians::unpack(i, c)\", \"points\": %zu, \"loop_us_per_gaussian\": %.2f, \"batched_gaussians\": %zu, \"batched_ms\": %.2f, "
+           "\"batched_mgaussians_s\": %.2f, \"loop_minus_batched\": %.6f}\n",
+           n, (t1 - t0) * 1e6 / loopN, many.size(), (t3 - t2) * 1e3, many.size() / (t3 - t2) / 1e6, acc);
   }
   return 0;
 }

@@ -25,6 +25,12 @@ case "$task" in
             name=$1; script=$2; shift 2 || true
             timeout 1500 python scripts/$script "$@" > gpurun_out/$name 2> gpurun_out/$name.err; echo "rc=$?"; cat gpurun_out/$name; tail -3 gpurun_out/$name.err ;;
   abr1)     timeout 1500 bash scripts/ab_vs_r1.sh "$@" > gpurun_out/ab_vs_r1.jsonl 2> gpurun_out/ab_vs_r1.err; echo "rc=$?"; cat gpurun_out/ab_vs_r1.jsonl; tail -3 gpurun_out/ab_vs_r1.err ;;
+  api)      # wall time of the C++ drop-in API on pageable std::vector planes (scripts/api_timing.cc); rep 0 includes context creation and pinned buffers
+            mkdir -p scripts/_build
+            g++ -std=c++17 -O2 -pthread -Iinclude/spz scripts/api_timing.cc -o scripts/_build/api_timing -Lspz_b200/_lib -lspz_b200 -Wl,-rpath,'$ORIGIN/../../spz_b200/_lib' || exit 1
+            { for n in 6e4 2e5 1e6 2e6 4e6 1e7; do echo "== $n gaussians SH3 (default policy)"; scripts/_build/api_timing $n 4; done
+              echo "== 1e7, SPZ_B200_ZEROFILL=1 (plain resize)"; SPZ_B200_ZEROFILL=1 scripts/_build/api_timing 1e7 4; } > gpurun_out/cxx_api_timing.txt 2>&1
+            echo "rc=$?"; cat gpurun_out/cxx_api_timing.txt ;;
   launches) # launch list of one short bench run (after the same command ran clean without ncu)
             timeout 900 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/launch_pre.json 2> gpurun_out/launch_pre.err || { echo "plain run failed"; exit 1; }
             timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Tiles|PerGaussian|Generic|unpackRecords|Ply|Tables|probePack' -c 400 --csv --log-file gpurun_out/launches.csv \
