@@ -489,7 +489,7 @@ std::vector<UnpackedGaussian> unpackGaussiansAt(const PackedGaussians &packed, c
     return out;
   std::vector<int64_t> idx(indices.begin(), indices.end());
   const SpzB200Packed in = viewOf(packed, streamFlavour(usesFloat16, packed.usesQuaternionSmallestThree));
-  out.resize(indices.size());
+  resizeUninitialized(out, indices.size());  // every float is written by the kernel (or the vector is cleared on failure)
   ContextLease lease(configuredDevices()[0]);
   if (!lease.get() || spzb200_unpack_gather_host(lease.get(), &in, idx.data(), (int64_t)idx.size(), c.flipP.data(),
                                                  reinterpret_cast<float *>(out.data())) != SPZB200_OK) {
