@@ -7,6 +7,9 @@
 //   * the 255 thresholds of the alpha quantizer  a -> toUint8(sigmoid(a) * 255)   (uses expf)
 //   * the 256 values of the alpha dequantizer    b -> invSigmoid(b / 255.0f)      (uses logf)
 #include <cuda_runtime.h>
+#if defined(__x86_64__) && (defined(__GNUC__) || defined(__clang__))
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -159,6 +162,45 @@ struct Stage {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
+// The bounce copies move each byte once and never read it back on the CPU, so large ones use non-temporal stores
+// (no read-for-ownership of the destination lines, no cache pollution): on x86-64 with AVX2, chosen at run time;
+// plain memcpy otherwise, for small pieces, and with SPZB200_NT_COPY=0 (profiles/r2_tuning_notes.txt section 15).
+#if defined(__x86_64__) && (defined(__GNUC__) || defined(__clang__))
+__attribute__((target("avx2"))) static void copyNonTemporalAvx2(uint8_t *dst, const uint8_t *src, size_t bytes) {
+  const size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+  if (head) {
+    std::memcpy(dst, src, head);
+    dst += head; src += head; bytes -= head;
+  }
+  size_t i = 0;
+  for (; i + 128 <= bytes; i += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
+    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+  }
+  _mm_sfence();
+  if (i < bytes) std::memcpy(dst + i, src + i, bytes - i);
+}
+static bool nonTemporalCopyUsable() {
+  static const bool ok = [] {
+    const char *env = std::getenv("SPZB200_NT_COPY");
+    return !(env && env[0] == '0') && __builtin_cpu_supports("avx2");
+  }();
+  return ok;
+}
+static void bounceCopy(void *dst, const void *src, size_t bytes) {
+  if (bytes >= ((size_t)256 << 10) && nonTemporalCopyUsable()) copyNonTemporalAvx2(static_cast<uint8_t *>(dst), static_cast<const uint8_t *>(src), bytes);
+  else std::memcpy(dst, src, bytes);
+}
+#else
+static void bounceCopy(void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); }
+#endif
+
 // A few host threads that copy between the caller's pageable planes and the pinned bounce buffers
 // (one memcpy thread moves ~10 GB/s; the PCIe link wants ~50).  Created on first pageable call.
 class CopyPool {
@@ -189,7 +231,7 @@ class CopyPool {
     cv_.notify_all();
     Job j;
     while (take(&j, false)) {
-      std::memcpy(j.dst, j.src, j.bytes);
+      bounceCopy(j.dst, j.src, j.bytes);
       done();
     }
     std::unique_lock<std::mutex> g(m_);
@@ -217,7 +259,7 @@ class CopyPool {
         if (stop_) return;
         continue;
       }
-      std::memcpy(j.dst, j.src, j.bytes);
+      bounceCopy(j.dst, j.src, j.bytes);
       done();
     }
   }
