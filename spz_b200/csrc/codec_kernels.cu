@@ -60,10 +60,14 @@ constexpr int gcdc(int a, int b) { return b == 0 ? a : gcdc(b, a % b); }
 // smaller for launches whose tail is a visible part of their duration (SH degree 0, 1, 2; at degree 3 the phase
 // cycle would be 45 rows long with S = 128, and small degree-3 clouds use the per-gaussian kernels anyway).
 constexpr int kSmallThreads = 128;
+#ifndef SPZ_SH1_SMALL_M
+#define SPZ_SH1_SMALL_M 3  // SH degree 1, 128-thread geometry: sub-tiles per tile = SH rows in flight per phase class.  Measured (encode GB/s at
+                           // 10M / 20M / 100M gaussians, profiles/r2_tuning_notes.txt section 16): M = 5 6290 / 6490 / 6750, M = 2 6375 / 6585 / 6636, M = 3 6478 / 6760 / 6866
+#endif
 template <int D, int S = kThreads>
 struct Geo {
   static_assert((4 * S) % 3 == 2, "the xyz phase of element e in row i is taken as (t + e + 2 i) mod 3");
-  static constexpr int M = (D == 3) ? 5 : 1;          // sub-tiles (4*S gaussians each) per tile
+  static constexpr int M = (D == 3) ? (S == kThreads ? 5 : SPZ_SH1_SMALL_M) : 1;  // sub-tiles (4*S gaussians each) per tile
   static constexpr int TG = 4 * S * M;                // gaussians per tile
   static constexpr int MOD = 3 * D;                   // floats per SH record
   static constexpr int STEP = D ? (4 * S) % (D ? MOD : 1) : 0;  // phase advance per row
