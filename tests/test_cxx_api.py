@@ -13,6 +13,7 @@ import gzip
 import os
 import struct
 import subprocess
+import sys
 import zlib
 
 import time
@@ -925,6 +926,28 @@ def test_short_lived_threads_share_pooled_contexts(mine):
     # measured: 464 / 455 / 183 ms (profiles/r2_pool_sweep.jsonl); per-thread contexts would add ~64 x 0.1-0.4 s of pinned allocation
     assert serial_ms < 3 * steady_ms + 50
     assert burst_ms < 3 * steady_ms + 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_contexts", ["1", "3"])
+def test_pool_limit_makes_callers_wait_not_fail(max_contexts):
+    """SPZ_B200_MAX_CONTEXTS bounds the contexts per device; callers beyond it block until a lease comes back.  With
+    a pool of ONE context, eight concurrent threads packing and unpacking still all finish with identical results
+    (no deadlock, no failure); the variable is read when the pool is first used, hence the fresh process."""
+    worker = (
+        "import os, sys\n"
+        "sys.path.insert(0, os.environ['REPO']); sys.path.insert(0, os.path.join(os.environ['REPO'], 'tests'))\n"
+        "import ctypes as C, numpy as np\n"
+        "from test_cxx_api import Shim\n"
+        "from util import random_cloud\n"
+        "mine = Shim('b200')\n"
+        "c = random_cloud(np.random.default_rng(5), 300_000, 3, False)\n"
+        "_, ip = mine._fplanes(c.planes())\n"
+        "diff = mine.fn('concurrent_roundtrip')(C.c_int32(c.n), C.c_int32(3), C.c_int32(6), C.c_int32(8), ip, C.c_int32(8))\n"
+        "print('diff', diff)\n")
+    r = subprocess.run([sys.executable, "-c", worker], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, REPO=ROOT, SPZ_B200_MAX_CONTEXTS=max_contexts, SPZB200_NO_REBUILD="1"))
+    assert r.returncode == 0 and "diff 0" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
 
 
 @pytest.mark.gpu
