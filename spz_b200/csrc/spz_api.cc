@@ -235,53 +235,72 @@ int64_t maxPointsToRead() {
   return std::numeric_limits<int32_t>::max();
 }
 
-PackedGaussians deserialize(const uint8_t *data, size_t size) {
+// What the 16 header bytes and the stream length say (load-spz.cc:548-574), validated before anything is allocated.
+struct Container {
+  int32_t numPoints = 0, shDegree = 0, fractionalBits = 0;
+  bool antialiased = false, half = false, smallestThree = true;
+  size_t offset[6] = {0, 0, 0, 0, 0, 0};  // stream order: positions, alphas, colors, scales, rotations, sh
+  size_t bytes[6] = {0, 0, 0, 0, 0, 0};
+};
+
+bool parseContainer(const uint8_t *data, size_t size, Container *c) {
   if (size < kHeaderBytes) {
     logLine("[SPZ ERROR] deserializePackedGaussians: header not found");
-    return {};
+    return false;
   }
   uint32_t words[3];
   std::memcpy(words, data, 12);
   if (words[0] != kMagic) {
     logLine("[SPZ ERROR] deserializePackedGaussians: header not found");
-    return {};
+    return false;
   }
   const uint32_t version = words[1], numPointsU = words[2];
   const uint8_t shDegree = data[12], fractionalBits = data[13], flags = data[14];
   if (version < 1 || version > 3) {
     logLine("[SPZ ERROR] deserializePackedGaussians: version not supported: %d", (int)version);
-    return {};
+    return false;
   }
   if ((int64_t)numPointsU > maxPointsToRead()) {
     logLine("[SPZ ERROR] deserializePackedGaussians: Too many points: %d", (int)numPointsU);
-    return {};
+    return false;
   }
   if (shDegree > 3) {
     logLine("[SPZ ERROR] deserializePackedGaussians: Unsupported SH degree: %d", (int)shDegree);
-    return {};
+    return false;
   }
   const size_t n = numPointsU;
   const size_t shDim = (size_t)shDimOf(shDegree);
-  const bool half = version == 1, s3 = version >= 3;
-  const size_t sizes[6] = {n * (half ? 6 : 9), n, n * 3, n * 3, n * (s3 ? 4 : 3), n * shDim * 3};  // stream order
+  c->half = version == 1;
+  c->smallestThree = version >= 3;
+  const size_t sizes[6] = {n * (c->half ? 6 : 9), n, n * 3, n * 3, n * (c->smallestThree ? 4 : 3), n * shDim * 3};
   size_t need = kHeaderBytes;
-  for (size_t s : sizes) need += s;
+  for (int i = 0; i < 6; i++) {
+    c->offset[i] = need;
+    c->bytes[i] = sizes[i];
+    need += sizes[i];
+  }
   if (size < need) {  // checked before anything is allocated: a corrupt count cannot exhaust memory
     logLine("[SPZ ERROR] deserializePackedGaussians: read error");
-    return {};
+    return false;
   }
+  c->numPoints = (int32_t)numPointsU;
+  c->shDegree = shDegree;
+  c->fractionalBits = fractionalBits;
+  c->antialiased = (flags & kFlagAntialiased) != 0;
+  return true;
+}
+
+PackedGaussians deserialize(const uint8_t *data, size_t size) {
+  Container c;
+  if (!parseContainer(data, size, &c)) return {};
   PackedGaussians r;
-  r.numPoints = (int32_t)numPointsU;
-  r.shDegree = shDegree;
-  r.fractionalBits = fractionalBits;
-  r.antialiased = (flags & kFlagAntialiased) != 0;
-  r.usesQuaternionSmallestThree = s3;
+  r.numPoints = c.numPoints;
+  r.shDegree = c.shDegree;
+  r.fractionalBits = c.fractionalBits;
+  r.antialiased = c.antialiased;
+  r.usesQuaternionSmallestThree = c.smallestThree;
   std::vector<uint8_t> *dst[6] = {&r.positions, &r.alphas, &r.colors, &r.scales, &r.rotations, &r.sh};
-  const uint8_t *src = data + kHeaderBytes;
-  for (int i = 0; i < 6; i++) {
-    dst[i]->assign(src, src + sizes[i]);
-    src += sizes[i];
-  }
+  for (int i = 0; i < 6; i++) dst[i]->assign(data + c.offset[i], data + c.offset[i] + c.bytes[i]);
   return r;
 }
 
@@ -306,6 +325,9 @@ bool readFile(const std::string &filename, std::vector<uint8_t> *out) {
 namespace {
 enum class PackStatus { Ok, Rejected, DeviceError };
 PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussians *result, int32_t streamVersion = SPZB200_STREAM_V3);
+PackStatus encodeInto(const GaussianCloud &g, const PackOptions &o, SpzB200Packed out, int32_t streamVersion);
+bool encodeContainer(const GaussianCloud &g, const PackOptions &o, int32_t streamVersion, std::vector<uint8_t> *stream, PackStatus *status);
+GaussianCloud decodeFrom(const SpzB200Packed &in, int32_t numPoints, int32_t shDegree, bool antialiased, const UnpackOptions &o);
 }  // namespace
 
 PackedGaussians packGaussians(const GaussianCloud &g, const PackOptions &o) {
@@ -326,13 +348,9 @@ PackedGaussians packGaussiansV2(const GaussianCloud &g, const PackOptions &o) {
 // ... and the container for it: header version 2 (the reference's writer always says 3, load-spz.cc:133), so that
 // the reference's loadSpz takes its first-three path.
 bool saveSpzV2(const GaussianCloud &g, const PackOptions &o, std::vector<uint8_t> *out) {
-  PackedGaussians packed;
-  if (packImpl(g, o, &packed, SPZB200_STREAM_V2) != PackStatus::Ok) return false;
   std::vector<uint8_t> stream;
-  resizeUninitialized(stream, serializedBytes(packed));
-  serializeInto(packed, stream.data());
-  const uint32_t two = 2;
-  std::memcpy(stream.data() + 4, &two, 4);
+  PackStatus st;
+  if (!encodeContainer(g, o, SPZB200_STREAM_V2, &stream, &st) || st != PackStatus::Ok) return false;
   const int threads = gzipThreads();
   if (threads > 1) return compressGzippedParallel(stream.data(), stream.size(), threads, out);
   return compressGzipped(stream.data(), stream.size(), out);
@@ -357,9 +375,12 @@ PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussian
   resizeUninitialized(packed.colors, n * 3);
   resizeUninitialized(packed.sh, n * shDim * 3);
   if (n == 0) return PackStatus::Ok;  // nothing to encode; no device needed (load_spz_test.py:753)
+  return encodeInto(g, o, viewOf(packed, streamVersion), streamVersion);
+}
 
+// The device part of packGaussians: the cloud's planes -> wherever `out` points (six vectors, or straight into a container).
+PackStatus encodeInto(const GaussianCloud &g, const PackOptions &o, SpzB200Packed out, int32_t streamVersion) {
   const SpzB200Cloud in = viewOf(g);
-  SpzB200Packed out = viewOf(packed, streamVersion);
   const std::vector<int32_t> devs = configuredDevices();
   int rc;
   if (devs.size() > 1 && streamVersion == SPZB200_STREAM_V3) {
@@ -375,33 +396,62 @@ PackStatus packImpl(const GaussianCloud &g, const PackOptions &o, PackedGaussian
   }
   return PackStatus::Ok;
 }
-}  // namespace
 
-GaussianCloud unpackGaussians(const PackedGaussians &packed, const UnpackOptions &o) {
-  const int64_t n = packed.numPoints;
-  const int shDim = shDimOf(packed.shDegree);
-  const bool usesFloat16 = packed.usesFloat16();
-  if (n < 0 || packed.shDegree < 0 || packed.shDegree > 3) {
-    // the reference indexes with these unchecked; refusing is the defined version of that
-    logLine("[SPZ ERROR] unpackGaussians: invalid numPoints / shDegree");
-    return {};
+// saveSpz's packGaussians + serializePackedGaussians (load-spz.cc:598-607) without the six vectors in between: the
+// container is laid out first -- 16 header bytes, then the planes in stream order at their offsets -- and the
+// encoder's copy-out writes every plane straight to its place in it (the north star's "each GPU
+// writes its slice of the plane-major output at a precomputed offset", here for the file image).  Returns false only
+// when the cloud is rejected by the size checks (the caller then serialises the empty struct, as the reference does).
+bool encodeContainer(const GaussianCloud &g, const PackOptions &o, int32_t streamVersion, std::vector<uint8_t> *stream, PackStatus *status) {
+  *status = PackStatus::Rejected;
+  if (!checkCloudSizes(g)) return false;
+  const size_t n = (size_t)g.numPoints, shDim = (size_t)shDimOf(g.shDegree);
+  const bool s3 = streamVersion != SPZB200_STREAM_V2;
+  const size_t sizes[6] = {n * 9, n, n * 3, n * 3, n * (s3 ? 4 : 3), n * shDim * 3};  // stream order
+  size_t offset[6], total = kHeaderBytes;
+  for (int i = 0; i < 6; i++) {
+    offset[i] = total;
+    total += sizes[i];
   }
-  if (!checkPackedSizes(packed, n, shDim, usesFloat16)) return {};
+  stream->clear();
+  resizeUninitialized(*stream, total);  // header written below, every plane byte by the encoder
+  uint8_t *base = stream->data();
+  const uint32_t words[3] = {kMagic, s3 ? 3u : 2u, (uint32_t)g.numPoints};
+  std::memcpy(base, words, 12);
+  base[12] = (uint8_t)g.shDegree;
+  base[13] = 12;  // fractionalBits, load-spz.cc:270
+  base[14] = g.antialiased ? kFlagAntialiased : 0;
+  base[15] = 0;
+  *status = PackStatus::Ok;
+  if (n == 0) return true;
+  SpzB200Packed out;
+  std::memset(&out, 0, sizeof out);
+  out.num_points = g.numPoints;
+  out.sh_degree = g.shDegree;
+  out.fractional_bits = 12;
+  out.version = streamVersion;
+  out.positions = base + offset[0]; out.alphas = base + offset[1]; out.colors = base + offset[2];
+  out.scales = base + offset[3]; out.rotations = base + offset[4]; out.sh = base + offset[5];
+  *status = encodeInto(g, o, out, streamVersion);
+  return true;
+}
 
+// The device part of unpackGaussians: packed planes wherever they lie (six vectors, or inside an inflated container) ->
+// a GaussianCloud.  The size checks are the caller's.
+GaussianCloud decodeFrom(const SpzB200Packed &in, int32_t numPoints, int32_t shDegree, bool antialiased, const UnpackOptions &o) {
+  const size_t n = (size_t)numPoints, shDim = (size_t)shDimOf(shDegree);
   GaussianCloud result;
-  result.numPoints = packed.numPoints;
-  result.shDegree = packed.shDegree;
-  result.antialiased = packed.antialiased;
+  result.numPoints = numPoints;
+  result.shDegree = shDegree;
+  result.antialiased = antialiased;
   // every float is written by the decoder (or the struct is discarded on failure)
-  resizeUninitialized(result.positions, (size_t)n * 3);
-  resizeUninitialized(result.scales, (size_t)n * 3);
-  resizeUninitialized(result.rotations, (size_t)n * 4);
-  resizeUninitialized(result.alphas, (size_t)n);
-  resizeUninitialized(result.colors, (size_t)n * 3);
-  resizeUninitialized(result.sh, (size_t)n * shDim * 3);
+  resizeUninitialized(result.positions, n * 3);
+  resizeUninitialized(result.scales, n * 3);
+  resizeUninitialized(result.rotations, n * 4);
+  resizeUninitialized(result.alphas, n);
+  resizeUninitialized(result.colors, n * 3);
+  resizeUninitialized(result.sh, n * shDim * 3);
   if (n == 0) return result;
-
-  const SpzB200Packed in = viewOf(packed, streamFlavour(usesFloat16, packed.usesQuaternionSmallestThree));
   SpzB200Cloud out = viewOf(result);
   const std::vector<int32_t> devs = configuredDevices();
   int rc;
@@ -417,6 +467,21 @@ GaussianCloud unpackGaussians(const PackedGaussians &packed, const UnpackOptions
     return {};
   }
   return result;
+}
+}  // namespace
+
+GaussianCloud unpackGaussians(const PackedGaussians &packed, const UnpackOptions &o) {
+  const int64_t n = packed.numPoints;
+  const int shDim = shDimOf(packed.shDegree);
+  const bool usesFloat16 = packed.usesFloat16();
+  if (n < 0 || packed.shDegree < 0 || packed.shDegree > 3) {
+    // the reference indexes with these unchecked; refusing is the defined version of that
+    logLine("[SPZ ERROR] unpackGaussians: invalid numPoints / shDegree");
+    return {};
+  }
+  if (!checkPackedSizes(packed, n, shDim, usesFloat16)) return {};
+  return decodeFrom(viewOf(packed, streamFlavour(usesFloat16, packed.usesQuaternionSmallestThree)), packed.numPoints, packed.shDegree,
+                    packed.antialiased, o);
 }
 
 // =================================================================================================
@@ -618,15 +683,15 @@ bool finishSpz(const PackedGaussians &packed, std::vector<uint8_t> *out) {
 
 bool saveSpz(const GaussianCloud &g, const PackOptions &o, std::vector<uint8_t> *out) {
   std::vector<uint8_t> stream;
-  {
-    PackedGaussians packed;
-    const PackStatus st = packImpl(g, o, &packed);
-    if (st == PackStatus::DeviceError) return false;  // no GPU: fail loudly, never write a file
+  PackStatus st;
+  if (!encodeContainer(g, o, SPZB200_STREAM_V3, &stream, &st)) {
     // A cloud the size checks reject yields the empty struct, which the reference goes on to
     // serialize as a 0-point file (load-spz.cc:598-607); same here.
-    if (st == PackStatus::Rejected) packed = PackedGaussians{};
-    resizeUninitialized(stream, serializedBytes(packed));  // serializeInto writes every byte
-    serializeInto(packed, stream.data());
+    const PackedGaussians empty;
+    resizeUninitialized(stream, serializedBytes(empty));
+    serializeInto(empty, stream.data());
+  } else if (st == PackStatus::DeviceError) {
+    return false;  // no GPU: fail loudly, never write a file
   }
   const int threads = gzipThreads();
   if (threads > 1) return compressGzippedParallel(stream.data(), stream.size(), threads, out);
@@ -664,11 +729,31 @@ PackedGaussians loadSpzPacked(const std::string &filename) {
 }
 
 GaussianCloud loadSpz(const std::vector<uint8_t> &data, const UnpackOptions &o) {
-  return unpackGaussians(loadSpzPacked(data), o);
+  return loadSpz(data.data(), static_cast<int>(data.size()), o);
 }
 
+// unpackGaussians(loadSpzPacked(data)) (load-spz.cc:635-641) without materialising the PackedGaussians: the planes are
+// decoded from where they lie in the inflated container.
 GaussianCloud loadSpz(const uint8_t *data, int32_t size, const UnpackOptions &o) {
-  return unpackGaussians(loadSpzPacked(data, size), o);
+  try {
+    std::vector<uint8_t> stream;
+    if (size < 0 || !decompressGzippedParallel(data, (size_t)size, gzipThreads(), &stream)) return unpackGaussians(PackedGaussians{}, o);
+    Container c;
+    if (!parseContainer(stream.data(), stream.size(), &c)) return unpackGaussians(PackedGaussians{}, o);
+    SpzB200Packed in;
+    std::memset(&in, 0, sizeof in);
+    in.num_points = c.numPoints;
+    in.sh_degree = c.shDegree;
+    in.fractional_bits = c.fractionalBits;
+    in.version = streamFlavour(c.half, c.smallestThree);
+    uint8_t *base = stream.data();
+    in.positions = base + c.offset[0]; in.alphas = base + c.offset[1]; in.colors = base + c.offset[2];
+    in.scales = base + c.offset[3]; in.rotations = base + c.offset[4]; in.sh = base + c.offset[5];
+    return decodeFrom(in, c.numPoints, c.shDegree, c.antialiased, o);
+  } catch (const std::exception &e) {  // out of memory on a hostile or huge file: a failed load, not a throw
+    logLine("[SPZ ERROR] loadSpz: %s", e.what());
+    return {};
+  }
 }
 
 GaussianCloud loadSpz(const std::string &filename, const UnpackOptions &o) {
