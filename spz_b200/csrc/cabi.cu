@@ -734,9 +734,23 @@ struct ContextPool {
     return rc;
   }
   void release(SpzB200Context *ctx) {
+    // A context whose stream reports an error (a failed launch, a lost device) must not be handed to the next caller:
+    // it is destroyed and its slot freed, so the next lease builds a fresh one (or fails with the real reason).
+    const int32_t device = ctx->device;
+    bool healthy = cudaSetDevice(device) == cudaSuccess;
+    if (healthy) {
+      const cudaError_t e = cudaStreamQuery(ctx->stage[0].stream);
+      healthy = e == cudaSuccess || e == cudaErrorNotReady;
+    }
+    if (!healthy) {
+      (void)cudaGetLastError();
+      ctx->pooled = false;
+      spzb200_destroy(ctx);
+    }
     {
       std::lock_guard<std::mutex> g(m);
-      of(ctx->device).idle.push_back(ctx);
+      if (healthy) of(device).idle.push_back(ctx);
+      else of(device).live--;
     }
     cv.notify_all();
   }
