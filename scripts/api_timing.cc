@@ -71,6 +71,14 @@ int main(int argc, char **argv) {
     const std::vector<spz::UnpackedGaussian> many = spz::unpackGaussiansAt(p, idx, c);
     const double t3 = now();
     for (int i = 0; i < loopN; i++) acc -= many[(size_t)i].position[0];
+    // the walk the accessor exists for: i = 0, 1, 2, ... (read-ahead windows; SPZ_B200_UNPACK_READAHEAD=0 turns them off)
+    const size_t walkN = std::min<size_t>(n, std::getenv("SPZ_B200_UNPACK_READAHEAD") ? 20000 : 1000000);
+    double walkAcc = 0;
+    const double t4 = now();
+    for (size_t i = 0; i < walkN; i++) walkAcc += p.unpack((int32_t)i, c).position[0];
+    const double t5 = now();
+    printf("{\"api\": \"PackedGaussians::unpack(i, c), i in order\", \"points\": %zu, \"walked\": %zu, \"walk_us_per_gaussian\": %.3f, \"walk_mgaussians_s\": %.2f, \"check\": %.4f}\n",
+           n, walkN, (t5 - t4) * 1e6 / walkN, walkN / (t5 - t4) / 1e6, walkAcc);
     printf("{\"api\": \"PackedGaussians::unpack(i, c)\", \"points\": %zu, \"loop_us_per_gaussian\": %.2f, \"batched_gaussians\": %zu, \"batched_ms\": %.2f, "
            "\"batched_mgaussians_s\": %.2f, \"loop_minus_batched\": %.6f}\n",
            n, (t1 - t0) * 1e6 / loopN, many.size(), (t3 - t2) * 1e3, many.size() / (t3 - t2) / 1e6, acc);

@@ -30,6 +30,7 @@ case "$task" in
             g++ -std=c++17 -O2 -pthread -Iinclude/spz scripts/api_timing.cc -o scripts/_build/api_timing -Lspz_b200/_lib -lspz_b200 -Wl,-rpath,'$ORIGIN/../../spz_b200/_lib' || exit 1
             { for n in 6e4 2e5 1e6 2e6 4e6 1e7; do echo "== $n gaussians SH3 (default policy)"; scripts/_build/api_timing $n 4; done
               echo "== 1e7, SPZ_B200_ZEROFILL=1 (plain resize)"; SPZ_B200_ZEROFILL=1 scripts/_build/api_timing 1e7 4
+              echo "== 1e6, SPZ_B200_UNPACK_READAHEAD=0 (every unpack(i, c) is its own launch)"; SPZ_B200_UNPACK_READAHEAD=0 scripts/_build/api_timing 1e6 2
               for n in 1e6 1e7; do echo "== $n, SPZB200_NT_COPY=0 (plain memcpy into / out of the bounce buffers)"; SPZB200_NT_COPY=0 scripts/_build/api_timing $n 4; done; } > gpurun_out/cxx_api_timing.txt 2>&1
             echo "rc=$?"; cat gpurun_out/cxx_api_timing.txt ;;
   launches) # launch list of one short bench run (after the same command ran clean without ncu)

@@ -20,6 +20,7 @@
 #include <mutex>
 #include <ostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #if defined(__linux__)
@@ -221,11 +222,29 @@ void serializeInto(const PackedGaussians &p, uint8_t *dst) {
   }
 }
 
-// SPZ_B200_GZIP_THREADS > 1 switches saveSpz / loadSpz* to the block-parallel zlib framing of
-// spz_gzip.cc; unset (or 1) keeps the reference's single-thread byte-identical output.
-int gzipThreads() {
+// gzip policy of saveSpz / loadSpz* (spz_gzip.cc has the block-parallel framing):
+//   SPZ_B200_GZIP_THREADS=1   the reference's single-thread deflate, compressed bytes identical to the reference's, always
+//   SPZ_B200_GZIP_THREADS=N   N > 1: block-parallel for every container of two blocks (2 MiB) or more
+//   unset                     containers below 64 MiB (~1M SH3 gaussians) as the reference writes them, byte for byte;
+//                             larger ones block-parallel on up to 16 threads -- one thread deflates ~10 MB/s, i.e. a
+//                             minute for a 10M-gaussian scene the GPU encodes in a millisecond.  The file is one
+//                             standard gzip member either way and inflates to the identical container.
+// Loading inflates the blocks of a member that carries the block table concurrently (N threads, default up to 16);
+// members without it -- anything the reference wrote -- take the serial inflater.
+constexpr size_t kAutoParallelGzipBytes = (size_t)64 << 20;
+int hostThreads() { return (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())); }
+int gzipThreadsEnv() {
   const char *env = std::getenv("SPZ_B200_GZIP_THREADS");
-  return env ? std::atoi(env) : 1;
+  return env && *env ? std::max(1, std::atoi(env)) : 0;
+}
+int deflateThreads(size_t containerBytes) {
+  const int env = gzipThreadsEnv();
+  if (env) return env;
+  return containerBytes >= kAutoParallelGzipBytes ? hostThreads() : 1;
+}
+int inflateThreads() {
+  const int env = gzipThreadsEnv();
+  return env ? env : hostThreads();
 }
 
 int64_t maxPointsToRead() {
@@ -330,30 +349,45 @@ bool encodeContainer(const GaussianCloud &g, const PackOptions &o, int32_t strea
 GaussianCloud decodeFrom(const SpzB200Packed &in, int32_t numPoints, int32_t shDegree, bool antialiased, const UnpackOptions &o);
 }  // namespace
 
+// (The reference cannot run out of memory gracefully either, but it promises "nothing throws": an allocation that
+// fails here is a logged, failed call -- an empty struct -- like every other failure.)
 PackedGaussians packGaussians(const GaussianCloud &g, const PackOptions &o) {
-  PackedGaussians packed;
-  if (packImpl(g, o, &packed) != PackStatus::Ok) return {};
-  return packed;
+  try {
+    PackedGaussians packed;
+    if (packImpl(g, o, &packed) != PackStatus::Ok) return {};
+    return packed;
+  } catch (const std::exception &e) {
+    logLine("[SPZ ERROR] packGaussians: %s", e.what());
+    return {};
+  }
 }
 
 // Extension, PARITY UNPINNED: the version-2 form of the stream -- rotations as the first three
 // components of the normalised, w >= 0 quaternion in 3 bytes, what unpackQuaternionFirstThree (load-spz.cc:333-345)
 // reads.  The reference tree holds no encoder for it; every other plane is what packGaussians writes.
 PackedGaussians packGaussiansV2(const GaussianCloud &g, const PackOptions &o) {
-  PackedGaussians packed;
-  if (packImpl(g, o, &packed, SPZB200_STREAM_V2) != PackStatus::Ok) return {};
-  return packed;
+  try {
+    PackedGaussians packed;
+    if (packImpl(g, o, &packed, SPZB200_STREAM_V2) != PackStatus::Ok) return {};
+    return packed;
+  } catch (const std::exception &e) {
+    logLine("[SPZ ERROR] packGaussiansV2: %s", e.what());
+    return {};
+  }
 }
 
 // ... and the container for it: header version 2 (the reference's writer always says 3, load-spz.cc:133), so that
 // the reference's loadSpz takes its first-three path.
 bool saveSpzV2(const GaussianCloud &g, const PackOptions &o, std::vector<uint8_t> *out) {
-  std::vector<uint8_t> stream;
-  PackStatus st;
-  if (!encodeContainer(g, o, SPZB200_STREAM_V2, &stream, &st) || st != PackStatus::Ok) return false;
-  const int threads = gzipThreads();
-  if (threads > 1) return compressGzippedParallel(stream.data(), stream.size(), threads, out);
-  return compressGzipped(stream.data(), stream.size(), out);
+  try {
+    std::vector<uint8_t> stream;
+    PackStatus st;
+    if (!encodeContainer(g, o, SPZB200_STREAM_V2, &stream, &st) || st != PackStatus::Ok) return false;
+    return compressGzippedParallel(stream.data(), stream.size(), deflateThreads(stream.size()), out);
+  } catch (const std::exception &e) {
+    logLine("[SPZ ERROR] saveSpzV2: %s", e.what());
+    return false;
+  }
 }
 
 namespace {
@@ -480,8 +514,13 @@ GaussianCloud unpackGaussians(const PackedGaussians &packed, const UnpackOptions
     return {};
   }
   if (!checkPackedSizes(packed, n, shDim, usesFloat16)) return {};
-  return decodeFrom(viewOf(packed, streamFlavour(usesFloat16, packed.usesQuaternionSmallestThree)), packed.numPoints, packed.shDegree,
-                    packed.antialiased, o);
+  try {
+    return decodeFrom(viewOf(packed, streamFlavour(usesFloat16, packed.usesQuaternionSmallestThree)), packed.numPoints, packed.shDegree,
+                      packed.antialiased, o);
+  } catch (const std::exception &e) {
+    logLine("[SPZ ERROR] unpackGaussians: %s", e.what());
+    return {};
+  }
 }
 
 // =================================================================================================
@@ -542,12 +581,27 @@ UnpackedGaussian PackedGaussian::unpack(bool usesFloat16, bool usesQuaternionSma
   return u;
 }
 
+namespace {
+std::vector<UnpackedGaussian> unpackAtImpl(const PackedGaussians &packed, const std::vector<int32_t> &indices, const CoordinateConverter &c);
+}
+
 // Extension: PackedGaussians::unpack(i, c) for a list of indices in one launch.
 // Returns an empty vector (after a logged line) when an index is out of range or no device is usable.
 std::vector<UnpackedGaussian> unpackGaussiansAt(const PackedGaussians &packed, const std::vector<int32_t> &indices,
                                                 const CoordinateConverter &c) {
   std::vector<UnpackedGaussian> out;
   if (indices.empty()) return out;
+  try {
+    return unpackAtImpl(packed, indices, c);
+  } catch (const std::exception &e) {
+    logLine("[SPZ ERROR] unpackGaussiansAt: %s", e.what());
+    return {};
+  }
+}
+
+namespace {
+std::vector<UnpackedGaussian> unpackAtImpl(const PackedGaussians &packed, const std::vector<int32_t> &indices, const CoordinateConverter &c) {
+  std::vector<UnpackedGaussian> out;
   const bool usesFloat16 = packed.usesFloat16();
   if (packed.numPoints < 0 || packed.shDegree < 0 || packed.shDegree > 3 ||
       !checkPackedSizes(packed, packed.numPoints, shDimOf(packed.shDegree), usesFloat16))
@@ -563,9 +617,89 @@ std::vector<UnpackedGaussian> unpackGaussiansAt(const PackedGaussians &packed, c
   }
   return out;
 }
+}  // namespace
+
+// A consumer that walks a cloud with `for (i...) packed.unpack(i, c)` -- what this accessor is for -- would pay one
+// launch + one synchronize (~16 us) per gaussian.  So the accessor reads ahead: once two calls in a row ask for
+// consecutive indices, a miss decodes a window of the following records in ONE launch (16, 64, ... up to 4096) and the
+// next calls are served from it.  The window is a memo, not a cache of the cloud: it keeps the 65 record bytes it was
+// decoded from, and a call is answered from it only if at(i) still yields exactly those bytes under the same stream
+// flavour, fractionalBits and converter -- the decoder is a pure function of those, so the answer cannot go stale
+// whatever the caller does to the planes between calls.  Random access stays on the one-record path.
+// SPZ_B200_UNPACK_READAHEAD=<records> caps the window (0 or 1: off).
+namespace {
+struct UnpackWindow {
+  std::vector<PackedGaussian> records;
+  std::vector<UnpackedGaussian> values;
+  int64_t first = 0, count = 0;
+  int32_t flavour = 0, fractionalBits = 0;
+  CoordinateConverter conv;
+  int64_t lastIndex = -2;
+};
+
+int64_t readAheadLimit() {
+  static const int64_t limit = [] {
+    const char *env = std::getenv("SPZ_B200_UNPACK_READAHEAD");
+    const long long v = env ? std::atoll(env) : 4096;
+    return (int64_t)std::min<long long>(std::max<long long>(v, 0), 1 << 16);
+  }();
+  return limit;
+}
+}  // namespace
 
 UnpackedGaussian PackedGaussians::unpack(int32_t i, const CoordinateConverter &c) const {
-  return at(i).unpack(usesFloat16(), usesQuaternionSmallestThree, fractionalBits, c);
+  const bool half = usesFloat16();
+  const PackedGaussian rec = at(i);
+  const int64_t limit = readAheadLimit();
+  if (limit <= 1) return rec.unpack(half, usesQuaternionSmallestThree, fractionalBits, c);
+  thread_local UnpackWindow w;
+  const int32_t flavour = streamFlavour(half, usesQuaternionSmallestThree);
+  const bool sequential = (int64_t)i == w.lastIndex + 1;
+  w.lastIndex = i;
+  const bool sameDecoder = w.count > 0 && flavour == w.flavour && fractionalBits == w.fractionalBits &&
+                           std::memcmp(&c, &w.conv, sizeof c) == 0;
+  if (sameDecoder && i >= w.first && i < w.first + w.count &&
+      std::memcmp(&rec, &w.records[(size_t)(i - w.first)], sizeof rec) == 0)
+    return w.values[(size_t)(i - w.first)];
+  // Reading ahead gathers records i+1.. with at(): only inside a struct whose planes really hold numPoints records
+  // (at(i) of an inconsistent struct is the caller's business, as in the reference; at(i + k) would be this function's).
+  const int64_t n = numPoints;
+  const size_t shDim = (size_t)shDimOf(shDegree);
+  const bool consistent = n > 0 && i >= 0 && i < n && shDegree >= 0 && shDegree <= 3 &&
+                          positions.size() == (size_t)n * (half ? 6 : 9) && scales.size() == (size_t)n * 3 &&
+                          rotations.size() == (size_t)n * (usesQuaternionSmallestThree ? 4 : 3) && alphas.size() == (size_t)n &&
+                          colors.size() == (size_t)n * 3 && sh.size() == (size_t)n * shDim * 3;
+  int64_t want = 1;
+  if (sequential && consistent) want = std::min<int64_t>({limit, std::max<int64_t>(16, 4 * w.count), n - i});
+  if (want <= 1) {
+    w.count = 0;  // the run is broken (or has not started): one record, nothing kept
+    return rec.unpack(half, usesQuaternionSmallestThree, fractionalBits, c);
+  }
+  try {
+    w.records.resize((size_t)want);
+    w.values.resize((size_t)want);
+  } catch (const std::exception &) {
+    w.count = 0;
+    return rec.unpack(half, usesQuaternionSmallestThree, fractionalBits, c);
+  }
+  w.records[0] = rec;
+  for (int64_t k = 1; k < want; k++) w.records[(size_t)k] = at((int32_t)(i + k));
+  w.count = 0;
+  ContextLease lease(configuredDevices()[0]);
+  if (!lease.get() ||
+      spzb200_unpack_records_host(lease.get(), reinterpret_cast<const uint8_t *>(w.records.data()), want, flavour, fractionalBits,
+                                  c.flipP.data(), reinterpret_cast<float *>(w.values.data())) != SPZB200_OK) {
+    if (lease.get()) logLine("[SPZ ERROR] spz_b200: %s", spzb200_last_error());
+    UnpackedGaussian u;
+    poison(&u, 1);
+    return u;
+  }
+  w.first = i;
+  w.count = want;
+  w.flavour = flavour;
+  w.fractionalBits = fractionalBits;
+  w.conv = c;
+  return w.values[0];
 }
 
 // =================================================================================================
@@ -675,27 +809,28 @@ bool finishSpz(const PackedGaussians &packed, std::vector<uint8_t> *out) {
   std::vector<uint8_t> stream;
   resizeUninitialized(stream, serializedBytes(packed));  // serializeInto writes every byte
   serializeInto(packed, stream.data());
-  const int threads = gzipThreads();
-  if (threads > 1) return compressGzippedParallel(stream.data(), stream.size(), threads, out);
-  return compressGzipped(stream.data(), stream.size(), out);
+  return compressGzippedParallel(stream.data(), stream.size(), deflateThreads(stream.size()), out);
 }
 }  // namespace detail
 
 bool saveSpz(const GaussianCloud &g, const PackOptions &o, std::vector<uint8_t> *out) {
-  std::vector<uint8_t> stream;
-  PackStatus st;
-  if (!encodeContainer(g, o, SPZB200_STREAM_V3, &stream, &st)) {
-    // A cloud the size checks reject yields the empty struct, which the reference goes on to
-    // serialize as a 0-point file (load-spz.cc:598-607); same here.
-    const PackedGaussians empty;
-    resizeUninitialized(stream, serializedBytes(empty));
-    serializeInto(empty, stream.data());
-  } else if (st == PackStatus::DeviceError) {
-    return false;  // no GPU: fail loudly, never write a file
+  try {
+    std::vector<uint8_t> stream;
+    PackStatus st;
+    if (!encodeContainer(g, o, SPZB200_STREAM_V3, &stream, &st)) {
+      // A cloud the size checks reject yields the empty struct, which the reference goes on to
+      // serialize as a 0-point file (load-spz.cc:598-607); same here.
+      const PackedGaussians empty;
+      resizeUninitialized(stream, serializedBytes(empty));
+      serializeInto(empty, stream.data());
+    } else if (st == PackStatus::DeviceError) {
+      return false;  // no GPU: fail loudly, never write a file
+    }
+    return compressGzippedParallel(stream.data(), stream.size(), deflateThreads(stream.size()), out);
+  } catch (const std::exception &e) {  // out of memory: a failed save, not a throw
+    logLine("[SPZ ERROR] saveSpz: %s", e.what());
+    return false;
   }
-  const int threads = gzipThreads();
-  if (threads > 1) return compressGzippedParallel(stream.data(), stream.size(), threads, out);
-  return compressGzipped(stream.data(), stream.size(), out);
 }
 
 bool saveSpz(const GaussianCloud &g, const PackOptions &o, const std::string &filename) {
@@ -710,7 +845,7 @@ bool saveSpz(const GaussianCloud &g, const PackOptions &o, const std::string &fi
 PackedGaussians loadSpzPacked(const uint8_t *data, int32_t size) {
   try {
     std::vector<uint8_t> stream;
-    if (size < 0 || !decompressGzippedParallel(data, (size_t)size, gzipThreads(), &stream)) return {};
+    if (size < 0 || !decompressGzippedParallel(data, (size_t)size, inflateThreads(), &stream)) return {};
     return deserialize(stream.data(), stream.size());
   } catch (const std::exception &e) {  // out of memory on a hostile or huge file: a failed load, not a throw
     logLine("[SPZ ERROR] loadSpzPacked: %s", e.what());
@@ -737,7 +872,7 @@ GaussianCloud loadSpz(const std::vector<uint8_t> &data, const UnpackOptions &o) 
 GaussianCloud loadSpz(const uint8_t *data, int32_t size, const UnpackOptions &o) {
   try {
     std::vector<uint8_t> stream;
-    if (size < 0 || !decompressGzippedParallel(data, (size_t)size, gzipThreads(), &stream)) return unpackGaussians(PackedGaussians{}, o);
+    if (size < 0 || !decompressGzippedParallel(data, (size_t)size, inflateThreads(), &stream)) return unpackGaussians(PackedGaussians{}, o);
     Container c;
     if (!parseContainer(stream.data(), stream.size(), &c)) return unpackGaussians(PackedGaussians{}, o);
     SpzB200Packed in;

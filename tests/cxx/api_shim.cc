@@ -327,6 +327,36 @@ int32_t SHIM(packed_unpack_many)(int32_t n, int32_t deg, int32_t fb, int32_t ver
   return count;
 }
 
+// A consumer's walk over a cloud: packed.unpack(idx[k], c) for k = 0..count-1 on ONE PackedGaussians that the caller
+// keeps editing while it walks -- before step k (k % every == every - 1) the bytes of the three gaussians after idx[k]
+// are XORed with 0x5a in every plane, and at k == count / 2 fractionalBits and the converter's sign of x change.  Any
+// read-ahead inside unpack() has to notice all of that; the reference has none, so the two must agree bit for bit.
+int32_t SHIM(packed_unpack_walk)(int32_t n, int32_t deg, int32_t fb, int32_t version, const uint8_t *const planes[6],
+                                 const int32_t *idx, int32_t count, const float *conv21, int32_t every, float *out) {
+  spz::PackedGaussians p = makePacked(n, deg, fb, version, 0, planes);
+  spz::CoordinateConverter c;
+  std::memcpy(c.flipP.data(), conv21, 12);
+  std::memcpy(c.flipQ.data(), conv21 + 3, 12);
+  std::memcpy(c.flipSh.data(), conv21 + 6, 60);
+  std::vector<uint8_t> *all[6] = {&p.positions, &p.scales, &p.rotations, &p.alphas, &p.colors, &p.sh};
+  for (int32_t k = 0; k < count; k++) {
+    if (every > 0 && k % every == every - 1) {
+      for (std::vector<uint8_t> *v : all) {
+        const size_t per = n ? v->size() / (size_t)n : 0;
+        for (int32_t g = idx[k] + 1; g <= idx[k] + 3 && g < n; g++)
+          for (size_t b = 0; b < per; b++) (*v)[(size_t)g * per + b] ^= 0x5a;
+      }
+    }
+    if (k == count / 2) {
+      p.fractionalBits = fb + 3;
+      c.flipP[0] = -c.flipP[0];
+    }
+    const spz::UnpackedGaussian u = p.unpack(idx[k], c);
+    std::memcpy(out + (size_t)k * 59, &u, sizeof u);
+  }
+  return count;
+}
+
 // `threads` short-lived host threads, each packing the cloud ONCE and exiting (a request-per-thread
 // server).  run_concurrently = 0 starts them one after the other, 2 = one thread does all the packs.  Returns the wall time in
 // milliseconds, or -1 if any result differs from the first thread's.

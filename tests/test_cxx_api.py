@@ -209,6 +209,16 @@ class Shim:
                                             C.c_int32(int(batch)), out.ctypes.data_as(_f32p))
         return out[:got]
 
+    def unpack_walk(self, p: Packed, idx, conv21, every: int) -> np.ndarray:
+        _, ip = self._bplanes(p.planes())
+        idx = np.ascontiguousarray(idx, np.int32)
+        conv = np.ascontiguousarray(conv21, np.float32)
+        out = np.zeros((idx.size, 59), np.float32)
+        self.fn("packed_unpack_walk")(C.c_int32(p.n), C.c_int32(p.sh_degree), C.c_int32(p.fractional_bits), C.c_int32(p.version), ip,
+                                      idx.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(idx.size), conv.ctypes.data_as(_f32p),
+                                      C.c_int32(every), out.ctypes.data_as(_f32p))
+        return out
+
     def short_lived_threads(self, c: Cloud, frm: int, threads: int, concurrently) -> float:
         _, ip = self._fplanes(c.planes())
         f = self.fn("short_lived_threads")
@@ -626,6 +636,17 @@ def test_save_load_use_parallel_gzip_when_asked(mine, theirs, tmp_path):
     finally:
         del os.environ["SPZ_B200_GZIP_THREADS"]
     assert meta["n"] == 100_000 and all(np.array_equal(a, b) for a, b in zip(planes, p.planes()))
+    # the default policy (variable unset): a member that carries the block table is inflated block-parallel, one the
+    # reference wrote serially; SPZ_B200_GZIP_THREADS=1 pins the serial inflater for both.  Same container every way.
+    for blob in (z, theirs.gzip(container(p))):
+        for env in (None, "1"):
+            if env:
+                os.environ["SPZ_B200_GZIP_THREADS"] = env
+            try:
+                meta, planes = mine.load_packed(blob)
+            finally:
+                os.environ.pop("SPZ_B200_GZIP_THREADS", None)
+            assert meta["n"] == 100_000 and all(np.array_equal(a, b) for a, b in zip(planes, p.planes()))
 
 
 def test_relinked_consumer_host_glue(relinked, theirs, tmp_path):
@@ -759,6 +780,26 @@ def test_save_spz_with_parallel_gzip_is_readable_by_the_reference(mine, theirs):
 
 
 @pytest.mark.gpu
+def test_save_spz_default_gzip_policy(mine, theirs):
+    """With SPZ_B200_GZIP_THREADS unset, a container below 64 MiB is deflated as the reference does it (same file bytes);
+    from 64 MiB up saveSpz takes the block-parallel framing on its own -- a different, standard gzip member holding the
+    identical container, which the unmodified reference loads to the same cloud.  SPZ_B200_GZIP_THREADS=1 pins the
+    reference's bytes at every size."""
+    rng = np.random.default_rng(311)
+    small = random_cloud(rng, 20_000, 3, False)
+    assert mine.save_spz(small, 6) == theirs.save_spz(small, 6)
+    c = random_cloud(rng, 1_100_000, 3, False)  # 16 + 65 * 1.1M = 71.5 MB of container
+    auto = mine.save_spz(c, 6)
+    assert auto[3] & 4, "FEXTRA block table expected above the threshold"
+    stream = gzip.decompress(auto)
+    assert len(stream) == 16 + 65 * c.n
+    r, p, m = theirs.pack(c, 6)
+    assert stream == container(p)
+    assert_cloud_bits_equal(mine.load_spz(auto, 8), theirs.unpack(p, 8)[1], "default policy: parallel member, parallel inflate")
+    assert theirs.load_spz(auto, 8).n == c.n
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("deg", [0, 1, 2, 3])
 def test_fused_ply_to_spz_matches_load_then_save(mine, theirs, tmp_path, deg):
     """plyToSpz (records -> GPU -> packed planes, ply_kernels.cu) against the reference's two-step
@@ -881,6 +922,29 @@ def test_unpack_many_matches_a_loop_over_the_reference(mine, theirs, relinked):
     got = mine.unpack_many(big, idx, convs[1], True)
     uniq = theirs.unpack_many(big, np.arange(5000, dtype=np.int32), convs[1], False)
     assert np.array_equal(bits(got), bits(uniq[idx]))
+
+
+@pytest.mark.gpu
+def test_unpack_walk_reads_ahead_without_going_stale(mine, theirs, relinked):
+    """A loop over packed.unpack(i, c) (load-spz.cc:461-463) is served from a read-ahead window after the first two
+    consecutive indices.  The window is a memo keyed on the record's own bytes, the stream flavour, fractionalBits and
+    the converter, so a caller that edits the planes, the header fields or the converter in the middle of the walk --
+    here: three gaussians AHEAD of the cursor every 5th step, fractionalBits and flipP.x at the half-way point -- gets
+    exactly what the reference returns.  Walks: in order over the whole cloud (windows of 16, 64, ... 4096 and a ragged
+    last one), in order with jumps back and forth, and a shuffled one (no read-ahead at all)."""
+    rng = np.random.default_rng(430)
+    odd = (rng.normal(size=21) * 2).astype(np.float32)
+    for ver, deg, n in ((3, 3, 6000), (2, 1, 300), (1, 0, 77), (4, 2, 1500)):
+        s = random_stream(rng, n, deg, ver, 12)
+        if ver >= 3:
+            s.rotations.view("<u4")[:] &= np.uint32(0xEFFBFEFF)
+        walks = [np.arange(n), np.concatenate([np.arange(40), np.arange(10, 200 if n > 200 else n), np.arange(n - 50, n), np.arange(0, n, 1)]),
+                 rng.permutation(n)[:200]]
+        for w, walk in enumerate(walks):
+            for every in (0, 5):
+                want = theirs.unpack_walk(s, walk, odd, every)
+                assert np.array_equal(bits(mine.unpack_walk(s, walk, odd, every)), bits(want)), (ver, deg, w, every)
+        assert np.array_equal(bits(relinked.unpack_walk(s, walks[0], odd, 5)), bits(theirs.unpack_walk(s, walks[0], odd, 5)))
 
 
 @pytest.mark.gpu
