@@ -104,7 +104,7 @@ typedef struct {
   int64_t d2h_bytes;
   int32_t kernel_launches;
   int32_t chunks;
-  double host_copy_ms;     /* host-thread time spent bouncing pageable planes through pinned buffers */
+  double host_copy_ms;     /* calling-thread time inside the copy pool (helping with / waiting for the bounce copies of pageable planes) */
   int32_t staged;          /* bit 0: input planes were pageable and bounced, bit 1: output planes */
   int32_t reserved;
 } SpzB200Timings;
@@ -293,8 +293,9 @@ void spzb200_set_pack_mode(SpzB200Context *ctx, int32_t mode);
  * the defaults (2M points for pinned planes, 256K for pageable ones). */
 void spzb200_set_chunk_points(SpzB200Context *ctx, int64_t points);
 /* Pageable host planes (plain malloc / std::vector memory) are bounced through pinned buffers by
- * `copy_threads` host threads (0 = auto: up to 8) so their transfers overlap: ~3x the speed of
- * handing them to cudaMemcpyAsync as they are (driver-staged, synchronous).  bounce: 0 = never,
+ * `copy_threads` host threads (0 = auto: three quarters of the hardware threads, at most 16; SPZB200_COPY_THREADS)
+ * in 2 MiB pieces whose DMAs overlap the copies: 4-5x the speed of handing them to cudaMemcpyAsync as they are
+ * (driver-staged, synchronous).  bounce: 0 = never,
  * 1 = calls of >= 32 MiB (SPZB200_BOUNCE_MIN_MB) or once the buffers exist (default: the pinned
  * allocation is a one-time cost small one-shot calls would not earn back), 2 = always. */
 void spzb200_set_host_staging(SpzB200Context *ctx, int32_t bounce, int32_t copy_threads);

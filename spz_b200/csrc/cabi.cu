@@ -17,8 +17,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <condition_variable>
+#include <atomic>
 #include <cstring>
+#include <deque>
 #include <exception>
+#include <functional>
+#include <memory>
 #include <limits>
 #include <mutex>
 #include <string>
@@ -160,6 +164,7 @@ struct Stage {
   uint8_t *hOut = nullptr;
   size_t hInCap = 0, hOutCap = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> pieceEv;  // bounced output: one per D2H piece of the range in flight
 };
 
 // The bounce copies move each byte once and never read it back on the CPU, so large ones use non-temporal stores
@@ -201,10 +206,13 @@ static void bounceCopy(void *dst, const void *src, size_t bytes) {
 static void bounceCopy(void *dst, const void *src, size_t bytes) { std::memcpy(dst, src, bytes); }
 #endif
 
-// A few host threads that copy between the caller's pageable planes and the pinned bounce buffers
-// (one memcpy thread moves ~10 GB/s; the PCIe link wants ~50).  Created on first pageable call.
+// A few host threads that move pieces between the caller's pageable planes and the pinned bounce buffers
+// (one thread copies ~11 GB/s, eight ~65 -- scripts/host_copy_probe.cu; the PCIe link wants ~55).  A task is a
+// closure: copy a piece and queue its DMA, or wait for a piece's DMA and copy it out (runBouncedStages below).
+// Created on the first pageable call of a context.
 class CopyPool {
  public:
+  using Task = std::function<void()>;
   explicit CopyPool(int threads) {
     for (int i = 0; i < threads; i++) workers_.emplace_back([this] { loop(); });
   }
@@ -216,58 +224,62 @@ class CopyPool {
     cv_.notify_all();
     for (auto &t : workers_) t.join();
   }
-  struct Job { void *dst; const void *src; size_t bytes; };
-  // Splits the jobs into <= 4 MiB pieces, runs them on the pool (the caller helps) and returns
-  // when all are done.
-  void run(const std::vector<Job> &jobs) {
-    constexpr size_t kPiece = (size_t)4 << 20;
+  void submit(std::vector<Task> &&tasks) {
     {
       std::lock_guard<std::mutex> g(m_);
-      for (const Job &j : jobs)
-        for (size_t off = 0; off < j.bytes; off += kPiece)
-          queue_.push_back({(uint8_t *)j.dst + off, (const uint8_t *)j.src + off, std::min(kPiece, j.bytes - off)});
-      pending_ += queue_.size();
+      for (Task &t : tasks) queue_.push_back(std::move(t));
     }
     cv_.notify_all();
-    Job j;
-    while (take(&j, false)) {
-      bounceCopy(j.dst, j.src, j.bytes);
-      done();
+  }
+  void resubmit(Task &&t) {  // a task that found its input not ready yet goes to the back of the queue
+    {
+      std::lock_guard<std::mutex> g(m_);
+      queue_.push_back(std::move(t));
     }
+    cv_.notify_one();
+  }
+  bool othersQueued() {
+    std::lock_guard<std::mutex> g(m_);
+    return !queue_.empty();
+  }
+  // The calling thread works through the queue too until done() holds; tasks announce progress with progressed().
+  template <class Pred>
+  void helpUntil(Pred done) {
     std::unique_lock<std::mutex> g(m_);
-    idle_.wait(g, [this] { return pending_ == 0; });
+    while (!done()) {
+      if (!queue_.empty()) {
+        Task t = std::move(queue_.front());
+        queue_.pop_front();
+        g.unlock();
+        t();
+        g.lock();
+      } else {
+        progress_.wait(g);
+      }
+    }
+  }
+  void progressed() {
+    std::lock_guard<std::mutex> g(m_);
+    progress_.notify_all();
   }
 
  private:
-  bool take(Job *j, bool wait) {
-    std::unique_lock<std::mutex> g(m_);
-    if (wait) cv_.wait(g, [this] { return stop_ || !queue_.empty(); });
-    if (queue_.empty()) return false;
-    *j = queue_.back();
-    queue_.pop_back();
-    return true;
-  }
-  void done() {
-    std::lock_guard<std::mutex> g(m_);
-    if (--pending_ == 0) idle_.notify_all();
-  }
   void loop() {
-    Job j;
+    std::unique_lock<std::mutex> g(m_);
     while (true) {
-      if (!take(&j, true)) {
-        std::lock_guard<std::mutex> g(m_);
-        if (stop_) return;
-        continue;
-      }
-      bounceCopy(j.dst, j.src, j.bytes);
-      done();
+      cv_.wait(g, [this] { return stop_ || !queue_.empty(); });
+      if (queue_.empty()) return;  // stop_
+      Task t = std::move(queue_.front());
+      queue_.pop_front();
+      g.unlock();
+      t();
+      g.lock();
     }
   }
   std::vector<std::thread> workers_;
-  std::vector<Job> queue_;
+  std::deque<Task> queue_;
   std::mutex m_;
-  std::condition_variable cv_, idle_;
-  size_t pending_ = 0;
+  std::condition_variable cv_, progress_;
   bool stop_ = false;
 };
 
@@ -296,7 +308,7 @@ struct SpzB200Context {
   bool adaptiveChunks = true;             // SPZB200_CHUNK_POINTS / spzb200_set_chunk_points pin the range size instead
   long long chunkPoints = 1 << 21;        // pinned / registered host planes: copied straight from the caller
   long long pageableChunkPoints = 1 << 18;  // pageable planes: bounced through pinned buffers of this many points
-  int copyThreads = 0;                      // 0 = auto (min(8, hardware threads))
+  int copyThreads = 0;                      // 0 = auto (3/4 of the hardware threads, at most 16)
   CopyPool *pool = nullptr;
   long long kernelLaunches = 0;
   float hThr[256];
@@ -482,103 +494,41 @@ size_t carveSet(uint8_t *base, const PlaneSet &set, long long points, uint8_t *o
 // The n gaussians are cut into contiguous point ranges (multiples of `granule`, the kernel tile).
 // Range c uses stage c % kStages: its own stream, device staging buffers and events, so the copy-in
 // of one range overlaps the kernel and the copy-out of its predecessors.  Pinned (or registered)
-// caller memory is copied directly.  Pageable caller memory -- what std::vector hands the C++ API --
-// would make every cudaMemcpyAsync a synchronous, driver-staged ~10 GB/s copy; instead the ranges
-// are bounced through pinned buffers owned by the stage, filled and drained by a small pool of host
-// threads while the GPU works on the neighbouring ranges.
+// caller memory is copied directly (runPinnedStages).  Pageable caller memory -- what std::vector hands
+// the C++ API -- would make every cudaMemcpyAsync a synchronous, driver-staged ~11 GB/s copy; instead the
+// ranges are bounced through pinned buffers owned by the stage (runBouncedStages).
 // launch(dIn, dOut, points, stream, &launches) queues the kernel(s) for one range.
+struct PipelinePlan {
+  long long n = 0, chunk = 0, numChunks = 0;
+  bool bounceIn = false, bounceOut = false;
+};
+
 template <class Launch>
-int runPipelineStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, long long n, long long granule,
-                      Launch &&launch, SpzB200Timings *timings) {
-  const double w0 = nowMs();
-  CU(cudaSetDevice(ctx->device));
-  // Bouncing costs a one-time pinned allocation per context (~1 GB/s on a VM), so small one-shot
-  // calls are cheaper through the driver's own staging; once the buffers exist they are always used.
-  const size_t callBytes = (size_t)n * (in.bytesPerGaussian() + out.bytesPerGaussian());
-  const bool wantBounce = ctx->bounceMode == 2 ||
-                          (ctx->bounceMode == 1 && (callBytes >= ctx->bounceMinBytes || ctx->stage[0].hIn || ctx->stage[0].hOut));
-  const bool bounceIn = n > 0 && wantBounce && isPageable(in.ptr[0]);
-  const bool bounceOut = n > 0 && wantBounce && isPageable(out.ptr[0]);
-  // (cutting a bounced cloud smaller than a few ranges into ~6 pieces for overlap was tried: the per-range costs --
-  // waking the copy pool, 12 copies, 4 events -- outweigh the overlap: 200K points 7.9 vs 5.1 ms, 1M 12.6 vs 10.2)
-  long long want = (bounceIn || bounceOut) ? ctx->pageableChunkPoints : ctx->chunkPoints;
-  // Pinned planes: 2M-point ranges keep the copy engines in long transfers, but a cloud of only a few such ranges
-  // spends a visible part of the call filling and draining the three-stage pipeline (10M points = 5 ranges: 0.84 of
-  // the link; in ~12 ranges: profiles/r2_tuning_notes.txt).  So mid-sized clouds are cut into about a dozen ranges,
-  // never below 256K points.
-  if (!(bounceIn || bounceOut) && ctx->adaptiveChunks) want = std::min(want, std::max<long long>(1 << 18, (n + 11) / 12));
-  long long chunk = std::max<long long>(granule, (want + granule - 1) / granule * granule);
-  if (chunk > n) chunk = std::max<long long>(n, 1);
-  const long long numChunks = n == 0 ? 0 : (n + chunk - 1) / chunk;
-  const int stages = (int)std::min<long long>(kStages, numChunks);
-
-  SpzB200Timings tm;
-  std::memset(&tm, 0, sizeof tm);
-  tm.staged = (bounceIn ? 1 : 0) | (bounceOut ? 2 : 0);
-  if (numChunks > 0) {
-    uint8_t *unused[6];
-    const size_t inBytes = carveSet(nullptr, in, chunk, unused);
-    const size_t outBytes = carveSet(nullptr, out, chunk, unused);
-    for (int s = 0; s < stages; s++) {
-      Stage &st = ctx->stage[s];
-      int rc = ensureStage(st, inBytes, outBytes);
-      if (rc == SPZB200_OK && bounceIn) rc = ensureBounce(st.hIn, st.hInCap, inBytes);
-      if (rc == SPZB200_OK && bounceOut) rc = ensureBounce(st.hOut, st.hOutCap, outBytes);
-      if (rc != SPZB200_OK) return rc;
-    }
-    if ((bounceIn || bounceOut) && !ctx->pool) {
-      int t = ctx->copyThreads > 0 ? ctx->copyThreads : (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
-      ctx->pool = new CopyPool(std::max(0, t - 1));  // the calling thread copies too
-    }
-  }
-
-  // Completes the range that last used `st`: waits for its copy-out, books its timings and, when
-  // the output is bounced, drains the pinned buffer into the caller's planes.
-  auto finish = [&](Stage &st, long long c) -> int {
-    const long long a = c * chunk, pts = std::min(n, a + chunk) - a;
+int runPinnedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, const PipelinePlan &pp, Launch &&launch, SpzB200Timings &tm) {
+  const long long n = pp.n, chunk = pp.chunk, numChunks = pp.numChunks;
+  // Completes the range that last used `st`: waits for its copy-out and books its timings.
+  auto finish = [&](Stage &st) -> int {
     CU(cudaEventSynchronize(st.ev[3]));
     float ms;
     CU(cudaEventElapsedTime(&ms, st.ev[0], st.ev[1])); tm.h2d_ms += ms;
     CU(cudaEventElapsedTime(&ms, st.ev[1], st.ev[2])); tm.kernel_ms += ms;
     CU(cudaEventElapsedTime(&ms, st.ev[2], st.ev[3])); tm.d2h_ms += ms;
-    if (bounceOut) {
-      const double t0 = nowMs();
-      uint8_t *ho[6];
-      carveSet(st.hOut, out, chunk, ho);
-      std::vector<CopyPool::Job> jobs;
-      for (int i = 0; i < out.count; i++)
-        if (out.per[i] * (size_t)pts) jobs.push_back({out.ptr[i] + out.per[i] * (size_t)a, ho[i], out.per[i] * (size_t)pts});
-      ctx->pool->run(jobs);
-      tm.host_copy_ms += nowMs() - t0;
-    }
     return SPZB200_OK;
   };
-
   for (long long c = 0; c < numChunks; c++) {
     Stage &st = ctx->stage[c % kStages];
     const long long a = c * chunk, b = std::min(n, a + chunk), pts = b - a;
     if (c >= kStages) {
-      int rc = finish(st, c - kStages);
+      int rc = finish(st);
       if (rc != SPZB200_OK) return rc;
     }
-    uint8_t *dIn[6], *dOut[6], *hi[6], *ho[6];
+    uint8_t *dIn[6], *dOut[6];
     carveSet(st.dIn, in, chunk, dIn);
     carveSet(st.dOut, out, chunk, dOut);
-    if (bounceIn) {
-      const double t0 = nowMs();
-      carveSet(st.hIn, in, chunk, hi);
-      std::vector<CopyPool::Job> jobs;
-      for (int i = 0; i < in.count; i++)
-        if (in.per[i] * (size_t)pts) jobs.push_back({hi[i], in.ptr[i] + in.per[i] * (size_t)a, in.per[i] * (size_t)pts});
-      ctx->pool->run(jobs);
-      tm.host_copy_ms += nowMs() - t0;
-    }
-    if (bounceOut) carveSet(st.hOut, out, chunk, ho);
     CU(cudaEventRecord(st.ev[0], st.stream));
     for (int i = 0; i < in.count; i++) {
       const size_t bytes = in.per[i] * (size_t)pts;
-      const uint8_t *src = bounceIn ? hi[i] : in.ptr[i] + in.per[i] * (size_t)a;
-      if (bytes) CU(cudaMemcpyAsync(dIn[i], src, bytes, cudaMemcpyHostToDevice, st.stream));
+      if (bytes) CU(cudaMemcpyAsync(dIn[i], in.ptr[i] + in.per[i] * (size_t)a, bytes, cudaMemcpyHostToDevice, st.stream));
       tm.h2d_bytes += (int64_t)bytes;
     }
     CU(cudaEventRecord(st.ev[1], st.stream));
@@ -589,18 +539,276 @@ int runPipelineStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &o
     CU(cudaEventRecord(st.ev[2], st.stream));
     for (int i = 0; i < out.count; i++) {
       const size_t bytes = out.per[i] * (size_t)pts;
-      uint8_t *dst = bounceOut ? ho[i] : out.ptr[i] + out.per[i] * (size_t)a;
-      if (bytes) CU(cudaMemcpyAsync(dst, dOut[i], bytes, cudaMemcpyDeviceToHost, st.stream));
+      if (bytes) CU(cudaMemcpyAsync(out.ptr[i] + out.per[i] * (size_t)a, dOut[i], bytes, cudaMemcpyDeviceToHost, st.stream));
       tm.d2h_bytes += (int64_t)bytes;
     }
     CU(cudaEventRecord(st.ev[3], st.stream));
   }
   // drain the ranges still in flight, oldest first
   for (long long c = std::max<long long>(0, numChunks - kStages); c < numChunks; c++) {
-    int rc = finish(ctx->stage[c % kStages], c);
+    int rc = finish(ctx->stage[c % kStages]);
     if (rc != SPZB200_OK) return rc;
   }
-  tm.chunks = (int32_t)numChunks;
+  return SPZB200_OK;
+}
+
+// Pageable planes.  The calling thread only coordinates; the copy pool moves the bytes, in pieces of <= 2 MiB:
+//   up    a worker copies a piece of the caller's plane into the stage's pinned buffer (non-temporal stores) and queues
+//         that piece's H2D itself, on the stage's stream -- the DMA of a range starts when its first piece has landed,
+//         not when its last has, and pieces of the next range are copied while this one's are on the link;
+//   down  every D2H piece is followed by an event; a worker waits for a piece's event and copies it out to the caller's
+//         plane while later pieces are still on the link.  The down tasks of range c are queued one range late (their
+//         DMA has had a range's time to land, so workers rarely sleep on an event), and a task whose piece has not landed
+//         yet steps aside for queued up tasks.
+// Input and output directions therefore copy concurrently (round 1/2a: one after the other on the calling thread --
+// 10M SH3 pack 100 ms, unpack 124 ms; scripts/bounce_probe.cu has the two shapes bare).  Reuse of a stage waits until
+// its previous range has been copied out completely, which also covers its pinned input buffer (that range's kernel
+// ran after its H2D pieces, and its D2H pieces after the kernel).
+template <class Launch>
+int runBouncedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, const PipelinePlan &pp, Launch &&launch, SpzB200Timings &tm) {
+  constexpr size_t kPiece = (size_t)2 << 20;
+  const long long n = pp.n, chunk = pp.chunk, numChunks = pp.numChunks;
+  const bool bounceIn = pp.bounceIn, bounceOut = pp.bounceOut;
+  CopyPool &pool = *ctx->pool;
+  struct DownPiece { uint8_t *dst; const uint8_t *src; size_t bytes; cudaEvent_t landed; };
+  struct Range {
+    std::atomic<int> upLeft{0}, downLeft{0};
+    std::vector<DownPiece> down;
+    bool downQueued = false;
+  };
+  std::unique_ptr<Range[]> ranges(new Range[(size_t)numChunks]);
+  std::atomic<int> firstError{(int)cudaSuccess};
+  auto note = [&](cudaError_t e) {
+    int expected = (int)cudaSuccess;
+    if (e != cudaSuccess) firstError.compare_exchange_strong(expected, (int)e);
+  };
+  const int device = ctx->device;
+
+  auto queueDown = [&](long long c) {
+    Range &r = ranges[(size_t)c];
+    if (r.downQueued) return;
+    r.downQueued = true;
+    std::vector<CopyPool::Task> tasks;
+    tasks.reserve(r.down.size());
+    for (const DownPiece &d : r.down) {
+      // std::function needs a copyable closure; the task re-queues a copy of itself when it steps aside
+      struct DownTask {
+        DownPiece d; Range *r; CopyPool *pool; std::atomic<int> *err; int device; int asides;
+        void operator()() const {
+          cudaSetDevice(device);
+          cudaError_t e = cudaEventQuery(d.landed);
+          if (e == cudaErrorNotReady) {
+            if (asides < 3 && pool->othersQueued()) {  // bounded: not-ready pieces must not chase each other round the queue
+              DownTask later = *this;
+              later.asides++;
+              pool->resubmit(CopyPool::Task(later));
+              return;
+            }
+            e = cudaEventSynchronize(d.landed);
+          }
+          if (e == cudaSuccess) bounceCopy(d.dst, d.src, d.bytes);
+          else {
+            int expected = (int)cudaSuccess;
+            err->compare_exchange_strong(expected, (int)e);
+          }
+          r->downLeft.fetch_sub(1);
+          pool->progressed();
+        }
+      };
+      tasks.emplace_back(DownTask{d, &r, &pool, &firstError, device, 0});
+    }
+    pool.submit(std::move(tasks));
+  };
+  // host time of the coordinator inside the pool (helping with / waiting for copies)
+  auto helpUntil = [&](std::atomic<int> &counter) {
+    const double t0 = nowMs();
+    pool.helpUntil([&] { return counter.load() == 0; });
+    tm.host_copy_ms += nowMs() - t0;
+  };
+  // everything queued so far must have run before the caller's planes and `ranges` go away
+  auto settle = [&](long long upTo) {
+    for (long long c = 0; c < upTo; c++) {
+      Range &r = ranges[(size_t)c];
+      helpUntil(r.upLeft);
+      if (r.downQueued) helpUntil(r.downLeft);
+    }
+  };
+  auto finish = [&](Stage &st, long long c) -> int {
+    if (bounceOut) {
+      queueDown(c);
+      helpUntil(ranges[(size_t)c].downLeft);
+    }
+    CU(cudaEventSynchronize(st.ev[3]));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, st.ev[0], st.ev[1])); tm.h2d_ms += ms;
+    CU(cudaEventElapsedTime(&ms, st.ev[1], st.ev[2])); tm.kernel_ms += ms;
+    CU(cudaEventElapsedTime(&ms, st.ev[2], st.ev[3])); tm.d2h_ms += ms;
+    if (firstError.load() != (int)cudaSuccess) return cudaFail((cudaError_t)firstError.load(), "bounced copy");
+    return SPZB200_OK;
+  };
+
+  long long issued = 0;  // ranges whose tasks may be in the pool
+  auto body = [&]() -> int {
+    for (long long c = 0; c < numChunks; c++) {
+      Stage &st = ctx->stage[c % kStages];
+      Range &r = ranges[(size_t)c];
+      const long long a = c * chunk, b = std::min(n, a + chunk), pts = b - a;
+      if (c >= kStages) {
+        int rc = finish(st, c - kStages);
+        if (rc != SPZB200_OK) return rc;
+      }
+      // the range before the previous one has had a range's time on the link: its pieces go out now, ahead of this
+      // range's up tasks in the queue
+      if (bounceOut && c >= kStages - 1 && kStages > 1) queueDown(c - (kStages - 1));
+      uint8_t *dIn[6], *dOut[6], *hi[6], *ho[6];
+      carveSet(st.dIn, in, chunk, dIn);
+      carveSet(st.dOut, out, chunk, dOut);
+      issued = c + 1;
+      CU(cudaEventRecord(st.ev[0], st.stream));
+      if (bounceIn) {
+        carveSet(st.hIn, in, chunk, hi);
+        std::vector<CopyPool::Task> tasks;
+        for (int i = 0; i < in.count; i++) {
+          const size_t bytes = in.per[i] * (size_t)pts;
+          const uint8_t *src = in.ptr[i] + in.per[i] * (size_t)a;
+          tm.h2d_bytes += (int64_t)bytes;
+          for (size_t off = 0; off < bytes; off += kPiece) {
+            const size_t len = std::min(kPiece, bytes - off);
+            uint8_t *pinned = hi[i] + off, *dev = dIn[i] + off;
+            const uint8_t *from = src + off;
+            cudaStream_t stream = st.stream;
+            Range *rp = &r;
+            CopyPool *pl = &pool;
+            std::atomic<int> *err = &firstError;
+            tasks.emplace_back([=] {
+              bounceCopy(pinned, from, len);
+              cudaSetDevice(device);
+              const cudaError_t e = cudaMemcpyAsync(dev, pinned, len, cudaMemcpyHostToDevice, stream);
+              if (e != cudaSuccess) {
+                int expected = (int)cudaSuccess;
+                err->compare_exchange_strong(expected, (int)e);
+              }
+              rp->upLeft.fetch_sub(1);
+              pl->progressed();
+            });
+          }
+        }
+        r.upLeft.store((int)tasks.size());
+        pool.submit(std::move(tasks));
+        helpUntil(r.upLeft);
+        if (firstError.load() != (int)cudaSuccess) return cudaFail((cudaError_t)firstError.load(), "bounced copy");
+      } else {
+        for (int i = 0; i < in.count; i++) {
+          const size_t bytes = in.per[i] * (size_t)pts;
+          if (bytes) CU(cudaMemcpyAsync(dIn[i], in.ptr[i] + in.per[i] * (size_t)a, bytes, cudaMemcpyHostToDevice, st.stream));
+          tm.h2d_bytes += (int64_t)bytes;
+        }
+      }
+      CU(cudaEventRecord(st.ev[1], st.stream));
+      int launches = 0;
+      CU(launch(dIn, dOut, pts, st.stream, &launches));
+      ctx->kernelLaunches += launches;
+      tm.kernel_launches += launches;
+      CU(cudaEventRecord(st.ev[2], st.stream));
+      if (bounceOut) {
+        carveSet(st.hOut, out, chunk, ho);
+        size_t pieces = 0;
+        for (int i = 0; i < out.count; i++) pieces += (out.per[i] * (size_t)pts + kPiece - 1) / kPiece;
+        while (st.pieceEv.size() < pieces) {
+          cudaEvent_t e;
+          CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          st.pieceEv.push_back(e);
+        }
+        size_t k = 0;
+        r.down.reserve(pieces);
+        for (int i = 0; i < out.count; i++) {
+          const size_t bytes = out.per[i] * (size_t)pts;
+          tm.d2h_bytes += (int64_t)bytes;
+          for (size_t off = 0; off < bytes; off += kPiece, k++) {
+            const size_t len = std::min(kPiece, bytes - off);
+            CU(cudaMemcpyAsync(ho[i] + off, dOut[i] + off, len, cudaMemcpyDeviceToHost, st.stream));
+            CU(cudaEventRecord(st.pieceEv[k], st.stream));
+            r.down.push_back({out.ptr[i] + out.per[i] * (size_t)a + off, ho[i] + off, len, st.pieceEv[k]});
+          }
+        }
+        r.downLeft.store((int)r.down.size());
+      } else {
+        for (int i = 0; i < out.count; i++) {
+          const size_t bytes = out.per[i] * (size_t)pts;
+          if (bytes) CU(cudaMemcpyAsync(out.ptr[i] + out.per[i] * (size_t)a, dOut[i], bytes, cudaMemcpyDeviceToHost, st.stream));
+          tm.d2h_bytes += (int64_t)bytes;
+        }
+      }
+      CU(cudaEventRecord(st.ev[3], st.stream));
+    }
+    for (long long c = std::max<long long>(0, numChunks - kStages); c < numChunks; c++) {
+      int rc = finish(ctx->stage[c % kStages], c);
+      if (rc != SPZB200_OK) return rc;
+    }
+    return SPZB200_OK;
+  };
+  const int rc = body();
+  if (rc != SPZB200_OK) {
+    // tasks still queued hold pointers into the caller's planes, the stage buffers and `ranges`: let them run out
+    // (a down task of a range whose D2H never got queued is never submitted; its counter is not waited on)
+    const std::string first = tlsError;
+    settle(issued);
+    tlsError = first;
+  }
+  return rc;
+}
+
+template <class Launch>
+int runPipelineStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, long long n, long long granule,
+                      Launch &&launch, SpzB200Timings *timings) {
+  const double w0 = nowMs();
+  CU(cudaSetDevice(ctx->device));
+  // Bouncing costs a one-time pinned allocation per context (~1 GB/s on a VM), so small one-shot
+  // calls are cheaper through the driver's own staging; once the buffers exist they are always used.
+  const size_t callBytes = (size_t)n * (in.bytesPerGaussian() + out.bytesPerGaussian());
+  const bool wantBounce = ctx->bounceMode == 2 ||
+                          (ctx->bounceMode == 1 && (callBytes >= ctx->bounceMinBytes || ctx->stage[0].hIn || ctx->stage[0].hOut));
+  PipelinePlan pp;
+  pp.n = n;
+  pp.bounceIn = n > 0 && wantBounce && isPageable(in.ptr[0]);
+  pp.bounceOut = n > 0 && wantBounce && isPageable(out.ptr[0]);
+  const bool bounced = pp.bounceIn || pp.bounceOut;
+  long long want = bounced ? ctx->pageableChunkPoints : ctx->chunkPoints;
+  // Pinned planes: 2M-point ranges keep the copy engines in long transfers, but a cloud of only a few such ranges
+  // spends a visible part of the call filling and draining the three-stage pipeline (10M points = 5 ranges: 0.84 of
+  // the link; in ~12 ranges: profiles/r2_tuning_notes.txt).  So mid-sized clouds are cut into about a dozen ranges,
+  // never below 256K points.
+  if (!bounced && ctx->adaptiveChunks) want = std::min(want, std::max<long long>(1 << 18, (n + 11) / 12));
+  long long chunk = std::max<long long>(granule, (want + granule - 1) / granule * granule);
+  if (chunk > n) chunk = std::max<long long>(n, 1);
+  pp.chunk = chunk;
+  pp.numChunks = n == 0 ? 0 : (n + chunk - 1) / chunk;
+  const int stages = (int)std::min<long long>(kStages, pp.numChunks);
+
+  SpzB200Timings tm;
+  std::memset(&tm, 0, sizeof tm);
+  tm.staged = (pp.bounceIn ? 1 : 0) | (pp.bounceOut ? 2 : 0);
+  if (pp.numChunks > 0) {
+    uint8_t *unused[6];
+    const size_t inBytes = carveSet(nullptr, in, chunk, unused);
+    const size_t outBytes = carveSet(nullptr, out, chunk, unused);
+    for (int s = 0; s < stages; s++) {
+      Stage &st = ctx->stage[s];
+      int rc = ensureStage(st, inBytes, outBytes);
+      if (rc == SPZB200_OK && pp.bounceIn) rc = ensureBounce(st.hIn, st.hInCap, inBytes);
+      if (rc == SPZB200_OK && pp.bounceOut) rc = ensureBounce(st.hOut, st.hOutCap, outBytes);
+      if (rc != SPZB200_OK) return rc;
+    }
+    if (bounced && !ctx->pool) {
+      // 10M SH3 through the C++ API on a 16-thread host, pack / unpack ms: 4 threads 117 / 187, 8: 70 / 110, 12: 62 / 92, 16: 62 / 86
+      const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+      int t = ctx->copyThreads > 0 ? ctx->copyThreads : (int)std::min<unsigned>(16, std::max(1u, hw * 3 / 4));
+      ctx->pool = new CopyPool(std::max(0, t - 1));  // the calling thread copies too while it waits
+    }
+    const int rc = bounced ? runBouncedStages(ctx, in, out, pp, launch, tm) : runPinnedStages(ctx, in, out, pp, launch, tm);
+    if (rc != SPZB200_OK) return rc;
+  }
+  tm.chunks = (int32_t)pp.numChunks;
   tm.wall_ms = nowMs() - w0;
   if (timings) *timings = tm;
   return SPZB200_OK;
@@ -909,6 +1117,11 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
   }
   if (const char *env = std::getenv("SPZB200_CTAS_PER_SM")) ctx->ctasPerSm = std::atoi(env);
   if (const char *env = std::getenv("SPZB200_BOUNCE_MIN_MB")) ctx->bounceMinBytes = (size_t)std::atoll(env) << 20;
+  if (const char *env = std::getenv("SPZB200_COPY_THREADS")) ctx->copyThreads = std::max(0, std::atoi(env));
+  if (const char *env = std::getenv("SPZB200_PAGEABLE_CHUNK_POINTS")) {
+    const long long v = std::atoll(env);
+    if (v > 0) ctx->pageableChunkPoints = v;
+  }
   if (const char *env = std::getenv("SPZB200_DECODE")) {
     ctx->decodeBulk = std::strcmp(env, "direct") != 0;
     ctx->decodePerGaussian = std::strcmp(env, "pergaussian") == 0 ? 2 : (std::strcmp(env, "bulk") == 0 || std::strcmp(env, "direct") == 0) ? 0 : 1;
@@ -963,6 +1176,7 @@ void spzb200_destroy(SpzB200Context *ctx) {
     if (st.hIn) cudaFreeHost(st.hIn);
     if (st.hOut) cudaFreeHost(st.hOut);
     for (int k = 0; k < 4; k++) if (st.ev[k]) cudaEventDestroy(st.ev[k]);
+    for (cudaEvent_t e : st.pieceEv) cudaEventDestroy(e);
     if (st.dIn) cudaFree(st.dIn);
     if (st.dOut) cudaFree(st.dOut);
     if (st.stream) cudaStreamDestroy(st.stream);

@@ -1030,3 +1030,66 @@ def test_reference_suite_fixture_roundtrip(mine, theirs):
     assert np.allclose(g.alphas, c.alphas, atol=0.01 * 8)
     assert np.allclose(g.sh, np.clip(c.sh, -1, 0.9922), atol=2 / 32 + 0.5 / 255)
     assert_cloud_bits_equal(g, theirs.load_spz(blob, 0), "fixture")
+
+
+# =================================================================================================
+# the reference's command-line tools, relinked
+# =================================================================================================
+
+def _cli(tool: str, flavour: str) -> str:
+    """tests/cxx/_build/<tool>_<flavour>: cli_tools/src/<tool>.cpp of the reference, compiled unchanged against the
+    reference's headers and linked to libspz_b200.so (`b200`) or to the reference's own sources (`ref`)."""
+    exe = os.path.join(CXX, "_build", f"{tool}_{flavour}")
+    if os.path.isdir("/root/reference/cli_tools/src"):
+        from spz_b200 import _native
+        _native.lib()
+        subprocess.run(["make", "-s", "-C", CXX, "cli"], check=True)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built and cannot be built here")
+    return exe
+
+
+def _run(exe: str, *args: str):
+    r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=300)
+    return r.returncode, r.stdout, r.stderr
+
+
+def test_reference_cli_tools_link_against_this_library(tmp_path):
+    """SURVEY.md 8b 'callers of the hot path: CLIs via the file API': the three tools build from the reference's
+    unchanged sources against libspz_b200.so with no undefined symbol, and behave like the reference's where no device is
+    needed (usage text; an unreadable or empty input)."""
+    for tool in ("ply_to_spz", "spz_to_ply", "spz_info"):
+        a, b = _cli(tool, "b200"), _cli(tool, "ref")
+        assert _run(a) == _run(b)  # usage
+    junk = tmp_path / "junk.spz"
+    junk.write_bytes(b"not a gzip member")
+    mine_out, ref_out = _run(_cli("spz_info", "b200"), str(junk)), _run(_cli("spz_info", "ref"), str(junk))
+    assert mine_out[0] == ref_out[0] == 0 and mine_out[1].splitlines()[-1] == ref_out[1].splitlines()[-1] == "Number of points: 0"
+    empty = tmp_path / "empty.spz"
+    empty.write_bytes(Shim("ref").save_spz(Cloud(0, 0, *[np.zeros(0, np.float32)] * 6), 0))
+    assert _run(_cli("spz_info", "b200"), str(empty)) == _run(_cli("spz_info", "ref"), str(empty))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deg", [0, 3])
+def test_reference_cli_tools_relinked_produce_the_same_files(theirs, tmp_path, deg):
+    """ply_to_spz, spz_to_ply and spz_info of the reference, relinked to this library, against the same tools built with
+    the reference's sources: identical .spz bytes, identical .ply bytes, identical report."""
+    rng = np.random.default_rng(700 + deg)
+    c = random_cloud(rng, 12_345, deg, False)
+    ply = str(tmp_path / "in.ply")
+    assert theirs.save_ply(c, ply, 0)
+    out = {}
+    for flavour in ("b200", "ref"):
+        spz_file, back = str(tmp_path / f"{flavour}.spz"), str(tmp_path / f"{flavour}.ply")
+        assert _run(_cli("ply_to_spz", flavour), ply, spz_file)[0] == 0
+        assert _run(_cli("spz_to_ply", flavour), spz_file, back)[0] == 0
+        info = _run(_cli("spz_info", flavour), spz_file)
+        assert info[0] == 0
+        out[flavour] = (open(spz_file, "rb").read(), open(back, "rb").read(), info[1])
+    assert out["b200"][0] == out["ref"][0], "ply_to_spz: .spz bytes"
+    assert out["b200"][1] == out["ref"][1], "spz_to_ply: .ply bytes"
+    assert out["b200"][2] == out["ref"][2] and f"Number of points: {c.n}" in out["ref"][2], "spz_info report"
+    # and crosswise: each side's tool reads the other side's file
+    assert _run(_cli("spz_info", "b200"), str(tmp_path / "ref.spz"))[1] == out["ref"][2]
+    assert _run(_cli("spz_info", "ref"), str(tmp_path / "b200.spz"))[1] == out["ref"][2]

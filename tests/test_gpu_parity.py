@@ -559,6 +559,40 @@ def test_host_pipeline_pageable_pinned_and_unstaged_agree(gpu_ctx, oracle):
         gpu_ctx.set_host_staging(1, 0)
 
 
+@pytest.mark.parametrize("deg,n,threads", [(3, 700_001, 0), (3, 300_000, 1), (0, 2_200_123, 3), (1, 1_000_000, 2)])
+def test_host_pipeline_bounced_pieces(gpu_ctx, oracle, deg, n, threads):
+    """The bounced pipeline at the sizes where it is more than one piece per plane and more ranges than stages: planes of
+    tens of MB cut into 2 MiB pieces copied by the pool while earlier pieces are on the link, down pieces copied out
+    behind their events, stages reused (9 ranges at SH degree 0).  Pageable on both sides, on the input side only and on
+    the output side only; one copy thread (the calling thread does everything), a few, and the default."""
+    from spz_b200.codec import alloc_cloud, alloc_packed
+    rng = np.random.default_rng(4300 + deg)
+    c = random_cloud(rng, n, deg, False)
+    want = oracle.pack(c, 7)
+    want_back = oracle.unpack(want, 5)
+    try:
+        gpu_ctx.set_host_staging(2, threads)
+        for pin_in, pin_out in ((False, False), (False, True), (True, False)):
+            src = alloc_cloud(n, deg, numpy_arrays=True, pinned=pin_in)
+            for a, b in zip(src.planes(), c.planes()):
+                a[...] = b
+            out = alloc_packed(n, deg, 3, numpy_arrays=True, pinned=pin_out)
+            got, tm = gpu_ctx.encode_host(src, 7, out=out)
+            assert tm["staged"] == (0 if pin_in else 1) | (0 if pin_out else 2), tm
+            assert tm["chunks"] == -(-n // (1 << 18)), tm  # 256K-point ranges
+            assert_packed_equal(Packed(n, deg, 12, 3, *got.planes()), want, f"encode pinned={pin_in},{pin_out}")
+            # decode: the packed planes take the role of the input
+            pk = alloc_packed(n, deg, 3, numpy_arrays=True, pinned=pin_in)
+            for a, b in zip(pk.planes(), want.planes()):
+                a[...] = b
+            back = alloc_cloud(n, deg, numpy_arrays=True, pinned=pin_out)
+            got_back, tm = gpu_ctx.decode_host(pk, 5, out=back)
+            assert tm["staged"] == (0 if pin_in else 1) | (0 if pin_out else 2), tm
+            assert_cloud_bits_equal(Cloud(n, deg, *got_back.planes()), want_back, f"decode pinned={pin_in},{pin_out}")
+    finally:
+        gpu_ctx.set_host_staging(1, 0)
+
+
 def test_host_multi_entry_point_single_device(oracle):
     """spzb200_*_host_multi with the devices present (1 here; more on a multi-GPU box): shards
     land at their precomputed offsets and the result is byte-identical to the unsharded one."""
