@@ -574,7 +574,7 @@ int runBouncedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &ou
   struct Range {
     std::atomic<int> upLeft{0}, downLeft{0};
     std::vector<DownPiece> down;
-    bool downQueued = false;
+    bool downQueued = false, launched = false;
   };
   std::unique_ptr<Range[]> ranges(new Range[(size_t)numChunks]);
   std::atomic<int> firstError{(int)cudaSuccess};
@@ -586,7 +586,7 @@ int runBouncedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &ou
 
   auto queueDown = [&](long long c) {
     Range &r = ranges[(size_t)c];
-    if (r.downQueued) return;
+    if (r.downQueued || !r.launched) return;
     r.downQueued = true;
     std::vector<CopyPool::Task> tasks;
     tasks.reserve(r.down.size());
@@ -648,98 +648,121 @@ int runBouncedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &ou
   };
 
   long long issued = 0;  // ranges whose tasks may be in the pool
+  // A range goes through the coordinator twice.  begin(c): its stage is free (the range that used it is copied out),
+  // its up tasks go to the pool.  launch(c), one iteration later: all its pieces are on the stream -> kernel, D2H
+  // pieces with their events.  So while the coordinator does the serial part of range c - 1 (a few dozen API calls),
+  // the pool already holds the pieces of range c: the workers never run dry between ranges.
+  auto begin = [&](long long c) -> int {
+    Stage &st = ctx->stage[c % kStages];
+    Range &r = ranges[(size_t)c];
+    const long long a = c * chunk, pts = std::min(n, a + chunk) - a;
+    if (c >= kStages) {
+      int rc = finish(st, c - kStages);
+      if (rc != SPZB200_OK) return rc;
+    }
+    // an older range's D2H has had an iteration on the link: its pieces go out now, ahead of this range's up tasks
+    if (bounceOut && c >= kStages - 1 && kStages > 1) queueDown(c - (kStages - 1));
+    uint8_t *dIn[6], *hi[6];
+    carveSet(st.dIn, in, chunk, dIn);
+    issued = c + 1;
+    CU(cudaEventRecord(st.ev[0], st.stream));
+    if (bounceIn) {
+      carveSet(st.hIn, in, chunk, hi);
+      std::vector<CopyPool::Task> tasks;
+      for (int i = 0; i < in.count; i++) {
+        const size_t bytes = in.per[i] * (size_t)pts;
+        const uint8_t *src = in.ptr[i] + in.per[i] * (size_t)a;
+        tm.h2d_bytes += (int64_t)bytes;
+        for (size_t off = 0; off < bytes; off += kPiece) {
+          const size_t len = std::min(kPiece, bytes - off);
+          uint8_t *pinned = hi[i] + off, *dev = dIn[i] + off;
+          const uint8_t *from = src + off;
+          cudaStream_t stream = st.stream;
+          Range *rp = &r;
+          CopyPool *pl = &pool;
+          std::atomic<int> *err = &firstError;
+          tasks.emplace_back([=] {
+            bounceCopy(pinned, from, len);
+            cudaSetDevice(device);
+            const cudaError_t e = cudaMemcpyAsync(dev, pinned, len, cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) {
+              int expected = (int)cudaSuccess;
+              err->compare_exchange_strong(expected, (int)e);
+            }
+            rp->upLeft.fetch_sub(1);
+            pl->progressed();
+          });
+        }
+      }
+      r.upLeft.store((int)tasks.size());
+      pool.submit(std::move(tasks));
+    } else {
+      for (int i = 0; i < in.count; i++) {
+        const size_t bytes = in.per[i] * (size_t)pts;
+        if (bytes) CU(cudaMemcpyAsync(dIn[i], in.ptr[i] + in.per[i] * (size_t)a, bytes, cudaMemcpyHostToDevice, st.stream));
+        tm.h2d_bytes += (int64_t)bytes;
+      }
+    }
+    return SPZB200_OK;
+  };
+  auto launchRange = [&](long long c) -> int {
+    Stage &st = ctx->stage[c % kStages];
+    Range &r = ranges[(size_t)c];
+    const long long a = c * chunk, pts = std::min(n, a + chunk) - a;
+    uint8_t *dIn[6], *dOut[6], *ho[6];
+    carveSet(st.dIn, in, chunk, dIn);
+    carveSet(st.dOut, out, chunk, dOut);
+    helpUntil(r.upLeft);
+    if (firstError.load() != (int)cudaSuccess) return cudaFail((cudaError_t)firstError.load(), "bounced copy");
+    CU(cudaEventRecord(st.ev[1], st.stream));
+    int launches = 0;
+    CU(launch(dIn, dOut, pts, st.stream, &launches));
+    ctx->kernelLaunches += launches;
+    tm.kernel_launches += launches;
+    CU(cudaEventRecord(st.ev[2], st.stream));
+    if (bounceOut) {
+      carveSet(st.hOut, out, chunk, ho);
+      size_t pieces = 0;
+      for (int i = 0; i < out.count; i++) pieces += (out.per[i] * (size_t)pts + kPiece - 1) / kPiece;
+      while (st.pieceEv.size() < pieces) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        st.pieceEv.push_back(e);
+      }
+      size_t k = 0;
+      r.down.reserve(pieces);
+      for (int i = 0; i < out.count; i++) {
+        const size_t bytes = out.per[i] * (size_t)pts;
+        tm.d2h_bytes += (int64_t)bytes;
+        for (size_t off = 0; off < bytes; off += kPiece, k++) {
+          const size_t len = std::min(kPiece, bytes - off);
+          CU(cudaMemcpyAsync(ho[i] + off, dOut[i] + off, len, cudaMemcpyDeviceToHost, st.stream));
+          CU(cudaEventRecord(st.pieceEv[k], st.stream));
+          r.down.push_back({out.ptr[i] + out.per[i] * (size_t)a + off, ho[i] + off, len, st.pieceEv[k]});
+        }
+      }
+      r.downLeft.store((int)r.down.size());
+    } else {
+      for (int i = 0; i < out.count; i++) {
+        const size_t bytes = out.per[i] * (size_t)pts;
+        if (bytes) CU(cudaMemcpyAsync(out.ptr[i] + out.per[i] * (size_t)a, dOut[i], bytes, cudaMemcpyDeviceToHost, st.stream));
+        tm.d2h_bytes += (int64_t)bytes;
+      }
+    }
+    CU(cudaEventRecord(st.ev[3], st.stream));
+    r.launched = true;
+    return SPZB200_OK;
+  };
   auto body = [&]() -> int {
-    for (long long c = 0; c < numChunks; c++) {
-      Stage &st = ctx->stage[c % kStages];
-      Range &r = ranges[(size_t)c];
-      const long long a = c * chunk, b = std::min(n, a + chunk), pts = b - a;
-      if (c >= kStages) {
-        int rc = finish(st, c - kStages);
+    for (long long c = 0; c <= numChunks; c++) {
+      if (c < numChunks) {
+        int rc = begin(c);
         if (rc != SPZB200_OK) return rc;
       }
-      // the range before the previous one has had a range's time on the link: its pieces go out now, ahead of this
-      // range's up tasks in the queue
-      if (bounceOut && c >= kStages - 1 && kStages > 1) queueDown(c - (kStages - 1));
-      uint8_t *dIn[6], *dOut[6], *hi[6], *ho[6];
-      carveSet(st.dIn, in, chunk, dIn);
-      carveSet(st.dOut, out, chunk, dOut);
-      issued = c + 1;
-      CU(cudaEventRecord(st.ev[0], st.stream));
-      if (bounceIn) {
-        carveSet(st.hIn, in, chunk, hi);
-        std::vector<CopyPool::Task> tasks;
-        for (int i = 0; i < in.count; i++) {
-          const size_t bytes = in.per[i] * (size_t)pts;
-          const uint8_t *src = in.ptr[i] + in.per[i] * (size_t)a;
-          tm.h2d_bytes += (int64_t)bytes;
-          for (size_t off = 0; off < bytes; off += kPiece) {
-            const size_t len = std::min(kPiece, bytes - off);
-            uint8_t *pinned = hi[i] + off, *dev = dIn[i] + off;
-            const uint8_t *from = src + off;
-            cudaStream_t stream = st.stream;
-            Range *rp = &r;
-            CopyPool *pl = &pool;
-            std::atomic<int> *err = &firstError;
-            tasks.emplace_back([=] {
-              bounceCopy(pinned, from, len);
-              cudaSetDevice(device);
-              const cudaError_t e = cudaMemcpyAsync(dev, pinned, len, cudaMemcpyHostToDevice, stream);
-              if (e != cudaSuccess) {
-                int expected = (int)cudaSuccess;
-                err->compare_exchange_strong(expected, (int)e);
-              }
-              rp->upLeft.fetch_sub(1);
-              pl->progressed();
-            });
-          }
-        }
-        r.upLeft.store((int)tasks.size());
-        pool.submit(std::move(tasks));
-        helpUntil(r.upLeft);
-        if (firstError.load() != (int)cudaSuccess) return cudaFail((cudaError_t)firstError.load(), "bounced copy");
-      } else {
-        for (int i = 0; i < in.count; i++) {
-          const size_t bytes = in.per[i] * (size_t)pts;
-          if (bytes) CU(cudaMemcpyAsync(dIn[i], in.ptr[i] + in.per[i] * (size_t)a, bytes, cudaMemcpyHostToDevice, st.stream));
-          tm.h2d_bytes += (int64_t)bytes;
-        }
+      if (c >= 1) {
+        int rc = launchRange(c - 1);
+        if (rc != SPZB200_OK) return rc;
       }
-      CU(cudaEventRecord(st.ev[1], st.stream));
-      int launches = 0;
-      CU(launch(dIn, dOut, pts, st.stream, &launches));
-      ctx->kernelLaunches += launches;
-      tm.kernel_launches += launches;
-      CU(cudaEventRecord(st.ev[2], st.stream));
-      if (bounceOut) {
-        carveSet(st.hOut, out, chunk, ho);
-        size_t pieces = 0;
-        for (int i = 0; i < out.count; i++) pieces += (out.per[i] * (size_t)pts + kPiece - 1) / kPiece;
-        while (st.pieceEv.size() < pieces) {
-          cudaEvent_t e;
-          CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-          st.pieceEv.push_back(e);
-        }
-        size_t k = 0;
-        r.down.reserve(pieces);
-        for (int i = 0; i < out.count; i++) {
-          const size_t bytes = out.per[i] * (size_t)pts;
-          tm.d2h_bytes += (int64_t)bytes;
-          for (size_t off = 0; off < bytes; off += kPiece, k++) {
-            const size_t len = std::min(kPiece, bytes - off);
-            CU(cudaMemcpyAsync(ho[i] + off, dOut[i] + off, len, cudaMemcpyDeviceToHost, st.stream));
-            CU(cudaEventRecord(st.pieceEv[k], st.stream));
-            r.down.push_back({out.ptr[i] + out.per[i] * (size_t)a + off, ho[i] + off, len, st.pieceEv[k]});
-          }
-        }
-        r.downLeft.store((int)r.down.size());
-      } else {
-        for (int i = 0; i < out.count; i++) {
-          const size_t bytes = out.per[i] * (size_t)pts;
-          if (bytes) CU(cudaMemcpyAsync(out.ptr[i] + out.per[i] * (size_t)a, dOut[i], bytes, cudaMemcpyDeviceToHost, st.stream));
-          tm.d2h_bytes += (int64_t)bytes;
-        }
-      }
-      CU(cudaEventRecord(st.ev[3], st.stream));
     }
     for (long long c = std::max<long long>(0, numChunks - kStages); c < numChunks; c++) {
       int rc = finish(ctx->stage[c % kStages], c);
