@@ -37,6 +37,7 @@
 namespace {
 
 thread_local std::string tlsError;
+thread_local int tlsShardCount = 1;  // > 1 on the per-device threads of a *_host_multi call
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -826,6 +827,8 @@ int runPipelineStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &o
       // 10M SH3 through the C++ API on a 16-thread host, pack / unpack ms: 4 threads 117 / 187, 8: 70 / 110, 12: 62 / 92, 16: 62 / 86
       const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
       int t = ctx->copyThreads > 0 ? ctx->copyThreads : (int)std::min<unsigned>(16, std::max(1u, hw * 3 / 4));
+      // a *_host_multi call runs one pipeline per device at once: they share the host's threads (and its memory bandwidth)
+      if (ctx->copyThreads <= 0 && tlsShardCount > 1) t = std::max(2, t / tlsShardCount);
       ctx->pool = new CopyPool(std::max(0, t - 1));  // the calling thread copies too while it waits
     }
     const int rc = bounced ? runBouncedStages(ctx, in, out, pp, launch, tm) : runPinnedStages(ctx, in, out, pp, launch, tm);
@@ -1009,6 +1012,7 @@ int runSharded(const int32_t *devices, int32_t numDevices, int64_t n, int32_t sh
         SpzB200Context *ctx = nullptr;
         rc[i] = contextPool().acquire(devices[i], &ctx);
         if (rc[i] == SPZB200_OK) {
+          tlsShardCount = numDevices;
           rc[i] = perShard(ctx, a, b, &tms[i]);
           if (rc[i] != SPZB200_OK) msg[i] = spzb200_last_error();
           contextPool().release(ctx);
