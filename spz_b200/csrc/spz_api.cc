@@ -225,13 +225,15 @@ void serializeInto(const PackedGaussians &p, uint8_t *dst) {
 // gzip policy of saveSpz / loadSpz* (spz_gzip.cc has the block-parallel framing):
 //   SPZ_B200_GZIP_THREADS=1   the reference's single-thread deflate, compressed bytes identical to the reference's, always
 //   SPZ_B200_GZIP_THREADS=N   N > 1: block-parallel for every container of two blocks (2 MiB) or more
-//   unset                     containers below 64 MiB (~1M SH3 gaussians) as the reference writes them, byte for byte;
-//                             larger ones block-parallel on up to 16 threads -- one thread deflates ~10 MB/s, i.e. a
-//                             minute for a 10M-gaussian scene the GPU encodes in a millisecond.  The file is one
-//                             standard gzip member either way and inflates to the identical container.
+//   unset                     containers below 8 MiB (~130K SH3 gaussians) as the reference writes them, byte for byte;
+//                             larger ones block-parallel on up to 16 threads -- one thread deflates ~10 MB/s, i.e.
+//                             7 s for a 1M-gaussian scene and a minute for a 10M-gaussian one that the GPU encodes in
+//                             milliseconds (same box, 4M SH3: reference saveSpz 28.0 s, this 1.8 s; loadSpz 2.6 s vs
+//                             0.11 s -- profiles/r2_file_api_timing.jsonl).  The file is one standard gzip member
+//                             either way and inflates to the identical container.
 // Loading inflates the blocks of a member that carries the block table concurrently (N threads, default up to 16);
 // members without it -- anything the reference wrote -- take the serial inflater.
-constexpr size_t kAutoParallelGzipBytes = (size_t)64 << 20;
+constexpr size_t kAutoParallelGzipBytes = (size_t)8 << 20;
 int hostThreads() { return (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())); }
 int gzipThreadsEnv() {
   const char *env = std::getenv("SPZ_B200_GZIP_THREADS");

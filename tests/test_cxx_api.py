@@ -767,13 +767,15 @@ def test_save_load_spz_bytes_and_files(mine, theirs, tmp_path):
 def test_save_spz_with_parallel_gzip_is_readable_by_the_reference(mine, theirs):
     rng = np.random.default_rng(310)
     c = random_cloud(rng, 150_000, 3, False)
-    serial = mine.save_spz(c, 6)
-    os.environ["SPZ_B200_GZIP_THREADS"] = "8"
+    os.environ["SPZ_B200_GZIP_THREADS"] = "1"
     try:
+        serial = mine.save_spz(c, 6)
+        os.environ["SPZ_B200_GZIP_THREADS"] = "8"
         par = mine.save_spz(c, 6)
         back = mine.load_spz(par, 8)
     finally:
         del os.environ["SPZ_B200_GZIP_THREADS"]
+    assert serial == theirs.save_spz(c, 6), "SPZ_B200_GZIP_THREADS=1 pins the reference's file bytes"
     assert par != serial and gzip.decompress(par) == gzip.decompress(serial)
     assert_cloud_bits_equal(theirs.load_spz(par, 8), theirs.load_spz(serial, 8), "reference reads the parallel member")
     assert_cloud_bits_equal(back, theirs.load_spz(serial, 8), "parallel inflate + decode")
@@ -781,14 +783,14 @@ def test_save_spz_with_parallel_gzip_is_readable_by_the_reference(mine, theirs):
 
 @pytest.mark.gpu
 def test_save_spz_default_gzip_policy(mine, theirs):
-    """With SPZ_B200_GZIP_THREADS unset, a container below 64 MiB is deflated as the reference does it (same file bytes);
-    from 64 MiB up saveSpz takes the block-parallel framing on its own -- a different, standard gzip member holding the
+    """With SPZ_B200_GZIP_THREADS unset, a container below 8 MiB is deflated as the reference does it (same file bytes);
+    from 8 MiB up saveSpz takes the block-parallel framing on its own -- a different, standard gzip member holding the
     identical container, which the unmodified reference loads to the same cloud.  SPZ_B200_GZIP_THREADS=1 pins the
     reference's bytes at every size."""
     rng = np.random.default_rng(311)
     small = random_cloud(rng, 20_000, 3, False)
     assert mine.save_spz(small, 6) == theirs.save_spz(small, 6)
-    c = random_cloud(rng, 1_100_000, 3, False)  # 16 + 65 * 1.1M = 71.5 MB of container
+    c = random_cloud(rng, 400_000, 3, False)  # 16 + 65 * 400K = 26 MB of container
     auto = mine.save_spz(c, 6)
     assert auto[3] & 4, "FEXTRA block table expected above the threshold"
     stream = gzip.decompress(auto)
