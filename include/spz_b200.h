@@ -296,7 +296,7 @@ void spzb200_set_chunk_points(SpzB200Context *ctx, int64_t points);
  * `copy_threads` host threads (0 = auto: three quarters of the hardware threads, at most 16; SPZB200_COPY_THREADS)
  * in 2 MiB pieces whose DMAs overlap the copies: 4-5x the speed of handing them to cudaMemcpyAsync as they are
  * (driver-staged, synchronous).  bounce: 0 = never,
- * 1 = calls of >= 32 MiB (SPZB200_BOUNCE_MIN_MB) or once the buffers exist (default: the pinned
+ * 1 = calls of >= 4 MiB (SPZB200_BOUNCE_MIN_MB) or once the buffers exist (default: the pinned
  * allocation is a one-time cost small one-shot calls would not earn back), 2 = always. */
 void spzb200_set_host_staging(SpzB200Context *ctx, int32_t bounce, int32_t copy_threads);
 

@@ -297,7 +297,7 @@ struct SpzB200Context {
   bool pooled = false;  // owned by the process-wide pool (spzb200_acquire): released, never destroyed by callers
   int ctasPerSm = 0;
   int bounceMode = 1;     // pageable planes: 0 never bounce, 1 bounce large calls (see bounceMinBytes), 2 always
-  size_t bounceMinBytes = (size_t)32 << 20;  // steady state the bounce path is 2-4x faster from ~100K gaussians up; the one-time pinned allocation (tens of ms at these sizes) is small next to CUDA initialisation
+  size_t bounceMinBytes = (size_t)4 << 20;  // pack / unpack ms, bounced vs direct: 20K SH3 gaussians (6 MB) 0.45 / 0.55 vs 0.5 / 0.6, 60K 0.9 / 0.85 vs 1.2 / 1.4, 100K 0.9 / 1.0 vs 2.0 / 2.1 (profiles/r2_small_api_staging.txt); the one-time pinned allocation (~1 ms per MB) is small next to CUDA initialisation
   int encodeBulk = 1;  // planar encoder through the bulk-copy per-gaussian kernel: 1 = where faster (default); SPZB200_ENCODE=bulk: 2, =tiles: 0
   int decodePerGaussian = 1;  // SPZB200_DECODE=pergaussian: 2 (also SH-less clouds); =bulk / =direct: 0 (tile kernels only)
   bool plyMapped = false;  // SPZB200_PLY=mapped: canonical-layout PLY kernels off (column-map kernels for everything)
