@@ -1,7 +1,9 @@
 // Development tool: wall time of the reference's file-level API -- saveSpz(cloud) -> bytes, loadSpz(bytes) -> cloud --
 // and of packGaussians / unpackGaussians, on a synthetic SH3 cloud in std::vector planes.  The same source is built
 // against this library (scripts/_build/file_api_timing) and against the reference's sources compiled in place
-// (scripts/_build/file_api_timing_ref; made here, where /root/reference exists).  Not part of the product or the tests.
+// (scripts/_build/file_api_timing_ref; made where /root/reference exists:
+//   g++ -std=c++17 -O2 -ffp-contract=off -pthread -w -I/root/reference/src/cc scripts/file_api_timing.cc /root/reference/src/cc/{load-spz,splat-types,splat-c-types}.cc -o scripts/_build/file_api_timing_ref -lz
+// ), run by `scripts/gpu.sh fileapi`.  Not part of the product or the tests.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>

@@ -33,6 +33,33 @@ case "$task" in
               echo "== 1e6, SPZ_B200_UNPACK_READAHEAD=0 (every unpack(i, c) is its own launch)"; SPZ_B200_UNPACK_READAHEAD=0 scripts/_build/api_timing 1e6 2
               for n in 1e6 1e7; do echo "== $n, SPZB200_NT_COPY=0 (plain memcpy into / out of the bounce buffers)"; SPZB200_NT_COPY=0 scripts/_build/api_timing $n 4; done; } > gpurun_out/cxx_api_timing.txt 2>&1
             echo "rc=$?"; cat gpurun_out/cxx_api_timing.txt ;;
+  smallapi) # small pageable clouds through the C++ API: default staging policy against always-bounce (needs scripts/_build/api_timing: run `api` once, or build here)
+            export SPZ_B200_UNPACK_READAHEAD=0
+            { for n in 2e4 6e4 1e5; do
+                echo "== $n default"; scripts/_build/api_timing $n 6 | grep packGaussians | tail -3
+                echo "== $n SPZB200_BOUNCE_MIN_MB=1000 (driver-staged copies)"; SPZB200_BOUNCE_MIN_MB=1000 scripts/_build/api_timing $n 6 | grep packGaussians | tail -3
+              done; } > gpurun_out/small_api.txt 2>&1; cat gpurun_out/small_api.txt ;;
+  pageable) # copy threads and range size of the bounced pipeline, 10M SH3 through the C++ API
+            export SPZ_B200_UNPACK_READAHEAD=0
+            run() { echo "== $*"; env "$@" | grep packGaussians | tail -2; }
+            { for n in 6e4 2e5 1e6 4e6 1e7; do run scripts/_build/api_timing $n 5; done
+              for t in 4 8 12 16; do run SPZB200_COPY_THREADS=$t scripts/_build/api_timing 1e7 4; done
+              for c in 131072 524288 1048576; do run SPZB200_PAGEABLE_CHUNK_POINTS=$c scripts/_build/api_timing 1e7 4; done
+              run SPZB200_NT_COPY=0 scripts/_build/api_timing 1e7 4; } > gpurun_out/pageable_api.txt 2>&1; cat gpurun_out/pageable_api.txt ;;
+  fileapi)  # saveSpz / loadSpz / pack / unpack through the C++ API: this library against the reference's own sources on the same box.
+            # scripts/_build/file_api_timing_ref is built where /root/reference exists (see the header of scripts/file_api_timing.cc) and travels with the snapshot.
+            g++ -std=c++17 -O2 -pthread -Iinclude/spz scripts/file_api_timing.cc -o scripts/_build/file_api_timing -Lspz_b200/_lib -lspz_b200 -Wl,-rpath,'$ORIGIN/../../spz_b200/_lib' || exit 1
+            { for n in 6e4 1e6 4e6; do
+                [ -x scripts/_build/file_api_timing_ref ] && scripts/_build/file_api_timing_ref $n 1 reference | grep -v "^\[SPZ"
+                scripts/_build/file_api_timing $n 3 spz_b200 | grep -v "^\[SPZ" | tail -2
+              done
+              scripts/_build/file_api_timing 1e7 2 spz_b200 | grep -v "^\[SPZ" | tail -1
+              SPZ_B200_GZIP_THREADS=1 scripts/_build/file_api_timing 1e6 2 "spz_b200 SPZ_B200_GZIP_THREADS=1" | tail -1; } > gpurun_out/file_api.jsonl 2>&1; cat gpurun_out/file_api.jsonl ;;
+  hostprobe) # what the host copies per second (threads, memcpy vs non-temporal) and the two shapes of the bounce stage, bare
+            nvcc -O2 -Wno-deprecated-gpu-targets -o scripts/_build/host_copy_probe scripts/host_copy_probe.cu -Xcompiler -pthread,-mavx2 || exit 1
+            nvcc -O2 -Wno-deprecated-gpu-targets -o scripts/_build/bounce_probe scripts/bounce_probe.cu -Xcompiler -pthread,-mavx2 || exit 1
+            timeout 300 scripts/_build/host_copy_probe 1.5e9 > gpurun_out/host_copy_probe.jsonl 2>&1; timeout 400 scripts/_build/bounce_probe 2.36e9 > gpurun_out/bounce_probe.jsonl 2>&1
+            cat gpurun_out/host_copy_probe.jsonl gpurun_out/bounce_probe.jsonl ;;
   launches) # launch list of one short bench run (after the same command ran clean without ncu)
             timeout 900 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-ply "$@" > gpurun_out/launch_pre.json 2> gpurun_out/launch_pre.err || { echo "plain run failed"; exit 1; }
             timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Tiles|PerGaussian|Generic|unpackRecords|Ply|Tables|probePack' -c 400 --csv --log-file gpurun_out/launches.csv \
