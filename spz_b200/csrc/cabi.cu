@@ -579,10 +579,6 @@ int runBouncedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &ou
   };
   std::unique_ptr<Range[]> ranges(new Range[(size_t)numChunks]);
   std::atomic<int> firstError{(int)cudaSuccess};
-  auto note = [&](cudaError_t e) {
-    int expected = (int)cudaSuccess;
-    if (e != cudaSuccess) firstError.compare_exchange_strong(expected, (int)e);
-  };
   const int device = ctx->device;
 
   auto queueDown = [&](long long c) {
