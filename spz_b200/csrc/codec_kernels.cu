@@ -59,7 +59,10 @@ constexpr int gcdc(int a, int b) { return b == 0 ? a : gcdc(b, a % b); }
 // S = threads per CTA.  320 is the geometry everything was tuned for at 100M points; 128 (round 2) gives tiles 2.5x
 // smaller for launches whose tail is a visible part of their duration (SH degree 0, 1, 2; at degree 3 the phase
 // cycle would be 45 rows long with S = 128, and small degree-3 clouds use the per-gaussian kernels anyway).
-constexpr int kSmallThreads = 128;
+#ifndef SPZ_SMALL_THREADS
+#define SPZ_SMALL_THREADS 128  // must be = 2 mod 3 (Geo): 128, 224, 320, 416 ...; 224 x 6 CTAs/SM and 416 x 3 were tried for the SH-less decoder (notes section 25)
+#endif
+constexpr int kSmallThreads = SPZ_SMALL_THREADS;
 #ifndef SPZ_SH1_SMALL_M
 #define SPZ_SH1_SMALL_M 3  // SH degree 1, 128-thread geometry: sub-tiles per tile = SH rows in flight per phase class.  Measured (encode GB/s at
                            // 10M / 20M / 100M gaussians, profiles/r2_tuning_notes.txt section 16): M = 5 6290 / 6490 / 6750, M = 2 6375 / 6585 / 6636, M = 3 6478 / 6760 / 6866
