@@ -123,6 +123,18 @@ def test_config3_10m_sh3_full_oracle_compare(gpu_ctx, oracle):
     want_g = oracle_unpack_big(oracle, want, 8)
     for name, got, exp in zip(PLANES, g_dev.planes(), want_g.planes()):
         assert np.array_equal(bits(got.cpu().numpy()), bits(exp)), name
+    del dev, p_dev, g_dev
+    # the same cloud through the host-pointer entry points on plain (pageable) numpy planes: 39 bounced ranges of 2 MiB
+    # pieces in each direction -- what spz::packGaussians / unpackGaussians do with std::vector planes at this size
+    from spz_b200.codec import PackedPlanes
+    p_host, tm = gpu_ctx.encode_host(CloudPlanes(n, deg, *c.planes()), 6)
+    assert tm["staged"] == 3 and tm["chunks"] == -(-n // (1 << 18)), tm
+    for name, got, exp in zip(PLANES, p_host.planes(), want.planes()):
+        assert np.array_equal(np.asarray(got), exp), name
+    g_host, tm = gpu_ctx.decode_host(PackedPlanes(n, deg, *want.planes()), 8)
+    assert tm["staged"] == 3, tm
+    for name, got, exp in zip(PLANES, g_host.planes(), want_g.planes()):
+        assert np.array_equal(bits(np.asarray(got)), bits(exp)), name
 
 
 # ---- config 4: synthetic 10M SH0; v3 with LUF/RUF conversion and the v2 8-bit quaternion path -----
