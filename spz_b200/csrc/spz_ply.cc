@@ -91,6 +91,7 @@ bool readPlyRows(const std::string &filename, PlyLayout *layout, std::vector<flo
   // property name -> column
   std::unordered_map<std::string, int> column;
   static const char kProp[] = "property float ";
+  int properties = 0;
   for (int i = 0;; i++) {
     if (!nextHeaderLine(in, &line)) {
       say("[SPZ ERROR] %s: unexpected EOF while reading header properties.", name);
@@ -102,6 +103,7 @@ bool readPlyRows(const std::string &filename, PlyLayout *layout, std::vector<flo
       return false;
     }
     column[line.substr(sizeof(kProp) - 1)] = i;
+    properties = i + 1;
   }
   bool missing = false;
   auto col = [&](const char *field) {
@@ -127,7 +129,10 @@ bool readPlyRows(const std::string &filename, PlyLayout *layout, std::vector<flo
     L.rest.push_back(it->second);
   }
   L.shDim = (int)(L.rest.size() / 3);
-  L.width = (int)column.size();
+  // floats per vertex record = property lines, not distinct names: the reference sizes records by its map
+  // (load-spz.cc:738), so a header that repeats a name makes it index past the end of its buffer; here every
+  // column index stays inside the record
+  L.width = properties;
   L.numPoints = count;
 
   rows->clear();

@@ -501,6 +501,19 @@ def test_ply_io_matches_reference(mine, theirs, tmp_path):
         assert ga.n == gb.n, name
         if gb.n:
             assert_cloud_bits_equal(ga, gb, name)
+    # A header that names a property twice: the reference sizes a vertex record by its name -> column map and then
+    # indexes it with the (larger) line numbers, i.e. past the end of its buffer (load-spz.cc:740,801), so there is
+    # nothing to compare with.  Here a record is as wide as the header has property lines and the later line wins.
+    last = good[body:]
+    rows = np.frombuffer(last, np.float32).reshape(257, -1)
+    wide = np.concatenate([rows, rows[:, :1] + 100.0], axis=1)  # one more column at the end: the second "x"
+    dup = good[:body].replace(b"end_header\n", b"property float x\nend_header\n") + wide.astype(np.float32).tobytes()
+    open(str(tmp_path / "dup.ply"), "wb").write(dup)
+    gd = mine.load_ply(str(tmp_path / "dup.ply"), 0)
+    ref_last = theirs.load_ply(pb, 0)
+    assert gd.n == 257
+    assert np.array_equal(gd.positions[0::3], ref_last.positions[0::3] + np.float32(100.0))
+    assert np.array_equal(bits(gd.positions[1::3]), bits(ref_last.positions[1::3])) and np.array_equal(bits(gd.sh), bits(ref_last.sh))
 
 
 def test_parallel_gzip_is_a_standard_member_with_identical_content(mine, theirs):
