@@ -8,7 +8,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -34,6 +36,21 @@ bool nextHeaderLine(std::istream &in, std::string *line) {
     return true;
   }
   return false;
+}
+
+// fn(a, b) over [0, n) cut into contiguous ranges, one per host thread (small n: the calling thread alone).  The
+// per-point shuffles below are memory-bound loops over GBs for a large cloud; one thread moves ~2 GB/s of them.
+template <class Fn>
+void overPointRanges(size_t n, Fn &&fn) {
+  const size_t threads = n < 65536 ? 1 : std::min<size_t>({(size_t)16, std::max<size_t>(1, std::thread::hardware_concurrency()), n / 32768});
+  if (threads <= 1) {
+    fn((size_t)0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < threads; t++) pool.emplace_back([&fn, n, t, threads] { fn(n * t / threads, n * (t + 1) / threads); });
+  fn((size_t)0, n / threads);
+  for (auto &th : pool) th.join();
 }
 
 bool startsWith(const std::string &s, const char *prefix) { return s.compare(0, std::strlen(prefix), prefix) == 0; }
@@ -163,20 +180,26 @@ GaussianCloud loadSplatFromPly(const std::string &filename, const UnpackOptions 
   detail::resizeUninitialized(g.alphas, numPoints);
   detail::resizeUninitialized(g.colors, numPoints * 3);
   detail::resizeUninitialized(g.sh, numPoints * shDim * 3);
-  for (size_t p = 0; p < numPoints; p++) {
-    const float *row = rows.data() + p * width;
-    for (int a = 0; a < 3; a++) {
-      g.positions[p * 3 + a] = row[L.pos[a]];
-      g.scales[p * 3 + a] = row[L.scale[a]];
-      g.colors[p * 3 + a] = row[L.color[a]];
+  // The reference shuffles, then runs convertCoordinates(RDF, to) over the finished cloud (load-spz.cc:818-848): every
+  // position, quaternion xyz and SH value multiplied by its +-1 factor.  Same multiplications here, applied to each
+  // point as it is shuffled, on several threads.
+  const CoordinateConverter cv = coordinateConverter(CoordinateSystem::RDF, o.to);
+  overPointRanges(numPoints, [&](size_t first, size_t last) {
+    for (size_t p = first; p < last; p++) {
+      const float *row = rows.data() + p * width;
+      for (int a = 0; a < 3; a++) {
+        g.positions[p * 3 + a] = row[L.pos[a]] * cv.flipP[a];
+        g.scales[p * 3 + a] = row[L.scale[a]];
+        g.colors[p * 3 + a] = row[L.color[a]];
+      }
+      for (int a = 0; a < 3; a++) g.rotations[p * 4 + a] = row[L.rot[a]] * cv.flipQ[a];
+      g.rotations[p * 4 + 3] = row[L.rot[3]];
+      g.alphas[p] = row[L.alpha];
+      float *sh = g.sh.data() + p * shDim * 3;
+      for (size_t s = 0; s < shDim; s++)
+        for (size_t c = 0; c < 3; c++) sh[s * 3 + c] = row[L.rest[c * shDim + s]] * cv.flipSh[s];  // [C][S] -> [S][C]
     }
-    for (int a = 0; a < 4; a++) g.rotations[p * 4 + a] = row[L.rot[a]];
-    g.alphas[p] = row[L.alpha];
-    float *sh = g.sh.data() + p * shDim * 3;
-    for (size_t s = 0; s < shDim; s++)
-      for (size_t c = 0; c < 3; c++) sh[s * 3 + c] = row[L.rest[c * shDim + s]];  // [C][S] -> [S][C]
-  }
-  g.convertCoordinates(CoordinateSystem::RDF, o.to);
+  });
   return g;
 }
 
@@ -322,11 +345,12 @@ bool saveSplatToPly(const GaussianCloud &g, const PackOptions &o, const std::str
   const std::string header = plyHeader(g.numPoints, shDim);
   out.write(header.data(), (std::streamsize)header.size());
 
-  constexpr size_t kBatch = 4096;  // points per write
-  std::vector<float> rows(kBatch * width);
+  const size_t kBatch = n < 65536 ? 4096 : 262144;  // points per write; large batches are filled by several threads
+  std::vector<float> rows(std::min(kBatch, std::max<size_t>(n, 1)) * width);
   for (size_t base = 0; base < n; base += kBatch) {
     const size_t m = std::min(kBatch, n - base);
-    for (size_t k = 0; k < m; k++) {
+    overPointRanges(m, [&](size_t first, size_t last) {
+    for (size_t k = first; k < last; k++) {
       const size_t p = base + k;
       float *row = rows.data() + k * width;
       for (int a = 0; a < 3; a++) {
@@ -344,6 +368,7 @@ bool saveSplatToPly(const GaussianCloud &g, const PackOptions &o, const std::str
       tail[4] = g.rotations[p * 4 + 3];  // w first
       for (int a = 0; a < 3; a++) tail[5 + a] = c.flipQ[a] * g.rotations[p * 4 + a];
     }
+    });
     out.write(reinterpret_cast<const char *>(rows.data()), (std::streamsize)(m * width * sizeof(float)));
   }
   out.close();

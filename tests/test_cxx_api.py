@@ -478,6 +478,13 @@ def test_ply_io_matches_reference(mine, theirs, tmp_path):
                 assert ga.n == gb.n == 257 and ga.sh_degree == gb.sh_degree == deg
                 assert_cloud_bits_equal(ga, gb, f"ply deg{deg} from{frm} to{to}")
     assert not mine.save_ply(c, "/nonexistent_dir/x.ply", 0)
+    # a cloud large enough for the multi-threaded shuffles (>= 64K points; 300K points = two write batches)
+    for n_big, deg_big in ((70_001, 1), (300_000, 0)):
+        big = random_cloud(rng, n_big, deg_big, False)
+        pa, pb2 = str(tmp_path / "big_a.ply"), str(tmp_path / "big_b.ply")
+        assert mine.save_ply(big, pa, 8) and theirs.save_ply(big, pb2, 8)
+        assert open(pa, "rb").read() == open(pb2, "rb").read()
+        assert_cloud_bits_equal(mine.load_ply(pb2, 7), theirs.load_ply(pb2, 7), f"large ply {n_big}")
     # malformed files: both hand back an empty cloud
     good = open(pb, "rb").read()
     body = good.index(b"end_header\n") + len(b"end_header\n")
