@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <algorithm>
 #include <string>
@@ -48,8 +49,14 @@ void overPointRanges(size_t n, Fn &&fn) {
     return;
   }
   std::vector<std::thread> pool;
-  for (size_t t = 1; t < threads; t++) pool.emplace_back([&fn, n, t, threads] { fn(n * t / threads, n * (t + 1) / threads); });
+  size_t started = 1;
+  try {
+    for (; started < threads; started++) pool.emplace_back([&fn, n, started, threads] { fn(n * started / threads, n * (started + 1) / threads); });
+  } catch (const std::exception &) {
+    // no more threads to be had: the calling thread takes the ranges that did not get one
+  }
   fn((size_t)0, n / threads);
+  for (size_t t = started; t < threads; t++) fn(n * t / threads, n * (t + 1) / threads);
   for (auto &th : pool) th.join();
 }
 
