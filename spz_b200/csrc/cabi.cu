@@ -215,7 +215,11 @@ class CopyPool {
  public:
   using Task = std::function<void()>;
   explicit CopyPool(int threads) {
-    for (int i = 0; i < threads; i++) workers_.emplace_back([this] { loop(); });
+    try {
+      for (int i = 0; i < threads; i++) workers_.emplace_back([this] { loop(); });
+    } catch (const std::exception &) {
+      // fewer threads than asked for (none, in the limit): helpUntil() makes the calling thread a worker too
+    }
   }
   ~CopyPool() {
     {

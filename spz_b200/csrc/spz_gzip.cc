@@ -48,7 +48,11 @@ void parallelFor(size_t count, int threads, Fn &&fn) {
   };
   std::vector<std::thread> pool;
   const int extra = (int)std::min<size_t>(count, (size_t)std::max(1, threads)) - 1;
-  for (int t = 0; t < extra; t++) pool.emplace_back(work);
+  try {
+    for (int t = 0; t < extra; t++) pool.emplace_back(work);
+  } catch (const std::exception &) {
+    // fewer threads than asked for: the ones that started (and this one) share the blocks
+  }
   work();
   for (auto &t : pool) t.join();
 }
