@@ -229,10 +229,19 @@ class CopyPool {
     cv_.notify_all();
     for (auto &t : workers_) t.join();
   }
-  void submit(std::vector<Task> &&tasks) {
+  void submit(std::vector<Task> &&tasks) {  // all or nothing: an allocation failure leaves the queue as it was and rethrows
     {
       std::lock_guard<std::mutex> g(m_);
-      for (Task &t : tasks) queue_.push_back(std::move(t));
+      size_t pushed = 0;
+      try {
+        for (Task &t : tasks) {
+          queue_.push_back(std::move(t));
+          pushed++;
+        }
+      } catch (...) {
+        while (pushed--) queue_.pop_back();
+        throw;
+      }
     }
     cv_.notify_all();
   }
@@ -588,7 +597,6 @@ int runBouncedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &ou
   auto queueDown = [&](long long c) {
     Range &r = ranges[(size_t)c];
     if (r.downQueued || !r.launched) return;
-    r.downQueued = true;
     std::vector<CopyPool::Task> tasks;
     tasks.reserve(r.down.size());
     for (const DownPiece &d : r.down) {
@@ -618,7 +626,8 @@ int runBouncedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &ou
       };
       tasks.emplace_back(DownTask{d, &r, &pool, &firstError, device, 0});
     }
-    pool.submit(std::move(tasks));
+    pool.submit(std::move(tasks));  // may throw (out of memory): nothing queued then, and downQueued stays false
+    r.downQueued = true;
   };
   // host time of the coordinator inside the pool (helping with / waiting for copies)
   auto helpUntil = [&](std::atomic<int> &counter) {
@@ -696,7 +705,12 @@ int runBouncedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &ou
         }
       }
       r.upLeft.store((int)tasks.size());
-      pool.submit(std::move(tasks));
+      try {
+        pool.submit(std::move(tasks));
+      } catch (...) {
+        r.upLeft.store(0);  // nothing was queued
+        throw;
+      }
     } else {
       for (int i = 0; i < in.count; i++) {
         const size_t bytes = in.per[i] * (size_t)pts;
@@ -771,7 +785,12 @@ int runBouncedStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &ou
     }
     return SPZB200_OK;
   };
-  const int rc = body();
+  int rc;
+  try {
+    rc = body();
+  } catch (const std::exception &e) {  // allocation failure while building a range's task list: a failed call, after the tasks already queued have run out
+    rc = fail(SPZB200_ERR_NOMEM, "host pipeline: %s", e.what());
+  }
   if (rc != SPZB200_OK) {
     // tasks still queued hold pointers into the caller's planes, the stage buffers and `ranges`: let them run out
     // (a down task of a range whose D2H never got queued is never submitted; its counter is not waited on)
@@ -846,7 +865,12 @@ int runPipelineStages(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &o
 template <class Launch>
 int runPipeline(SpzB200Context *ctx, const PlaneSet &in, const PlaneSet &out, long long n, long long granule,
                 Launch &&launch, SpzB200Timings *timings) {
-  const int rc = runPipelineStages(ctx, in, out, n, granule, launch, timings);
+  int rc;
+  try {
+    rc = runPipelineStages(ctx, in, out, n, granule, launch, timings);
+  } catch (const std::exception &e) {  // nothing may cross the C boundary
+    rc = fail(SPZB200_ERR_NOMEM, "host pipeline: %s", e.what());
+  }
   if (rc != SPZB200_OK) {
     const std::string first = tlsError;
     for (int s = 0; s < kStages; s++)
@@ -1003,8 +1027,7 @@ int runSharded(const int32_t *devices, int32_t numDevices, int64_t n, int32_t sh
   std::vector<SpzB200Timings> tms(numDevices);
   std::vector<std::thread> threads;
   const double w0 = nowMs();
-  for (int32_t i = 0; i < numDevices; i++) {
-    threads.emplace_back([&, i]() {
+  auto shard = [&](int32_t i) {
       std::memset(&tms[i], 0, sizeof(SpzB200Timings));
       int64_t a = 0, b = 0;
       rc[i] = spzb200_shard_range(n, shDegree, numDevices, i, &a, &b);
@@ -1014,12 +1037,19 @@ int runSharded(const int32_t *devices, int32_t numDevices, int64_t n, int32_t sh
         if (rc[i] == SPZB200_OK) {
           tlsShardCount = numDevices;
           rc[i] = perShard(ctx, a, b, &tms[i]);
+          tlsShardCount = 1;
           if (rc[i] != SPZB200_OK) msg[i] = spzb200_last_error();
           contextPool().release(ctx);
         }
       }
       if (rc[i] != SPZB200_OK && msg[i].empty()) msg[i] = spzb200_last_error();
-    });
+  };
+  for (int32_t i = 0; i < numDevices; i++) {
+    try {
+      threads.emplace_back(shard, i);
+    } catch (const std::exception &) {
+      shard(i);  // no thread to be had: this device's range runs on the calling thread
+    }
   }
   for (auto &t : threads) t.join();
   for (int32_t i = 0; i < numDevices; i++)
@@ -1177,7 +1207,12 @@ int spzb200_create(int32_t device, SpzB200Context **out) {
 
 int spzb200_acquire(int32_t device, SpzB200Context **out) {
   if (!out) return fail(SPZB200_ERR_INVALID, "spzb200_acquire: null out");
-  return contextPool().acquire(device, out);
+  try {
+    return contextPool().acquire(device, out);
+  } catch (const std::exception &e) {
+    *out = nullptr;
+    return fail(SPZB200_ERR_NOMEM, "spzb200_acquire: %s", e.what());
+  }
 }
 
 void spzb200_release(SpzB200Context *ctx) {
@@ -1819,8 +1854,14 @@ int spzb200_unpack_gather_host(SpzB200Context *ctx, const SpzB200Packed *packed,
       return;
     }
     std::vector<std::thread> th;
-    for (int w = 1; w < workers; w++) th.emplace_back(part, count * w / workers, count * (w + 1) / workers);
+    int started = 1;
+    try {
+      for (; started < workers; started++) th.emplace_back(part, count * started / workers, count * (started + 1) / workers);
+    } catch (const std::exception &) {
+      // no more threads to be had: the rest of the chunk is gathered on this one
+    }
     part(0, count / workers);
+    for (int w = started; w < workers; w++) part(count * w / workers, count * (w + 1) / workers);
     for (auto &t : th) t.join();
   }));
 }
