@@ -93,7 +93,7 @@ struct LaunchPlan {
   bool flatGrid;       // one CTA per tile (default) instead of persistent grid-stride CTAs
   bool decodeBulk;     // decode the SH plane through bulk async copies (TMA) instead of registers
   int encodeBulk;      // planar encoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it measured
-                       // faster (SH degree 3, at most 24M gaussians per launch; default), 2 wherever it exists
+                       // faster (SH degree 3 up to 24M gaussians per launch, degree 2 from 1M to 24M, degree 1 up to 6M; default), 2 wherever it exists
   int decodePerGaussian;   // planar decoder through the one-thread-per-gaussian bulk-copy kernel: 0 never, 1 where it
                            // measured faster (SH degree 1 - 3; default), 2 also for SH-less clouds
   int smallTilesEncode, smallTilesDecode;  // 128-thread tile geometry for SH degree 0 - 2: 0 never, 1 up to 16M gaussians per launch, 2 always.

@@ -142,8 +142,7 @@ struct PlanarSource {
     bulkLoadOn(buf + oColor, a.colors + g0 * 3, 12 * G, bar);
     if constexpr (D > 0) bulkLoadOn(buf + oSh, a.sh + g0 * (3 * D), 12 * D * G, bar);
   }
-  // lane strides of 3 and 3*D words are odd (D = 0, 3, 15; D = 8 keeps the register-path kernel), so the
-  // 32-bit loads are bank-conflict free
+  // lane strides of 3 and 3*D words are odd (D = 0, 3, 15), so the 32-bit loads are bank-conflict free; D = 8 below
   static __device__ __forceinline__ void read(const unsigned char *buf, int t, float (&r)[C::W]) {
     const float *f = reinterpret_cast<const float *>(buf);
 #pragma unroll
@@ -159,8 +158,24 @@ struct PlanarSource {
     r[C::kRot + 2] = q.y;
     r[C::kRot + 3] = q.z;
     r[C::kAlpha] = f[oAlpha / 4 + t];
+    if constexpr (D == 8) {
+      // 24-word lane stride: 32-bit loads would be 8-way bank conflicts; six 128-bit loads per lane are 2-way
+      // (quarter-warp phases, stride 6 quad-words), which the shared-memory bandwidth has room for
+      const float4 *s4 = reinterpret_cast<const float4 *>(buf + oSh) + 6 * t;
 #pragma unroll
-    for (int k = 0; k < 3 * D; k++) r[C::kRest + (k % 3) * D + k / 3] = f[oSh / 4 + 3 * D * t + k];
+      for (int j = 0; j < 6; j++) {
+        const float4 v = s4[j];
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int k = 4 * j + q;
+          r[C::kRest + (k % 3) * D + k / 3] = e[q];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3 * D; k++) r[C::kRest + (k % 3) * D + k / 3] = f[oSh / 4 + 3 * D * t + k];
+    }
   }
 };
 
@@ -532,17 +547,21 @@ cudaError_t launchEncodePlyCanonical(const PlyEncodeArgs &a, const LaunchPlan &p
 // packGaussians on planar float planes through the same kernel; *done as above.  By default only where it measured
 // faster than the register-path tile encoder: SH degree 3 clouds (or shards, or pipeline ranges) of at most 24M
 // gaussians -- 10M points 7045 vs 6414 GB/s, 2.5M 5616 vs 5215, 20M 6902 vs 6793; from 40M up the tile encoder
-// leads by about 1 % (6761 vs 6671 at 100M), and at degree 1 by more.  Degree 2 has no planar form here (24-word
-// lane stride on the 32-bit shared-memory reads).
+// leads by about 1 % (6761 vs 6671 at 100M), and at degree 1 by more.
 constexpr long long kEncodePerGaussianMaxPoints = 24000000;
 // Round 2, SH degree 1 (profiles/r2_ab_encode_pergaussian_vs_tiles.jsonl): the tile encoder's 6400-gaussian tiles quantise small launches
 // badly (1.25M points = 195 CTAs on 148 SMs).  Per-gaussian vs tiles, same box, GB/s: 1.25M 5062 vs 2734, 2.5M 5583 vs 4780, 5M 5862 vs 5327,
 // 10M 6056 vs 6267, 20M 6141 vs 6424 -> per-gaussian up to 6M points.
 constexpr long long kEncodePerGaussianMaxPointsSh1 = 6000000;
+// SH degree 2 (planar source with 128-bit shared-memory reads of the 24-word SH records; profiles/r2_ab_encode_pergaussian_sh2.jsonl), per-gaussian vs
+// 128-thread tiles, GB/s: 600K 5204 vs 5410, 1.25M 6051 vs 5759, 2.5M 6558 vs 6237, 5M 6857 vs 6689, 10M 7005 vs 6865, 20M 7094 vs 6981, 40M 6950 vs 7006
+// -> per-gaussian from 1M to 24M points.
+constexpr long long kEncodePerGaussianMinPointsSh2 = 1000000, kEncodePerGaussianMaxPointsSh2 = 24000000;
 cudaError_t launchEncodePerGaussianPlanar(const EncodeArgs &a, const LaunchPlan &plan, cudaStream_t stream, long long *done) {
   *done = 0;
-  if (plan.forceGeneric || plan.encodeBulk == 0 || a.shDim == 8 || a.version != 3) return cudaSuccess;  // version-2 streams: tile encoder only
-  if (plan.encodeBulk < 2 && !((a.shDim == 15 && a.n <= kEncodePerGaussianMaxPoints) || (a.shDim == 3 && a.n <= kEncodePerGaussianMaxPointsSh1)))
+  if (plan.forceGeneric || plan.encodeBulk == 0 || a.version != 3) return cudaSuccess;  // version-2 streams: tile encoder only
+  if (plan.encodeBulk < 2 && !((a.shDim == 15 && a.n <= kEncodePerGaussianMaxPoints) || (a.shDim == 3 && a.n <= kEncodePerGaussianMaxPointsSh1) ||
+                               (a.shDim == 8 && a.n >= kEncodePerGaussianMinPointsSh2 && a.n <= kEncodePerGaussianMaxPointsSh2)))
     return cudaSuccess;
   if (!(aligned16(a.positions) && aligned16(a.scales) && aligned16(a.rotations) && aligned16(a.alphas) && aligned16(a.colors) &&
         (a.shDim == 0 || aligned16(a.sh)) && aligned16(a.oPositions) && aligned16(a.oScales) && aligned16(a.oRotations) &&

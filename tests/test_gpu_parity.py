@@ -505,6 +505,17 @@ def test_rotation_encode_decode_large_random(gpu_ctx, oracle):
         assert np.array_equal(bits(gpu_unpack(gpu_ctx, s, to).rotations), bits(oracle.unpack(s, to).rotations))
 
 
+@pytest.mark.parametrize("deg,n", [(2, 1_200_037), (1, 1_100_011), (3, 1_000_003), (2, 999_000)])
+def test_default_encoder_dispatch_by_size(gpu_ctx, oracle, deg, n):
+    """The default encoder depends on the launch size: one thread per gaussian with bulk copies for SH degree 3 up to
+    24M gaussians, degree 2 from 1M to 24M (128-bit shared-memory reads of the 24-word SH records), degree 1 up to 6M;
+    register-path tiles elsewhere (pergaussian_kernels.cu: launchEncodePerGaussianPlanar).  Sizes on both sides of the
+    degree-2 switch, with a ragged remainder, against the oracle -- NaN / Inf / huge inputs included."""
+    rng = np.random.default_rng(5200 + deg)
+    c = random_cloud(rng, n, deg, True)
+    assert_packed_equal(gpu_pack(gpu_ctx, c, 7), oracle.pack(c, 7), f"deg{deg} n{n}")
+
+
 # ---- the host-pointer pipeline (what the C++/Python drop-in API calls) -----------------------------
 
 @pytest.mark.parametrize("deg", [0, 3])
