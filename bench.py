@@ -249,6 +249,34 @@ def small_cloud_latency(ctx, codec, torch_cloud, dev, n, deg, args):
         torch.cuda.synchronize()
         if i >= 10:
             dev_us.append(e[0].elapsed_time(e[1]) * 1e3)
+    # the same pair captured once in a CUDA graph and replayed: what a consumer that decodes every frame would do, and
+    # the kernels' own latency without the Python -> ctypes launch path (~10-20 us per call)
+    graph_us = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ctx.encode_device(c, args.from_coord, out=p)
+            ctx.decode_device(p, args.to_coord, out=g)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ctx.encode_device(c, args.from_coord, out=p)
+            ctx.decode_device(p, args.to_coord, out=g)
+        ts = []
+        for i in range(60):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            e[0].record()
+            graph.replay()
+            e[1].record()
+            torch.cuda.synchronize()
+            if i >= 10:
+                ts.append(e[0].elapsed_time(e[1]) * 1e3)
+        graph_us = statistics.median(ts)
+        del graph
+    except Exception as ex:  # noqa: BLE001 -- an optional extra; the bench line does not depend on it
+        graph_us = f"unavailable: {ex!r}"[:200]
     hc = codec.alloc_cloud(n, deg, pinned=True, numpy_arrays=True)
     hp = codec.alloc_packed(n, deg, 3, pinned=True, numpy_arrays=True)
     hb = codec.alloc_cloud(n, deg, pinned=True, numpy_arrays=True)
@@ -263,8 +291,9 @@ def small_cloud_latency(ctx, codec, torch_cloud, dev, n, deg, args):
         if i >= 10:
             host_us.append((time.perf_counter() - t0) * 1e6)
     return {"points": n, "sh_degree": deg, "device_encode_plus_decode_us": statistics.median(dev_us),
+            "device_encode_plus_decode_cuda_graph_us": graph_us,
             "host_api_encode_plus_decode_us": statistics.median(host_us),
-            "note": "median of 50; device = two launches (encode, decode; the sub-tile remainder rides in each) on resident planes, issued from Python through ctypes, so it is launch-bound, not bandwidth-bound (the data moves in ~6 us); host = spzb200_encode_host + spzb200_decode_host with pinned planes, i.e. 18 MB over PCIe each way"}
+            "note": "median of 50; device = two launches (encode, decode; the sub-tile remainder rides in each) on resident planes, issued from Python through ctypes, so it is launch-bound, not bandwidth-bound (the data moves in ~6 us); cuda_graph = the same two launches captured once and replayed (no host launch path); host = spzb200_encode_host + spzb200_decode_host with pinned planes, i.e. 18 MB over PCIe each way"}
 
 
 def time_host_zlib(packed, deg, sample_points):
