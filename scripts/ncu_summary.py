@@ -34,9 +34,11 @@ def main(path):
             if any(re.search(k, h) for k in KEYS):
                 print(f"{h:85s} {r[i]:>18s} {units[i]}")
         try:
-            rd = float(r[hdr.index('dram__bytes_read.sum')]); wr = float(r[hdr.index('dram__bytes_write.sum')])
-            u = units[hdr.index('dram__bytes_read.sum')]
-            print(f"{'TRAFFIC dram read+write':85s} {rd + wr:18.6f} {u}")
+            # this ncu prints each column in a unit of its own choosing (read in Gbyte beside write in Mbyte): sum in bytes
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            i_rd, i_wr = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+            total = float(r[i_rd]) * scale[units[i_rd]] + float(r[i_wr]) * scale[units[i_wr]]
+            print(f"{'TRAFFIC dram read+write':85s} {total / 1e9:18.6f} Gbyte")
         except Exception:  # noqa: BLE001
             pass
 
